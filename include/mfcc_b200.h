@@ -1,0 +1,172 @@
+/*
+ * mfcc_b200.h — C ABI of the B200-native MFCC front end (libmfcc_b200.so).
+ *
+ * Boundary note.  The nominal reference, simotin13/mfcc, is a toy C compiler
+ * ("mf C Compiler"); it has no MFCC API to bind to.  Its
+ * only public entry points are
+ *     int tokenize(char*, unsigned, Vector*)                    src/mfcc/lex.h:75
+ *     int parse_tokens(Vector*, Vector*, Program*)              src/mfcc/parser.h:17
+ *     int generate_binary(char*, Vector*, Program*, BuildTargetType)
+ *                                                               src/mfcc/codegen.h:18
+ * and the header the north star imagines holds the MFCC parameters,
+ * src/mfcc/mfcc.h:1-22, only defines STRING_MAX / CODE_LEN_MAX / BuildTargetType.
+ * What IS kept from the reference is its convention:
+ *   - plain C, plain pointers and sizes, caller-owned buffers filled in place
+ *     (src/mfcc/main.c:64-66);
+ *   - `int` return, 0 = ok, negative = failure (src/mfcc/main.c:72-76,78-82,
+ *     src/mfcc/lex.c:165,197,320) — but a library never exit()s or assert()s.
+ * The parameter list is the one BASELINE.json's north_star names: sample rate,
+ * frame length / hop, pre-emphasis, window, FFT size, mel-band count, cepstral
+ * count.  Every self-chosen convention is a field so a real reference can be
+ * matched later.
+ *
+ * There is NO CPU fallback behind any entry point that computes: every
+ * compute call runs hand-written sm_100a kernels or fails with MFCC_ECUDA.
+ */
+#ifndef MFCC_B200_H_
+#define MFCC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (0 = ok, negative = failure; cf. src/mfcc/main.c:72-76) ---- */
+#define MFCC_OK        0
+#define MFCC_EINVAL   (-1)  /* bad parameter / NULL pointer / inconsistent offsets */
+#define MFCC_ENOMEM   (-2)  /* host or device allocation failed */
+#define MFCC_ECUDA    (-3)  /* CUDA runtime error or no sm_100 device */
+#define MFCC_ENOTSUP  (-4)  /* valid request this build does not implement */
+
+/* ---- enumerations ---- */
+#define MFCC_WINDOW_RECT     0
+#define MFCC_WINDOW_HAMMING  1   /* 0.54 - 0.46 cos(2 pi n / (L-1)) */
+#define MFCC_WINDOW_HANN     2   /* 0.5  - 0.5  cos(2 pi n / (L-1)) */
+
+#define MFCC_PAD_NONE        0   /* n_frames = n < L ? 0 : 1 + (n - L) / hop  (truncate) */
+#define MFCC_PAD_ZERO_TAIL   1   /* n_frames = n <= 0 ? 0 : 1 + ceil(max(n - L, 0) / hop), zeros past the end */
+
+#define MFCC_OUT_CEPSTRA     0   /* [frames][n_cep]  DCT-II of log mel energies */
+#define MFCC_OUT_LOGMEL      1   /* [frames][n_mel]  log mel energies ("fbank") */
+
+#define MFCC_KERNEL_AUTO     0   /* fused tile kernel when the geometry has one, else generic */
+#define MFCC_KERNEL_GENERIC  1   /* one-frame-at-a-time shared-memory radix-2 kernel (any geometry) */
+#define MFCC_KERNEL_FUSED    2   /* fused 32-frame-tile kernel; plan creation fails if unavailable */
+
+/* ---- parameters (all conventions explicit; see DESIGN.md "Spec") ---- */
+typedef struct mfcc_params {
+    int32_t sample_rate;  /* Hz */
+    int32_t frame_len;    /* samples per frame (25 ms -> 400 @ 16 kHz) */
+    int32_t hop_len;      /* samples between frame starts (10 ms -> 160) */
+    int32_t nfft;         /* power of two, frame_len <= nfft <= 4096 */
+    int32_t n_mel;        /* mel bands, 1..128 */
+    int32_t n_cep;        /* cepstra kept, 1..n_mel */
+    float   preemph;      /* y[n] = x[n] - preemph * x[n-1] over the whole utterance, y[0] = x[0] */
+    int32_t window;       /* MFCC_WINDOW_* */
+    float   f_lo;         /* lowest mel edge, Hz */
+    float   f_hi;         /* highest mel edge, Hz; <= 0 means sample_rate / 2 */
+    float   log_floor;    /* L[m] = ln(max(E[m], log_floor)) */
+    int32_t lifter;       /* 0 = none; Q > 0: c[k] *= 1 + (Q/2) sin(pi k / Q) */
+    int32_t pad_mode;     /* MFCC_PAD_* */
+    int32_t output;       /* MFCC_OUT_* */
+} mfcc_params;
+
+typedef struct mfcc_plan  mfcc_plan;   /* immutable after creation; owns device tables */
+typedef struct mfcc_batch mfcc_batch;  /* the shape of one batch: offsets -> frame rows -> tiles */
+
+/* Fill *p with the repo defaults for a sample rate: 25 ms frame, 10 ms hop,
+ * nfft = next power of two, 26 mel, 13 cepstra, preemph 0.97, Hamming,
+ * f_lo 0, f_hi sr/2, floor 1e-10, no lifter, no padding, cepstra out. */
+int mfcc_params_init(mfcc_params *p, int32_t sample_rate);
+
+/* 0 if the parameter set is usable, MFCC_EINVAL otherwise.  Pure host code. */
+int mfcc_params_validate(const mfcc_params *p);
+
+/* Frames an utterance of n_samples yields under p->pad_mode (pure host code;
+ * bit-exact framing contract).  Negative on bad parameters. */
+int64_t mfcc_num_frames(const mfcc_params *p, int64_t n_samples);
+
+/* Floats per output frame: n_cep or n_mel depending on p->output. */
+int32_t mfcc_out_dim(const mfcc_params *p);
+
+/* Build window / mel / DCT / twiddle tables in double, round once to f32 and
+ * upload them to CUDA device `device` (-1 = current).  `kernel` is MFCC_KERNEL_*. */
+int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_plan **out);
+void mfcc_plan_destroy(mfcc_plan *plan);
+int mfcc_plan_params(const mfcc_plan *plan, mfcc_params *out);
+/* Name of the kernel family the plan launches ("fused_r16x16_n512", "generic_radix2", ...). */
+const char *mfcc_plan_kernel_name(const mfcc_plan *plan);
+
+/* Host copies of the plan's f32 tables, for tests and for callers that want to
+ * reproduce the arithmetic.  Each returns the element count (or negative);
+ * pass NULL to query the count.
+ *   window : frame_len               mel_bins : n_mel + 2 (int32 bin edges)
+ *   mel_w  : n_mel * (nfft/2 + 1)    dct      : n_out_cep * n_mel (lifter folded in) */
+int64_t mfcc_plan_window(const mfcc_plan *plan, float *dst);
+int64_t mfcc_plan_mel_bins(const mfcc_plan *plan, int32_t *dst);
+int64_t mfcc_plan_mel_weights(const mfcc_plan *plan, float *dst);
+int64_t mfcc_plan_dct(const mfcc_plan *plan, float *dst);
+
+/* Describe a batch: utterance u is pcm[h_offsets[u] .. h_offsets[u+1]) in one
+ * concatenated int16 array (h_offsets is HOST memory, n_utts + 1 entries,
+ * non-decreasing).  Computes frame rows and the tile table and uploads it. */
+int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts,
+                      mfcc_batch **out);
+void mfcc_batch_destroy(mfcc_batch *batch);
+int64_t mfcc_batch_total_frames(const mfcc_batch *batch);
+int64_t mfcc_batch_total_samples(const mfcc_batch *batch);
+/* frame_offsets[u] = first output row of utterance u; n_utts + 1 entries. */
+int mfcc_batch_frame_offsets(const mfcc_batch *batch, int64_t *h_frame_offsets);
+
+/* THE HOT ENTRY.  Device pointers, asynchronous on `cuda_stream` (a
+ * cudaStream_t passed as void*, NULL = default stream):
+ *   d_pcm : int16, total_samples elements, device memory
+ *   d_out : f32, total_frames * out_dim elements, device memory, row = frame
+ * Allocates nothing; launches only kernels.  Reentrant for distinct streams. */
+int mfcc_compute_batch(const mfcc_plan *plan, const mfcc_batch *batch,
+                       const int16_t *d_pcm, float *d_out, void *cuda_stream);
+/* Same for f32 PCM already scaled to int16 range (value = sample * 32768). */
+int mfcc_compute_batch_f32(const mfcc_plan *plan, const mfcc_batch *batch,
+                           const float *d_pcm, float *d_out, void *cuda_stream);
+
+/* End-to-end call with HOST buffers: H2D copy of the PCM, the kernels, D2H
+ * copy of the features, pipelined in chunks over internal streams; returns
+ * after the features are in h_out.  Pinned host buffers (mfcc_host_alloc)
+ * make the copies asynchronous.  h_frame_offsets may be NULL. */
+int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets,
+                      int64_t n_utts, float *h_out, int64_t *h_frame_offsets);
+
+/* Single-clip convenience (the shape a C caller of an embedded MFCC routine
+ * expects): n samples in, *n_frames rows of out_dim floats out. */
+int mfcc_compute(mfcc_plan *plan, const int16_t *pcm, int64_t n_samples,
+                 float *out, int64_t *n_frames);
+
+/* Post-processing on the feature matrix in place on the device (SURVEY.md §8f
+ * rank 2): per-utterance cepstral mean (and optionally variance)
+ * normalisation, and delta / delta-delta regression (window N, HTK formula)
+ * written to d_delta / d_delta2 (either may be NULL). */
+int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_feat,
+                    int32_t norm_var, void *cuda_stream);
+int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat,
+                     int32_t window, float *d_delta, void *cuda_stream);
+
+/* Input format widening: G.711 mu-law / A-law bytes to
+ * int16 PCM on the device, elementwise, async on the stream. */
+int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst,
+                     void *cuda_stream);
+
+/* Pinned host memory helpers for the end-to-end path. */
+int mfcc_host_alloc(void **ptr, int64_t bytes);
+int mfcc_host_free(void *ptr);
+
+/* Kernel launches issued by this library in this process (bench.py's gpu_launches). */
+uint64_t mfcc_launch_count(void);
+
+const char *mfcc_strerror(int err);
+const char *mfcc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFCC_B200_H_ */
