@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — MFCC frames/sec on B200 (BASELINE.json `metric`), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|B|C]
+
+A "step" is one pass of the hot path (mfcc_compute_batch) over one resident
+batch of synthetic PCM.  At N=1 the workload is BASELINE.json configs[1]:
+1,024 x 10 s of 16 kHz int16, 25 ms / 10 ms, 512-pt FFT, 26 mel, 13 MFCC
+(1,021,952 frames, 327.7 MB in — larger than the 126 MB L2, so every step
+re-reads its input from HBM).  At N>1 every rank holds its own such batch
+(weak scaling, configs[4]: "10k hours sharded", iterated over a resident buffer)
+and there is no data-path collective.
+
+value     device-timed frames/s, inputs resident in HBM, CUDA events, max over ranks
+e2e       same metric through mfcc_compute_host: pinned HOST buffers, H2D + kernels + D2H timed
+roofline  FFT FLOPs (2.5 N log2 N per frame) against the FP32 FMA peak measured live by
+          tools/microbench; `roofline_hbm` is the stream-bytes view (hop*2 + n_cep*4 B per frame)
+cpu_baseline / --impl reference
+          the in-repo scalar C oracle on the host cores (the nominal reference,
+          simotin13/mfcc, is a C compiler with no MFCC path to time — SURVEY.md §0)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mfcc_b200 import CONFIGS  # noqa: E402
+from mfcc_b200.synth import fast_fixed_batch  # noqa: E402
+
+WORKLOADS = {
+    # name: (config, n_utts, samples per utterance, description)
+    "A": ("A", 1024, 160000, "configs[1]: 1024 x 10 s 16 kHz int16; frame 400 / hop 160 / nfft 512 / 26 mel / 13 cep"),
+    "B": ("B", 16384, 16000, "configs[2] fixed-2.0 s variant: 16384 x 2 s 8 kHz int16; 200/80/256/20/13"),
+    "C": ("C", 8, 28800000 // 4, "configs[3] reduced: 8 x 150 s 48 kHz int16; 1200/480/2048/80/40"),
+}
+
+
+def fft_flops(nfft: int) -> float:
+    return 2.5 * nfft * math.log2(nfft)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
+
+
+def measured_fp32_peak():
+    """FP32 FMA peak in TFLOP/s measured live by tools/microbench (scalar FFMA line)."""
+    exe = os.path.join(ROOT, "tools", "microbench")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        for line in out.splitlines():
+            d = json.loads(line)
+            if d.get("bench", "").startswith("ffma_scalar"):
+                return 2.0 * d["fma_per_s"] / 1e12, "measured live: tools/microbench scalar FFMA, 32 warps/SM"
+    except Exception:
+        pass
+    return 148 * 128 * 2 * 1.965e9 / 1e12, "derived 148 SM x 128 lanes x 2 x 1.965 GHz (microbench unavailable)"
+
+
+def cpu_leg(p, pcm, offsets, n_utts_sample, threads, repeats=1):
+    """Time the oracle on a bounded sample (the first n_utts_sample utterances)."""
+    import oracle
+    off = offsets[: n_utts_sample + 1]
+    x = pcm[: int(off[-1])]
+    oracle.mfcc_batch(p, x[: int(off[1])], off[:2], nthreads=1)  # build + page in
+    best = float("inf")
+    frames = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out, fo = oracle.mfcc_batch(p, x, off, nthreads=threads)
+        best = min(best, time.perf_counter() - t0)
+        frames = int(fo[-1])
+    return frames / best, frames, best
+
+
+def run_reference(args, p, cfg_name, desc, n_utts, n_samp):
+    """--impl reference: the CPU implementation of the path on the host cores.  The nominal
+    reference has none, so this is the in-repo scalar C oracle ("port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_utts = max(cores, min(n_utts, 64))
+    pcm, off = fast_fixed_batch(sample_utts, n_samp, seed=1000)
+    import oracle
+    oracle.mfcc_batch(p, pcm[:n_samp], off[:2], nthreads=1)
+    for _ in range(args.warmup):
+        oracle.mfcc_batch(p, pcm, off, nthreads=cores)
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        _, fo = oracle.mfcc_batch(p, pcm, off, nthreads=cores)
+        frames += int(fo[-1])
+    dt = time.perf_counter() - t0
+    v = frames / dt
+    sample = f"{sample_utts} utterances x {n_samp} samples per step ({frames // args.steps} frames), {cores} pthreads"
+    line = {
+        "impl": "reference", "metric": "mfcc_frames_per_sec", "value": v, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "params": cfg_name},
+        "audio_seconds_per_s": v * p.hop_len / p.sample_rate,
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "in-repo scalar C oracle; simotin13/mfcc has no MFCC path to time"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    cfg_name, n_utts, n_samp, desc = WORKLOADS[args.workload]
+    p = CONFIGS[cfg_name]()
+    if args.impl == "reference":
+        run_reference(args, p, cfg_name, desc, n_utts, n_samp)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mfcc_b200 import api, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the MFCC path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    kernel = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}[args.kernel]
+    plan = api.Plan(p, device=local, kernel=kernel)
+
+    # Synthetic batch, generated on the host, resident in HBM before timing.
+    pcm, off = fast_fixed_batch(n_utts, n_samp, seed=1000 + rank)
+    batch = plan.batch(off)
+    frames = batch.total_frames
+    in_bytes, out_bytes = pcm.nbytes, frames * plan.out_dim * 4
+    d_pcm = torch.from_numpy(pcm).cuda()
+    d_out = torch.empty((frames, plan.out_dim), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        plan.compute_batch(batch, d_pcm, d_out, stream)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    # keep the GPU busy long enough for nvidia-smi to see load: untimed pre-roll, then the timed K steps
+    for _ in range(50):
+        plan.compute_batch(batch, d_pcm, d_out, stream)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = api.launch_count()
+    t_host0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        plan.compute_batch(batch, d_pcm, d_out, stream)
+    ev1.record(stream)
+    barrier()
+    t_host1 = time.perf_counter()
+    launches = api.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    # hold the load a little longer so the sampler has rows inside the region even for short runs
+    t_hold = time.perf_counter()
+    while time.perf_counter() - t_hold < 0.6:
+        plan.compute_batch(batch, d_pcm, d_out, stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop(t_host0 - 0.3, time.perf_counter()) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+        total_frames = int(fr.item())
+    else:
+        total_frames = frames
+    value = total_frames * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through mfcc_compute_host (H2D + kernels + D2H inside the timed region) ----
+    h_in = api.PinnedBuffer((pcm.size,), np.int16)
+    h_in.array[:] = pcm
+    h_out = api.PinnedBuffer((frames, plan.out_dim), np.float32)
+    plan.compute_host(h_in.array, off, h_out.array)  # warm: allocates the plan's device buffers
+    plan.compute_host(h_in.array, off, h_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        plan.compute_host(h_in.array, off, h_out.array)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = total_frames * args.e2e_steps / e2e_dt
+    e2e_ok = bool(np.array_equal(h_out.array, d_out.cpu().numpy()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the only kernel in the step) ----
+    per_launch_s = ms * 1e-3 / max(launches, 1)
+    frames_per_launch = frames  # one launch covers the rank's whole batch
+    fp32_peak, fp32_how = measured_fp32_peak()
+    flops = fft_flops(p.nfft) * frames_per_launch
+    ach_tf = flops / per_launch_s / 1e12
+    bytes_alg = (p.hop_len * 2 + plan.out_dim * 4) * frames_per_launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fp32_peak, "traffic": None, "kernel": plan.kernel_name,
+                "algorithmic": f"2.5*N*log2(N) = {fft_flops(p.nfft):.0f} FLOP/frame x {frames_per_launch} frames/launch",
+                "peak_source": fp32_how}
+    roofline_hbm = {"bound": "hbm", "achieved": bytes_alg / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_alg / per_launch_s / 1e9 / hbm_peak, "traffic": None,
+                    "algorithmic": f"{p.hop_len * 2 + plan.out_dim * 4} B/frame x {frames_per_launch} frames/launch",
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            t = json.load(open(prof)).get(plan.kernel_name)
+            if t:
+                roofline["traffic"] = roofline_hbm["traffic"] = t
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu and args.workload == "A":
+        cores = os.cpu_count() or 1
+        n_s = max(cores, 32)
+        v, fr_s, dt = cpu_leg(p, pcm, off, n_s, cores)
+        v1, fr_1, dt1 = cpu_leg(p, pcm, off, 4, 1)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_s} utterances of the same batch ({fr_s} frames), {cores} pthreads, {dt:.2f} s",
+               "single_thread_value": v1,
+               "note": "in-repo scalar C oracle (gcc -O2); simotin13/mfcc has no MFCC path to time"}
+
+    line = {
+        "metric": "mfcc_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "params": cfg_name, "frames_per_step_per_gpu": frames,
+                   "kernel": plan.kernel_name, "l2": f"input {in_bytes / 1e6:.1f} MB per step > 126 MB L2 (no flush needed)",
+                   "parallelism": f"utterance-sharded x{world}, no data-path collective"},
+        "audio_seconds_per_s": value * p.hop_len / p.sample_rate,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "steps": args.e2e_steps, "api": "mfcc_compute_host (pinned host buffers, 3-stream chunk pipeline)",
+                "matches_device_path": e2e_ok},
+        "gpu_launches": launches,
+        "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,277 @@
+"""Host-side mirror of the C ABI (include/mfcc_b200.h) over ctypes.
+
+PyTorch is plumbing here: it owns device memory and streams; every number is
+produced by libmfcc_b200.so's own sm_100a kernels.  There is no CPU fallback —
+:func:`load` raises if the shared library is missing, and the library itself
+returns MFCC_ECUDA when no sm_100 device is present.
+
+The reference exposes no operator/plugin API for this path (its entry points
+are tokenize / parse_tokens / generate_binary, src/mfcc/lex.h:75,
+src/mfcc/parser.h:17, src/mfcc/codegen.h:18); what is mirrored is its calling
+convention: int status codes, caller-owned output buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .params import (MfccParams, KERNEL_AUTO, MFCC_OK)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmfcc_b200.so")
+_lib: Optional[C.CDLL] = None
+
+# name -> (restype, argtypes); every symbol include/mfcc_b200.h declares.
+_P = C.POINTER(MfccParams)
+_vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
+ABI = {
+    "mfcc_params_init": (C.c_int, [_P, _i32]),
+    "mfcc_params_validate": (C.c_int, [_P]),
+    "mfcc_num_frames": (_i64, [_P, _i64]),
+    "mfcc_out_dim": (_i32, [_P]),
+    "mfcc_plan_create": (C.c_int, [_P, _i32, _i32, C.POINTER(_vp)]),
+    "mfcc_plan_destroy": (None, [_vp]),
+    "mfcc_plan_params": (C.c_int, [_vp, _P]),
+    "mfcc_plan_kernel_name": (C.c_char_p, [_vp]),
+    "mfcc_plan_window": (_i64, [_vp, _vp]),
+    "mfcc_plan_mel_bins": (_i64, [_vp, _vp]),
+    "mfcc_plan_mel_weights": (_i64, [_vp, _vp]),
+    "mfcc_plan_dct": (_i64, [_vp, _vp]),
+    "mfcc_batch_create": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp)]),
+    "mfcc_batch_destroy": (None, [_vp]),
+    "mfcc_batch_total_frames": (_i64, [_vp]),
+    "mfcc_batch_total_samples": (_i64, [_vp]),
+    "mfcc_batch_frame_offsets": (C.c_int, [_vp, _vp]),
+    "mfcc_compute_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mfcc_compute_batch_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mfcc_compute_host": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "mfcc_compute": (C.c_int, [_vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "mfcc_cmvn_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "mfcc_delta_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "mfcc_decode_g711": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "mfcc_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
+    "mfcc_host_free": (C.c_int, [_vp]),
+    "mfcc_launch_count": (C.c_uint64, []),
+    "mfcc_strerror": (C.c_char_p, [C.c_int]),
+    "mfcc_version": (C.c_char_p, []),
+}
+
+
+class MfccError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = load().mfcc_strerror(code).decode() if _lib is not None else str(code)
+        super().__init__(f"{where}: {msg} ({code})")
+
+
+def load() -> C.CDLL:
+    """Load libmfcc_b200.so (built by ``__graft_entry__.build()`` / ``make -C mfcc_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for the MFCC path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library drift
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, where: str) -> None:
+    if rc != MFCC_OK:
+        raise MfccError(rc, where)
+
+
+def num_frames(p: MfccParams, n_samples: int) -> int:
+    return int(load().mfcc_num_frames(C.byref(p), n_samples))
+
+
+def launch_count() -> int:
+    return int(load().mfcc_launch_count())
+
+
+def _stream_handle(stream) -> Optional[int]:
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return getattr(stream, "cuda_stream", stream)
+
+
+class Batch:
+    """The shape of one batch: utterance offsets -> frame rows -> tile table (device-resident)."""
+
+    def __init__(self, plan: "Plan", offsets: Sequence[int]):
+        self.plan = plan
+        self.offsets = np.ascontiguousarray(offsets, np.int64)
+        if self.offsets.ndim != 1 or self.offsets.size < 1:
+            raise ValueError("offsets must be a 1-D array of n_utts + 1 entries")
+        self.n_utts = self.offsets.size - 1
+        h = _vp()
+        _check(load().mfcc_batch_create(plan._h, self.offsets.ctypes.data, self.n_utts, C.byref(h)),
+               "mfcc_batch_create")
+        self._h = h
+        self.total_frames = int(load().mfcc_batch_total_frames(h))
+        self.total_samples = int(load().mfcc_batch_total_samples(h))
+        self.frame_offsets = np.empty(self.n_utts + 1, np.int64)
+        _check(load().mfcc_batch_frame_offsets(h, self.frame_offsets.ctypes.data), "mfcc_batch_frame_offsets")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().mfcc_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Plan:
+    """Validated parameters + device tables on one GPU (``mfcc_plan`` in the C ABI)."""
+
+    def __init__(self, params: MfccParams, device: int = -1, kernel: int = KERNEL_AUTO):
+        self.params = params.copy()
+        h = _vp()
+        _check(load().mfcc_plan_create(C.byref(self.params), device, kernel, C.byref(h)), "mfcc_plan_create")
+        self._h = h
+        self.out_dim = self.params.out_dim
+        self.kernel_name = load().mfcc_plan_kernel_name(h).decode()
+        if device < 0:
+            import torch
+            device = torch.cuda.current_device()
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().mfcc_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- tables (host copies of what the kernels read) ----
+    def window(self) -> np.ndarray:
+        a = np.empty(load().mfcc_plan_window(self._h, None), np.float32)
+        load().mfcc_plan_window(self._h, a.ctypes.data)
+        return a
+
+    def mel_bins(self) -> np.ndarray:
+        a = np.empty(load().mfcc_plan_mel_bins(self._h, None), np.int32)
+        load().mfcc_plan_mel_bins(self._h, a.ctypes.data)
+        return a
+
+    def mel_weights(self) -> np.ndarray:
+        a = np.empty(load().mfcc_plan_mel_weights(self._h, None), np.float32)
+        load().mfcc_plan_mel_weights(self._h, a.ctypes.data)
+        return a.reshape(self.params.n_mel, self.params.nfft // 2 + 1)
+
+    def dct(self) -> np.ndarray:
+        a = np.empty(load().mfcc_plan_dct(self._h, None), np.float32)
+        load().mfcc_plan_dct(self._h, a.ctypes.data)
+        return a.reshape(self.params.n_cep, self.params.n_mel)
+
+    # ---- the hot entry: device tensors in, device tensor out ----
+    def batch(self, offsets: Sequence[int]) -> Batch:
+        return Batch(self, offsets)
+
+    def compute_batch(self, batch: Batch, pcm, out=None, stream=None):
+        """``pcm``: torch CUDA tensor, int16 (or float32 scaled to int16 range), >= total_samples
+        elements.  Returns ``out`` [total_frames, out_dim] float32 on the same device.  Asynchronous."""
+        import torch
+        if not pcm.is_cuda or pcm.device.index != self.device or not pcm.is_contiguous():
+            raise ValueError("pcm must be a contiguous CUDA tensor on the plan's device")
+        if pcm.numel() < batch.total_samples:
+            raise ValueError("pcm is shorter than the batch's offsets")
+        if out is None:
+            out = torch.empty((batch.total_frames, self.out_dim), dtype=torch.float32, device=pcm.device)
+        elif (out.dtype != torch.float32 or not out.is_contiguous() or out.device != pcm.device
+              or out.numel() < batch.total_frames * self.out_dim):
+            raise ValueError("out must be a contiguous float32 CUDA tensor of total_frames * out_dim")
+        if pcm.dtype == torch.int16:
+            fn, where = load().mfcc_compute_batch, "mfcc_compute_batch"
+        elif pcm.dtype == torch.float32:
+            fn, where = load().mfcc_compute_batch_f32, "mfcc_compute_batch_f32"
+        else:
+            raise TypeError("pcm must be int16 or float32")
+        with torch.cuda.device(self.device):
+            _check(fn(self._h, batch._h, pcm.data_ptr(), out.data_ptr(), _stream_handle(stream)), where)
+        return out
+
+    # ---- end to end with host buffers (H2D + kernels + D2H inside) ----
+    def compute_host(self, pcm: np.ndarray, offsets: Sequence[int], out: Optional[np.ndarray] = None):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n_utts = offsets.size - 1
+        fo = np.empty(n_utts + 1, np.int64)
+        if out is None:
+            total = 0
+            for u in range(n_utts):
+                nf = num_frames(self.params, int(offsets[u + 1] - offsets[u]))
+                if nf < 0:
+                    raise MfccError(int(nf), "mfcc_num_frames")
+                total += nf
+            out = np.empty((total, self.out_dim), np.float32)
+        _check(load().mfcc_compute_host(self._h, pcm.ctypes.data, offsets.ctypes.data, n_utts,
+                                        out.ctypes.data, fo.ctypes.data), "mfcc_compute_host")
+        return out, fo
+
+    def compute(self, pcm: np.ndarray) -> np.ndarray:
+        """Single clip, host in / host out (``mfcc_compute``)."""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        nf = num_frames(self.params, pcm.size)
+        out = np.empty((max(nf, 0), self.out_dim), np.float32)
+        got = _i64(0)
+        _check(load().mfcc_compute(self._h, pcm.ctypes.data, pcm.size, out.ctypes.data, C.byref(got)),
+               "mfcc_compute")
+        assert got.value == nf
+        return out
+
+    # ---- §8(f) widening ----
+    def cmvn(self, batch: Batch, feat, norm_var: bool = False, stream=None):
+        _check(load().mfcc_cmvn_batch(self._h, batch._h, feat.data_ptr(), int(norm_var),
+                                      _stream_handle(stream)), "mfcc_cmvn_batch")
+        return feat
+
+    def delta(self, batch: Batch, feat, window: int = 2, stream=None):
+        import torch
+        d = torch.empty_like(feat)
+        _check(load().mfcc_delta_batch(self._h, batch._h, feat.data_ptr(), window, d.data_ptr(),
+                                       _stream_handle(stream)), "mfcc_delta_batch")
+        return d
+
+
+def decode_g711(codes, alaw: bool = False, stream=None):
+    """uint8 CUDA tensor of G.711 codes -> int16 CUDA tensor of PCM."""
+    import torch
+    if codes.dtype != torch.uint8 or not codes.is_cuda or not codes.is_contiguous():
+        raise ValueError("codes must be a contiguous uint8 CUDA tensor")
+    out = torch.empty(codes.numel(), dtype=torch.int16, device=codes.device)
+    with torch.cuda.device(codes.device):
+        _check(load().mfcc_decode_g711(codes.data_ptr(), codes.numel(), int(alaw), out.data_ptr(),
+                                       _stream_handle(stream)), "mfcc_decode_g711")
+    return out
+
+
+class PinnedBuffer:
+    """Pinned host memory from the library (``mfcc_host_alloc``), viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, tuple) else shape
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = _vp()
+        _check(load().mfcc_host_alloc(C.byref(p), max(n, 1)), "mfcc_host_alloc")
+        self._p = p
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            load().mfcc_host_free(self._p)
+            self._p = None
+
+    __del__ = close

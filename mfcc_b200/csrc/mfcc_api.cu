@@ -1,0 +1,404 @@
+// mfcc_api.cu — the C ABI of libmfcc_b200.so (include/mfcc_b200.h) and the thin
+// host layer behind it: plan = validated parameters + device tables; batch =
+// offsets -> frame rows -> tile table; compute = kernel launches only.
+//
+// Convention kept from the reference: int return, 0 ok,
+// negative on failure (src/mfcc/main.c:72-76); caller-owned buffers filled in
+// place (src/mfcc/main.c:64-66).  Dropped: exit()/assert() on error
+// (src/mfcc/main.c:124-127, src/mfcc/codegen.c:166) — a library reports.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "mfcc_host.h"
+
+using mfcc::Tile;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename PcmT>
+int compute_batch_impl(const mfcc_plan *plan, const mfcc_batch *batch, const PcmT *d_pcm, float *d_out,
+                       int64_t tile0, int64_t n_tiles, cudaStream_t stream)
+{
+    if (plan->kernel == MFCC_KERNEL_FUSED)
+        return mfcc::launch_fused<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, stream);
+    return mfcc::launch_generic<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, stream);
+}
+
+int grow(void **ptr, size_t *have, size_t need)
+{
+    if (*have >= need) return MFCC_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    const size_t want = align_up(need + need / 8, 1 << 20);
+    if (cudaMalloc(ptr, want) != cudaSuccess) { cudaGetLastError(); return MFCC_ENOMEM; }
+    *have = want;
+    return MFCC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_plan **out)
+{
+    if (out == nullptr) return MFCC_EINVAL;
+    *out = nullptr;
+    if (mfcc::validate_params(p) != MFCC_OK) return MFCC_EINVAL;
+    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED) return MFCC_EINVAL;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return MFCC_ECUDA; }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MFCC_ECUDA;
+    if (device >= count) return MFCC_EINVAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MFCC_ECUDA;
+    if (prop.major != 10) return MFCC_ECUDA;  // the only code in this library is sm_100a SASS
+
+    mfcc_plan *plan = new (std::nothrow) mfcc_plan();
+    if (plan == nullptr) return MFCC_ENOMEM;
+    plan->p = *p;
+    plan->device = device;
+    plan->sm_count = prop.multiProcessorCount;
+    int rc = mfcc::build_tables(plan->p, plan->host);
+    if (rc != MFCC_OK) { delete plan; return rc; }
+
+    plan->fused = mfcc::find_fused(plan->p);
+    if (kernel == MFCC_KERNEL_FUSED && plan->fused == nullptr) { delete plan; return MFCC_ENOTSUP; }
+    plan->kernel = (kernel != MFCC_KERNEL_GENERIC && plan->fused) ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
+    plan->kernel_name = plan->kernel == MFCC_KERNEL_FUSED ? mfcc::fused_name(plan->fused) : "generic_radix2";
+
+    DeviceGuard guard(device);
+    if (!guard.ok) { delete plan; return MFCC_ECUDA; }
+
+    // One device blob for all generic-path tables.
+    const mfcc::HostTables &h = plan->host;
+    const int N = p->nfft, nb = h.nbins, M = p->n_mel;
+    size_t off = 0;
+    const size_t o_window = off;  off = align_up(off + sizeof(float) * N, 256);
+    const size_t o_twiddle = off; off = align_up(off + sizeof(float2) * (N / 2), 256);
+    const size_t o_melw = off;    off = align_up(off + sizeof(float) * M * nb, 256);
+    const size_t o_bins = off;    off = align_up(off + sizeof(int32_t) * (M + 2), 256);
+    const size_t o_dct = off;     off = align_up(off + sizeof(float) * h.dct.size(), 256);
+    const size_t o_rise = off;    off = align_up(off + sizeof(float) * nb, 256);
+    const size_t o_fall = off;    off = align_up(off + sizeof(float) * nb, 256);
+    std::vector<char> blob(off, 0);
+    std::memcpy(blob.data() + o_window, h.window.data(), sizeof(float) * h.window.size());
+    float2 *tw = reinterpret_cast<float2 *>(blob.data() + o_twiddle);
+    for (int k = 0; k < N / 2; ++k) tw[k] = make_float2(h.tw_re[k], h.tw_im[k]);
+    std::memcpy(blob.data() + o_melw, h.mel_w.data(), sizeof(float) * h.mel_w.size());
+    std::memcpy(blob.data() + o_bins, h.mel_bins.data(), sizeof(int32_t) * h.mel_bins.size());
+    std::memcpy(blob.data() + o_dct, h.dct.data(), sizeof(float) * h.dct.size());
+    std::memcpy(blob.data() + o_rise, h.rise.data(), sizeof(float) * nb);
+    std::memcpy(blob.data() + o_fall, h.fall.data(), sizeof(float) * nb);
+    if (cudaMalloc(&plan->dev_blob, off) != cudaSuccess) { cudaGetLastError(); delete plan; return MFCC_ENOMEM; }
+    if (cudaMemcpy(plan->dev_blob, blob.data(), off, cudaMemcpyHostToDevice) != cudaSuccess) {
+        mfcc_plan_destroy(plan);
+        return MFCC_ECUDA;
+    }
+    char *base = static_cast<char *>(plan->dev_blob);
+    plan->dev.window = reinterpret_cast<const float *>(base + o_window);
+    plan->dev.twiddle = reinterpret_cast<const float2 *>(base + o_twiddle);
+    plan->dev.mel_w = reinterpret_cast<const float *>(base + o_melw);
+    plan->dev.mel_bins = reinterpret_cast<const int32_t *>(base + o_bins);
+    plan->dev.dct = reinterpret_cast<const float *>(base + o_dct);
+    plan->dev.rise = reinterpret_cast<const float *>(base + o_rise);
+    plan->dev.fall = reinterpret_cast<const float *>(base + o_fall);
+
+    if (plan->kernel == MFCC_KERNEL_FUSED) {
+        rc = mfcc::fused_prepare(plan);
+        if (rc != MFCC_OK) { mfcc_plan_destroy(plan); return rc; }
+    }
+    *out = plan;
+    return MFCC_OK;
+}
+
+void mfcc_plan_destroy(mfcc_plan *plan)
+{
+    if (plan == nullptr) return;
+    DeviceGuard guard(plan->device);
+    for (auto &s : plan->streams)
+        if (s) cudaStreamDestroy(s);
+    if (plan->h2d_pcm) cudaFree(plan->h2d_pcm);
+    if (plan->d2h_out) cudaFree(plan->d2h_out);
+    if (plan->dev_blob) cudaFree(plan->dev_blob);
+    mfcc::fused_release(plan);
+    delete plan;
+}
+
+int mfcc_plan_params(const mfcc_plan *plan, mfcc_params *out)
+{
+    if (plan == nullptr || out == nullptr) return MFCC_EINVAL;
+    *out = plan->p;
+    return MFCC_OK;
+}
+
+const char *mfcc_plan_kernel_name(const mfcc_plan *plan)
+{
+    return plan ? plan->kernel_name.c_str() : "";
+}
+
+int64_t mfcc_plan_window(const mfcc_plan *plan, float *dst)
+{
+    if (plan == nullptr) return MFCC_EINVAL;
+    if (dst) std::memcpy(dst, plan->host.window.data(), sizeof(float) * plan->host.window.size());
+    return static_cast<int64_t>(plan->host.window.size());
+}
+
+int64_t mfcc_plan_mel_bins(const mfcc_plan *plan, int32_t *dst)
+{
+    if (plan == nullptr) return MFCC_EINVAL;
+    if (dst) std::memcpy(dst, plan->host.mel_bins.data(), sizeof(int32_t) * plan->host.mel_bins.size());
+    return static_cast<int64_t>(plan->host.mel_bins.size());
+}
+
+int64_t mfcc_plan_mel_weights(const mfcc_plan *plan, float *dst)
+{
+    if (plan == nullptr) return MFCC_EINVAL;
+    if (dst) std::memcpy(dst, plan->host.mel_w.data(), sizeof(float) * plan->host.mel_w.size());
+    return static_cast<int64_t>(plan->host.mel_w.size());
+}
+
+int64_t mfcc_plan_dct(const mfcc_plan *plan, float *dst)
+{
+    if (plan == nullptr) return MFCC_EINVAL;
+    if (dst) std::memcpy(dst, plan->host.dct.data(), sizeof(float) * plan->host.dct.size());
+    return static_cast<int64_t>(plan->host.dct.size());
+}
+
+int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out)
+{
+    if (out == nullptr) return MFCC_EINVAL;
+    *out = nullptr;
+    if (plan == nullptr || n_utts < 0 || (n_utts > 0 && h_offsets == nullptr)) return MFCC_EINVAL;
+    mfcc_batch *b = new (std::nothrow) mfcc_batch();
+    if (b == nullptr) return MFCC_ENOMEM;
+    b->device = plan->device;
+    b->n_utts = n_utts;
+    b->out_dim = plan->host.out_dim;
+    const mfcc_params &p = plan->p;
+    try {
+        b->offsets.assign(n_utts + 1, 0);
+        b->frame_offsets.assign(n_utts + 1, 0);
+        b->utt_first_tile.assign(n_utts + 1, 0);
+        if (n_utts > 0) std::memcpy(b->offsets.data(), h_offsets, sizeof(int64_t) * (n_utts + 1));
+        for (int64_t u = 0; u < n_utts; ++u) {
+            const int64_t begin = b->offsets[u], end = b->offsets[u + 1];
+            if (begin < 0 || end < begin) { delete b; return MFCC_EINVAL; }
+            const int64_t nf = mfcc_num_frames(&p, end - begin);
+            b->frame_offsets[u + 1] = b->frame_offsets[u] + nf;
+            b->utt_first_tile[u] = static_cast<int64_t>(b->tiles.size());
+            for (int64_t f = 0; f < nf; f += mfcc::kTileFrames) {
+                Tile t;
+                t.utt_begin = begin;
+                t.utt_end = end;
+                t.first_sample = begin + f * p.hop_len;
+                t.out_row = b->frame_offsets[u] + f;
+                t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, nf - f));
+                t.reserved = 0;
+                b->tiles.push_back(t);
+            }
+        }
+        b->utt_first_tile[n_utts] = static_cast<int64_t>(b->tiles.size());
+    } catch (const std::bad_alloc &) {
+        delete b;
+        return MFCC_ENOMEM;
+    }
+    b->total_frames = b->frame_offsets[n_utts];
+    b->total_samples = n_utts > 0 ? b->offsets[n_utts] : 0;
+
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) { delete b; return MFCC_ECUDA; }
+    const size_t tb = sizeof(Tile) * std::max<size_t>(b->tiles.size(), 1);
+    const size_t fb = sizeof(int64_t) * (n_utts + 1);
+    if (cudaMalloc(&b->d_tiles, tb) != cudaSuccess || cudaMalloc(&b->d_frame_offsets, fb) != cudaSuccess) {
+        cudaGetLastError();
+        mfcc_batch_destroy(b);
+        return MFCC_ENOMEM;
+    }
+    bool ok = true;
+    if (!b->tiles.empty())
+        ok = cudaMemcpy(b->d_tiles, b->tiles.data(), sizeof(Tile) * b->tiles.size(),
+                        cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(b->d_frame_offsets, b->frame_offsets.data(), fb, cudaMemcpyHostToDevice) ==
+                   cudaSuccess;
+    if (!ok) { mfcc_batch_destroy(b); return MFCC_ECUDA; }
+    *out = b;
+    return MFCC_OK;
+}
+
+void mfcc_batch_destroy(mfcc_batch *b)
+{
+    if (b == nullptr) return;
+    DeviceGuard guard(b->device);
+    if (b->d_tiles) cudaFree(b->d_tiles);
+    if (b->d_frame_offsets) cudaFree(b->d_frame_offsets);
+    delete b;
+}
+
+int64_t mfcc_batch_total_frames(const mfcc_batch *b) { return b ? b->total_frames : MFCC_EINVAL; }
+int64_t mfcc_batch_total_samples(const mfcc_batch *b) { return b ? b->total_samples : MFCC_EINVAL; }
+
+int mfcc_batch_frame_offsets(const mfcc_batch *b, int64_t *dst)
+{
+    if (b == nullptr || dst == nullptr) return MFCC_EINVAL;
+    std::memcpy(dst, b->frame_offsets.data(), sizeof(int64_t) * b->frame_offsets.size());
+    return MFCC_OK;
+}
+
+int mfcc_compute_batch(const mfcc_plan *plan, const mfcc_batch *batch, const int16_t *d_pcm, float *d_out,
+                       void *cuda_stream)
+{
+    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
+    if (batch->out_dim != plan->host.out_dim) return MFCC_EINVAL;
+    if (batch->total_frames == 0) return MFCC_OK;
+    if (d_pcm == nullptr || d_out == nullptr) return MFCC_EINVAL;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    return compute_batch_impl<int16_t>(plan, batch, d_pcm, d_out, 0, static_cast<int64_t>(batch->tiles.size()),
+                                       static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mfcc_compute_batch_f32(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_pcm, float *d_out,
+                           void *cuda_stream)
+{
+    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
+    if (batch->out_dim != plan->host.out_dim) return MFCC_EINVAL;
+    if (batch->total_frames == 0) return MFCC_OK;
+    if (d_pcm == nullptr || d_out == nullptr) return MFCC_EINVAL;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    return compute_batch_impl<float>(plan, batch, d_pcm, d_out, 0, static_cast<int64_t>(batch->tiles.size()),
+                                     static_cast<cudaStream_t>(cuda_stream));
+}
+
+// End-to-end: chunks of whole utterances flow H2D -> kernel -> D2H on three
+// streams so that the copy of chunk i+1 overlaps the kernel of chunk i and the
+// read-back of chunk i-1.
+int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets, int64_t n_utts,
+                      float *h_out, int64_t *h_frame_offsets)
+{
+    if (plan == nullptr || n_utts < 0) return MFCC_EINVAL;
+    mfcc_batch *batch = nullptr;
+    int rc = mfcc_batch_create(plan, h_offsets, n_utts, &batch);
+    if (rc != MFCC_OK) return rc;
+    if (h_frame_offsets) mfcc_batch_frame_offsets(batch, h_frame_offsets);
+    if (batch->total_frames == 0) { mfcc_batch_destroy(batch); return MFCC_OK; }
+    if (h_pcm == nullptr || h_out == nullptr) { mfcc_batch_destroy(batch); return MFCC_EINVAL; }
+
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) { mfcc_batch_destroy(batch); return MFCC_ECUDA; }
+    const int od = batch->out_dim;
+    rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(batch->total_samples));
+    if (rc == MFCC_OK)
+        rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(batch->total_frames) * od);
+    for (auto &s : plan->streams)
+        if (rc == MFCC_OK && s == nullptr && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess)
+            rc = MFCC_ECUDA;
+    if (rc != MFCC_OK) { mfcc_batch_destroy(batch); return rc; }
+
+    int16_t *d_pcm = static_cast<int16_t *>(plan->h2d_pcm);
+    float *d_out = static_cast<float *>(plan->d2h_out);
+    const int64_t chunk_samples = 16ll << 20;  // ~32 MiB of PCM per chunk
+    int64_t u0 = 0;
+    int c = 0;
+    bool ok = true;
+    while (u0 < n_utts && ok) {
+        int64_t u1 = u0 + 1;
+        while (u1 < n_utts && batch->offsets[u1 + 1] - batch->offsets[u0] <= chunk_samples) ++u1;
+        cudaStream_t s = plan->streams[c % 3];
+        const int64_t s0 = batch->offsets[u0], s1 = batch->offsets[u1];
+        const int64_t f0 = batch->frame_offsets[u0], f1 = batch->frame_offsets[u1];
+        const int64_t t0 = batch->utt_first_tile[u0], t1 = batch->utt_first_tile[u1];
+        if (s1 > s0)
+            ok = ok && cudaMemcpyAsync(d_pcm + s0, h_pcm + s0, sizeof(int16_t) * (s1 - s0),
+                                       cudaMemcpyHostToDevice, s) == cudaSuccess;
+        if (ok && t1 > t0)
+            ok = compute_batch_impl<int16_t>(plan, batch, d_pcm, d_out, t0, t1 - t0, s) == MFCC_OK;
+        if (ok && f1 > f0)
+            ok = cudaMemcpyAsync(h_out + f0 * od, d_out + f0 * od, sizeof(float) * (f1 - f0) * od,
+                                 cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        u0 = u1;
+        ++c;
+    }
+    for (auto &s : plan->streams)
+        if (s && cudaStreamSynchronize(s) != cudaSuccess) ok = false;
+    mfcc_batch_destroy(batch);
+    if (!ok) { cudaGetLastError(); return MFCC_ECUDA; }
+    return MFCC_OK;
+}
+
+int mfcc_compute(mfcc_plan *plan, const int16_t *pcm, int64_t n_samples, float *out, int64_t *n_frames)
+{
+    if (plan == nullptr || n_samples < 0) return MFCC_EINVAL;
+    const int64_t offsets[2] = {0, n_samples};
+    int64_t fo[2] = {0, 0};
+    const int rc = mfcc_compute_host(plan, pcm, offsets, 1, out, fo);
+    if (rc == MFCC_OK && n_frames) *n_frames = fo[1];
+    return rc;
+}
+
+int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_feat, int32_t norm_var,
+                    void *cuda_stream)
+{
+    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
+    if (batch->total_frames == 0) return MFCC_OK;
+    if (d_feat == nullptr) return MFCC_EINVAL;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    return mfcc::launch_cmvn(batch, d_feat, batch->out_dim, norm_var != 0, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t window,
+                     float *d_delta, void *cuda_stream)
+{
+    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
+    if (window < 1 || window > 8) return MFCC_EINVAL;
+    if (batch->total_frames == 0) return MFCC_OK;
+    if (d_feat == nullptr || d_delta == nullptr) return MFCC_EINVAL;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    return mfcc::launch_delta(batch, d_feat, batch->out_dim, window, d_delta, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst, void *cuda_stream)
+{
+    if (n < 0 || (n > 0 && (d_src == nullptr || d_dst == nullptr))) return MFCC_EINVAL;
+    return mfcc::launch_g711(d_src, n, alaw != 0, d_dst, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mfcc_host_alloc(void **ptr, int64_t bytes)
+{
+    if (ptr == nullptr || bytes <= 0) return MFCC_EINVAL;
+    if (cudaHostAlloc(ptr, static_cast<size_t>(bytes), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return MFCC_ENOMEM;
+    }
+    return MFCC_OK;
+}
+
+int mfcc_host_free(void *ptr)
+{
+    if (ptr == nullptr) return MFCC_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+uint64_t mfcc_launch_count(void) { return mfcc::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

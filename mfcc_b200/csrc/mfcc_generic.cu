@@ -1,0 +1,280 @@
+// mfcc_generic.cu — the any-geometry kernel and the small post-processing kernels.
+//
+// generic_radix2: one CTA per tile (<= 32 consecutive frames of one utterance),
+// one frame at a time through shared memory: framing + pre-emphasis + window,
+// in-place radix-2 complex FFT, power, dense mel rows in ascending-bin order,
+// log, DCT.  It exists so that EVERY valid mfcc_params has a CUDA path (there
+// is no CPU fallback) and as an independent cross-check of the fused kernels;
+// its summation orders are the same as the oracle's.  The fused kernels in
+// mfcc_fused.cu are the performance path.
+//
+// No reference code corresponds to any of this ("Ref file:line
+// = none"); stage definitions are DESIGN.md "Spec".
+#include <cuda_runtime.h>
+
+#include "mfcc_host.h"
+
+namespace mfcc {
+
+std::atomic<uint64_t> g_launches{0};
+
+namespace {
+
+constexpr int kGenericThreads = 128;
+
+__device__ __forceinline__ float load_sample(const int16_t *p, int64_t i) { return static_cast<float>(p[i]); }
+__device__ __forceinline__ float load_sample(const float *p, int64_t i) { return p[i]; }
+
+template <typename PcmT>
+__global__ void __launch_bounds__(kGenericThreads)
+generic_radix2_kernel(const Tile *__restrict__ tiles, const PcmT *__restrict__ pcm,
+                      float *__restrict__ out, DevTables tb, int frame_len, int hop, int nfft,
+                      int log2n, int n_mel, int n_cep, int logmel, float preemph, float log_floor)
+{
+    extern __shared__ float smem[];
+    float *re = smem;                 // [nfft]
+    float *im = re + nfft;            // [nfft]
+    float *pw = im + nfft;            // [nfft/2 + 1]
+    float *lg = pw + (nfft / 2 + 1);  // [n_mel]
+    const int nbins = nfft / 2 + 1;
+    const int out_dim = logmel ? n_mel : n_cep;
+    const Tile tile = tiles[blockIdx.x];
+    const float inv_n = 1.0f / static_cast<float>(nfft);
+
+    for (int f = 0; f < tile.n_frames; ++f) {
+        const int64_t s0 = tile.first_sample + static_cast<int64_t>(f) * hop;
+        // Framing + pre-emphasis + window, stored bit-reversed for the DIT FFT.
+        for (int i = threadIdx.x; i < nfft; i += kGenericThreads) {
+            float v = 0.0f;
+            const int64_t s = s0 + i;
+            if (i < frame_len && s < tile.utt_end) {
+                const float x0 = load_sample(pcm, s);
+                const float x1 = s > tile.utt_begin ? load_sample(pcm, s - 1) : 0.0f;
+                v = __fmul_rn(__fsub_rn(x0, __fmul_rn(preemph, x1)), tb.window[i]);
+            }
+            const int r = static_cast<int>(__brev(static_cast<unsigned>(i)) >> (32 - log2n));
+            re[r] = v;
+            im[r] = 0.0f;
+        }
+        __syncthreads();
+        for (int len = 2; len <= nfft; len <<= 1) {
+            const int half = len >> 1, step = nfft / len;
+            for (int b = threadIdx.x; b < nfft / 2; b += kGenericThreads) {
+                const int k = b & (half - 1);
+                const int a = ((b - k) << 1) + k, c = a + half;
+                const float2 w = tb.twiddle[k * step];
+                const float xr = __fsub_rn(__fmul_rn(re[c], w.x), __fmul_rn(im[c], w.y));
+                const float xi = __fadd_rn(__fmul_rn(re[c], w.y), __fmul_rn(im[c], w.x));
+                const float ar = re[a], ai = im[a];
+                re[c] = ar - xr; im[c] = ai - xi;
+                re[a] = ar + xr; im[a] = ai + xi;
+            }
+            __syncthreads();
+        }
+        for (int k = threadIdx.x; k < nbins; k += kGenericThreads)
+            pw[k] = __fmul_rn(__fadd_rn(__fmul_rn(re[k], re[k]), __fmul_rn(im[k], im[k])), inv_n);
+        __syncthreads();
+        for (int m = threadIdx.x; m < n_mel; m += kGenericThreads) {
+            const float *w = tb.mel_w + static_cast<size_t>(m) * nbins;
+            int k1 = tb.mel_bins[m + 2];
+            if (k1 > nbins - 1) k1 = nbins - 1;
+            float e = 0.0f;
+            for (int k = tb.mel_bins[m]; k <= k1; ++k) e = __fadd_rn(e, __fmul_rn(w[k], pw[k]));
+            lg[m] = logf(fmaxf(e, log_floor));
+        }
+        __syncthreads();
+        float *o = out + (tile.out_row + f) * out_dim;
+        for (int k = threadIdx.x; k < out_dim; k += kGenericThreads) {
+            if (logmel) {
+                o[k] = lg[k];
+            } else {
+                const float *d = tb.dct + static_cast<size_t>(k) * n_mel;
+                float c = 0.0f;
+                for (int m = 0; m < n_mel; ++m) c = __fadd_rn(c, __fmul_rn(d[m], lg[m]));
+                o[k] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- §8(f) rank 2: per-utterance CMVN, one CTA per (utterance, coefficient group) ----
+__global__ void __launch_bounds__(256)
+cmvn_kernel(const int64_t *__restrict__ frame_offsets, float *__restrict__ feat, int dim, int norm_var)
+{
+    const int64_t f0 = frame_offsets[blockIdx.x], f1 = frame_offsets[blockIdx.x + 1];
+    const int64_t T = f1 - f0;
+    if (T <= 0) return;
+    __shared__ double s_sum[8][32];
+    __shared__ double s_stat[2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Each lane owns coefficient d = lane (+32 per outer pass); warps stride over frames.
+    for (int d0 = 0; d0 < dim; d0 += 32) {
+        const int d = d0 + lane;
+        double acc = 0.0;
+        if (d < dim)
+            for (int64_t f = f0 + warp; f < f1; f += 8) acc += static_cast<double>(feat[f * dim + d]);
+        s_sum[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_sum[w][lane];
+            s_stat[0][lane] = t / static_cast<double>(T);
+        }
+        __syncthreads();
+        const double mu = s_stat[0][lane];
+        acc = 0.0;
+        if (d < dim)
+            for (int64_t f = f0 + warp; f < f1; f += 8) {
+                const double c = static_cast<double>(feat[f * dim + d]) - mu;
+                acc += c * c;
+            }
+        s_sum[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_sum[w][lane];
+            t /= static_cast<double>(T);
+            s_stat[1][lane] = norm_var ? 1.0 / sqrt(t > 1e-20 ? t : 1e-20) : 1.0;
+        }
+        __syncthreads();
+        const double inv = s_stat[1][lane];
+        if (d < dim)
+            for (int64_t f = f0 + warp; f < f1; f += 8)
+                feat[f * dim + d] = static_cast<float>((static_cast<double>(feat[f * dim + d]) - mu) * inv);
+        __syncthreads();
+    }
+}
+
+// ---- §8(f) rank 2: HTK regression deltas, one thread per output element ----
+__global__ void __launch_bounds__(256)
+delta_kernel(const int64_t *__restrict__ frame_offsets, int64_t n_utts, const float *__restrict__ feat,
+             int dim, int window, float *__restrict__ delta, int64_t total)
+{
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int64_t f = idx / dim;
+    const int d = static_cast<int>(idx - f * dim);
+    // binary search: utterance u with frame_offsets[u] <= f < frame_offsets[u+1]
+    int64_t lo = 0, hi = n_utts;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (frame_offsets[mid] <= f) lo = mid; else hi = mid;
+    }
+    const int64_t f0 = frame_offsets[lo], f1 = frame_offsets[lo + 1];
+    double acc = 0.0, den = 0.0;
+    for (int n = 1; n <= window; ++n) {
+        const int64_t fp = f + n < f1 ? f + n : f1 - 1;
+        const int64_t fm = f - n >= f0 ? f - n : f0;
+        acc += static_cast<double>(n) *
+               (static_cast<double>(feat[fp * dim + d]) - static_cast<double>(feat[fm * dim + d]));
+        den += 2.0 * n * n;
+    }
+    delta[idx] = static_cast<float>(acc / den);
+}
+
+// ---- §8(f) rank 3: G.711 expansion, 16 codes per thread (uint4 in, 2 x uint4 out) ----
+__device__ __forceinline__ int ulaw_expand(unsigned b)
+{
+    const unsigned u = (~b) & 0xFFu;
+    const int mag = static_cast<int>((((u & 0x0Fu) << 3) + 0x84u) << ((u >> 4) & 7u)) - 0x84;
+    return (u & 0x80u) ? -mag : mag;
+}
+__device__ __forceinline__ int alaw_expand(unsigned b)
+{
+    const unsigned a = b ^ 0x55u;
+    const unsigned seg = (a >> 4) & 7u, man = a & 0x0Fu;
+    const int mag = seg == 0 ? static_cast<int>((man << 4) + 8u)
+                             : static_cast<int>(((man << 4) + 0x108u) << (seg - 1));
+    return (a & 0x80u) ? mag : -mag;
+}
+
+__global__ void __launch_bounds__(256)
+g711_kernel(const uint8_t *__restrict__ src, int64_t n, int alaw, int16_t *__restrict__ dst)
+{
+    const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    const bool vec = (i0 + 16 <= n) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (vec) {
+        const uint4 in = *reinterpret_cast<const uint4 *>(src + i0);
+        const unsigned w[4] = {in.x, in.y, in.z, in.w};
+        unsigned o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned b0 = (w[j] >> (16 * h)) & 0xFFu, b1 = (w[j] >> (16 * h + 8)) & 0xFFu;
+                const int s0 = alaw ? alaw_expand(b0) : ulaw_expand(b0);
+                const int s1 = alaw ? alaw_expand(b1) : ulaw_expand(b1);
+                o[2 * j + h] = (static_cast<unsigned>(s0) & 0xFFFFu) | (static_cast<unsigned>(s1) << 16);
+            }
+        }
+        uint4 *d = reinterpret_cast<uint4 *>(dst + i0);
+        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+        for (int64_t i = i0; i < n && i < i0 + 16; ++i)
+            dst[i] = static_cast<int16_t>(alaw ? alaw_expand(src[i]) : ulaw_expand(src[i]));
+    }
+}
+
+}  // namespace
+
+template <typename PcmT>
+int launch_generic(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
+                   float *d_out, cudaStream_t stream)
+{
+    if (n_tiles <= 0) return MFCC_OK;
+    const mfcc_params &p = plan->p;
+    int log2n = 0;
+    while ((1 << log2n) < p.nfft) ++log2n;
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(p.nfft) + p.nfft / 2 + 1 + p.n_mel);
+    int64_t done = 0;
+    while (done < n_tiles) {  // gridDim.x limit is 2^31-1; chunk anyway
+        const int64_t n = n_tiles - done > (1 << 30) ? (1 << 30) : n_tiles - done;
+        generic_radix2_kernel<PcmT><<<static_cast<unsigned>(n), kGenericThreads, smem, stream>>>(
+            d_tiles + done, d_pcm, d_out, plan->dev, p.frame_len, p.hop_len, p.nfft, log2n, p.n_mel,
+            p.n_cep, p.output == MFCC_OUT_LOGMEL, p.preemph, p.log_floor);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        done += n;
+    }
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+template int launch_generic<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *,
+                                     cudaStream_t);
+template int launch_generic<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *,
+                                   cudaStream_t);
+
+int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s)
+{
+    if (batch->n_utts <= 0) return MFCC_OK;
+    cmvn_kernel<<<static_cast<unsigned>(batch->n_utts), 256, 0, s>>>(batch->d_frame_offsets, d_feat, dim,
+                                                                     norm_var);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
+                 cudaStream_t s)
+{
+    const int64_t total = batch->total_frames * dim;
+    if (total <= 0) return MFCC_OK;
+    const int64_t blocks = (total + 255) / 256;
+    delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(batch->d_frame_offsets, batch->n_utts,
+                                                               d_feat, dim, window, d_delta, total);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+int launch_g711(const uint8_t *d_src, int64_t n, int alaw, int16_t *d_dst, cudaStream_t s)
+{
+    if (n <= 0) return MFCC_OK;
+    const int64_t threads = (n + 15) / 16, blocks = (threads + 255) / 256;
+    g711_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(d_src, n, alaw, d_dst);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+}  // namespace mfcc

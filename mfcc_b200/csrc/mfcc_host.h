@@ -1,0 +1,118 @@
+// mfcc_host.h — internal types shared by the host layer and the kernels of
+// libmfcc_b200.so.  Not installed; the public surface is include/mfcc_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/mfcc_b200.h"
+
+namespace mfcc {
+
+constexpr int kTileFrames = 32;  // frames per tile: one frame per lane in the fused kernels
+
+// One tile = up to kTileFrames consecutive frames of ONE utterance.
+// All sample positions index the concatenated PCM array of the batch.
+struct Tile {
+    int64_t utt_begin;     // first sample of the utterance (pre-emphasis boundary: x[-1] = 0)
+    int64_t utt_end;       // one past the last sample (zero beyond it under MFCC_PAD_ZERO_TAIL)
+    int64_t first_sample;  // start of the tile's frame 0
+    int64_t out_row;       // output row of the tile's frame 0
+    int32_t n_frames;      // 1..kTileFrames
+    int32_t reserved;
+};
+
+// Host-side tables, evaluated in double and rounded once to f32 (DESIGN.md "Tables").
+struct HostTables {
+    int nbins = 0;                   // nfft/2 + 1
+    int out_dim = 0;                 // n_cep or n_mel
+    std::vector<float> window;       // [frame_len]
+    std::vector<int32_t> mel_bins;   // [n_mel + 2]
+    std::vector<float> mel_w;        // [n_mel][nbins] dense
+    std::vector<float> dct;          // [n_cep][n_mel], lifter folded in
+    std::vector<float> tw_re, tw_im; // [nfft/2] exp(-2 pi i k / nfft)
+    // Segment form of the filterbank used by the fused kernels: bin k in segment
+    // j = [bins[j], bins[j+1]) feeds filter j with rise[k] and filter j-1 with fall[k].
+    std::vector<float> rise, fall;   // [nbins]
+};
+
+int build_tables(const mfcc_params &p, HostTables &t);
+int validate_params(const mfcc_params *p);
+
+// Device-side view handed to kernels by value.
+struct DevTables {
+    const float *window;    // [nfft], zero past frame_len
+    const float2 *twiddle;  // [nfft/2]
+    const float *mel_w;     // [n_mel][nbins]
+    const int32_t *mel_bins;// [n_mel + 2]
+    const float *dct;       // [n_cep][n_mel]
+    const float *rise;      // [nbins]
+    const float *fall;      // [nbins]
+};
+
+struct FusedKernel;  // opaque per-geometry launcher (mfcc_fused.cu)
+
+}  // namespace mfcc
+
+struct mfcc_plan {
+    mfcc_params p{};
+    int device = 0;
+    int kernel = MFCC_KERNEL_GENERIC;   // resolved: GENERIC or FUSED
+    int sm_count = 0;
+    std::string kernel_name;
+    mfcc::HostTables host;
+    mfcc::DevTables dev{};
+    void *dev_blob = nullptr;           // one allocation backing every DevTables pointer
+    const mfcc::FusedKernel *fused = nullptr;
+    void *fused_blob = nullptr;         // device tables of the fused kernel
+    void *fused_tables = nullptr;       // host struct of device pointers into fused_blob
+    // mfcc_compute_host state (grown on demand, reused across calls)
+    void *h2d_pcm = nullptr;   size_t h2d_pcm_bytes = 0;
+    void *d2h_out = nullptr;   size_t d2h_out_bytes = 0;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+};
+
+struct mfcc_batch {
+    int device = 0;
+    int64_t n_utts = 0;
+    int64_t total_frames = 0;
+    int64_t total_samples = 0;
+    int out_dim = 0;
+    std::vector<int64_t> offsets;        // [n_utts + 1]
+    std::vector<int64_t> frame_offsets;  // [n_utts + 1]
+    std::vector<mfcc::Tile> tiles;       // host copy
+    std::vector<int64_t> utt_first_tile; // [n_utts + 1] tile index range per utterance
+    mfcc::Tile *d_tiles = nullptr;
+    int64_t *d_frame_offsets = nullptr;
+};
+
+namespace mfcc {
+
+extern std::atomic<uint64_t> g_launches;
+
+// Kernel launchers.  `tile0`/`n_tiles` select a range of the batch's tile table;
+// d_pcm / d_out are the bases of the WHOLE batch arrays.
+template <typename PcmT>
+int launch_generic(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
+                   float *d_out, cudaStream_t stream);
+
+// Returns nullptr when no fused kernel exists for the geometry.
+const FusedKernel *find_fused(const mfcc_params &p);
+const char *fused_name(const FusedKernel *k);
+template <typename PcmT>
+int launch_fused(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
+                 float *d_out, cudaStream_t stream);
+// Upload whatever constant tables the fused kernel needs (called at plan creation).
+int fused_prepare(mfcc_plan *plan);
+void fused_release(mfcc_plan *plan);
+
+int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s);
+int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
+                 cudaStream_t s);
+int launch_g711(const uint8_t *d_src, int64_t n, int alaw, int16_t *d_dst, cudaStream_t s);
+
+}  // namespace mfcc

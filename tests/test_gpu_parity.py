@@ -1,0 +1,229 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes ->
+libmfcc_b200.so), against the CPU oracle on the same seeded inputs, against the
+committed golden fixtures, and — at BASELINE.json's full sizes — through
+size-independent properties.
+
+Tolerance (BASELINE.json north_star): max abs <= 1e-3 and max rel <= 1e-4 on the
+cepstra (rel against max(|ref|, 1)); framing (frame counts, row offsets) bit-exact.
+PARITY UNPINNED: the oracle is this repo's own (the reference has no MFCC code).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from mfcc_b200 import (api, config_a, config_b, config_c, make_params, KERNEL_GENERIC, KERNEL_FUSED,
+                       KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
+from mfcc_b200.synth import clip_config1, fast_fixed_batch, noise_utterance, ragged_batch
+from util import assert_parity, golden, parity_errors
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+CFG = {"A": config_a, "B": config_b, "C": config_c}
+KERNELS = {"generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}
+
+
+def make_plan(p, kernel):
+    try:
+        return api.Plan(p, kernel=KERNELS[kernel])
+    except api.MfccError as e:
+        if e.code == -4 and kernel == "fused":
+            pytest.skip("no fused kernel for this geometry yet")
+        raise
+
+
+def run_device(plan, pcm, offsets):
+    b = plan.batch(offsets)
+    d_pcm = torch.from_numpy(np.ascontiguousarray(pcm)).cuda()
+    out = plan.compute_batch(b, d_pcm)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), b.frame_offsets.copy()
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fused"])
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_ragged_batch_matches_oracle(name, kernel):
+    p = CFG[name]()
+    plan = make_plan(p, kernel)
+    L, H = p.frame_len, p.hop_len
+    # lengths hit every framing edge: empty, < L, == L, one hop more, tile boundaries (32, 33 frames), long
+    lens = [0, 1, L - 1, L, L + 1, L + H - 1, L + H, L + 31 * H, L + 32 * H, L + 32 * H + 1, L + 100 * H + 7,
+            3 * L, L + 63 * H, L + 64 * H]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pcm = noise_utterance(int(off[-1]), seed=21)
+    got, fo = run_device(plan, pcm, off)
+    ref, fo_ref = oracle.mfcc_batch(p, pcm, off)
+    assert np.array_equal(fo, fo_ref)              # framing: bit-exact
+    assert got.shape == ref.shape
+    assert_parity(got, ref, what=f"{name}/{kernel}")
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fused"])
+def test_golden_fixtures(kernel):
+    g = golden()
+    a, b, c = config_a(), config_b(), config_c()
+    cases = [
+        ("A_cep", a, g["A_pcm"]), ("A_logmel", a.copy(output=OUT_LOGMEL), g["A_pcm"]),
+        ("A_lifter22", a.copy(lifter=22), g["A_pcm"]),
+        ("A_padtail", a.copy(pad_mode=PAD_ZERO_TAIL), g["A_pcm"][:15000]),
+        ("B_cep", b, g["B_pcm"]), ("C_cep", c, g["C_pcm"]),
+    ]
+    for key, p, x in cases:
+        plan = make_plan(p, kernel)
+        got, _ = run_device(plan, x, np.array([0, x.size]))
+        assert_parity(got, g[key], what=f"{key}/{kernel}")
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fused"])
+def test_option_matrix_matches_oracle(kernel):
+    base = config_a()
+    variants = [
+        base.copy(window=WINDOW_HANN), base.copy(window=WINDOW_RECT, preemph=0.0),
+        base.copy(n_mel=40, n_cep=20), base.copy(n_mel=23, n_cep=13, f_lo=64.0, f_hi=7600.0),
+        base.copy(frame_len=512, hop_len=128), base.copy(frame_len=320, hop_len=100, preemph=0.95),
+        base.copy(pad_mode=PAD_ZERO_TAIL, lifter=22), base.copy(output=OUT_LOGMEL, n_mel=80, n_cep=80),
+        make_params(sample_rate=8000, frame_len=256, hop_len=64, nfft=256, n_mel=24, n_cep=12),
+    ]
+    off = np.array([0, 5000, 5100, 12345, 12345, 20000], np.int64)
+    pcm = noise_utterance(int(off[-1]), seed=22)
+    for p in variants:
+        plan = make_plan(p, kernel)
+        got, fo = run_device(plan, pcm, off)
+        ref, fo_ref = oracle.mfcc_batch(p, pcm, off)
+        assert np.array_equal(fo, fo_ref)
+        assert_parity(got, ref, what=f"{p.as_dict()}/{kernel}")
+
+
+def test_known_answers_on_device():
+    p = config_a()
+    plan = api.Plan(p)
+    # all-zero PCM: every band at the floor -> c0 = sqrt(M) ln(floor), c_k = 0
+    z = plan.compute(np.zeros(4000, np.int16))
+    assert np.allclose(z[:, 0], np.sqrt(26) * np.log(np.float32(1e-10)), atol=1e-4)
+    assert np.abs(z[:, 1:]).max() < 1e-4
+    # full-scale square wave (clipping extremes) stays finite and matches
+    x = np.where(np.arange(8000) % 50 < 25, 32767, -32768).astype(np.int16)
+    x = (x.astype(np.int32) + np.random.default_rng(1).integers(-200, 200, x.size)).clip(-32768, 32767).astype(np.int16)
+    assert_parity(plan.compute(x), oracle.mfcc(p, x), what="square")
+
+
+def test_float_pcm_entry_matches_int16():
+    p = config_a()
+    plan = api.Plan(p)
+    pcm, off = ragged_batch(6, 3000, 9000, seed=5)
+    b = plan.batch(off)
+    d16 = torch.from_numpy(pcm).cuda()
+    o16 = plan.compute_batch(b, d16)
+    o32 = plan.compute_batch(b, d16.float())
+    torch.cuda.synchronize()
+    assert torch.equal(o16, o32)
+
+
+def test_host_entry_points_match_device_path():
+    p = config_b()
+    plan = api.Plan(p)
+    pcm, off = ragged_batch(300, 100, 20000, seed=6)
+    dev, fo = run_device(plan, pcm, off)
+    host, fo2 = plan.compute_host(pcm, off)
+    assert np.array_equal(fo, fo2) and np.array_equal(dev, host)
+    one = plan.compute(pcm[off[3]:off[4]])
+    assert np.array_equal(one, dev[fo[3]:fo[4]])
+    # empty batch and all-too-short batch are fine
+    e, foe = plan.compute_host(np.zeros(0, np.int16), np.array([0]))
+    assert e.shape == (0, 13) and foe.tolist() == [0]
+    e, foe = plan.compute_host(np.zeros(10, np.int16), np.array([0, 5, 10]))
+    assert e.shape == (0, 13) and foe.tolist() == [0, 0, 0]
+
+
+def test_bad_calls_fail_loudly():
+    plan = api.Plan(config_a())
+    with pytest.raises(api.MfccError):
+        plan.batch(np.array([0, 100, 50]))          # decreasing offsets
+    with pytest.raises(api.MfccError):
+        api.Plan(make_params(nfft=500))
+    with pytest.raises(api.MfccError) as e:
+        api.Plan(config_a().copy(hop_len=161), kernel=KERNEL_FUSED)   # odd hop: fused unsupported
+    assert e.value.code == -4
+    b = plan.batch(np.array([0, 16000]))
+    with pytest.raises(ValueError):
+        plan.compute_batch(b, torch.zeros(100, dtype=torch.int16, device="cuda"))
+    assert api.Plan(config_a().copy(hop_len=161)).kernel_name == "generic_radix2"
+
+
+# ---- BASELINE.json full sizes, through size-independent properties ----
+def test_config2_full_size_properties():
+    """1,024 x 10 s @ 16 kHz: frame rows exact, fused == generic
+    within tolerance everywhere, oracle parity on a sample of utterances, and
+    shift-by-one-hop equivariance (tile decomposition independence), bit-exact."""
+    p = config_a()
+    pcm, off = fast_fixed_batch(1024, 160000, seed=1000)
+    plan = api.Plan(p, kernel=KERNEL_AUTO)
+    b = plan.batch(off)
+    assert b.total_frames == 1_021_952 and np.array_equal(np.diff(b.frame_offsets), np.full(1024, 998))
+    d_pcm = torch.from_numpy(pcm).cuda()
+    out = plan.compute_batch(b, d_pcm)
+    gen = api.Plan(p, kernel=KERNEL_GENERIC)
+    out_g = gen.compute_batch(gen.batch(off), d_pcm)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    a, r = parity_errors(out.cpu().numpy(), out_g.cpu().numpy())
+    assert a <= 1e-3 and r <= 1e-4, (a, r)
+    o = out.cpu().numpy()
+    for u in (0, 1, 511, 1023):
+        ref = oracle.mfcc(p, pcm[off[u]:off[u + 1]])
+        assert_parity(o[b.frame_offsets[u]:b.frame_offsets[u + 1]], ref, what=f"utt {u}")
+    # drop the first hop of utterance 7: frame t of the shifted clip == frame t+1 of the original (t >= 1;
+    # t = 0 differs through the pre-emphasis boundary y[0] = x[0])
+    x = pcm[off[7]:off[8]]
+    s = plan.compute(x[p.hop_len:])
+    full = o[b.frame_offsets[7]:b.frame_offsets[8]]
+    assert np.array_equal(s[1:], full[2:])
+
+
+def test_config3_ragged_telephony_batch():
+    """8 kHz, 16,384 short utterances in ONE launch, reduced
+    utterance count for the oracle but full raggedness."""
+    p = config_b()
+    pcm, off = ragged_batch(2048, 4000, 24000, seed=3)
+    plan = api.Plan(p)
+    n0 = api.launch_count()
+    got, fo = run_device(plan, pcm, off)
+    assert api.launch_count() - n0 == 1
+    ref, fo_ref = oracle.mfcc_batch(p, pcm, off, nthreads=8)
+    assert np.array_equal(fo, fo_ref)
+    assert_parity(got, ref, what="config3")
+
+
+def test_config4_long_stream():
+    """48 kHz long-form stream, 20 s here: many tiles of one utterance."""
+    p = config_c()
+    x = noise_utterance(48000 * 20, seed=4000)
+    plan = api.Plan(p)
+    got = plan.compute(x)
+    ref = oracle.mfcc(p, x)
+    assert got.shape == ref.shape == (1998, 40)
+    assert_parity(got, ref, what="config4")
+
+
+# ---- §8(f) widening ----
+def test_cmvn_delta_g711_on_device():
+    p = config_a()
+    plan = api.Plan(p)
+    pcm, off = ragged_batch(40, 300, 30000, seed=8)
+    b = plan.batch(off)
+    feat = plan.compute_batch(b, torch.from_numpy(pcm).cuda())
+    torch.cuda.synchronize()
+    f_host = feat.cpu().numpy()
+    d = plan.delta(b, feat, 2)
+    d2 = plan.delta(b, d, 2)
+    ref_d = oracle.delta(f_host, b.frame_offsets, 2)
+    assert np.abs(d.cpu().numpy() - ref_d).max() < 1e-5
+    assert np.abs(d2.cpu().numpy() - oracle.delta(ref_d, b.frame_offsets, 2)).max() < 1e-5
+    for nv in (False, True):
+        g = plan.cmvn(b, feat.clone(), nv)
+        assert np.abs(g.cpu().numpy() - oracle.cmvn(f_host, b.frame_offsets, nv)).max() < 2e-5
+    codes = np.random.default_rng(2).integers(0, 256, 100003).astype(np.uint8)
+    for alaw in (False, True):
+        for view in (codes, codes[1:]):   # aligned and misaligned starts
+            got = api.decode_g711(torch.from_numpy(view.copy()).cuda()[...], alaw)
+            assert np.array_equal(got.cpu().numpy(), oracle.decode_g711(view, alaw))   # bit-exact
