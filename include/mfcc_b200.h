@@ -53,6 +53,7 @@ extern "C" {
 #define MFCC_KERNEL_AUTO     0   /* fused tile kernel when the geometry has one, else generic */
 #define MFCC_KERNEL_GENERIC  1   /* one-frame-at-a-time shared-memory radix-2 kernel (any geometry) */
 #define MFCC_KERNEL_FUSED    2   /* fused 32-frame-tile kernel; plan creation fails if unavailable */
+#define MFCC_KERNEL_FUSED_RT 3   /* fused kernel with run-time geometry (skips the specialised variants) */
 
 /* ---- parameters (all conventions explicit; see DESIGN.md "Spec") ---- */
 typedef struct mfcc_params {

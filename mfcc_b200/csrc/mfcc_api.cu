@@ -36,7 +36,8 @@ int compute_batch_impl(const mfcc_plan *plan, const mfcc_batch *batch, const Pcm
                        int64_t tile0, int64_t n_tiles, cudaStream_t stream)
 {
     if (plan->kernel == MFCC_KERNEL_FUSED)
-        return mfcc::launch_fused<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, stream);
+        return mfcc::launch_fused<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out,
+                                        stream);
     return mfcc::launch_generic<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, stream);
 }
 
@@ -61,7 +62,7 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     if (out == nullptr) return MFCC_EINVAL;
     *out = nullptr;
     if (mfcc::validate_params(p) != MFCC_OK) return MFCC_EINVAL;
-    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED) return MFCC_EINVAL;
+    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED_RT) return MFCC_EINVAL;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return MFCC_ECUDA; }
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MFCC_ECUDA;
@@ -78,10 +79,15 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     int rc = mfcc::build_tables(plan->p, plan->host);
     if (rc != MFCC_OK) { delete plan; return rc; }
 
+    // Kernel choice: compile-time-geometry fused > runtime-geometry fused > generic.
     plan->fused = mfcc::find_fused(plan->p);
-    if (kernel == MFCC_KERNEL_FUSED && plan->fused == nullptr) { delete plan; return MFCC_ENOTSUP; }
-    plan->kernel = (kernel != MFCC_KERNEL_GENERIC && plan->fused) ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
-    plan->kernel_name = plan->kernel == MFCC_KERNEL_FUSED ? mfcc::fused_name(plan->fused) : "generic_radix2";
+    const char *ct_name = kernel == MFCC_KERNEL_FUSED_RT ? nullptr : mfcc::ct_match(plan->p);
+    const bool want_fused = kernel != MFCC_KERNEL_GENERIC;
+    if ((kernel == MFCC_KERNEL_FUSED || kernel == MFCC_KERNEL_FUSED_RT) && plan->fused == nullptr && ct_name == nullptr) {
+        delete plan;
+        return MFCC_ENOTSUP;
+    }
+    plan->kernel = (want_fused && (plan->fused || ct_name)) ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
 
     DeviceGuard guard(device);
     if (!guard.ok) { delete plan; return MFCC_ECUDA; }
@@ -121,9 +127,15 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     plan->dev.fall = reinterpret_cast<const float *>(base + o_fall);
 
     if (plan->kernel == MFCC_KERNEL_FUSED) {
-        rc = mfcc::fused_prepare(plan);
+        rc = ct_name ? mfcc::ct_prepare(plan) : MFCC_ENOTSUP;
+        if (rc == MFCC_ENOTSUP) {   // no compile-time variant (or its tables do not fit): runtime-geometry kernel
+            if (plan->fused != nullptr) rc = mfcc::fused_prepare(plan);
+            else if (kernel == MFCC_KERNEL_AUTO) { plan->kernel = MFCC_KERNEL_GENERIC; rc = MFCC_OK; }
+        }
         if (rc != MFCC_OK) { mfcc_plan_destroy(plan); return rc; }
     }
+    plan->kernel_name = plan->kernel != MFCC_KERNEL_FUSED ? "generic_radix2"
+                        : plan->ct_state ? ct_name : mfcc::fused_name(plan->fused);
     *out = plan;
     return MFCC_OK;
 }
@@ -138,6 +150,7 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     if (plan->d2h_out) cudaFree(plan->d2h_out);
     if (plan->dev_blob) cudaFree(plan->dev_blob);
     mfcc::fused_release(plan);
+    mfcc::ct_release(plan);
     delete plan;
 }
 

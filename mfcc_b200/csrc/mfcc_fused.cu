@@ -23,6 +23,7 @@
 #include <cstring>
 #include <vector>
 
+#include "mfcc_fft.cuh"
 #include "mfcc_host.h"
 
 namespace mfcc {
@@ -57,96 +58,9 @@ struct FusedArgs {
 __device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
-struct cplx { float re, im; };
-
-__device__ __forceinline__ cplx cmulc(cplx a, float cr, float ci)
-{
-    cplx r;
-    r.re = fmaf(-a.im, ci, a.re * cr);
-    r.im = fmaf(a.im, cr, a.re * ci);
-    return r;
-}
-
-// Forward 4-point DFT (W4 = -i), in place on four named values.
-__device__ __forceinline__ void dft4(cplx &x0, cplx &x1, cplx &x2, cplx &x3)
-{
-    const cplx t0{x0.re + x2.re, x0.im + x2.im}, t1{x0.re - x2.re, x0.im - x2.im};
-    const cplx t2{x1.re + x3.re, x1.im + x3.im}, t3{x1.re - x3.re, x1.im - x3.im};
-    x0 = cplx{t0.re + t2.re, t0.im + t2.im};
-    x2 = cplx{t0.re - t2.re, t0.im - t2.im};
-    x1 = cplx{t1.re + t3.im, t1.im - t3.re};
-    x3 = cplx{t1.re - t3.im, t1.im + t3.re};
-}
-
-// Forward 16-point DFT, natural order in and out, everything statically indexed.
-// n = nb + 4 na, k = ka + 4 kb:  4-point DFTs over na, twiddle W16^(nb ka), 4-point DFTs over nb.
-__device__ __forceinline__ void dft16(cplx (&x)[16])
-{
-    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb) dft4(x[nb], x[nb + 4], x[nb + 8], x[nb + 12]);
-    // after this, x[nb + 4 ka] holds y[nb][ka]
-    x[1 + 4 * 1] = cmulc(x[1 + 4 * 1], c1, -s1);   // W^1
-    x[1 + 4 * 2] = cmulc(x[1 + 4 * 2], h, -h);     // W^2
-    x[1 + 4 * 3] = cmulc(x[1 + 4 * 3], s1, -c1);   // W^3
-    x[2 + 4 * 1] = cmulc(x[2 + 4 * 1], h, -h);     // W^2
-    x[2 + 4 * 2] = cplx{x[2 + 4 * 2].im, -x[2 + 4 * 2].re};  // W^4 = -i
-    x[2 + 4 * 3] = cmulc(x[2 + 4 * 3], -h, -h);    // W^6
-    x[3 + 4 * 1] = cmulc(x[3 + 4 * 1], s1, -c1);   // W^3
-    x[3 + 4 * 2] = cmulc(x[3 + 4 * 2], -h, -h);    // W^6
-    x[3 + 4 * 3] = cmulc(x[3 + 4 * 3], -c1, s1);   // W^9
-#pragma unroll
-    for (int ka = 0; ka < 4; ++ka) dft4(x[4 * ka], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);
-    // now x[4 ka + kb] holds X[ka + 4 kb]; transpose the 4x4 index to natural order
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = a + 1; b < 4; ++b) {
-            const cplx t = x[4 * a + b];
-            x[4 * a + b] = x[4 * b + a];
-            x[4 * b + a] = t;
-        }
-}
-
-// Forward 8-point DFT, natural order: n = nb + 2 na (na<4), k = ka + 4 kb (ka<4, kb<2).
-__device__ __forceinline__ void dft8(cplx (&x)[8])
-{
-    constexpr float h = 0.70710678118654752f;
-    dft4(x[0], x[2], x[4], x[6]);  // nb = 0: y[0][ka] in x[2 ka]
-    dft4(x[1], x[3], x[5], x[7]);  // nb = 1: y[1][ka] in x[2 ka + 1]
-    x[3] = cmulc(x[3], h, -h);               // W8^1
-    x[5] = cplx{x[5].im, -x[5].re};          // W8^2 = -i
-    x[7] = cmulc(x[7], -h, -h);              // W8^3
-    cplx r[8];
-#pragma unroll
-    for (int ka = 0; ka < 4; ++ka) {
-        r[ka] = cplx{x[2 * ka].re + x[2 * ka + 1].re, x[2 * ka].im + x[2 * ka + 1].im};
-        r[ka + 4] = cplx{x[2 * ka].re - x[2 * ka + 1].re, x[2 * ka].im - x[2 * ka + 1].im};
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = r[i];
-}
-
-template <int R> struct Dft;
-template <> struct Dft<16> { static __device__ __forceinline__ void run(cplx (&x)[16]) { dft16(x); } };
-template <> struct Dft<8>  { static __device__ __forceinline__ void run(cplx (&x)[8]) { dft8(x); } };
-
-// Real-FFT split of one (k, N/2-k) pair of the packed transform followed by the
-// power spectrum.  zk = Z[k], zm = Z[N/2-k], w = exp(-2 pi i k / N).
-// Returns |2 X[k]|^2 and |2 X[N/2-k]|^2 (caller scales by 1/(4N)).
-__device__ __forceinline__ void split_power(cplx zk, cplx zm, float2 w, float &pk, float &pm)
-{
-    const float er = zk.re + zm.re, ei = zk.im - zm.im;   // Z[k] + conj(Z[m])
-    const float p = zk.im + zm.im, q = zm.re - zk.re;     // -i (Z[k] - conj(Z[m]))
-    const float tr = fmaf(-w.y, q, w.x * p), ti = fmaf(w.y, p, w.x * q);
-    const float ar = er + tr, ai = ei + ti, br = er - tr, bi = ei - ti;
-    pk = fmaf(ar, ar, ai * ai);
-    pm = fmaf(br, br, bi * bi);
-}
-
 // NFFT = 2 * R1 * R2.  R2 must be 16 (one pass-1 butterfly per half... see mapping below).
 template <typename PcmT, int R1, int R2>
-__global__ void __launch_bounds__(kThreads, 2) fused_tile_kernel(const PcmT *__restrict__ pcm, FusedArgs a)
+__global__ void __launch_bounds__(kThreads, 2) fused_rt_kernel(const PcmT *__restrict__ pcm, FusedArgs a)
 {
     constexpr int N2 = R1 * R2;       // complex points
     constexpr int NFFT = 2 * N2;
@@ -320,8 +234,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_tile_kernel(const PcmT *__r
 
 struct Geometry { int nfft, r1, r2; const char *name; };
 constexpr Geometry kGeoms[] = {
-    {512, 16, 16, "fused_tile32_r16x16_n512"},
-    {256, 8, 16, "fused_tile32_r8x16_n256"},
+    {512, 16, 16, "fused_rt_tile32_r16x16_n512"},
+    {256, 8, 16, "fused_rt_tile32_r8x16_n256"},
 };
 
 size_t staged_words_for(const mfcc_params &p)
@@ -457,7 +371,7 @@ static int launch_geom(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_til
     const mfcc_params &p = plan->p;
     const size_t smem = smem_bytes_for(p);
     static thread_local const void *configured = nullptr;
-    auto kern = fused_tile_kernel<PcmT, R1, R2>;
+    auto kern = fused_rt_kernel<PcmT, R1, R2>;
     if (configured != reinterpret_cast<const void *>(kern)) {
         // idempotent; cheap enough to redo per thread
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -489,10 +403,11 @@ static int launch_geom(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_til
 }
 
 template <typename PcmT>
-int launch_fused(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-                 cudaStream_t stream)
+int launch_fused(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
+                 float *d_out, cudaStream_t stream)
 {
     if (n_tiles <= 0) return MFCC_OK;
+    if (plan->ct_state != nullptr) return ct_launch<PcmT>(plan, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
     if (plan->fused == nullptr || plan->fused_tables == nullptr) return MFCC_ENOTSUP;
     switch (plan->fused->g.nfft) {
         case 512: return launch_geom<PcmT, 16, 16>(plan, d_tiles, n_tiles, d_pcm, d_out, stream);
@@ -501,8 +416,9 @@ int launch_fused(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, co
     }
 }
 
-template int launch_fused<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *,
+template int launch_fused<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *,
                                    cudaStream_t);
-template int launch_fused<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *, cudaStream_t);
+template int launch_fused<float>(const mfcc_plan *, const Tile *, int64_t, const float *, int64_t, float *,
+                                 cudaStream_t);
 
 }  // namespace mfcc

@@ -1,0 +1,592 @@
+// mfcc_fused_ct.cu — fused tile kernel with COMPILE-TIME geometry (frame length,
+// hop, radix split), persistent CTAs and all tables in shared memory.
+//
+// Why this shape (numbers from tools/microbench*.cu on the B200):
+//   * hot code must stay under ~32 KB: at 16 warps/SM the FFMA rate falls from
+//     107 to 50 (77 KB) and 23 lanes/clk/SM (154 KB) once the instruction stream
+//     outgrows the instruction caches -> no per-warp role specialisation, every
+//     warp runs the same compact code and picks its butterfly by index;
+//   * register-indexed constant-bank loads (LDC) manage only 0.37 warp-loads/clk/SM
+//     -> per-butterfly constants are read from a shared-memory copy of the tables
+//     with uniform-address LDS.128 (0.58 warp-loads/clk/SM, 4 constants each);
+//   * I2F runs on the 16-lane XU pipe -> int16 samples are converted with the
+//     2^23 mantissa trick (one LOP3 + one FADD);
+//   * integer division by a runtime hop costs ~20 instructions -> frame length
+//     and hop are template parameters.
+//
+// Phases per tile (lane = frame, 8 warps, CTA barriers between phases):
+//   S0 stage, S1 pass 1 (+window, +inter-pass twiddle), S2 pass 2 + real-FFT split
+//   + power, S3 sparse mel (segment form, 4-bin chunks), S4 log + symmetric/
+//   antisymmetric halves, S5 DCT on the halves, coalesced store.
+//
+// No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mfcc_fft.cuh"
+#include "mfcc_host.h"
+
+namespace mfcc {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kPad = 2;
+
+// Offsets (in floats) of the tables inside the shared-memory blob; set by the host.
+struct CtLayout {
+    int win;      // [R2][R1] float2: window pair of z[n2 + R2 n1]
+    int tw;       // [R2][R1] float2: W_{N/2}^{n2 k1}
+    int post;     // [R1/2][R2] float2: split twiddles of work item `it`
+    int seg;      // int4 per segment: {first bin, chunks, weight offset (floats from melw), 0}
+    int seg_lo;   // int[kWarps + 1]: segment range of each warp
+    int melw;     // per chunk: 4 rise weights then 4 fall weights (scaled by 1/(4 NFFT))
+    int dct;      // [n_cep][halfp] floats: DCT row restricted to m < ceil(M/2), zero padded to halfp
+    int total;    // floats, multiple of 4
+    int n_seg, half, halfp;
+};
+
+struct CtArgs {
+    const Tile *tiles;
+    int64_t n_tiles;
+    int64_t pcm_len;
+    float *out;
+    const float *tab;   // global copy of the table blob
+    CtLayout lay;
+    int n_mel, n_cep, logmel;
+    float preemph, log_floor;
+};
+
+template <int L, int HOP, int R1, int R2>
+struct Geo {
+    static constexpr int N2 = R1 * R2, NFFT = 2 * N2, NB = N2 + 1;
+    static constexpr int L2 = (L + 1) / 2;                 // complex points that carry samples
+    static constexpr int STRIDE = HOP + kPad;              // staged words per hop block
+    static constexpr int padded(int i) { return i + kPad * (i / HOP); }
+    static constexpr int STAGED = 31 * STRIDE + padded(L + 1) + 2;
+    static constexpr int PW = (NB + 3) * 32;               // 3 slack rows for 4-bin chunks
+    static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
+    static constexpr int WS = N2 * 32 * 2;                 // floats
+    // pass-1 rows: n1 < FULL are valid for every n2, row FULL is valid for n2 < PART, the rest is padding
+    static constexpr int FULL = L2 / R2, PART = L2 % R2;
+    static constexpr int ROWS = FULL + (PART ? 1 : 0);     // rows that can be non-zero
+    static_assert(HOP % 2 == 0, "float2 pairs must not straddle a hop block");
+    static_assert(L <= NFFT && ROWS <= R1, "frame does not fit the transform");
+};
+
+__device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+__device__ __forceinline__ float4 lds_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// int16 pair -> two exact floats without the XU pipe: (v ^ 0x8000) in the mantissa of 2^23.
+__device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
+{
+    const uint32_t lo = ((w & 0xFFFFu) ^ 0x4B008000u);
+    const uint32_t hi = ((w >> 16) ^ 0x4B008000u);
+    return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
+}
+
+__device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+
+template <typename PcmT, int L, int HOP, int R1, int R2>
+__global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__restrict__ pcm, const CtArgs a)
+{
+    using G = Geo<L, HOP, R1, R2>;
+    constexpr int N2 = G::N2, STRIDE = G::STRIDE;
+    extern __shared__ __align__(16) float smem[];
+    float *tab = smem;
+    float *staged = smem + a.lay.total;   // S0-S1
+    float *pw = staged;                   // S2-S3 (aliases staged)
+    float2 *ws = reinterpret_cast<float2 *>(staged + G::UNION);
+    float *scr = reinterpret_cast<float *>(ws);   // S3-S5 scratch (aliases ws)
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // one-time: tables -> shared memory, zero the slack rows of P
+    for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
+        *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
+    for (int i = G::NB * 32 + threadIdx.x; i < G::PW; i += kThreads) pw[i] = 0.0f;
+
+    const float *t_win = tab + a.lay.win, *t_tw = tab + a.lay.tw, *t_post = tab + a.lay.post;
+    const int4 *t_seg = reinterpret_cast<const int4 *>(tab + a.lay.seg);
+    const int *t_seglo = reinterpret_cast<const int *>(tab + a.lay.seg_lo);
+    const float *t_melw = tab + a.lay.melw, *t_dct = tab + a.lay.dct;
+    const int n_seg = a.lay.n_seg, half = a.lay.half, halfp = a.lay.halfp;
+    float *er = scr, *ef = scr + n_seg * 32;
+    float *ls = scr + 2 * n_seg * 32, *ld = ls + halfp * 32;
+    float *ostage = ld + halfp * 32;
+
+    for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        const Tile tile = a.tiles[t];
+        __syncthreads();   // previous tile's readers of ws/scr and pw are done; tables are visible
+
+        // ---- S0: stage y[s] = x[s] - a x[s-1] once per sample, padded by kPad words per hop ----
+        {
+            const int T = (tile.n_frames - 1) * HOP + L;
+            const int64_t room_lo = tile.first_sample - tile.utt_begin;
+            const int64_t room_hi = tile.utt_end - tile.first_sample;
+            bool fast = false;
+            if constexpr (sizeof(PcmT) == 2)
+                fast = ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0) && ((tile.first_sample & 1) == 0);
+            if (fast) {
+                const uint32_t *xw = reinterpret_cast<const uint32_t *>(pcm) + (tile.first_sample >> 1);
+                const int64_t avail = a.pcm_len - tile.first_sample;   // samples readable from i = 0
+                for (int qb = warp * 32; 2 * qb <= T; qb += kThreads) {   // warp-uniform bound: the shuffle stays converged
+                    const int q = qb + lane, i0 = 2 * q;
+                    uint32_t w = 0;
+                    if (i0 + 1 < avail) w = __ldg(xw + q);
+                    else if (i0 < avail) w = reinterpret_cast<const uint16_t *>(xw)[i0];
+                    // previous sample: high half of the previous word (lane - 1), or a load at lane 0
+                    uint32_t wp = __shfl_up_sync(0xffffffffu, w, 1);
+                    if (lane == 0)
+                        wp = (i0 > -room_lo) ? (static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(xw) + i0 - 1)) << 16) : 0u;
+                    const float2 x = s16x2_to_f32(w);
+                    float xp = s16x2_to_f32(wp).y;
+                    if (i0 <= -room_lo) xp = 0.0f;                 // i0 is the first sample of the utterance
+                    float y0 = fmaf(-a.preemph, xp, x.x), y1 = fmaf(-a.preemph, x.x, x.y);
+                    if (i0 >= room_hi) y0 = 0.0f;
+                    if (i0 + 1 >= room_hi) y1 = 0.0f;
+                    if (i0 <= T) *reinterpret_cast<float2 *>(staged + G::padded(i0)) = make_float2(y0, y1);
+                }
+            } else {
+                const PcmT *x = pcm + tile.first_sample;
+                for (int i = threadIdx.x; i <= T; i += kThreads) {
+                    float y = 0.0f;
+                    if (i < room_hi) {
+                        const float x0 = to_f32(x[i]);
+                        const float x1 = (i > -room_lo) ? to_f32(x[i - 1]) : 0.0f;
+                        y = fmaf(-a.preemph, x1, x0);
+                    }
+                    staged[G::padded(i)] = y;
+                }
+            }
+        }
+        if (tile.n_frames < 32) {
+            // partial tile: lanes >= n_frames would otherwise transform stale words (possibly NaN)
+            const int T = (tile.n_frames - 1) * HOP + L;
+            for (int i = T + 2 - (T & 1) + 2 * threadIdx.x; i < 31 * HOP + L + 1; i += 2 * kThreads)
+                *reinterpret_cast<float2 *>(staged + G::padded(i)) = make_float2(0.0f, 0.0f);
+        }
+        __syncthreads();
+
+        // ---- S1: pass 1.  Butterfly n2 takes z[n2 + R2 n1] = (y[2n], y[2n+1]) * window ----
+        {
+            const float *base = staged + lane * STRIDE;
+            constexpr int PER_WARP = R2 / kWarps;
+#pragma unroll 1
+            for (int j = 0; j < PER_WARP; ++j) {
+                const int n2 = warp * PER_WARP + j;
+                const float *wrow = t_win + n2 * (2 * R1);
+                cplx x[R1];
+#pragma unroll
+                for (int n1 = 0; n1 < R1; ++n1) x[n1] = cplx{0.0f, 0.0f};   // rows >= ROWS are zero padding
+#pragma unroll
+                for (int n1 = 0; n1 < G::ROWS; ++n1) {
+                    // rows below FULL carry samples for every butterfly, row FULL only for n2 < PART
+                    // (warp-uniform); never multiply unstaged words by a zero window: they may be NaN
+                    if (n1 < G::FULL || n2 < G::PART) {
+                        const float2 w = lds_f2(wrow + 2 * n1);
+                        const float2 y = lds_f2(base + G::padded(2 * (n2 + R2 * n1)));
+                        x[n1] = cplx{y.x * w.x, y.y * w.y};
+                    }
+                }
+                if constexpr (R1 == 16) dft16<(G::ROWS <= 13 ? 13 : 16)>(x);
+                else Dft<R1>::run(x);
+                const float *trow = t_tw + n2 * (2 * R1);
+                ws[(0 * R2 + n2) * 32 + lane] = make_float2(x[0].re, x[0].im);
+#pragma unroll
+                for (int k1 = 0; k1 < R1; k1 += 2) {
+                    const float4 tw = lds_f4(trow + 2 * k1);      // twiddles of k1, k1 + 1
+                    if (k1 > 0) {
+                        const cplx v = cmulc(x[k1], tw.x, tw.y);
+                        ws[(k1 * R2 + n2) * 32 + lane] = make_float2(v.re, v.im);
+                    }
+                    const cplx v = cmulc(x[k1 + 1], tw.z, tw.w);
+                    ws[((k1 + 1) * R2 + n2) * 32 + lane] = make_float2(v.re, v.im);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- S2: pass 2 on butterflies (ka, R1 - ka) together, real-FFT split, power ----
+        {
+            constexpr int ITEMS = R1 / 2;
+#pragma unroll 1
+            for (int it = warp; it < ITEMS; it += kWarps) {
+                const int ka = it, kb = it == 0 ? R1 / 2 : R1 - it;
+                cplx u[R2], v[R2];
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    const float2 p = ws[(ka * R2 + n2) * 32 + lane];
+                    u[n2] = cplx{p.x, p.y};
+                }
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    const float2 p = ws[(kb * R2 + n2) * 32 + lane];
+                    v[n2] = cplx{p.x, p.y};
+                }
+                Dft<R2>::run(u);  // u[k2] = Z[ka + R1 k2]
+                Dft<R2>::run(v);  // v[k2] = Z[kb + R1 k2]
+                const float *prow = t_post + it * (2 * R2);
+                if (it != 0) {
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; k2 += 2) {
+                        const float4 w = lds_f4(prow + 2 * k2);
+                        float pk, pm;
+                        int k = ka + R1 * k2;
+                        split_power(u[k2], v[R2 - 1 - k2], make_float2(w.x, w.y), pk, pm);
+                        pw[k * 32 + lane] = pk;
+                        pw[(N2 - k) * 32 + lane] = pm;
+                        k += R1;
+                        split_power(u[k2 + 1], v[R2 - 2 - k2], make_float2(w.z, w.w), pk, pm);
+                        pw[k * 32 + lane] = pk;
+                        pw[(N2 - k) * 32 + lane] = pm;
+                    }
+                } else {
+                    // row 0 of the table: entries [0, R2/2) serve v (bins R1/2 + R1 k2),
+                    // entries [R2/2, R2) serve u (bins R1 k2, k2 = 0 unused)
+                    {
+                        const float dc = u[0].re + u[0].im, ny = u[0].re - u[0].im;
+                        pw[0 * 32 + lane] = 4.0f * dc * dc;
+                        pw[N2 * 32 + lane] = 4.0f * ny * ny;
+                        const cplx z = u[R2 / 2];
+                        pw[(N2 / 2) * 32 + lane] = 4.0f * fmaf(z.re, z.re, z.im * z.im);
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < R2 / 2; k2 += 2) {
+                        const float4 wv = lds_f4(prow + 2 * k2);
+                        const float4 wu = lds_f4(prow + 2 * (R2 / 2 + k2));
+                        float pk, pm;
+                        int k = R1 / 2 + R1 * k2;
+                        split_power(v[k2], v[R2 - 1 - k2], make_float2(wv.x, wv.y), pk, pm);
+                        pw[k * 32 + lane] = pk;
+                        pw[(N2 - k) * 32 + lane] = pm;
+                        k += R1;
+                        split_power(v[k2 + 1], v[R2 - 2 - k2], make_float2(wv.z, wv.w), pk, pm);
+                        pw[k * 32 + lane] = pk;
+                        pw[(N2 - k) * 32 + lane] = pm;
+                        if (k2 > 0) {
+                            k = R1 * k2;
+                            split_power(u[k2], u[R2 - k2], make_float2(wu.x, wu.y), pk, pm);
+                            pw[k * 32 + lane] = pk;
+                            pw[(N2 - k) * 32 + lane] = pm;
+                        }
+                        k = R1 * (k2 + 1);
+                        split_power(u[k2 + 1], u[R2 - 1 - k2], make_float2(wu.z, wu.w), pk, pm);
+                        pw[k * 32 + lane] = pk;
+                        pw[(N2 - k) * 32 + lane] = pm;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- S3: sparse mel in segment form, 4 bins per step (weights zero past the segment) ----
+        {
+            const int j0 = t_seglo[warp], j1 = t_seglo[warp + 1];
+#pragma unroll 1
+            for (int j = j0; j < j1; ++j) {
+                const int4 sg = t_seg[j];
+                const float *p = pw + sg.x * 32 + lane;
+                const float *w = t_melw + sg.z;
+                float r0 = 0.0f, r1 = 0.0f, f0 = 0.0f, f1 = 0.0f;
+#pragma unroll 1
+                for (int c = 0; c < sg.y; ++c) {
+                    const float4 wr = lds_f4(w), wf = lds_f4(w + 4);
+                    const float p0 = p[0], p1 = p[32], p2 = p[64], p3 = p[96];
+                    r0 = fmaf(wr.x, p0, r0); f0 = fmaf(wf.x, p0, f0);
+                    r1 = fmaf(wr.y, p1, r1); f1 = fmaf(wf.y, p1, f1);
+                    r0 = fmaf(wr.z, p2, r0); f0 = fmaf(wf.z, p2, f0);
+                    r1 = fmaf(wr.w, p3, r1); f1 = fmaf(wf.w, p3, f1);
+                    p += 128;
+                    w += 8;
+                }
+                er[j * 32 + lane] = r0 + r1;
+                ef[j * 32 + lane] = f0 + f1;
+            }
+        }
+        __syncthreads();
+
+        // ---- S4: log; symmetric / antisymmetric halves for the DCT (cos(pi k (M-1-m+1/2)/M) = (-1)^k cos(...)) ----
+        const bool live = lane < tile.n_frames;
+        {
+            const int M = a.n_mel;
+#pragma unroll 1
+            for (int mh = warp; mh < half; mh += kWarps) {
+                const int m2 = M - 1 - mh;
+                const float l1 = __logf(fmaxf(er[mh * 32 + lane] + ef[(mh + 1) * 32 + lane], a.log_floor));
+                float l2 = 0.0f;
+                if (m2 != mh) l2 = __logf(fmaxf(er[m2 * 32 + lane] + ef[(m2 + 1) * 32 + lane], a.log_floor));
+                if (a.logmel) {
+                    if (live) {
+                        float *o = a.out + (tile.out_row + lane) * M;
+                        o[mh] = l1;
+                        if (m2 != mh) o[m2] = l2;
+                    }
+                } else {
+                    ls[mh * 32 + lane] = m2 != mh ? l1 + l2 : l1;
+                    ld[mh * 32 + lane] = m2 != mh ? l1 - l2 : 0.0f;
+                }
+            }
+            // rows [half, halfp) are read by S5 with zero weights; the scratch aliases ws, whose
+            // float2 layout puts OTHER lanes' data there, so they must be finite: zero them
+            for (int r = half + warp; r < halfp; r += kWarps) {
+                ls[r * 32 + lane] = 0.0f;
+                ld[r * 32 + lane] = 0.0f;
+            }
+        }
+        if (a.logmel) continue;   // next tile starts with a barrier
+        __syncthreads();
+
+        // ---- S5: DCT-II on the halves; even rows read ls, odd rows ld ----
+        {
+#pragma unroll 1
+            for (int k = warp; k < a.n_cep; k += kWarps) {
+                const float *src = ((k & 1) ? ld : ls) + lane;
+                const float *d = t_dct + k * halfp;
+                float c0 = 0.0f, c1 = 0.0f;
+#pragma unroll 1
+                for (int m = 0; m < halfp; m += 4) {
+                    const float4 dv = lds_f4(d + m);
+                    c0 = fmaf(dv.x, src[(m + 0) * 32], c0);
+                    c1 = fmaf(dv.y, src[(m + 1) * 32], c1);
+                    c0 = fmaf(dv.z, src[(m + 2) * 32], c0);
+                    c1 = fmaf(dv.w, src[(m + 3) * 32], c1);
+                }
+                ostage[lane * a.n_cep + k] = c0 + c1;
+            }
+        }
+        __syncthreads();
+        {
+            const int total = tile.n_frames * a.n_cep;
+            float *o = a.out + tile.out_row * a.n_cep;
+            for (int i = threadIdx.x; i < total; i += kThreads) o[i] = ostage[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct CtVariant {
+    int L, hop, r1, r2;
+    const char *name;
+};
+constexpr CtVariant kVariants[] = {
+    {400, 160, 16, 16, "fused_ct_tile32_L400_H160_r16x16"},   // BASELINE.json configs 1, 2, 5 (16 kHz)
+    {200, 80, 16, 8, "fused_ct_tile32_L200_H80_r16x8"},       // BASELINE.json config 3 (8 kHz telephony)
+};
+
+struct CtState {
+    const CtVariant *v = nullptr;
+    CtLayout lay{};
+    float *d_tab = nullptr;
+    size_t smem = 0;
+    int sm_count = 0;
+};
+
+template <int L, int HOP, int R1, int R2>
+size_t smem_floats_fixed() { return Geo<L, HOP, R1, R2>::UNION + Geo<L, HOP, R1, R2>::WS; }
+
+size_t smem_fixed(const CtVariant &v)
+{
+    if (v.L == 400) return smem_floats_fixed<400, 160, 16, 16>();
+    return smem_floats_fixed<200, 80, 16, 8>();
+}
+
+}  // namespace
+
+const char *ct_match(const mfcc_params &p)
+{
+    for (const auto &v : kVariants) {
+        if (p.frame_len != v.L || p.hop_len != v.hop || p.nfft != 2 * v.r1 * v.r2) continue;
+        // scratch (er | ef | ls | ld | ostage) must fit in the workspace, tables in the smem budget
+        const int n_seg = p.n_mel + 1, halfp = ((p.n_mel + 1) / 2 + 3) / 4 * 4;
+        const size_t scratch = static_cast<size_t>(2 * n_seg + 2 * halfp) * 32 + 32ull * p.n_cep;
+        if (scratch > static_cast<size_t>(v.r1) * v.r2 * 64) return nullptr;
+        return v.name;
+    }
+    return nullptr;
+}
+
+int ct_prepare(mfcc_plan *plan)
+{
+    const mfcc_params &p = plan->p;
+    const CtVariant *var = nullptr;
+    for (const auto &v : kVariants)
+        if (p.frame_len == v.L && p.hop_len == v.hop && p.nfft == 2 * v.r1 * v.r2) var = &v;
+    if (var == nullptr) return MFCC_ENOTSUP;
+    const int R1 = var->r1, R2 = var->r2, N2 = R1 * R2, N = 2 * N2, M = p.n_mel;
+    const HostTables &h = plan->host;
+    std::vector<float> tab;
+    CtLayout lay{};
+    auto align4 = [&]() { while (tab.size() % 4) tab.push_back(0.0f); };
+    auto push_int = [&](int v) { float f; std::memcpy(&f, &v, 4); tab.push_back(f); };
+
+    // window pairs per butterfly row
+    lay.win = static_cast<int>(tab.size());
+    for (int n2 = 0; n2 < R2; ++n2)
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i = 2 * (n2 + R2 * n1);
+            tab.push_back(i < p.frame_len ? h.window[i] : 0.0f);
+            tab.push_back(i + 1 < p.frame_len ? h.window[i + 1] : 0.0f);
+        }
+    // inter-pass twiddles
+    lay.tw = static_cast<int>(tab.size());
+    for (int n2 = 0; n2 < R2; ++n2)
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const double ang = -2.0 * M_PI * static_cast<double>(n2) * k1 / N2;
+            tab.push_back(static_cast<float>(std::cos(ang)));
+            tab.push_back(static_cast<float>(std::sin(ang)));
+        }
+    // split twiddles per work item
+    lay.post = static_cast<int>(tab.size());
+    auto push_post = [&](int k) {
+        const double ang = -2.0 * M_PI * k / N;
+        tab.push_back(static_cast<float>(std::cos(ang)));
+        tab.push_back(static_cast<float>(std::sin(ang)));
+    };
+    for (int it = 0; it < R1 / 2; ++it)
+        for (int k2 = 0; k2 < R2; ++k2) {
+            if (it != 0) push_post(it + R1 * k2);
+            else if (k2 < R2 / 2) push_post(R1 / 2 + R1 * k2);
+            else push_post(R1 * (k2 - R2 / 2));
+        }
+    // mel segments in 4-bin chunks, weights pre-scaled by 1/(4 N) (the split leaves |2X|^2)
+    const int n_seg = M + 1;
+    std::vector<float> melw;
+    std::vector<int> seg;   // 4 ints per segment
+    const double scale = 1.0 / (4.0 * N);
+    for (int j = 0; j < n_seg; ++j) {
+        const int k0 = h.mel_bins[j], k1 = h.mel_bins[j + 1];
+        const int chunks = (k1 - k0 + 3) / 4;
+        seg.push_back(k0);
+        seg.push_back(chunks);
+        seg.push_back(static_cast<int>(melw.size()));
+        seg.push_back(0);
+        for (int c = 0; c < chunks; ++c) {
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + 4 * c + e;
+                melw.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.rise[k]) * scale) : 0.0f);
+            }
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + 4 * c + e;
+                melw.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.fall[k]) * scale) : 0.0f);
+            }
+        }
+    }
+    align4();
+    lay.seg = static_cast<int>(tab.size());
+    for (int v : seg) push_int(v);
+    lay.seg_lo = static_cast<int>(tab.size());
+    {
+        // contiguous split of the segments over the warps, balanced by cost (3 per chunk + 2 per segment)
+        std::vector<int> cost(n_seg);
+        int total = 0;
+        for (int j = 0; j < n_seg; ++j) { cost[j] = seg[4 * j + 1] * 3 + 2; total += cost[j]; }
+        int j = 0, acc = 0;
+        for (int w = 0; w < kWarps; ++w) {
+            push_int(j);
+            const double target = static_cast<double>(total) * (w + 1) / kWarps;
+            while (j < n_seg && acc + cost[j] * 0.5 <= target) acc += cost[j++];
+        }
+        push_int(n_seg);   // the last warp ends at n_seg (its target is the total)
+    }
+    align4();
+    lay.melw = static_cast<int>(tab.size());
+    tab.insert(tab.end(), melw.begin(), melw.end());
+    align4();
+    // DCT rows on the first half (symmetry), zero padded to a multiple of 4
+    const int half = (M + 1) / 2, halfp = (half + 3) / 4 * 4;
+    lay.dct = static_cast<int>(tab.size());
+    for (int k = 0; k < p.n_cep; ++k)
+        for (int m = 0; m < halfp; ++m) tab.push_back(m < half ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f);
+    align4();
+    lay.total = static_cast<int>(tab.size());
+    lay.n_seg = n_seg;
+    lay.half = half;
+    lay.halfp = halfp;
+    if (static_cast<size_t>(lay.total) * 4 > 12 * 1024) return MFCC_ENOTSUP;   // keeps 2 CTAs/SM at N = 512
+
+    CtState *st = new CtState();
+    st->v = var;
+    st->lay = lay;
+    st->sm_count = plan->sm_count;
+    st->smem = sizeof(float) * (static_cast<size_t>(lay.total) + smem_fixed(*var));
+    if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
+        cudaGetLastError();
+        delete st;
+        return MFCC_ENOMEM;
+    }
+    if (cudaMemcpy(st->d_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(st->d_tab);
+        delete st;
+        return MFCC_ECUDA;
+    }
+    plan->ct_state = st;
+    return MFCC_OK;
+}
+
+void ct_release(mfcc_plan *plan)
+{
+    CtState *st = static_cast<CtState *>(plan->ct_state);
+    if (st == nullptr) return;
+    if (st->d_tab) cudaFree(st->d_tab);
+    delete st;
+    plan->ct_state = nullptr;
+}
+
+template <typename PcmT, int L, int HOP, int R1, int R2>
+static int launch_variant(const mfcc_plan *plan, const CtState *st, const Tile *d_tiles, int64_t n_tiles,
+                          const PcmT *d_pcm, int64_t pcm_len, float *d_out, cudaStream_t stream)
+{
+    auto kern = fused_ct_kernel<PcmT, L, HOP, R1, R2>;
+    static thread_local const void *configured = nullptr;
+    if (configured != reinterpret_cast<const void *>(kern)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return MFCC_ECUDA;
+        }
+        configured = reinterpret_cast<const void *>(kern);
+    }
+    const mfcc_params &p = plan->p;
+    CtArgs a;
+    a.tiles = d_tiles;
+    a.n_tiles = n_tiles;
+    a.pcm_len = pcm_len;
+    a.out = d_out;
+    a.tab = st->d_tab;
+    a.lay = st->lay;
+    a.n_mel = p.n_mel;
+    a.n_cep = p.n_cep;
+    a.logmel = p.output == MFCC_OUT_LOGMEL;
+    a.preemph = p.preemph;
+    a.log_floor = p.log_floor;
+    const int per_sm = st->smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+    const int64_t grid = std::min<int64_t>(n_tiles, static_cast<int64_t>(st->sm_count) * per_sm);
+    kern<<<static_cast<unsigned>(grid), kThreads, st->smem, stream>>>(d_pcm, a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+template <typename PcmT>
+int ct_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
+              float *d_out, cudaStream_t stream)
+{
+    const CtState *st = static_cast<const CtState *>(plan->ct_state);
+    if (st == nullptr) return MFCC_ENOTSUP;
+    if (st->v->L == 400)
+        return launch_variant<PcmT, 400, 160, 16, 16>(plan, st, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
+    return launch_variant<PcmT, 200, 80, 16, 8>(plan, st, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
+}
+
+template int ct_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *,
+                                cudaStream_t);
+template int ct_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, int64_t, float *,
+                              cudaStream_t);
+
+}  // namespace mfcc

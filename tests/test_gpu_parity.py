@@ -12,7 +12,7 @@ import pytest
 
 import oracle
 from mfcc_b200 import (api, config_a, config_b, config_c, make_params, KERNEL_GENERIC, KERNEL_FUSED,
-                       KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
+                       KERNEL_FUSED_RT, KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
 from mfcc_b200.synth import clip_config1, fast_fixed_batch, noise_utterance, ragged_batch
 from util import assert_parity, golden, parity_errors
 
@@ -20,14 +20,14 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 CFG = {"A": config_a, "B": config_b, "C": config_c}
-KERNELS = {"generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}
+KERNELS = {"generic": KERNEL_GENERIC, "fused": KERNEL_FUSED, "fused_rt": KERNEL_FUSED_RT}
 
 
 def make_plan(p, kernel):
     try:
         return api.Plan(p, kernel=KERNELS[kernel])
     except api.MfccError as e:
-        if e.code == -4 and kernel == "fused":
+        if e.code == -4 and kernel.startswith("fused"):
             pytest.skip("no fused kernel for this geometry yet")
         raise
 
@@ -40,7 +40,7 @@ def run_device(plan, pcm, offsets):
     return out.cpu().numpy(), b.frame_offsets.copy()
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fused"])
+@pytest.mark.parametrize("kernel", ["generic", "fused", "fused_rt"])
 @pytest.mark.parametrize("name", ["A", "B", "C"])
 def test_ragged_batch_matches_oracle(name, kernel):
     p = CFG[name]()
@@ -58,7 +58,7 @@ def test_ragged_batch_matches_oracle(name, kernel):
     assert_parity(got, ref, what=f"{name}/{kernel}")
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fused"])
+@pytest.mark.parametrize("kernel", ["generic", "fused", "fused_rt"])
 def test_golden_fixtures(kernel):
     g = golden()
     a, b, c = config_a(), config_b(), config_c()
@@ -74,7 +74,7 @@ def test_golden_fixtures(kernel):
         assert_parity(got, g[key], what=f"{key}/{kernel}")
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fused"])
+@pytest.mark.parametrize("kernel", ["generic", "fused", "fused_rt"])
 def test_option_matrix_matches_oracle(kernel):
     base = config_a()
     variants = [
@@ -148,6 +148,10 @@ def test_bad_calls_fail_loudly():
     with pytest.raises(ValueError):
         plan.compute_batch(b, torch.zeros(100, dtype=torch.int16, device="cuda"))
     assert api.Plan(config_a().copy(hop_len=161)).kernel_name == "generic_radix2"
+    assert api.Plan(config_a()).kernel_name.startswith("fused_ct_")
+    assert api.Plan(config_b()).kernel_name.startswith("fused_ct_")
+    assert api.Plan(config_a().copy(hop_len=128)).kernel_name.startswith("fused_rt_")
+    assert api.Plan(config_a(), kernel=KERNEL_FUSED_RT).kernel_name.startswith("fused_rt_")
 
 
 # ---- BASELINE.json full sizes, through size-independent properties ----
