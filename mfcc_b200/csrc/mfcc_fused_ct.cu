@@ -120,39 +120,67 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
     float *ls = scr + 2 * n_seg * 32, *ld = ls + halfp * 32;
     float *ostage = ld + halfp * 32;
 
+    // ---- S0 machinery.  Fast path (int16, 4-byte aligned, even tile start, no utterance end inside
+    // the tile): every warp owns CH consecutive 32-bit words (2 samples each) of the tile and
+    // PREFETCHES them into registers one tile ahead, so the HBM latency hides behind S1..S5.
+    constexpr int QWORDS = (31 * HOP + L) / 2 + 1;            // words covering i = 0 .. T_max
+    constexpr int CH = (QWORDS + kWarps - 1) / kWarps;        // words per warp
+    constexpr int NQ = (CH + 31) / 32;                        // steps of 32 words
+    uint32_t wreg[NQ];
+    float edge = 0.0f;                                        // lane 31: the sample before the warp's first word
+    auto tile_fast = [&](const Tile &tl) -> bool {
+        if constexpr (sizeof(PcmT) != 2) return false;
+        const int T = (tl.n_frames - 1) * HOP + L;
+        return ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0) && ((tl.first_sample & 1) == 0) &&
+               (tl.utt_end - tl.first_sample >= T + 2) && (a.pcm_len - tl.first_sample >= T + 2);
+    };
+    auto prefetch = [&](const Tile &tl) {
+        const int T = (tl.n_frames - 1) * HOP + L;
+        const uint32_t *xw = reinterpret_cast<const uint32_t *>(pcm) + (tl.first_sample >> 1) + warp * CH + lane;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            const int ql = 32 * j + lane;
+            wreg[j] = (ql < CH && 2 * (warp * CH + ql) <= T) ? __ldg(xw + 32 * j) : 0u;
+        }
+        edge = 0.0f;
+        const int ie = 2 * warp * CH - 1;                     // tile-relative index of the edge sample
+        if (lane == 31 && ie <= T && (warp > 0 || tl.first_sample > tl.utt_begin))
+            edge = to_f32(pcm[tl.first_sample + ie]);
+    };
+
+    Tile tile{};
+    bool fast = false;
+    if (static_cast<int64_t>(blockIdx.x) < a.n_tiles) {
+        tile = a.tiles[blockIdx.x];
+        fast = tile_fast(tile);
+        if (fast) prefetch(tile);
+    }
     for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-        const Tile tile = a.tiles[t];
+        const int n_frames = tile.n_frames;
+        const int64_t out_row = tile.out_row;
         __syncthreads();   // previous tile's readers of ws/scr and pw are done; tables are visible
 
         // ---- S0: stage y[s] = x[s] - a x[s-1] once per sample, padded by kPad words per hop ----
         {
-            const int T = (tile.n_frames - 1) * HOP + L;
-            const int64_t room_lo = tile.first_sample - tile.utt_begin;
-            const int64_t room_hi = tile.utt_end - tile.first_sample;
-            bool fast = false;
-            if constexpr (sizeof(PcmT) == 2)
-                fast = ((reinterpret_cast<uintptr_t>(pcm) & 3) == 0) && ((tile.first_sample & 1) == 0);
+            const int T = (n_frames - 1) * HOP + L;
             if (fast) {
-                const uint32_t *xw = reinterpret_cast<const uint32_t *>(pcm) + (tile.first_sample >> 1);
-                const int64_t avail = a.pcm_len - tile.first_sample;   // samples readable from i = 0
-                for (int qb = warp * 32; 2 * qb <= T; qb += kThreads) {   // warp-uniform bound: the shuffle stays converged
-                    const int q = qb + lane, i0 = 2 * q;
-                    uint32_t w = 0;
-                    if (i0 + 1 < avail) w = __ldg(xw + q);
-                    else if (i0 < avail) w = reinterpret_cast<const uint16_t *>(xw)[i0];
-                    // previous sample: high half of the previous word (lane - 1), or a load at lane 0
-                    uint32_t wp = __shfl_up_sync(0xffffffffu, w, 1);
-                    if (lane == 0)
-                        wp = (i0 > -room_lo) ? (static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(xw) + i0 - 1)) << 16) : 0u;
-                    const float2 x = s16x2_to_f32(w);
-                    float xp = s16x2_to_f32(wp).y;
-                    if (i0 <= -room_lo) xp = 0.0f;                 // i0 is the first sample of the utterance
-                    float y0 = fmaf(-a.preemph, xp, x.x), y1 = fmaf(-a.preemph, x.x, x.y);
-                    if (i0 >= room_hi) y0 = 0.0f;
-                    if (i0 + 1 >= room_hi) y1 = 0.0f;
-                    if (i0 <= T) *reinterpret_cast<float2 *>(staged + G::padded(i0)) = make_float2(y0, y1);
+                float vp = edge;
+                const int ib = 2 * (warp * CH + lane);
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const int i0 = ib + 64 * j;
+                    const float2 x = s16x2_to_f32(wreg[j]);
+                    // previous sample = lane-1's second sample; lane 0 takes lane 31's from the step before
+                    const float u = lane == 31 ? vp : x.y;
+                    const float xp = __shfl_sync(0xffffffffu, u, (lane + 31) & 31);
+                    vp = x.y;
+                    const float y0 = fmaf(-a.preemph, xp, x.x), y1 = fmaf(-a.preemph, x.x, x.y);
+                    if (32 * j + lane < CH && i0 <= T)
+                        *reinterpret_cast<float2 *>(staged + G::padded(i0)) = make_float2(y0, y1);
                 }
             } else {
+                const int64_t room_lo = tile.first_sample - tile.utt_begin;
+                const int64_t room_hi = tile.utt_end - tile.first_sample;
                 const PcmT *x = pcm + tile.first_sample;
                 for (int i = threadIdx.x; i <= T; i += kThreads) {
                     float y = 0.0f;
@@ -165,9 +193,15 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
                 }
             }
         }
-        if (tile.n_frames < 32) {
+        // the registers are free again: fetch the next tile while this one is transformed
+        if (t + gridDim.x < a.n_tiles) {
+            tile = a.tiles[t + gridDim.x];
+            fast = tile_fast(tile);
+            if (fast) prefetch(tile);
+        }
+        if (n_frames < 32) {
             // partial tile: lanes >= n_frames would otherwise transform stale words (possibly NaN)
-            const int T = (tile.n_frames - 1) * HOP + L;
+            const int T = (n_frames - 1) * HOP + L;
             for (int i = T + 2 - (T & 1) + 2 * threadIdx.x; i < 31 * HOP + L + 1; i += 2 * kThreads)
                 *reinterpret_cast<float2 *>(staged + G::padded(i)) = make_float2(0.0f, 0.0f);
         }
@@ -312,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
         __syncthreads();
 
         // ---- S4: log; symmetric / antisymmetric halves for the DCT (cos(pi k (M-1-m+1/2)/M) = (-1)^k cos(...)) ----
-        const bool live = lane < tile.n_frames;
+        const bool live = lane < n_frames;
         {
             const int M = a.n_mel;
 #pragma unroll 1
@@ -323,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
                 if (m2 != mh) l2 = __logf(fmaxf(er[m2 * 32 + lane] + ef[(m2 + 1) * 32 + lane], a.log_floor));
                 if (a.logmel) {
                     if (live) {
-                        float *o = a.out + (tile.out_row + lane) * M;
+                        float *o = a.out + (out_row + lane) * M;
                         o[mh] = l1;
                         if (m2 != mh) o[m2] = l2;
                     }
@@ -362,8 +396,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
         }
         __syncthreads();
         {
-            const int total = tile.n_frames * a.n_cep;
-            float *o = a.out + tile.out_row * a.n_cep;
+            const int total = n_frames * a.n_cep;
+            float *o = a.out + out_row * a.n_cep;
             for (int i = threadIdx.x; i < total; i += kThreads) o[i] = ostage[i];
         }
     }
