@@ -1,8 +1,5 @@
 // mfcc_fft.cuh — register-resident small DFTs and the real-FFT split used by the
 // fused tile kernels.  Everything is statically indexed so arrays stay in registers.
-// The value type V is either `float` (one butterfly per thread) or `pf2` (two
-// butterflies in lock-step on sm_100's packed FP32 pipe: FADD2 / FMUL2 / FFMA2,
-// i.e. PTX add/mul/fma.rn.f32x2 — half the issue slots for the same FLOPs).
 // No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
 #pragma once
 #include <cuda_runtime.h>
@@ -10,90 +7,43 @@
 namespace mfcc {
 namespace {
 
-// ---- packed pair of floats with IEEE round-to-nearest ops on both halves ----
-struct pf2 {
-    float2 v;
-    __device__ __forceinline__ pf2() {}
-    __device__ __forceinline__ pf2(float2 a) : v(a) {}
-    __device__ __forceinline__ pf2(float lo, float hi) : v(make_float2(lo, hi)) {}
-    __device__ __forceinline__ explicit pf2(float s) : v(make_float2(s, s)) {}
-};
-__device__ __forceinline__ pf2 operator+(pf2 a, pf2 b) { return pf2(__fadd2_rn(a.v, b.v)); }
-__device__ __forceinline__ pf2 operator-(pf2 a, pf2 b) { return pf2(__ffma2_rn(b.v, make_float2(-1.0f, -1.0f), a.v)); }
-__device__ __forceinline__ pf2 operator*(pf2 a, pf2 b) { return pf2(__fmul2_rn(a.v, b.v)); }
-__device__ __forceinline__ pf2 operator-(pf2 a) { return pf2(make_float2(-a.v.x, -a.v.y)); }
+struct cplx { float re, im; };
 
-// a * b + c and c - a * b for both value types
-__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ float vfnma(float a, float b, float c) { return fmaf(-a, b, c); }
-__device__ __forceinline__ pf2 vfma(pf2 a, pf2 b, pf2 c) { return pf2(__ffma2_rn(a.v, b.v, c.v)); }
-__device__ __forceinline__ pf2 vfnma(pf2 a, pf2 b, pf2 c)
+__device__ __forceinline__ cplx cmulc(cplx a, float cr, float ci)
 {
-    return pf2(__ffma2_rn(a.v, make_float2(-b.v.x, -b.v.y), c.v));
-}
-// multiply by a compile-time scalar on both halves
-__device__ __forceinline__ float vscale(float a, float s) { return a * s; }
-__device__ __forceinline__ pf2 vscale(pf2 a, float s) { return pf2(__fmul2_rn(a.v, make_float2(s, s))); }
-__device__ __forceinline__ float vfma_s(float a, float s, float c) { return fmaf(a, s, c); }
-__device__ __forceinline__ pf2 vfma_s(pf2 a, float s, pf2 c) { return pf2(__ffma2_rn(a.v, make_float2(s, s), c.v)); }
-__device__ __forceinline__ float vzero(float) { return 0.0f; }
-__device__ __forceinline__ pf2 vzero(pf2) { return pf2(0.0f, 0.0f); }
-
-template <typename V>
-struct cx {
-    V re, im;
-};
-using cplx = cx<float>;
-
-// a * (cr + i ci) with compile-time scalar constants
-template <typename V>
-__device__ __forceinline__ cx<V> cmulc(cx<V> a, float cr, float ci)
-{
-    cx<V> r;
-    r.re = vfma_s(a.im, -ci, vscale(a.re, cr));
-    r.im = vfma_s(a.im, cr, vscale(a.re, ci));
-    return r;
-}
-
-// a * (tr + i ti) with run-time (table) constants of the value type
-template <typename V>
-__device__ __forceinline__ cx<V> cmulv(cx<V> a, V tr, V ti)
-{
-    cx<V> r;
-    r.re = vfnma(a.im, ti, a.re * tr);
-    r.im = vfma(a.im, tr, a.re * ti);
+    cplx r;
+    r.re = fmaf(-a.im, ci, a.re * cr);
+    r.im = fmaf(a.im, cr, a.re * ci);
     return r;
 }
 
 // Forward 4-point DFT (W4 = -i), in place on four named values.
-template <typename V>
-__device__ __forceinline__ void dft4(cx<V> &x0, cx<V> &x1, cx<V> &x2, cx<V> &x3)
+__device__ __forceinline__ void dft4(cplx &x0, cplx &x1, cplx &x2, cplx &x3)
 {
-    const cx<V> t0{x0.re + x2.re, x0.im + x2.im}, t1{x0.re - x2.re, x0.im - x2.im};
-    const cx<V> t2{x1.re + x3.re, x1.im + x3.im}, t3{x1.re - x3.re, x1.im - x3.im};
-    x0 = cx<V>{t0.re + t2.re, t0.im + t2.im};
-    x2 = cx<V>{t0.re - t2.re, t0.im - t2.im};
-    x1 = cx<V>{t1.re + t3.im, t1.im - t3.re};
-    x3 = cx<V>{t1.re - t3.im, t1.im + t3.re};
+    const cplx t0{x0.re + x2.re, x0.im + x2.im}, t1{x0.re - x2.re, x0.im - x2.im};
+    const cplx t2{x1.re + x3.re, x1.im + x3.im}, t3{x1.re - x3.re, x1.im - x3.im};
+    x0 = cplx{t0.re + t2.re, t0.im + t2.im};
+    x2 = cplx{t0.re - t2.re, t0.im - t2.im};
+    x1 = cplx{t1.re + t3.im, t1.im - t3.re};
+    x3 = cplx{t1.re - t3.im, t1.im + t3.re};
 }
 
 // dft4 with x3 == 0 (zero-padded tail of the frame): two complex adds fewer.
-template <typename V>
-__device__ __forceinline__ void dft4_z3(cx<V> &x0, cx<V> &x1, cx<V> &x2, cx<V> &x3)
+__device__ __forceinline__ void dft4_z3(cplx &x0, cplx &x1, cplx &x2, cplx &x3)
 {
-    const cx<V> t0{x0.re + x2.re, x0.im + x2.im}, t1{x0.re - x2.re, x0.im - x2.im};
-    const cx<V> a = x1;
-    x0 = cx<V>{t0.re + a.re, t0.im + a.im};
-    x2 = cx<V>{t0.re - a.re, t0.im - a.im};
-    x1 = cx<V>{t1.re + a.im, t1.im - a.re};
-    x3 = cx<V>{t1.re - a.im, t1.im + a.re};
+    const cplx t0{x0.re + x2.re, x0.im + x2.im}, t1{x0.re - x2.re, x0.im - x2.im};
+    const cplx a = x1;
+    x0 = cplx{t0.re + a.re, t0.im + a.im};
+    x2 = cplx{t0.re - a.re, t0.im - a.im};
+    x1 = cplx{t1.re + a.im, t1.im - a.re};
+    x3 = cplx{t1.re - a.im, t1.im + a.re};
 }
 
 // Forward 16-point DFT, natural order in and out, everything statically indexed.
 // n = nb + 4 na, k = ka + 4 kb:  4-point DFTs over na, twiddle W16^(nb ka), 4-point DFTs over nb.
 // NZ = number of leading inputs that can be non-zero (13 when x[13..15] are zero padding).
-template <int NZ = 16, typename V = float>
-__device__ __forceinline__ void dft16(cx<V> (&x)[16])
+template <int NZ = 16>
+__device__ __forceinline__ void dft16(cplx (&x)[16])
 {
     constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
 #pragma unroll
@@ -106,7 +56,7 @@ __device__ __forceinline__ void dft16(cx<V> (&x)[16])
     x[1 + 4 * 2] = cmulc(x[1 + 4 * 2], h, -h);     // W^2
     x[1 + 4 * 3] = cmulc(x[1 + 4 * 3], s1, -c1);   // W^3
     x[2 + 4 * 1] = cmulc(x[2 + 4 * 1], h, -h);     // W^2
-    x[2 + 4 * 2] = cx<V>{x[2 + 4 * 2].im, -x[2 + 4 * 2].re};  // W^4 = -i
+    x[2 + 4 * 2] = cplx{x[2 + 4 * 2].im, -x[2 + 4 * 2].re};  // W^4 = -i
     x[2 + 4 * 3] = cmulc(x[2 + 4 * 3], -h, -h);    // W^6
     x[3 + 4 * 1] = cmulc(x[3 + 4 * 1], s1, -c1);   // W^3
     x[3 + 4 * 2] = cmulc(x[3 + 4 * 2], -h, -h);    // W^6
@@ -118,39 +68,34 @@ __device__ __forceinline__ void dft16(cx<V> (&x)[16])
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = a + 1; b < 4; ++b) {
-            const cx<V> t = x[4 * a + b];
+            const cplx t = x[4 * a + b];
             x[4 * a + b] = x[4 * b + a];
             x[4 * b + a] = t;
         }
 }
 
 // Forward 8-point DFT, natural order: n = nb + 2 na (na<4), k = ka + 4 kb (ka<4, kb<2).
-template <typename V>
-__device__ __forceinline__ void dft8(cx<V> (&x)[8])
+__device__ __forceinline__ void dft8(cplx (&x)[8])
 {
     constexpr float h = 0.70710678118654752f;
     dft4(x[0], x[2], x[4], x[6]);  // nb = 0: y[0][ka] in x[2 ka]
     dft4(x[1], x[3], x[5], x[7]);  // nb = 1: y[1][ka] in x[2 ka + 1]
     x[3] = cmulc(x[3], h, -h);               // W8^1
-    x[5] = cx<V>{x[5].im, -x[5].re};         // W8^2 = -i
+    x[5] = cplx{x[5].im, -x[5].re};          // W8^2 = -i
     x[7] = cmulc(x[7], -h, -h);              // W8^3
-    cx<V> r[8];
+    cplx r[8];
 #pragma unroll
     for (int ka = 0; ka < 4; ++ka) {
-        r[ka] = cx<V>{x[2 * ka].re + x[2 * ka + 1].re, x[2 * ka].im + x[2 * ka + 1].im};
-        r[ka + 4] = cx<V>{x[2 * ka].re - x[2 * ka + 1].re, x[2 * ka].im - x[2 * ka + 1].im};
+        r[ka] = cplx{x[2 * ka].re + x[2 * ka + 1].re, x[2 * ka].im + x[2 * ka + 1].im};
+        r[ka + 4] = cplx{x[2 * ka].re - x[2 * ka + 1].re, x[2 * ka].im - x[2 * ka + 1].im};
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = r[i];
 }
 
 template <int R> struct Dft;
-template <> struct Dft<16> {
-    template <typename V> static __device__ __forceinline__ void run(cx<V> (&x)[16]) { dft16<16, V>(x); }
-};
-template <> struct Dft<8> {
-    template <typename V> static __device__ __forceinline__ void run(cx<V> (&x)[8]) { dft8<V>(x); }
-};
+template <> struct Dft<16> { static __device__ __forceinline__ void run(cplx (&x)[16]) { dft16<16>(x); } };
+template <> struct Dft<8>  { static __device__ __forceinline__ void run(cplx (&x)[8]) { dft8(x); } };
 
 // Real-FFT split of one (k, N/2-k) pair of the packed transform followed by the
 // power spectrum.  zk = Z[k], zm = Z[N/2-k], w = exp(-2 pi i k / N).
@@ -164,6 +109,7 @@ __device__ __forceinline__ void split_power(cplx zk, cplx zm, float2 w, float &p
     pk = fmaf(ar, ar, ai * ai);
     pm = fmaf(br, br, bi * bi);
 }
+
 
 }  // namespace
 }  // namespace mfcc

@@ -15,9 +15,15 @@
 //     and hop are template parameters.
 //
 // Phases per tile (lane = frame, 8 warps, CTA barriers between phases):
-//   S0 stage, S1 pass 1 (+window, +inter-pass twiddle), S2 pass 2 + real-FFT split
-//   + power, S3 sparse mel (segment form, 4-bin chunks), S4 log + symmetric/
-//   antisymmetric halves, S5 DCT on the halves, coalesced store.
+//   S0 stage, S1 pass 1 (window, REAL DFT-RB over b for a pair of columns a, inter-pass
+//   twiddle), S2 pass 2 (complex DFT-RA over a for one row k1) + power, S3 sparse mel
+//   (segment form, 4-bin chunks), S4 log + symmetric/antisymmetric halves, S5 DCT on the
+//   halves, coalesced store.
+//
+// The transform is a two-pass REAL FFT, N = RB * RA, n = a + RA b, k = k1 + RB k2
+// (mfcc_rfft.cuh): pass 1 keeps only the Hermitian half k1 = 0 .. RB/2 of each column,
+// so the workspace holds N/2 complex words per frame and pass 2 delivers bins directly —
+// there is no "two reals in one complex" packing and therefore no split step.
 //
 // No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
 #include <cuda_runtime.h>
@@ -26,7 +32,7 @@
 #include <cstring>
 #include <vector>
 
-#include "mfcc_fft.cuh"
+#include "mfcc_rfft.cuh"
 #include "mfcc_host.h"
 
 namespace mfcc {
@@ -39,9 +45,9 @@ constexpr int kPad = 2;
 
 // Offsets (in floats) of the tables inside the shared-memory blob; set by the host.
 struct CtLayout {
-    int win;      // [R2][R1] float2: window pair of z[n2 + R2 n1]
-    int tw;       // [R2][R1] float2: W_{N/2}^{n2 k1}
-    int post;     // [R1/2][R2] float2: split twiddles of work item `it`
+    int win;      // [RA/2][NZP] float2: window of samples (a, a + 1) + RA b, a = 2 pair
+    int tw;       // [RA][RB/2] float2: W_N^(a k1) at slot k1 - 1, k1 = 1 .. RB/2 - 1 (last slot unused)
+    int twh;      // [RA] float2: W_(2 RA)^a, the twiddle of row k1 = RB/2
     int seg;      // int4 per segment: {first bin, chunks, weight offset (floats from melw), 0}
     int seg_lo;   // int[kWarps + 1]: segment range of each warp
     int melw;     // per chunk: 4 rise weights then 4 fall weights (scaled by 1/(4 NFFT))
@@ -61,21 +67,23 @@ struct CtArgs {
     float preemph, log_floor;
 };
 
-template <int L, int HOP, int R1, int R2>
+template <int L, int HOP, int RB, int RA>
 struct Geo {
-    static constexpr int N2 = R1 * R2, NFFT = 2 * N2, NB = N2 + 1;
-    static constexpr int L2 = (L + 1) / 2;                 // complex points that carry samples
+    static constexpr int NFFT = RB * RA, NB = NFFT / 2 + 1, H = RB / 2;
+    static constexpr int NZ = (L + RA - 1) / RA;           // rows b of a column that carry samples
+    static constexpr int NZP = (NZ + 1) / 2 * 2;
     static constexpr int STRIDE = HOP + kPad;              // staged words per hop block
     static constexpr int padded(int i) { return i + kPad * (i / HOP); }
-    static constexpr int STAGED = 31 * STRIDE + padded(L + 1) + 2;
+    static constexpr int SLACK = RA * NZ - L;              // words past the last frame read with zero window
+    static constexpr int MAXS = (L + 1 > RA * NZ ? L + 1 : RA * NZ);
+    static constexpr int STAGED = 31 * STRIDE + padded(MAXS) + 2;
     static constexpr int PW = (NB + 3) * 32;               // 3 slack rows for 4-bin chunks
     static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
-    static constexpr int WS = N2 * 32 * 2;                 // floats
-    // pass-1 rows: n1 < FULL are valid for every n2, row FULL is valid for n2 < PART, the rest is padding
-    static constexpr int FULL = L2 / R2, PART = L2 % R2;
-    static constexpr int ROWS = FULL + (PART ? 1 : 0);     // rows that can be non-zero
+    static constexpr int WS = H * RA * 32 * 2;             // floats: rows 1 .. H-1 complex, rows 0 and H (real) share the last
     static_assert(HOP % 2 == 0, "float2 pairs must not straddle a hop block");
-    static_assert(L <= NFFT && ROWS <= R1, "frame does not fit the transform");
+    static_assert(HOP % RA == 0, "a column pair must not straddle a hop block");
+    static_assert(RA == 2 * kWarps && RA == 16, "one column pair per warp, 16-point second pass");
+    static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -92,11 +100,11 @@ __device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
 __device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
-template <typename PcmT, int L, int HOP, int R1, int R2>
+template <typename PcmT, int L, int HOP, int RB, int RA>
 __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__restrict__ pcm, const CtArgs a)
 {
-    using G = Geo<L, HOP, R1, R2>;
-    constexpr int N2 = G::N2, STRIDE = G::STRIDE;
+    using G = Geo<L, HOP, RB, RA>;
+    constexpr int STRIDE = G::STRIDE, H = G::H, NZ = G::NZ;
     extern __shared__ __align__(16) float smem[];
     float *tab = smem;
     float *staged = smem + a.lay.total;   // S0-S1
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     for (int i = G::NB * 32 + threadIdx.x; i < G::PW; i += kThreads) pw[i] = 0.0f;
 
-    const float *t_win = tab + a.lay.win, *t_tw = tab + a.lay.tw, *t_post = tab + a.lay.post;
+    const float *t_win = tab + a.lay.win, *t_tw = tab + a.lay.tw, *t_twh = tab + a.lay.twh;
     const int4 *t_seg = reinterpret_cast<const int4 *>(tab + a.lay.seg);
     const int *t_seglo = reinterpret_cast<const int *>(tab + a.lay.seg_lo);
     const float *t_melw = tab + a.lay.melw, *t_dct = tab + a.lay.dct;
@@ -199,121 +207,102 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
             fast = tile_fast(tile);
             if (fast) prefetch(tile);
         }
-        if (n_frames < 32) {
-            // partial tile: lanes >= n_frames would otherwise transform stale words (possibly NaN)
+        if constexpr (G::SLACK > 0) {
+            // the last frame's columns read SLACK words past its end (zero window): keep them finite
             const int T = (n_frames - 1) * HOP + L;
-            for (int i = T + 2 - (T & 1) + 2 * threadIdx.x; i < 31 * HOP + L + 1; i += 2 * kThreads)
-                *reinterpret_cast<float2 *>(staged + G::padded(i)) = make_float2(0.0f, 0.0f);
+            if (threadIdx.x <= G::SLACK) staged[G::padded(T + 1 + threadIdx.x)] = 0.0f;
         }
         __syncthreads();
 
-        // ---- S1: pass 1.  Butterfly n2 takes z[n2 + R2 n1] = (y[2n], y[2n+1]) * window ----
+        // ---- S1: pass 1.  Warp = column pair (a, a + 1): windowed real DFT-RB over b, inter-pass twiddle ----
         {
-            const float *base = staged + lane * STRIDE;
-            constexpr int PER_WARP = R2 / kWarps;
-#pragma unroll 1
-            for (int j = 0; j < PER_WARP; ++j) {
-                const int n2 = warp * PER_WARP + j;
-                const float *wrow = t_win + n2 * (2 * R1);
-                cplx x[R1];
+            const int pr = warp;
+            const float *base = staged + lane * STRIDE + 2 * pr;
+            const float *wrow = t_win + pr * (2 * G::NZP);
+            float2 in[NZ];
 #pragma unroll
-                for (int n1 = 0; n1 < R1; ++n1) x[n1] = cplx{0.0f, 0.0f};   // rows >= ROWS are zero padding
-#pragma unroll
-                for (int n1 = 0; n1 < G::ROWS; ++n1) {
-                    // rows below FULL carry samples for every butterfly, row FULL only for n2 < PART
-                    // (warp-uniform); never multiply unstaged words by a zero window: they may be NaN
-                    if (n1 < G::FULL || n2 < G::PART) {
-                        const float2 w = lds_f2(wrow + 2 * n1);
-                        const float2 y = lds_f2(base + G::padded(2 * (n2 + R2 * n1)));
-                        x[n1] = cplx{y.x * w.x, y.y * w.y};
-                    }
+            for (int b = 0; b < NZ; b += 2) {
+                const float4 w = lds_f4(wrow + 2 * b);
+                const float2 y0 = lds_f2(base + G::padded(RA * b));
+                in[b] = make_float2(y0.x * w.x, y0.y * w.y);
+                if (b + 1 < NZ) {
+                    const float2 y1 = lds_f2(base + G::padded(RA * (b + 1)));
+                    in[b + 1] = make_float2(y1.x * w.z, y1.y * w.w);
                 }
-                if constexpr (R1 == 16) dft16<(G::ROWS <= 13 ? 13 : 16)>(x);
-                else Dft<R1>::run(x);
-                const float *trow = t_tw + n2 * (2 * R1);
-                ws[(0 * R2 + n2) * 32 + lane] = make_float2(x[0].re, x[0].im);
+            }
 #pragma unroll
-                for (int k1 = 0; k1 < R1; k1 += 2) {
-                    const float4 tw = lds_f4(trow + 2 * k1);      // twiddles of k1, k1 + 1
-                    if (k1 > 0) {
-                        const cplx v = cmulc(x[k1], tw.x, tw.y);
-                        ws[(k1 * R2 + n2) * 32 + lane] = make_float2(v.re, v.im);
+            for (int half = 0; half < 2; ++half) {
+                const int col = 2 * pr + half;
+                float x[RB];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) x[b] = b < NZ ? (half ? in[b < NZ ? b : 0].y : in[b < NZ ? b : 0].x) : 0.0f;
+                rf::cplx X[H + 1];
+                rf::RDft<RB>::template run<NZ>(x, X);
+                float2 *wsa = ws + col * 32 + lane;
+                wsa[(H - 1) * RA * 32] = make_float2(X[0].re, X[H].re);   // rows 0 and H are real here
+                const float *trow = t_tw + col * (2 * H);
+#pragma unroll
+                for (int k1 = 1; k1 < H; k1 += 2) {
+                    const float4 tw = lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
+                    const rf::cplx v = rf::cmulc(X[k1], tw.x, tw.y);
+                    wsa[(k1 - 1) * RA * 32] = make_float2(v.re, v.im);
+                    if (k1 + 1 < H) {
+                        const rf::cplx u = rf::cmulc(X[k1 + 1], tw.z, tw.w);
+                        wsa[k1 * RA * 32] = make_float2(u.re, u.im);
                     }
-                    const cplx v = cmulc(x[k1 + 1], tw.z, tw.w);
-                    ws[((k1 + 1) * R2 + n2) * 32 + lane] = make_float2(v.re, v.im);
                 }
             }
         }
         __syncthreads();
 
-        // ---- S2: pass 2 on butterflies (ka, R1 - ka) together, real-FFT split, power ----
+        // ---- S2: pass 2.  Item = one row k1: complex DFT-RA over a gives bins k1 + RB k2; power ----
         {
-            constexpr int ITEMS = R1 / 2;
 #pragma unroll 1
-            for (int it = warp; it < ITEMS; it += kWarps) {
-                const int ka = it, kb = it == 0 ? R1 / 2 : R1 - it;
-                cplx u[R2], v[R2];
+            for (int it = warp; it < H; it += kWarps) {
+                if (it < H - 1) {
+                    const int k1 = it + 1;
+                    const float2 *row = ws + (k1 - 1) * RA * 32 + lane;
+                    rf::cplx z[RA];
 #pragma unroll
-                for (int n2 = 0; n2 < R2; ++n2) {
-                    const float2 p = ws[(ka * R2 + n2) * 32 + lane];
-                    u[n2] = cplx{p.x, p.y};
-                }
-#pragma unroll
-                for (int n2 = 0; n2 < R2; ++n2) {
-                    const float2 p = ws[(kb * R2 + n2) * 32 + lane];
-                    v[n2] = cplx{p.x, p.y};
-                }
-                Dft<R2>::run(u);  // u[k2] = Z[ka + R1 k2]
-                Dft<R2>::run(v);  // v[k2] = Z[kb + R1 k2]
-                const float *prow = t_post + it * (2 * R2);
-                if (it != 0) {
-#pragma unroll
-                    for (int k2 = 0; k2 < R2; k2 += 2) {
-                        const float4 w = lds_f4(prow + 2 * k2);
-                        float pk, pm;
-                        int k = ka + R1 * k2;
-                        split_power(u[k2], v[R2 - 1 - k2], make_float2(w.x, w.y), pk, pm);
-                        pw[k * 32 + lane] = pk;
-                        pw[(N2 - k) * 32 + lane] = pm;
-                        k += R1;
-                        split_power(u[k2 + 1], v[R2 - 2 - k2], make_float2(w.z, w.w), pk, pm);
-                        pw[k * 32 + lane] = pk;
-                        pw[(N2 - k) * 32 + lane] = pm;
+                    for (int c = 0; c < RA; ++c) {
+                        const float2 p = row[c * 32];
+                        z[c] = rf::cplx{p.x, p.y};
                     }
+                    rf::cdft16(z);
+                    float *p_lo = pw + k1 * 32 + lane;            // bins k1 + RB k2, k2 < RA/2
+                    float *p_hi = pw + (RB - k1) * 32 + lane;     // mirrored: N - k = (RB - k1) + RB (RA - 1 - k2)
+#pragma unroll
+                    for (int k2 = 0; k2 < RA / 2; ++k2)
+                        p_lo[RB * k2 * 32] = fmaf(z[k2].re, z[k2].re, z[k2].im * z[k2].im);
+#pragma unroll
+                    for (int k2 = RA / 2; k2 < RA; ++k2)
+                        p_hi[RB * (RA - 1 - k2) * 32] = fmaf(z[k2].re, z[k2].re, z[k2].im * z[k2].im);
                 } else {
-                    // row 0 of the table: entries [0, R2/2) serve v (bins R1/2 + R1 k2),
-                    // entries [R2/2, R2) serve u (bins R1 k2, k2 = 0 unused)
-                    {
-                        const float dc = u[0].re + u[0].im, ny = u[0].re - u[0].im;
-                        pw[0 * 32 + lane] = 4.0f * dc * dc;
-                        pw[N2 * 32 + lane] = 4.0f * ny * ny;
-                        const cplx z = u[R2 / 2];
-                        pw[(N2 / 2) * 32 + lane] = 4.0f * fmaf(z.re, z.re, z.im * z.im);
-                    }
+                    // rows 0 and H: both real after pass 1.  Row 0 -> real DFT-16 -> bins RB k2;
+                    // row H times W_(2 RA)^a -> complex DFT-16 -> bins H + RB k2, k2 < RA/2
+                    const float2 *row = ws + (H - 1) * RA * 32 + lane;
+                    float r0[RA];
+                    rf::cplx zh[RA];
 #pragma unroll
-                    for (int k2 = 0; k2 < R2 / 2; k2 += 2) {
-                        const float4 wv = lds_f4(prow + 2 * k2);
-                        const float4 wu = lds_f4(prow + 2 * (R2 / 2 + k2));
-                        float pk, pm;
-                        int k = R1 / 2 + R1 * k2;
-                        split_power(v[k2], v[R2 - 1 - k2], make_float2(wv.x, wv.y), pk, pm);
-                        pw[k * 32 + lane] = pk;
-                        pw[(N2 - k) * 32 + lane] = pm;
-                        k += R1;
-                        split_power(v[k2 + 1], v[R2 - 2 - k2], make_float2(wv.z, wv.w), pk, pm);
-                        pw[k * 32 + lane] = pk;
-                        pw[(N2 - k) * 32 + lane] = pm;
-                        if (k2 > 0) {
-                            k = R1 * k2;
-                            split_power(u[k2], u[R2 - k2], make_float2(wu.x, wu.y), pk, pm);
-                            pw[k * 32 + lane] = pk;
-                            pw[(N2 - k) * 32 + lane] = pm;
-                        }
-                        k = R1 * (k2 + 1);
-                        split_power(u[k2 + 1], u[R2 - 1 - k2], make_float2(wu.z, wu.w), pk, pm);
-                        pw[k * 32 + lane] = pk;
-                        pw[(N2 - k) * 32 + lane] = pm;
+                    for (int c = 0; c < RA; c += 2) {
+                        const float4 tw = lds_f4(t_twh + 2 * c);
+                        const float2 p = row[c * 32], q = row[(c + 1) * 32];
+                        r0[c] = p.x;
+                        r0[c + 1] = q.x;
+                        zh[c] = rf::cplx{p.y * tw.x, p.y * tw.y};
+                        zh[c + 1] = rf::cplx{q.y * tw.z, q.y * tw.w};
                     }
+                    rf::cplx X0[RA / 2 + 1];
+                    rf::rdft16<16>(r0, X0);
+                    pw[lane] = X0[0].re * X0[0].re;
+                    pw[(RB * (RA / 2)) * 32 + lane] = X0[RA / 2].re * X0[RA / 2].re;
+#pragma unroll
+                    for (int k2 = 1; k2 < RA / 2; ++k2)
+                        pw[(RB * k2) * 32 + lane] = fmaf(X0[k2].re, X0[k2].re, X0[k2].im * X0[k2].im);
+                    rf::cdft16(zh);
+#pragma unroll
+                    for (int k2 = 0; k2 < RA / 2; ++k2)
+                        pw[(H + RB * k2) * 32 + lane] = fmaf(zh[k2].re, zh[k2].re, zh[k2].im * zh[k2].im);
                 }
             }
         }
@@ -407,12 +396,12 @@ __global__ void __launch_bounds__(kThreads, 2) fused_ct_kernel(const PcmT *__res
 // host side
 // ---------------------------------------------------------------------------------------
 struct CtVariant {
-    int L, hop, r1, r2;
+    int L, hop, rb, ra;
     const char *name;
 };
 constexpr CtVariant kVariants[] = {
-    {400, 160, 16, 16, "fused_ct_tile32_L400_H160_r16x16"},   // BASELINE.json configs 1, 2, 5 (16 kHz)
-    {200, 80, 16, 8, "fused_ct_tile32_L200_H80_r16x8"},       // BASELINE.json config 3 (8 kHz telephony)
+    {400, 160, 32, 16, "fused_ct_tile32_L400_H160_real32x16"},   // BASELINE.json configs 1, 2, 5 (16 kHz)
+    {200, 80, 16, 16, "fused_ct_tile32_L200_H80_real16x16"},     // BASELINE.json config 3 (8 kHz telephony)
 };
 
 struct CtState {
@@ -423,13 +412,13 @@ struct CtState {
     int sm_count = 0;
 };
 
-template <int L, int HOP, int R1, int R2>
-size_t smem_floats_fixed() { return Geo<L, HOP, R1, R2>::UNION + Geo<L, HOP, R1, R2>::WS; }
+template <int L, int HOP, int RB, int RA>
+size_t smem_floats_fixed() { return Geo<L, HOP, RB, RA>::UNION + Geo<L, HOP, RB, RA>::WS; }
 
 size_t smem_fixed(const CtVariant &v)
 {
-    if (v.L == 400) return smem_floats_fixed<400, 160, 16, 16>();
-    return smem_floats_fixed<200, 80, 16, 8>();
+    if (v.L == 400) return smem_floats_fixed<400, 160, 32, 16>();
+    return smem_floats_fixed<200, 80, 16, 16>();
 }
 
 }  // namespace
@@ -437,11 +426,11 @@ size_t smem_fixed(const CtVariant &v)
 const char *ct_match(const mfcc_params &p)
 {
     for (const auto &v : kVariants) {
-        if (p.frame_len != v.L || p.hop_len != v.hop || p.nfft != 2 * v.r1 * v.r2) continue;
+        if (p.frame_len != v.L || p.hop_len != v.hop || p.nfft != v.rb * v.ra) continue;
         // scratch (er | ef | ls | ld | ostage) must fit in the workspace, tables in the smem budget
         const int n_seg = p.n_mel + 1, halfp = ((p.n_mel + 1) / 2 + 3) / 4 * 4;
         const size_t scratch = static_cast<size_t>(2 * n_seg + 2 * halfp) * 32 + 32ull * p.n_cep;
-        if (scratch > static_cast<size_t>(v.r1) * v.r2 * 64) return nullptr;
+        if (scratch > static_cast<size_t>(v.rb) * v.ra * 32) return nullptr;
         return v.name;
     }
     return nullptr;
@@ -452,49 +441,44 @@ int ct_prepare(mfcc_plan *plan)
     const mfcc_params &p = plan->p;
     const CtVariant *var = nullptr;
     for (const auto &v : kVariants)
-        if (p.frame_len == v.L && p.hop_len == v.hop && p.nfft == 2 * v.r1 * v.r2) var = &v;
+        if (p.frame_len == v.L && p.hop_len == v.hop && p.nfft == v.rb * v.ra) var = &v;
     if (var == nullptr) return MFCC_ENOTSUP;
-    const int R1 = var->r1, R2 = var->r2, N2 = R1 * R2, N = 2 * N2, M = p.n_mel;
+    const int RB = var->rb, RA = var->ra, N = RB * RA, H = RB / 2, M = p.n_mel;
+    const int NZ = (p.frame_len + RA - 1) / RA, NZP = (NZ + 1) / 2 * 2;
     const HostTables &h = plan->host;
     std::vector<float> tab;
     CtLayout lay{};
     auto align4 = [&]() { while (tab.size() % 4) tab.push_back(0.0f); };
     auto push_int = [&](int v) { float f; std::memcpy(&f, &v, 4); tab.push_back(f); };
 
-    // window pairs per butterfly row
+    // window of the sample pairs (a, a + 1) + RA b per column pair, zero past the frame
     lay.win = static_cast<int>(tab.size());
-    for (int n2 = 0; n2 < R2; ++n2)
-        for (int n1 = 0; n1 < R1; ++n1) {
-            const int i = 2 * (n2 + R2 * n1);
-            tab.push_back(i < p.frame_len ? h.window[i] : 0.0f);
-            tab.push_back(i + 1 < p.frame_len ? h.window[i + 1] : 0.0f);
-        }
-    // inter-pass twiddles
+    for (int pr = 0; pr < RA / 2; ++pr)
+        for (int b = 0; b < NZP; ++b)
+            for (int e = 0; e < 2; ++e) {
+                const int i = 2 * pr + e + RA * b;
+                tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
+            }
+    // inter-pass twiddles W_N^(a k1), k1 = 1 .. H-1 at slot k1 - 1
     lay.tw = static_cast<int>(tab.size());
-    for (int n2 = 0; n2 < R2; ++n2)
-        for (int k1 = 0; k1 < R1; ++k1) {
-            const double ang = -2.0 * M_PI * static_cast<double>(n2) * k1 / N2;
+    for (int col = 0; col < RA; ++col)
+        for (int sl = 0; sl < H; ++sl) {
+            const double ang = sl < H - 1 ? -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N : 0.0;
             tab.push_back(static_cast<float>(std::cos(ang)));
             tab.push_back(static_cast<float>(std::sin(ang)));
         }
-    // split twiddles per work item
-    lay.post = static_cast<int>(tab.size());
-    auto push_post = [&](int k) {
-        const double ang = -2.0 * M_PI * k / N;
+    // twiddle of row H: W_N^(a H) = W_(2 RA)^a
+    lay.twh = static_cast<int>(tab.size());
+    for (int col = 0; col < RA; ++col) {
+        const double ang = -2.0 * M_PI * col / (2.0 * RA);
         tab.push_back(static_cast<float>(std::cos(ang)));
         tab.push_back(static_cast<float>(std::sin(ang)));
-    };
-    for (int it = 0; it < R1 / 2; ++it)
-        for (int k2 = 0; k2 < R2; ++k2) {
-            if (it != 0) push_post(it + R1 * k2);
-            else if (k2 < R2 / 2) push_post(R1 / 2 + R1 * k2);
-            else push_post(R1 * (k2 - R2 / 2));
-        }
-    // mel segments in 4-bin chunks, weights pre-scaled by 1/(4 N) (the split leaves |2X|^2)
+    }
+    // mel segments in 4-bin chunks, weights pre-scaled by 1/N (pass 2 leaves |X|^2)
     const int n_seg = M + 1;
     std::vector<float> melw;
     std::vector<int> seg;   // 4 ints per segment
-    const double scale = 1.0 / (4.0 * N);
+    const double scale = 1.0 / N;
     for (int j = 0; j < n_seg; ++j) {
         const int k0 = h.mel_bins[j], k1 = h.mel_bins[j + 1];
         const int chunks = (k1 - k0 + 3) / 4;
@@ -574,11 +558,11 @@ void ct_release(mfcc_plan *plan)
     plan->ct_state = nullptr;
 }
 
-template <typename PcmT, int L, int HOP, int R1, int R2>
+template <typename PcmT, int L, int HOP, int RB, int RA>
 static int launch_variant(const mfcc_plan *plan, const CtState *st, const Tile *d_tiles, int64_t n_tiles,
                           const PcmT *d_pcm, int64_t pcm_len, float *d_out, cudaStream_t stream)
 {
-    auto kern = fused_ct_kernel<PcmT, L, HOP, R1, R2>;
+    auto kern = fused_ct_kernel<PcmT, L, HOP, RB, RA>;
     static thread_local const void *configured = nullptr;
     if (configured != reinterpret_cast<const void *>(kern)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -614,8 +598,8 @@ int ct_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const
     const CtState *st = static_cast<const CtState *>(plan->ct_state);
     if (st == nullptr) return MFCC_ENOTSUP;
     if (st->v->L == 400)
-        return launch_variant<PcmT, 400, 160, 16, 16>(plan, st, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
-    return launch_variant<PcmT, 200, 80, 16, 8>(plan, st, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
+        return launch_variant<PcmT, 400, 160, 32, 16>(plan, st, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
+    return launch_variant<PcmT, 200, 80, 16, 16>(plan, st, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
 }
 
 template int ct_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *,

@@ -1,0 +1,240 @@
+// mfcc_rfft.cuh — register-resident REAL-input DFT codelets (16 and 32 points, with the
+// zero-padded tail pruned at compile time) and the complex 4/8/16-point DFTs that the
+// two-pass real FFT of the fused kernel is made of (mfcc_fused_ct.cu):
+//
+//   N = RB * RA real points, n = a + RA b, k = k1 + RB k2
+//   pass 1: for each a, real DFT-RB over b          -> Y[k1][a], k1 = 0 .. RB/2 (Hermitian half)
+//           times W_N^(a k1)
+//   pass 2: for each k1, complex DFT-RA over a      -> X[k1 + RB k2]
+//
+// No packing of two real points into one complex point, hence no split step after the
+// transform.  Everything is statically indexed so that arrays stay in registers.
+// The functions are host+device so that tests/codelets (g++) can check them against a
+// direct double-precision DFT without a GPU.
+// No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MFCC_HD __host__ __device__ __forceinline__
+#else
+#define MFCC_HD inline
+#endif
+
+namespace mfcc {
+namespace rf {
+
+struct cplx { float re, im; };
+
+constexpr float kH = 0.70710678118654752f;    // cos(pi/4)
+constexpr float kC1 = 0.92387953251128674f;   // cos(pi/8)
+constexpr float kS1 = 0.38268343236508977f;   // sin(pi/8)
+
+// a * (cr + i ci): 2 FMUL + 2 FFMA
+MFCC_HD cplx cmulc(cplx a, float cr, float ci)
+{
+    cplx r;
+    r.re = fmaf(-a.im, ci, a.re * cr);
+    r.im = fmaf(a.im, cr, a.re * ci);
+    return r;
+}
+MFCC_HD cplx conj(cplx a) { return cplx{a.re, -a.im}; }
+
+// Forward 4-point DFT (W4 = -i), natural order, in place.
+MFCC_HD void cdft4(cplx &x0, cplx &x1, cplx &x2, cplx &x3)
+{
+    const cplx t0{x0.re + x2.re, x0.im + x2.im}, t1{x0.re - x2.re, x0.im - x2.im};
+    const cplx t2{x1.re + x3.re, x1.im + x3.im}, t3{x1.re - x3.re, x1.im - x3.im};
+    x0 = cplx{t0.re + t2.re, t0.im + t2.im};
+    x2 = cplx{t0.re - t2.re, t0.im - t2.im};
+    x1 = cplx{t1.re + t3.im, t1.im - t3.re};
+    x3 = cplx{t1.re - t3.im, t1.im + t3.re};
+}
+
+// Outputs 0 and 1 only of the 4-point DFT.
+MFCC_HD void cdft4_01(cplx a0, cplx a1, cplx a2, cplx a3, cplx &y0, cplx &y1)
+{
+    const cplx s02{a0.re + a2.re, a0.im + a2.im}, d02{a0.re - a2.re, a0.im - a2.im};
+    const cplx s13{a1.re + a3.re, a1.im + a3.im}, d13{a1.re - a3.re, a1.im - a3.im};
+    y0 = cplx{s02.re + s13.re, s02.im + s13.im};
+    y1 = cplx{d02.re + d13.im, d02.im - d13.re};
+}
+
+// Forward 8-point DFT, natural order in and out: n = nb + 2 na, k = ka + 4 kb.
+MFCC_HD void cdft8(cplx (&x)[8])
+{
+    cdft4(x[0], x[2], x[4], x[6]);
+    cdft4(x[1], x[3], x[5], x[7]);
+    x[3] = cmulc(x[3], kH, -kH);             // W8^1
+    x[5] = cplx{x[5].im, -x[5].re};          // W8^2 = -i
+    x[7] = cmulc(x[7], -kH, -kH);            // W8^3
+    cplx r[8];
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        r[ka] = cplx{x[2 * ka].re + x[2 * ka + 1].re, x[2 * ka].im + x[2 * ka + 1].im};
+        r[ka + 4] = cplx{x[2 * ka].re - x[2 * ka + 1].re, x[2 * ka].im - x[2 * ka + 1].im};
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = r[i];
+}
+
+// Forward 16-point DFT, natural order in and out: n = nb + 4 na, k = ka + 4 kb.
+MFCC_HD void cdft16(cplx (&x)[16])
+{
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) cdft4(x[nb], x[nb + 4], x[nb + 8], x[nb + 12]);
+    // y[nb][ka] sits in x[nb + 4 ka]; multiply by W16^(nb ka)
+    x[1 + 4 * 1] = cmulc(x[1 + 4 * 1], kC1, -kS1);
+    x[1 + 4 * 2] = cmulc(x[1 + 4 * 2], kH, -kH);
+    x[1 + 4 * 3] = cmulc(x[1 + 4 * 3], kS1, -kC1);
+    x[2 + 4 * 1] = cmulc(x[2 + 4 * 1], kH, -kH);
+    x[2 + 4 * 2] = cplx{x[2 + 4 * 2].im, -x[2 + 4 * 2].re};
+    x[2 + 4 * 3] = cmulc(x[2 + 4 * 3], -kH, -kH);
+    x[3 + 4 * 1] = cmulc(x[3 + 4 * 1], kS1, -kC1);
+    x[3 + 4 * 2] = cmulc(x[3 + 4 * 2], -kH, -kH);
+    x[3 + 4 * 3] = cmulc(x[3 + 4 * 3], -kC1, kS1);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) cdft4(x[4 * ka], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);
+    // X[ka + 4 kb] sits in x[4 ka + kb]: transpose to natural order (register renaming)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+            const cplx t = x[4 * a + b];
+            x[4 * a + b] = x[4 * b + a];
+            x[4 * b + a] = t;
+        }
+}
+
+// First stage of the real transforms: 4-point DFT over m of the REAL values x_m with the
+// last 4 - C of them known to be zero.  t0 = sum, t2 = alternating sum, t1 = bin 1 (bin 3 = conj).
+template <int C>
+MFCC_HD void rstage(float x0, float x1, float x2, float x3, float &t0, float &t2, cplx &t1)
+{
+    if constexpr (C >= 4) {
+        const float s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = x1 - x3;
+        t0 = s02 + s13; t2 = s02 - s13; t1 = cplx{d02, -d13};
+    } else if constexpr (C == 3) {
+        const float s02 = x0 + x2, d02 = x0 - x2;
+        t0 = s02 + x1; t2 = s02 - x1; t1 = cplx{d02, -x1};
+    } else if constexpr (C == 2) {
+        t0 = x0 + x1; t2 = x0 - x1; t1 = cplx{x0, -x1};
+    } else if constexpr (C == 1) {
+        t0 = x0; t2 = x0; t1 = cplx{x0, 0.0f};
+    } else {
+        t0 = 0.0f; t2 = 0.0f; t1 = cplx{0.0f, 0.0f};
+    }
+}
+// how many of x[j], x[j + M], x[j + 2M], x[j + 3M] lie below NZ
+constexpr int live4(int j, int M, int NZ) { return NZ <= j ? 0 : (NZ - j + M - 1) / M > 4 ? 4 : (NZ - j + M - 1) / M; }
+
+// Real 8-point DFT: X[0], X[4] real, X[1..3] complex.  20 operations.
+MFCC_HD void rdft8(const float (&t)[8], float &x0, cplx &x1, cplx &x2, cplx &x3, float &x4)
+{
+    const float a0 = t[0] + t[4], a1 = t[0] - t[4], b0 = t[2] + t[6], b1 = t[2] - t[6];
+    const float c0 = t[1] + t[5], c1 = t[1] - t[5], d0 = t[3] + t[7], d1 = t[3] - t[7];
+    const float e0 = a0 + b0, e1 = a0 - b0, f0 = c0 + d0, f1 = c0 - d0;
+    x0 = e0 + f0;
+    x4 = e0 - f0;
+    x2 = cplx{e1, -f1};
+    const float g = c1 - d1, s = c1 + d1;
+    x1 = cplx{fmaf(kH, g, a1), -fmaf(kH, s, b1)};
+    x3 = cplx{fmaf(-kH, g, a1), fmaf(-kH, s, b1)};
+}
+
+// Real 16-point DFT of x[0 .. NZ) (x[NZ .. 16) taken as zero): X[0 .. 8], X[0].im = X[8].im = 0.
+template <int NZ>
+MFCC_HD void rdft16(const float (&x)[16], cplx (&X)[9])
+{
+    float t0[4], t2[4];
+    cplx u[4];
+    rstage<live4(0, 4, NZ)>(x[0], x[4], x[8], x[12], t0[0], t2[0], u[0]);
+    rstage<live4(1, 4, NZ)>(x[1], x[5], x[9], x[13], t0[1], t2[1], u[1]);
+    rstage<live4(2, 4, NZ)>(x[2], x[6], x[10], x[14], t0[2], t2[2], u[2]);
+    rstage<live4(3, 4, NZ)>(x[3], x[7], x[11], x[15], t0[3], t2[3], u[3]);
+    {   // q = 0: real 4-point DFT of t0 -> X[0], X[4], X[8]
+        const float s0 = t0[0] + t0[2], d0 = t0[0] - t0[2], s1 = t0[1] + t0[3], d1 = t0[1] - t0[3];
+        X[0] = cplx{s0 + s1, 0.0f};
+        X[8] = cplx{s0 - s1, 0.0f};
+        X[4] = cplx{d0, -d1};
+    }
+    {   // q = 2: sum_j t2[j] W8^j W4^(j r) -> X[2], X[6]
+        const float g = t2[1] - t2[3], s = t2[1] + t2[3];
+        X[2] = cplx{fmaf(kH, g, t2[0]), -fmaf(kH, s, t2[2])};
+        X[6] = cplx{fmaf(-kH, g, t2[0]), fmaf(-kH, s, t2[2])};
+    }
+    // q = 1: (u[j] W16^j) through a complex 4-point DFT -> X[1], X[5], X[9] = conj X[7], X[13] = conj X[3]
+    u[1] = cmulc(u[1], kC1, -kS1);
+    u[2] = cmulc(u[2], kH, -kH);
+    u[3] = cmulc(u[3], kS1, -kC1);
+    cdft4(u[0], u[1], u[2], u[3]);
+    X[1] = u[0];
+    X[5] = u[1];
+    X[7] = conj(u[2]);
+    X[3] = conj(u[3]);
+}
+
+// Real 32-point DFT of x[0 .. NZ) (the rest zero): X[0 .. 16], X[0].im = X[16].im = 0.
+// tw32[j] = W32^j = exp(-2 pi i j / 32) for j = 1 .. 7 are passed in (compile-time literals at the call site).
+template <int NZ>
+MFCC_HD void rdft32(const float (&x)[32], cplx (&X)[17])
+{
+    float t0[8], t2[8];
+    cplx u[8];
+    rstage<live4(0, 8, NZ)>(x[0], x[8], x[16], x[24], t0[0], t2[0], u[0]);
+    rstage<live4(1, 8, NZ)>(x[1], x[9], x[17], x[25], t0[1], t2[1], u[1]);
+    rstage<live4(2, 8, NZ)>(x[2], x[10], x[18], x[26], t0[2], t2[2], u[2]);
+    rstage<live4(3, 8, NZ)>(x[3], x[11], x[19], x[27], t0[3], t2[3], u[3]);
+    rstage<live4(4, 8, NZ)>(x[4], x[12], x[20], x[28], t0[4], t2[4], u[4]);
+    rstage<live4(5, 8, NZ)>(x[5], x[13], x[21], x[29], t0[5], t2[5], u[5]);
+    rstage<live4(6, 8, NZ)>(x[6], x[14], x[22], x[30], t0[6], t2[6], u[6]);
+    rstage<live4(7, 8, NZ)>(x[7], x[15], x[23], x[31], t0[7], t2[7], u[7]);
+    {   // q = 0: real 8-point DFT of t0 -> X[0], X[4], X[8], X[12], X[16]
+        float x0, x4;
+        rdft8(t0, x0, X[4], X[8], X[12], x4);
+        X[0] = cplx{x0, 0.0f};
+        X[16] = cplx{x4, 0.0f};
+    }
+    {   // q = 2: X[2 + 4 r] = sum_{j<4} W16^(j (1 + 2 r)) (t2[j] - i (-1)^r t2[j + 4])
+        // r even: outputs 0, 1 of the 4-point DFT of W16^j (t2[j], -t2[j+4])  -> X[2], X[10]
+        const cplx a0{t2[0], -t2[4]};
+        const cplx a1 = cmulc(cplx{t2[1], -t2[5]}, kC1, -kS1);
+        const cplx a2 = cmulc(cplx{t2[2], -t2[6]}, kH, -kH);
+        const cplx a3 = cmulc(cplx{t2[3], -t2[7]}, kS1, -kC1);
+        cdft4_01(a0, a1, a2, a3, X[2], X[10]);
+        // r odd: outputs 0, 1 of the 4-point DFT of W16^(3 j) (t2[j], +t2[j+4]) -> X[6], X[14]
+        const cplx b0{t2[0], t2[4]};
+        const cplx b1 = cmulc(cplx{t2[1], t2[5]}, kS1, -kC1);    // W16^3
+        const cplx b2 = cmulc(cplx{t2[2], t2[6]}, -kH, -kH);     // W16^6
+        const cplx b3 = cmulc(cplx{t2[3], t2[7]}, -kC1, kS1);    // W16^9
+        cdft4_01(b0, b1, b2, b3, X[6], X[14]);
+    }
+    // q = 1: (u[j] W32^j) through a complex 8-point DFT -> X[1 + 4 r]; r >= 4 gives the conjugates of X[15], X[11], X[7], X[3]
+    u[1] = cmulc(u[1], 0.98078528040323044f, -0.19509032201612827f);
+    u[2] = cmulc(u[2], kC1, -kS1);
+    u[3] = cmulc(u[3], 0.83146961230254524f, -0.55557023301960222f);
+    u[4] = cmulc(u[4], kH, -kH);
+    u[5] = cmulc(u[5], 0.55557023301960222f, -0.83146961230254524f);
+    u[6] = cmulc(u[6], kS1, -kC1);
+    u[7] = cmulc(u[7], 0.19509032201612827f, -0.98078528040323044f);
+    cdft8(u);
+    X[1] = u[0];
+    X[5] = u[1];
+    X[9] = u[2];
+    X[13] = u[3];
+    X[15] = conj(u[4]);
+    X[11] = conj(u[5]);
+    X[7] = conj(u[6]);
+    X[3] = conj(u[7]);
+}
+
+template <int RB> struct RDft;
+template <> struct RDft<16> {
+    template <int NZ> static MFCC_HD void run(const float (&x)[16], cplx (&X)[9]) { rdft16<NZ>(x, X); }
+};
+template <> struct RDft<32> {
+    template <int NZ> static MFCC_HD void run(const float (&x)[32], cplx (&X)[17]) { rdft32<NZ>(x, X); }
+};
+
+}  // namespace rf
+}  // namespace mfcc
