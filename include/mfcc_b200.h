@@ -54,6 +54,7 @@ extern "C" {
 #define MFCC_KERNEL_GENERIC  1   /* one-frame-at-a-time shared-memory radix-2 kernel (any geometry) */
 #define MFCC_KERNEL_FUSED    2   /* fused 32-frame-tile kernel; plan creation fails if unavailable */
 #define MFCC_KERNEL_FUSED_RT 3   /* fused kernel with run-time geometry (skips the specialised variants) */
+#define MFCC_KERNEL_FUSED_CT 4   /* fused kernel with compile-time frame geometry, run-time filterbank */
 
 /* ---- parameters (all conventions explicit; see DESIGN.md "Spec") ---- */
 typedef struct mfcc_params {

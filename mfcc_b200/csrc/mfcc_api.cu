@@ -62,7 +62,7 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     if (out == nullptr) return MFCC_EINVAL;
     *out = nullptr;
     if (mfcc::validate_params(p) != MFCC_OK) return MFCC_EINVAL;
-    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED_RT) return MFCC_EINVAL;
+    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED_CT) return MFCC_EINVAL;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return MFCC_ECUDA; }
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MFCC_ECUDA;
@@ -79,15 +79,18 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     int rc = mfcc::build_tables(plan->p, plan->host);
     if (rc != MFCC_OK) { delete plan; return rc; }
 
-    // Kernel choice: compile-time-geometry fused > runtime-geometry fused > generic.
+    // Kernel choice: fully specialised > compile-time-geometry fused > runtime-geometry fused > generic.
     plan->fused = mfcc::find_fused(plan->p);
+    const char *sp_name = (kernel == MFCC_KERNEL_AUTO || kernel == MFCC_KERNEL_FUSED)
+                              ? mfcc::sp_match(plan->p, plan->host) : nullptr;
     const char *ct_name = kernel == MFCC_KERNEL_FUSED_RT ? nullptr : mfcc::ct_match(plan->p);
     const bool want_fused = kernel != MFCC_KERNEL_GENERIC;
-    if ((kernel == MFCC_KERNEL_FUSED || kernel == MFCC_KERNEL_FUSED_RT) && plan->fused == nullptr && ct_name == nullptr) {
+    if (kernel >= MFCC_KERNEL_FUSED && plan->fused == nullptr && ct_name == nullptr && sp_name == nullptr) {
         delete plan;
         return MFCC_ENOTSUP;
     }
-    plan->kernel = (want_fused && (plan->fused || ct_name)) ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
+    if (kernel == MFCC_KERNEL_FUSED_CT && ct_name == nullptr) { delete plan; return MFCC_ENOTSUP; }
+    plan->kernel = (want_fused && (plan->fused || ct_name || sp_name)) ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
 
     DeviceGuard guard(device);
     if (!guard.ok) { delete plan; return MFCC_ECUDA; }
@@ -126,7 +129,11 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     plan->dev.rise = reinterpret_cast<const float *>(base + o_rise);
     plan->dev.fall = reinterpret_cast<const float *>(base + o_fall);
 
-    if (plan->kernel == MFCC_KERNEL_FUSED) {
+    if (plan->kernel == MFCC_KERNEL_FUSED && sp_name != nullptr) {
+        rc = mfcc::sp_prepare(plan);
+        if (rc != MFCC_OK && rc != MFCC_ENOTSUP) { mfcc_plan_destroy(plan); return rc; }
+    }
+    if (plan->kernel == MFCC_KERNEL_FUSED && plan->sp_state == nullptr) {
         rc = ct_name ? mfcc::ct_prepare(plan) : MFCC_ENOTSUP;
         if (rc == MFCC_ENOTSUP) {   // no compile-time variant (or its tables do not fit): runtime-geometry kernel
             if (plan->fused != nullptr) rc = mfcc::fused_prepare(plan);
@@ -135,6 +142,7 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
         if (rc != MFCC_OK) { mfcc_plan_destroy(plan); return rc; }
     }
     plan->kernel_name = plan->kernel != MFCC_KERNEL_FUSED ? "generic_radix2"
+                        : plan->sp_state ? sp_name
                         : plan->ct_state ? ct_name : mfcc::fused_name(plan->fused);
     *out = plan;
     return MFCC_OK;
@@ -151,6 +159,7 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     if (plan->dev_blob) cudaFree(plan->dev_blob);
     mfcc::fused_release(plan);
     mfcc::ct_release(plan);
+    mfcc::sp_release(plan);
     delete plan;
 }
 

@@ -71,6 +71,7 @@ struct mfcc_plan {
     void *fused_blob = nullptr;         // device tables of the fused kernel
     void *fused_tables = nullptr;       // host struct of device pointers into fused_blob
     void *ct_state = nullptr;           // compile-time-geometry fused kernel state (mfcc_fused_ct.cu)
+    void *sp_state = nullptr;           // fully specialised fused kernel state (mfcc_fused_sp.cu)
     // mfcc_compute_host state (grown on demand, reused across calls)
     void *h2d_pcm = nullptr;   size_t h2d_pcm_bytes = 0;
     void *d2h_out = nullptr;   size_t d2h_out_bytes = 0;
@@ -114,6 +115,13 @@ void ct_release(mfcc_plan *plan);
 template <typename PcmT>
 int ct_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
               float *d_out, cudaStream_t stream);
+// Fully specialised variant (mfcc_fused_sp.cu): geometry AND mel bin edges compile-time.
+const char *sp_match(const mfcc_params &p, const HostTables &h);
+int sp_prepare(mfcc_plan *plan);
+void sp_release(mfcc_plan *plan);
+template <typename PcmT>
+int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
+              cudaStream_t stream);
 // Upload whatever constant tables the fused kernel needs (called at plan creation).
 int fused_prepare(mfcc_plan *plan);
 void fused_release(mfcc_plan *plan);

@@ -12,7 +12,7 @@ import pytest
 
 import oracle
 from mfcc_b200 import (api, config_a, config_b, config_c, make_params, KERNEL_GENERIC, KERNEL_FUSED,
-                       KERNEL_FUSED_RT, KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
+                       KERNEL_FUSED_RT, KERNEL_FUSED_CT, KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
 from mfcc_b200.synth import clip_config1, fast_fixed_batch, noise_utterance, ragged_batch
 from util import assert_parity, golden, parity_errors
 
@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 CFG = {"A": config_a, "B": config_b, "C": config_c}
-KERNELS = {"generic": KERNEL_GENERIC, "fused": KERNEL_FUSED, "fused_rt": KERNEL_FUSED_RT}
+KERNELS = {"generic": KERNEL_GENERIC, "fused": KERNEL_FUSED, "fused_rt": KERNEL_FUSED_RT, "fused_ct": KERNEL_FUSED_CT}
+ALL_KERNELS = ["generic", "fused", "fused_ct", "fused_rt"]
 
 
 def make_plan(p, kernel):
@@ -40,7 +41,7 @@ def run_device(plan, pcm, offsets):
     return out.cpu().numpy(), b.frame_offsets.copy()
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fused", "fused_rt"])
+@pytest.mark.parametrize("kernel", ALL_KERNELS)
 @pytest.mark.parametrize("name", ["A", "B", "C"])
 def test_ragged_batch_matches_oracle(name, kernel):
     p = CFG[name]()
@@ -58,7 +59,36 @@ def test_ragged_batch_matches_oracle(name, kernel):
     assert_parity(got, ref, what=f"{name}/{kernel}")
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fused", "fused_rt"])
+@pytest.mark.parametrize("kernel", ["fused", "fused_ct"])
+@pytest.mark.parametrize("name", ["A", "B"])
+def test_aligned_ragged_batch_takes_bulk_copy_path(name, kernel):
+    """Utterances whose starts are multiples of 8 samples (16-byte aligned int16): the specialised
+    kernel stages these tiles by bulk async copy; mixed with short, tile-boundary and tail tiles.
+    Also an utterance that starts right after another one (the 8 lead samples belong to the
+    neighbour and must not leak into y[0] = x[0])."""
+    p = CFG[name]()
+    plan = make_plan(p, kernel)
+    L, H = p.frame_len, p.hop_len
+    rng = np.random.default_rng(31)
+    lens = [8 * int(v) for v in rng.integers(1, 4000, 40)]
+    lens += [L + 31 * H, L + 32 * H, L + 33 * H, 0, 8, L + 95 * H + 8, 10 * H * 32 + L]
+    lens = [v - v % 8 for v in lens]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pcm = noise_utterance(int(off[-1]), seed=32)
+    got, fo = run_device(plan, pcm, off)
+    ref, fo_ref = oracle.mfcc_batch(p, pcm, off)
+    assert np.array_equal(fo, fo_ref)
+    assert_parity(got, ref, what=f"aligned {name}/{kernel}")
+    # same data, whole array shifted by one sample: nothing is aligned any more, results identical
+    pcm1 = np.concatenate([[0], pcm]).astype(np.int16)
+    b = plan.batch(off)
+    d = torch.from_numpy(pcm1).cuda()[1:]
+    out1 = plan.compute_batch(b, d)
+    torch.cuda.synchronize()
+    assert np.array_equal(out1.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("kernel", ALL_KERNELS)
 def test_golden_fixtures(kernel):
     g = golden()
     a, b, c = config_a(), config_b(), config_c()
@@ -74,7 +104,7 @@ def test_golden_fixtures(kernel):
         assert_parity(got, g[key], what=f"{key}/{kernel}")
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fused", "fused_rt"])
+@pytest.mark.parametrize("kernel", ALL_KERNELS)
 def test_option_matrix_matches_oracle(kernel):
     base = config_a()
     variants = [
@@ -148,8 +178,11 @@ def test_bad_calls_fail_loudly():
     with pytest.raises(ValueError):
         plan.compute_batch(b, torch.zeros(100, dtype=torch.int16, device="cuda"))
     assert api.Plan(config_a().copy(hop_len=161)).kernel_name == "generic_radix2"
-    assert api.Plan(config_a()).kernel_name.startswith("fused_ct_")
-    assert api.Plan(config_b()).kernel_name.startswith("fused_ct_")
+    assert api.Plan(config_a()).kernel_name.startswith("fused_sp_")
+    assert api.Plan(config_b()).kernel_name.startswith("fused_sp_")
+    assert api.Plan(config_a().copy(output=OUT_LOGMEL, lifter=22)).kernel_name.startswith("fused_sp_")
+    assert api.Plan(config_a().copy(n_mel=40)).kernel_name.startswith("fused_ct_")       # other filterbank structure
+    assert api.Plan(config_a(), kernel=KERNEL_FUSED_CT).kernel_name.startswith("fused_ct_")
     assert api.Plan(config_a().copy(hop_len=128)).kernel_name.startswith("fused_rt_")
     assert api.Plan(config_a(), kernel=KERNEL_FUSED_RT).kernel_name.startswith("fused_rt_")
 

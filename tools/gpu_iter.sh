@@ -1,23 +1,26 @@
 #!/bin/bash
-# Iteration pass: parity tests then a bench line (and optionally workload B).
+# Iteration pass: parity tests, bench lines (A with the specialised and the ct kernel, B), then one
+# ncu capture of the top kernel.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-tail -12 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-python - <<'PY'
-import json
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_gpu.log
+for spec in "A auto bench" "A fused_ct bench_ct" "B auto bench_B"; do
+  set -- $spec
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload $1 --kernel $2 > gpurun_out/$3.json 2> gpurun_out/$3.err; echo "$3 rc=$?"
+  python - "$3" <<'PY'
+import json, sys
+n = sys.argv[1]
 try:
-    d=json.load(open('gpurun_out/bench.json'))
-    print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['config']['kernel'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], d['clocks'])
+    d = json.load(open(f'gpurun_out/{n}.json'))
+    print(n, {k: d[k] for k in ('value', 'ms_per_step', 'gpu_launches')}, d['config']['kernel'], 'e2e', d['e2e']['value'],
+          'frac', d['roofline']['frac'], d['clocks'])
 except Exception as e:
-    print('bench parse failed', e); print(open('gpurun_out/bench.err').read()[-2000:])
+    print(n, 'parse failed', e); print(open(f'gpurun_out/{n}.err').read()[-2000:])
 PY
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload B > gpurun_out/bench_B.json 2>> gpurun_out/bench.err; echo "benchB rc=$?"
-python - <<'PY'
-import json
-try:
-    d=json.load(open('gpurun_out/bench_B.json'))
-    print('B', {k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['config']['kernel'], 'frac', d['roofline']['frac'])
-except Exception as e:
-    print('benchB parse failed', e)
-PY
+done
+if [ "$1" != "noncu" ]; then
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:fused -s 5 -c 1 -f -o gpurun_out/prof_fused $CMD > gpurun_out/ncu.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/ncu.log
+fi
