@@ -1,9 +1,6 @@
-// mfcc_fused_sp.cu — fully SPECIALISED fused tile kernel: frame geometry AND the mel
-// filterbank's bin edges are compile-time, so the sparse filterbank, the log and the DCT
-// unroll into straight-line code with immediate shared-memory offsets and constant-bank
-// (kernel-parameter) weights.  Runtime values — window, twiddles, mel weights, DCT rows
-// (lifter folded in), pre-emphasis, log floor — stay data, so a plan only needs its
-// *structure* (frame/hop/NFFT/n_mel/n_cep and the integer bin edges) to match a variant.
+// mfcc_fused_sp.cu — the streamlined fused tile kernel ("sp"): compile-time frame geometry,
+// table-driven filterbank, bulk-copy staging, one 512-thread CTA per SM working as two
+// independent 8-warp halves.
 //
 // What changed against mfcc_fused_ct.cu and why (profiles/r1_v4_real32x16_A.md: the two FFT
 // passes were 56 % of the instructions but 37 % of the time; staging, mel, log, DCT and store
@@ -12,19 +9,25 @@
 //     into a raw int16 buffer while the current tile is transformed — no prefetch registers,
 //     no LDG/LDL instructions, completion on an mbarrier.  Staging then converts 8 samples per
 //     thread (LDS.128) instead of 2.
-//   * tail: each warp OWNS a contiguous group of mel filters (balanced at compile time), sums
+//   * tail: each warp OWNS a contiguous group of mel filters (balanced on the host), sums
 //     their bins from P, takes the log and accumulates its share of every cepstrum in
 //     registers; one barrier later the 8 partial cepstra per frame are added and stored
-//     coalesced.  4 CTA barriers per tile instead of 7.
+//     coalesced.  4 barriers per tile instead of 7.
+//   * hot code stays under 32 KB: profiles/r1_v5_sp_unrolled_tail_A.md shows what happens when the
+//     tail is unrolled per warp (60 KB of code, 44 % of stall samples = no_instruction), so the
+//     tail is a table-driven loop shared by all warps.
+//   * one CTA per SM, two halves: the tables are held once per SM, which is what makes the raw
+//     buffer fit; each half has its own staging/workspace/raw buffers, mbarrier and NAMED barrier,
+//     so the halves drift apart like two CTAs would and cover each other's barrier waits.
 // Phases S1 (windowed real DFT-RB per column pair + inter-pass twiddle) and S2 (complex DFT-RA per
 // row + power) are those of mfcc_fused_ct.cu.
 //
 // No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <utility>
 #include <vector>
 
 #include "mfcc_rfft.cuh"
@@ -34,46 +37,17 @@ namespace mfcc {
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
+constexpr int kWarps = 8;                 // per half
+constexpr int kHalfThreads = kWarps * 32;
+constexpr int kThreads = 2 * kHalfThreads;
 constexpr int kPad = 2;
+constexpr int KC = 16;                    // cepstra accumulated per frame (n_cep <= KC)
+constexpr int PS = KC + 1;                // partial-cepstra row stride (odd: conflict-free)
+constexpr size_t kSmemMax = 227 * 1024;
 
-// ---- compile-time loops ----
-template <class F, int... I>
-__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>)
-{
-    (f(std::integral_constant<int, I>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F &&f)
-{
-    static_for_impl(f, std::make_integer_sequence<int, N>{});
-}
-
-// ---- variants: structure only (BASELINE.json configs; bin edges = floor((N+1) f / sr) on HTK mel) ----
-struct Var16k {   // configs[0], [1], [4]: 16 kHz, 25/10 ms, 512-pt, 26 mel over 0 .. 8 kHz, 13 cepstra
-    static constexpr int L = 400, HOP = 160, RB = 32, RA = 16, NMEL = 26, NCEP = 13;
-    static constexpr int bin(int j)
-    {
-        constexpr int b[NMEL + 2] = {0, 2, 4, 7, 10, 13, 16, 20, 24, 29, 34, 40, 46, 53,
-                                     60, 68, 77, 87, 97, 109, 122, 136, 152, 169, 188, 209, 231, 256};
-        return b[j];
-    }
-    static constexpr const char *name() { return "fused_sp_tile32_L400_H160_real32x16_mel26_cep13"; }
-};
-struct Var8k {    // configs[2]: 8 kHz telephony, 25/10 ms, 256-pt, 20 mel over 0 .. 4 kHz, 13 cepstra
-    static constexpr int L = 200, HOP = 80, RB = 16, RA = 16, NMEL = 20, NCEP = 13;
-    static constexpr int bin(int j)
-    {
-        constexpr int b[NMEL + 2] = {0, 2, 4, 7, 9, 12, 16, 19, 23, 28, 33, 38, 44, 50, 57, 65, 73, 82, 92, 103, 115, 128};
-        return b[j];
-    }
-    static constexpr const char *name() { return "fused_sp_tile32_L200_H80_real16x16_mel20_cep13"; }
-};
-
-template <class V>
+template <int L_, int HOP_, int RB_, int RA_>
 struct Geo {
-    static constexpr int L = V::L, HOP = V::HOP, RB = V::RB, RA = V::RA, NMEL = V::NMEL, NCEP = V::NCEP;
+    static constexpr int L = L_, HOP = HOP_, RB = RB_, RA = RA_;
     static constexpr int NFFT = RB * RA, NB = NFFT / 2 + 1, H = RB / 2;
     static constexpr int NZ = (L + RA - 1) / RA;           // rows b of a column that carry samples
     static constexpr int NZP = (NZ + 1) / 2 * 2;
@@ -83,56 +57,43 @@ struct Geo {
     static constexpr int tceil(int n_frames) { return ((n_frames - 1) * HOP + L + SLACK + 7) / 8 * 8; }
     static constexpr int TCEIL = tceil(32);                // samples staged for a full tile
     static constexpr int STAGED = padded(TCEIL) + 8;
-    static constexpr int PW = NB * 32;
+    static constexpr int PW = (NB + 3) * 32;               // 3 zeroed slack rows: 4-bin chunks read past the last bin
     static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
     static constexpr int WS = H * RA * 32 * 2;             // floats
     static constexpr int RAW = (TCEIL + 8) / 2;            // floats holding TCEIL + 8 int16 samples
-    // table blob (floats)
+    static constexpr int HALF = UNION + WS + RAW + 4;      // + mbarrier (8 B in a 16-B slot)
+    // fixed part of the table blob (floats); the filterbank tables follow at run-time offsets
     static constexpr int T_WIN = 0;                        // [RA/2][NZP] float2
     static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;  // [RA][H] float2, slot k1 - 1
     static constexpr int T_TWH = T_TW + RA * H * 2;        // [RA] float2
     static constexpr int TABF = T_TWH + RA * 2;
-    static constexpr int SMEM_FLOATS = TABF + UNION + WS + RAW + 4;   // + mbarrier (8 B, 16-B slot)
-    static constexpr int PS = NCEP | 1;                    // partial-cepstra row stride (odd: conflict-free)
-    static constexpr int LS = NMEL | 1;                    // log-mel staging row stride
     static_assert(HOP % 8 == 0, "an 8-sample chunk must not straddle a hop block");
     static_assert(HOP % RA == 0, "a column pair must not straddle a hop block");
     static_assert(RA == 2 * kWarps && RA == 16, "one column pair per warp, 16-point second pass");
     static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
     static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0 && RAW % 4 == 0, "16-byte aligned regions");
-    static_assert(kWarps * 32 * PS <= WS && 32 * LS <= WS, "tail scratch must fit in the workspace");
-    static_assert(V::bin(NMEL + 1) <= NFFT / 2 && V::bin(0) >= 0, "bin edges inside the spectrum");
+    static_assert(kWarps * 32 * PS <= WS && 32 * 129 <= WS, "tail scratch must fit in the workspace");
 };
 
-// Filters [beg(w), beg(w+1)) belong to warp w: contiguous, balanced by FMA count
-// (bins of the triangle + the filter's column of the DCT + the log).
-template <class V>
-struct Part {
-    static constexpr int cost(int m) { return (V::bin(m + 2) - V::bin(m)) + V::NCEP + 6; }
-    static constexpr int beg(int w)
-    {
-        if (w <= 0) return 0;
-        if (w >= kWarps) return V::NMEL;
-        int total = 0;
-        for (int m = 0; m < V::NMEL; ++m) total += cost(m);
-        int acc = 0, m = 0;
-        // first filter whose midpoint lies past w/kWarps of the total cost
-        while (m < V::NMEL && (2 * acc + cost(m)) * kWarps <= 2 * total * w) acc += cost(m++);
-        return m;
-    }
+// Run-time part of the table blob (offsets in floats from its start).
+struct SpLayout {
+    int wseg;     // int2 per warp: first and last segment (inclusive) of the warp's filter group
+    int seg;      // int4 per segment: {first bin * 32, chunks, weight offset (floats from melw), 0}
+    int melw;     // per chunk: 4 rise weights then 4 fall weights (scaled by 1/NFFT, zero past the segment)
+    int dct;      // [n_mel][KC]: DCT column of filter m, zero past n_cep
+    int total;    // floats, multiple of 4
 };
 
-template <class V>
 struct SpArgs {
     const Tile *tiles;
     int64_t n_tiles;
     float *out;
-    const float *tab;               // global copy of the table blob (Geo::TABF floats)
-    int logmel;
+    const float *tab;     // global copy of the table blob
+    SpLayout lay;
+    int n_mel, n_cep, logmel;
+    int ls;               // log-mel staging row stride (n_mel | 1)
+    int mel_magic;        // i / n_mel == (i * mel_magic) >> 20 for i < 32 * n_mel
     float preemph, log_floor;
-    float rise[Geo<V>::NB];         // pre-scaled by 1 / NFFT (pass 2 leaves |X|^2)
-    float fall[Geo<V>::NB];
-    float dct[V::NCEP * V::NMEL];   // [k][m]
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -148,7 +109,7 @@ __device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
 __device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
-// ---- mbarrier + bulk async copy (TMA engine, 1-D) ----
+// ---- mbarrier + bulk async copy (TMA engine, 1-D) + named barrier ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -176,80 +137,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-
-// ---- tail: warp W's filters -> log -> its share of every cepstrum ----
-template <class V, int W>
-__device__ __forceinline__ void tail_group(const float *__restrict__ pl, const SpArgs<V> &a, float *__restrict__ scr,
-                                           int lane)
+__device__ __forceinline__ void half_sync(int half)
 {
-    using G = Geo<V>;
-    constexpr int m0 = Part<V>::beg(W), m1 = Part<V>::beg(W + 1), NF = m1 - m0;
-    if constexpr (NF > 0) {
-        float acc[2 * NF];
-#pragma unroll
-        for (int i = 0; i < 2 * NF; ++i) acc[i] = 0.0f;
-        // segments j = m0 .. m1: bin k of segment j rises into filter j and falls out of filter j - 1
-        static_for<NF + 1>([&](auto jc) {
-            constexpr int j = m0 + decltype(jc)::value;
-            constexpr int k0 = V::bin(j), k1 = V::bin(j + 1);
-            static_for<(k1 > k0 ? k1 - k0 : 0)>([&](auto kc) {
-                constexpr int k = k0 + decltype(kc)::value;
-                const float p = pl[k * 32];
-                if constexpr (j < m1) acc[2 * (j - m0) + (k & 1)] = fmaf(a.rise[k], p, acc[2 * (j - m0) + (k & 1)]);
-                if constexpr (j > m0)
-                    acc[2 * (j - 1 - m0) + (k & 1)] = fmaf(a.fall[k], p, acc[2 * (j - 1 - m0) + (k & 1)]);
-            });
-        });
-        float lg[NF];
-#pragma unroll
-        for (int i = 0; i < NF; ++i) lg[i] = __logf(fmaxf(acc[2 * i] + acc[2 * i + 1], a.log_floor));
-        if (a.logmel) {
-#pragma unroll
-            for (int i = 0; i < NF; ++i) scr[lane * G::LS + m0 + i] = lg[i];
-        } else {
-            float c[V::NCEP];
-#pragma unroll
-            for (int k = 0; k < V::NCEP; ++k) c[k] = 0.0f;
-            static_for<NF>([&](auto mc) {
-                constexpr int i = decltype(mc)::value;
-                static_for<V::NCEP>([&](auto kc) {
-                    constexpr int k = decltype(kc)::value;
-                    c[k] = fmaf(a.dct[k * V::NMEL + m0 + i], lg[i], c[k]);
-                });
-            });
-            float *dst = scr + (W * 32 + lane) * G::PS;
-#pragma unroll
-            for (int k = 0; k < V::NCEP; ++k) dst[k] = c[k];
-        }
-    } else if (!a.logmel) {
-        float *dst = scr + (W * 32 + lane) * G::PS;
-#pragma unroll
-        for (int k = 0; k < V::NCEP; ++k) dst[k] = 0.0f;
-    }
+    asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kHalfThreads) : "memory");
 }
 
-template <typename PcmT, class V>
-__global__ void __launch_bounds__(kThreads, 2)
-fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> a)
+template <typename PcmT, int L_, int HOP_, int RB_, int RA_>
+__global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__restrict__ pcm, const SpArgs a)
 {
-    using G = Geo<V>;
-    constexpr int L = G::L, HOP = G::HOP, RB = G::RB, RA = G::RA, STRIDE = G::STRIDE, H = G::H, NZ = G::NZ;
+    using G = Geo<L_, HOP_, RB_, RA_>;
+    constexpr int HOP = G::HOP, RB = G::RB, RA = G::RA, STRIDE = G::STRIDE, H = G::H, NZ = G::NZ;
     extern __shared__ __align__(16) float smem[];
-    float *tab = smem;
-    float *staged = smem + G::TABF;       // S0-S1
+    const int half = threadIdx.x >> 8, tid = threadIdx.x & (kHalfThreads - 1);
+    const int lane = tid & 31, warp = tid >> 5;
+
+    float *tab = smem;                                        // shared by both halves
+    float *mine = smem + a.lay.total + half * G::HALF;
+    float *staged = mine;                 // S0-S1
     float *pw = staged;                   // S2-S3 (aliases staged)
-    float2 *ws = reinterpret_cast<float2 *>(staged + G::UNION);
-    float *scr = reinterpret_cast<float *>(ws);   // tail scratch (aliases ws)
-    const int16_t *raw16 = reinterpret_cast<const int16_t *>(staged + G::UNION + G::WS);
+    float2 *ws = reinterpret_cast<float2 *>(mine + G::UNION);
+    float *scr = reinterpret_cast<float *>(ws);               // tail scratch (aliases ws)
+    const int16_t *raw16 = reinterpret_cast<const int16_t *>(mine + G::UNION + G::WS);
     const uint32_t raw_s = smem_u32(raw16);
-    const uint32_t bar = smem_u32(staged + G::UNION + G::WS + G::RAW);
+    const uint32_t bar = smem_u32(mine + G::UNION + G::WS + G::RAW);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    for (int i = threadIdx.x * 4; i < G::TABF; i += kThreads * 4)
+    if (tid == 0) mbar_init(bar, 1);
+    // slack rows of P: read with zero weights, so they must hold finite values (0 * NaN would turn a
+    // band into NaN and fmaxf would then silently replace it by the floor)
+    for (int i = G::NB * 32 + tid; i < G::PW; i += kHalfThreads) pw[i] = 0.0f;
+    for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW, *t_twh = tab + G::T_TWH;
+    const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
+    const int4 *t_seg = reinterpret_cast<const int4 *>(tab + a.lay.seg);
+    const float *t_melw = tab + a.lay.melw, *t_dct = tab + a.lay.dct;
 
     // A tile takes the bulk-copy path when its samples are 16-byte aligned in HBM and lie inside
     // the utterance up to the staging granule (no zero fill needed).
@@ -266,20 +187,21 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
         bulk_g2s(raw_s + (8 - lead) * 2, pcm + tl.first_sample - lead, bytes, bar);
     };
 
-    __syncthreads();   // mbarrier initialised, tables visible
+    __syncthreads();   // mbarriers initialised, tables visible; from here on the halves only meet themselves
+    const int64_t first = 2 * static_cast<int64_t>(blockIdx.x) + half, step = 2 * static_cast<int64_t>(gridDim.x);
     Tile nt{};
     bool nfast = false;
-    if (static_cast<int64_t>(blockIdx.x) < a.n_tiles) {
-        nt = a.tiles[blockIdx.x];
+    if (first < a.n_tiles) {
+        nt = a.tiles[first];
         nfast = tile_fast(nt);
-        if (threadIdx.x == 0 && nfast) issue_copy(nt);
+        if (tid == 0 && nfast) issue_copy(nt);
     }
     uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    for (int64_t t = first; t < a.n_tiles; t += step) {
         const Tile tile = nt;
         const bool fast = nfast;
-        const bool has_next = t + gridDim.x < a.n_tiles;
-        if (has_next) nt = a.tiles[t + gridDim.x];   // arrives while S0 runs
+        const bool has_next = t + step < a.n_tiles;
+        if (has_next) nt = a.tiles[t + step];   // arrives while S0 runs
         const int n_frames = tile.n_frames;
         const int tc = G::tceil(n_frames);
 
@@ -289,15 +211,15 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
             phase ^= 1u;
             const bool at_start = tile.first_sample == tile.utt_begin;
             const int nchunks = tc >> 3;
+            const float na = -a.preemph;
 #pragma unroll 1
-            for (int c = threadIdx.x; c < nchunks; c += kThreads) {
+            for (int c = tid; c < nchunks; c += kHalfThreads) {
                 const uint4 q = *reinterpret_cast<const uint4 *>(raw16 + 8 + 8 * c);
                 const uint32_t pwd = *reinterpret_cast<const uint32_t *>(raw16 + 6 + 8 * c);
                 const float2 x01 = s16x2_to_f32(q.x), x23 = s16x2_to_f32(q.y);
                 const float2 x45 = s16x2_to_f32(q.z), x67 = s16x2_to_f32(q.w);
                 float xp = s16x2_to_f32(pwd).y;
                 if (c == 0 && at_start) xp = 0.0f;
-                const float na = -a.preemph;
                 float *dst = staged + 8 * c + kPad * (c / (HOP / 8));
                 *reinterpret_cast<float2 *>(dst + 0) = make_float2(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y));
                 *reinterpret_cast<float2 *>(dst + 2) = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
@@ -308,7 +230,7 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
             const int64_t room_lo = tile.first_sample - tile.utt_begin;
             const int64_t room_hi = tile.utt_end - tile.first_sample;
             const PcmT *x = pcm + tile.first_sample;
-            for (int i = threadIdx.x; i < tc; i += kThreads) {
+            for (int i = tid; i < tc; i += kHalfThreads) {
                 float y = 0.0f;
                 if (i < room_hi) {
                     const float x0 = to_f32(x[i]);
@@ -318,11 +240,11 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
                 staged[G::padded(i)] = y;
             }
         }
-        __syncthreads();   // B1: staged complete; raw buffer and (previous tile's) scratch free
+        half_sync(half);   // B1: staged complete; raw buffer and (previous tile's) scratch free
         nfast = false;
         if (has_next) {
             nfast = tile_fast(nt);
-            if (threadIdx.x == 0 && nfast) issue_copy(nt);
+            if (tid == 0 && nfast) issue_copy(nt);
         }
 
         // ---- S1: pass 1.  Warp = column pair (a, a + 1): windowed real DFT-RB over b, inter-pass twiddle ----
@@ -342,11 +264,11 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
                 }
             }
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int col = 2 * pr + half;
+            for (int hh = 0; hh < 2; ++hh) {
+                const int col = 2 * pr + hh;
                 float x[RB];
 #pragma unroll
-                for (int b = 0; b < RB; ++b) x[b] = b < NZ ? (half ? in[b < NZ ? b : 0].y : in[b < NZ ? b : 0].x) : 0.0f;
+                for (int b = 0; b < RB; ++b) x[b] = b < NZ ? (hh ? in[b < NZ ? b : 0].y : in[b < NZ ? b : 0].x) : 0.0f;
                 rf::cplx X[H + 1];
                 rf::RDft<RB>::template run<NZ>(x, X);
                 float2 *wsa = ws + col * 32 + lane;
@@ -364,7 +286,7 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
                 }
             }
         }
-        __syncthreads();   // B2
+        half_sync(half);   // B2
 
         // ---- S2: pass 2.  Item = one row k1: complex DFT-RA over a gives bins k1 + RB k2; power ----
         {
@@ -417,42 +339,81 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
                 }
             }
         }
-        __syncthreads();   // B3: P complete, workspace free
+        half_sync(half);   // B3: P complete, workspace free
 
-        // ---- S3: per-warp filter group: sparse mel -> log -> partial DCT (or log-mel staging) ----
+        // ---- S3: the warp's filter group.  Segment j = bins [b_j, b_j+1) rises into filter j and
+        // falls out of filter j - 1; filter m is complete after segment m + 1: log, then either the
+        // log-mel staging row or the filter's column of the DCT into 16 running cepstra. ----
         {
-            const float *pl = pw + lane;
-            switch (warp) {
-                case 0: tail_group<V, 0>(pl, a, scr, lane); break;
-                case 1: tail_group<V, 1>(pl, a, scr, lane); break;
-                case 2: tail_group<V, 2>(pl, a, scr, lane); break;
-                case 3: tail_group<V, 3>(pl, a, scr, lane); break;
-                case 4: tail_group<V, 4>(pl, a, scr, lane); break;
-                case 5: tail_group<V, 5>(pl, a, scr, lane); break;
-                case 6: tail_group<V, 6>(pl, a, scr, lane); break;
-                default: tail_group<V, 7>(pl, a, scr, lane); break;
+            const int2 wr = t_wseg[warp];
+            float c[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) c[k] = 0.0f;
+            float r_prev = 0.0f;
+#pragma unroll 1
+            for (int j = wr.x; j <= wr.y; ++j) {
+                const int4 sg = t_seg[j];
+                const float *p = pw + sg.x + lane;
+                const float *w = t_melw + sg.z;
+                float r0 = 0.0f, r1 = 0.0f, f0 = 0.0f, f1 = 0.0f;
+#pragma unroll 1
+                for (int ch = 0; ch < sg.y; ++ch) {
+                    const float4 wr4 = lds_f4(w), wf4 = lds_f4(w + 4);
+                    const float p0 = p[0], p1 = p[32], p2 = p[64], p3 = p[96];
+                    r0 = fmaf(wr4.x, p0, r0); f0 = fmaf(wf4.x, p0, f0);
+                    r1 = fmaf(wr4.y, p1, r1); f1 = fmaf(wf4.y, p1, f1);
+                    r0 = fmaf(wr4.z, p2, r0); f0 = fmaf(wf4.z, p2, f0);
+                    r1 = fmaf(wr4.w, p3, r1); f1 = fmaf(wf4.w, p3, f1);
+                    p += 128;
+                    w += 8;
+                }
+                if (j > wr.x) {
+                    const int m = j - 1;
+                    const float lg = __logf(fmaxf(r_prev + (f0 + f1), a.log_floor));
+                    if (a.logmel) {
+                        scr[lane * a.ls + m] = lg;
+                    } else {
+                        const float *d = t_dct + m * KC;
+#pragma unroll
+                        for (int q = 0; q < KC; q += 4) {
+                            const float4 dv = lds_f4(d + q);
+                            c[q + 0] = fmaf(dv.x, lg, c[q + 0]);
+                            c[q + 1] = fmaf(dv.y, lg, c[q + 1]);
+                            c[q + 2] = fmaf(dv.z, lg, c[q + 2]);
+                            c[q + 3] = fmaf(dv.w, lg, c[q + 3]);
+                        }
+                    }
+                }
+                r_prev = r0 + r1;
+            }
+            if (!a.logmel) {
+                float *dst = scr + (warp * 32 + lane) * PS;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) dst[k] = c[k];
             }
         }
-        __syncthreads();   // B4
+        half_sync(half);   // B4
 
-        // ---- S4: add the partial cepstra of the 8 warps and store coalesced ----
+        // ---- S4: add the partial cepstra of the 8 warps and store (16 lanes per frame, n_cep of them live) ----
         if (a.logmel) {
-            const int total = n_frames * V::NMEL;
-            float *o = a.out + tile.out_row * V::NMEL;
-            for (int i = threadIdx.x; i < total; i += kThreads) {
-                const int f = i / V::NMEL, m = i - f * V::NMEL;
-                o[i] = scr[f * G::LS + m];
+            const int M = a.n_mel, total = n_frames * M;
+            float *o = a.out + tile.out_row * M;
+            for (int i = tid; i < total; i += kHalfThreads) {
+                const int f = (i * a.mel_magic) >> 20, m = i - f * M;
+                o[i] = scr[f * a.ls + m];
             }
         } else {
-            const int total = n_frames * V::NCEP;
-            float *o = a.out + tile.out_row * V::NCEP;
-            for (int i = threadIdx.x; i < total; i += kThreads) {
-                const int f = i / V::NCEP, k = i - f * V::NCEP;
-                const float *src = scr + f * G::PS + k;
-                float s = src[0];
+            const int k = tid & (KC - 1);
 #pragma unroll
-                for (int w = 1; w < kWarps; ++w) s += src[w * 32 * G::PS];
-                o[i] = s;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int f = pass * (kHalfThreads / KC) + (tid >> 4);
+                if (f < n_frames && k < a.n_cep) {
+                    const float *src = scr + f * PS + k;
+                    float s = src[0];
+#pragma unroll
+                    for (int w = 1; w < kWarps; ++w) s += src[w * 32 * PS];
+                    a.out[(tile.out_row + f) * a.n_cep + k] = s;
+                }
             }
         }
         // no barrier here: the next S0 writes `staged`, which nobody reads any more; the scratch is
@@ -463,119 +424,177 @@ fused_sp_kernel(const PcmT *__restrict__ pcm, const __grid_constant__ SpArgs<V> 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+struct SpVariant {
+    int L, hop, rb, ra;
+    const char *name;
+};
+constexpr SpVariant kVariants[] = {
+    {400, 160, 32, 16, "fused_sp_tile32_L400_H160_real32x16"},   // BASELINE.json configs 1, 2, 5 (16 kHz)
+    {200, 80, 16, 16, "fused_sp_tile32_L200_H80_real16x16"},     // BASELINE.json config 3 (8 kHz telephony)
+};
+
 struct SpState {
-    int variant = -1;          // 0 = Var16k, 1 = Var8k
-    std::vector<char> args;    // SpArgs<V> image with the per-launch fields blank
+    const SpVariant *v = nullptr;
+    SpArgs args{};             // per-launch fields blank
     float *d_tab = nullptr;
+    size_t smem = 0;
     int sm_count = 0;
 };
 
-template <class V>
-bool structure_matches(const mfcc_params &p, const HostTables &h)
+const SpVariant *find_variant(const mfcc_params &p)
 {
-    if (p.frame_len != V::L || p.hop_len != V::HOP || p.nfft != V::RB * V::RA) return false;
-    if (p.n_mel != V::NMEL || p.n_cep != V::NCEP) return false;
-    if (static_cast<int>(h.mel_bins.size()) != V::NMEL + 2) return false;
-    for (int j = 0; j < V::NMEL + 2; ++j)
-        if (h.mel_bins[j] != V::bin(j)) return false;
-    return true;
+    for (const auto &v : kVariants)
+        if (p.frame_len == v.L && p.hop_len == v.hop && p.nfft == v.rb * v.ra) return &v;
+    return nullptr;
 }
 
-template <class V>
-void build_tab_and_args(const mfcc_plan *plan, std::vector<float> &tab, std::vector<char> &args_img)
+template <int L, int HOP, int RB, int RA>
+void geo_sizes(int &tabf, int &half_floats) { tabf = Geo<L, HOP, RB, RA>::TABF; half_floats = Geo<L, HOP, RB, RA>::HALF; }
+
+void variant_sizes(const SpVariant &v, int &tabf, int &half_floats)
 {
-    using G = Geo<V>;
-    const mfcc_params &p = plan->p;
-    const HostTables &h = plan->host;
-    constexpr int RB = V::RB, RA = V::RA, N = RB * RA, H = RB / 2;
-    tab.assign(G::TABF, 0.0f);
-    // window of the sample pairs (a, a + 1) + RA b per column pair, zero past the frame
-    for (int pr = 0; pr < RA / 2; ++pr)
-        for (int b = 0; b < G::NZP; ++b)
-            for (int e = 0; e < 2; ++e) {
-                const int i = 2 * pr + e + RA * b;
-                tab[G::T_WIN + (pr * G::NZP + b) * 2 + e] = (b < G::NZ && i < p.frame_len) ? h.window[i] : 0.0f;
+    if (v.L == 400) geo_sizes<400, 160, 32, 16>(tabf, half_floats);
+    else geo_sizes<200, 80, 16, 16>(tabf, half_floats);
+}
+
+// Chunks of 4 bins a segment needs.
+inline int seg_chunks(const HostTables &h, int j) { return (h.mel_bins[j + 1] - h.mel_bins[j] + 3) / 4; }
+
+// Contiguous split of the M filters over the warps that minimises the heaviest warp.  A warp owning
+// filters [m0, m1) walks segments m0 .. m1 (the boundary segment is walked by both neighbours).
+std::vector<int> split_filters(const HostTables &h, int M)
+{
+    auto cost = [&](int m0, int m1) {   // instruction estimate of the S3 loop
+        if (m1 <= m0) return 0;
+        int c = 0;
+        for (int j = m0; j <= m1; ++j) c += 18 * seg_chunks(h, j) + 14;
+        return c + 30 * (m1 - m0);
+    };
+    const int INF = 1 << 30;
+    std::vector<std::vector<int>> best(kWarps + 1, std::vector<int>(M + 1, INF)), arg(kWarps + 1, std::vector<int>(M + 1, 0));
+    best[0][0] = 0;
+    for (int w = 1; w <= kWarps; ++w)
+        for (int m1 = 0; m1 <= M; ++m1)
+            for (int m0 = 0; m0 <= m1; ++m0) {
+                if (best[w - 1][m0] == INF) continue;
+                const int v = std::max(best[w - 1][m0], cost(m0, m1));
+                if (v < best[w][m1]) { best[w][m1] = v; arg[w][m1] = m0; }
             }
-    // inter-pass twiddles W_N^(a k1), k1 = 1 .. H-1 at slot k1 - 1 (last slot: 1)
-    for (int col = 0; col < RA; ++col)
-        for (int sl = 0; sl < H; ++sl) {
-            const double ang = sl < H - 1 ? -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N : 0.0;
-            tab[G::T_TW + (col * H + sl) * 2 + 0] = static_cast<float>(std::cos(ang));
-            tab[G::T_TW + (col * H + sl) * 2 + 1] = static_cast<float>(std::sin(ang));
-        }
-    // twiddle of row H: W_N^(a H) = W_(2 RA)^a
-    for (int col = 0; col < RA; ++col) {
-        const double ang = -2.0 * M_PI * col / (2.0 * RA);
-        tab[G::T_TWH + col * 2 + 0] = static_cast<float>(std::cos(ang));
-        tab[G::T_TWH + col * 2 + 1] = static_cast<float>(std::sin(ang));
-    }
-    args_img.assign(sizeof(SpArgs<V>), 0);
-    SpArgs<V> *a = reinterpret_cast<SpArgs<V> *>(args_img.data());
-    const double scale = 1.0 / N;
-    for (int k = 0; k < G::NB; ++k) {
-        a->rise[k] = static_cast<float>(static_cast<double>(h.rise[k]) * scale);
-        a->fall[k] = static_cast<float>(static_cast<double>(h.fall[k]) * scale);
-    }
-    for (int k = 0; k < V::NCEP; ++k)
-        for (int m = 0; m < V::NMEL; ++m) a->dct[k * V::NMEL + m] = h.dct[static_cast<size_t>(k) * V::NMEL + m];
-    a->logmel = p.output == MFCC_OUT_LOGMEL;
-    a->preemph = p.preemph;
-    a->log_floor = p.log_floor;
-}
-
-template <typename PcmT, class V>
-int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-                   cudaStream_t stream)
-{
-    using G = Geo<V>;
-    constexpr size_t smem = sizeof(float) * G::SMEM_FLOATS;
-    auto kern = fused_sp_kernel<PcmT, V>;
-    static thread_local const void *configured = nullptr;
-    if (configured != reinterpret_cast<const void *>(kern)) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
-            cudaSuccess) {
-            cudaGetLastError();
-            return MFCC_ECUDA;
-        }
-        configured = reinterpret_cast<const void *>(kern);
-    }
-    SpArgs<V> a;
-    std::memcpy(&a, st->args.data(), sizeof(a));
-    a.tiles = d_tiles;
-    a.n_tiles = n_tiles;
-    a.out = d_out;
-    a.tab = st->d_tab;
-    const int per_sm = (smem + 1024) * 2 <= 228 * 1024 ? 2 : 1;
-    const int64_t grid = std::min<int64_t>(n_tiles, static_cast<int64_t>(st->sm_count) * per_sm);
-    kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(d_pcm, a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+    std::vector<int> beg(kWarps + 1, 0);
+    beg[kWarps] = M;
+    for (int w = kWarps; w >= 1; --w) beg[w - 1] = arg[w][beg[w]];
+    return beg;
 }
 
 }  // namespace
 
 const char *sp_match(const mfcc_params &p, const HostTables &h)
 {
-    if (structure_matches<Var16k>(p, h)) return Var16k::name();
-    if (structure_matches<Var8k>(p, h)) return Var8k::name();
-    return nullptr;
+    const SpVariant *v = find_variant(p);
+    if (v == nullptr) return nullptr;
+    if (p.output == MFCC_OUT_CEPSTRA && p.n_cep > KC) return nullptr;
+    for (int j = 0; j + 1 < static_cast<int>(h.mel_bins.size()); ++j)
+        if (h.mel_bins[j + 1] < h.mel_bins[j]) return nullptr;
+    // the run-time tables must fit next to the two halves
+    int tabf = 0, half_floats = 0;
+    variant_sizes(*v, tabf, half_floats);
+    int chunks = 0;
+    for (int j = 0; j <= p.n_mel; ++j) chunks += seg_chunks(h, j);
+    const size_t total = tabf + 2 * kWarps + 4 * (p.n_mel + 1) + 8 * static_cast<size_t>(chunks) +
+                         static_cast<size_t>(KC) * p.n_mel + 16;
+    if ((total + 2 * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
+    return v->name;
 }
 
 int sp_prepare(mfcc_plan *plan)
 {
-    SpState *st = new SpState();
+    const mfcc_params &p = plan->p;
+    const HostTables &h = plan->host;
+    const SpVariant *var = find_variant(p);
+    if (var == nullptr || sp_match(p, h) == nullptr) return MFCC_ENOTSUP;
+    const int RB = var->rb, RA = var->ra, N = RB * RA, H = RB / 2, M = p.n_mel;
+    const int NZ = (p.frame_len + RA - 1) / RA, NZP = (NZ + 1) / 2 * 2;
+    int tabf = 0, half_floats = 0;
+    variant_sizes(*var, tabf, half_floats);
     std::vector<float> tab;
-    if (structure_matches<Var16k>(plan->p, plan->host)) {
-        st->variant = 0;
-        build_tab_and_args<Var16k>(plan, tab, st->args);
-    } else if (structure_matches<Var8k>(plan->p, plan->host)) {
-        st->variant = 1;
-        build_tab_and_args<Var8k>(plan, tab, st->args);
-    } else {
-        delete st;
-        return MFCC_ENOTSUP;
+    auto align4 = [&]() { while (tab.size() % 4) tab.push_back(0.0f); };
+    auto push_int = [&](int v) { float f; std::memcpy(&f, &v, 4); tab.push_back(f); };
+
+    // fixed part, in Geo's order: window pairs, inter-pass twiddles, row-H twiddles
+    for (int pr = 0; pr < RA / 2; ++pr)
+        for (int b = 0; b < NZP; ++b)
+            for (int e = 0; e < 2; ++e) {
+                const int i = 2 * pr + e + RA * b;
+                tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
+            }
+    for (int col = 0; col < RA; ++col)
+        for (int sl = 0; sl < H; ++sl) {
+            const double ang = sl < H - 1 ? -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N : 0.0;
+            tab.push_back(static_cast<float>(std::cos(ang)));
+            tab.push_back(static_cast<float>(std::sin(ang)));
+        }
+    for (int col = 0; col < RA; ++col) {
+        const double ang = -2.0 * M_PI * col / (2.0 * RA);
+        tab.push_back(static_cast<float>(std::cos(ang)));
+        tab.push_back(static_cast<float>(std::sin(ang)));
     }
+    if (static_cast<int>(tab.size()) != tabf) return MFCC_ECUDA;   // layout drifted from Geo
+
+    SpLayout lay{};
+    // warp -> segments
+    const std::vector<int> beg = split_filters(h, M);
+    lay.wseg = static_cast<int>(tab.size());
+    for (int w = 0; w < kWarps; ++w) {
+        const int m0 = beg[w], m1 = beg[w + 1];
+        push_int(m1 > m0 ? m0 : 1);    // empty group: first > last
+        push_int(m1 > m0 ? m1 : 0);
+    }
+    align4();
+    // segments and their chunk weights, pre-scaled by 1/N (pass 2 leaves |X|^2)
+    std::vector<float> melw;
+    lay.seg = static_cast<int>(tab.size());
+    const double scale = 1.0 / N;
+    for (int j = 0; j <= M; ++j) {
+        const int k0 = h.mel_bins[j], k1 = h.mel_bins[j + 1], chunks = seg_chunks(h, j);
+        push_int(k0 * 32);
+        push_int(chunks);
+        push_int(static_cast<int>(melw.size()));
+        push_int(0);
+        for (int c = 0; c < chunks; ++c) {
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + 4 * c + e;
+                melw.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.rise[k]) * scale) : 0.0f);
+            }
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + 4 * c + e;
+                melw.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.fall[k]) * scale) : 0.0f);
+            }
+        }
+    }
+    lay.melw = static_cast<int>(tab.size());
+    tab.insert(tab.end(), melw.begin(), melw.end());
+    align4();
+    // DCT columns, zero past n_cep
+    lay.dct = static_cast<int>(tab.size());
+    for (int m = 0; m < M; ++m)
+        for (int k = 0; k < KC; ++k)
+            tab.push_back(p.output == MFCC_OUT_CEPSTRA && k < p.n_cep ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f);
+    align4();
+    lay.total = static_cast<int>(tab.size());
+
+    SpState *st = new SpState();
+    st->v = var;
     st->sm_count = plan->sm_count;
+    st->smem = sizeof(float) * (static_cast<size_t>(lay.total) + 2 * static_cast<size_t>(half_floats));
+    if (st->smem > kSmemMax) { delete st; return MFCC_ENOTSUP; }
+    st->args.lay = lay;
+    st->args.n_mel = M;
+    st->args.n_cep = p.n_cep;
+    st->args.logmel = p.output == MFCC_OUT_LOGMEL;
+    st->args.ls = M | 1;
+    st->args.mel_magic = (1 << 20) / M + 1;
+    st->args.preemph = p.preemph;
+    st->args.log_floor = p.log_floor;
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
         cudaGetLastError();
         delete st;
@@ -599,14 +618,39 @@ void sp_release(mfcc_plan *plan)
     plan->sp_state = nullptr;
 }
 
+template <typename PcmT, int L, int HOP, int RB, int RA>
+static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
+                          cudaStream_t stream)
+{
+    auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA>;
+    static thread_local const void *configured = nullptr;
+    if (configured != reinterpret_cast<const void *>(kern)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return MFCC_ECUDA;
+        }
+        configured = reinterpret_cast<const void *>(kern);
+    }
+    SpArgs a = st->args;
+    a.tiles = d_tiles;
+    a.n_tiles = n_tiles;
+    a.out = d_out;
+    a.tab = st->d_tab;
+    const int64_t grid = std::min<int64_t>((n_tiles + 1) / 2, st->sm_count);
+    kern<<<static_cast<unsigned>(grid), kThreads, st->smem, stream>>>(d_pcm, a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
 template <typename PcmT>
 int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
               cudaStream_t stream)
 {
     const SpState *st = static_cast<const SpState *>(plan->sp_state);
     if (st == nullptr) return MFCC_ENOTSUP;
-    if (st->variant == 0) return launch_variant<PcmT, Var16k>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
-    return launch_variant<PcmT, Var8k>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    if (st->v->L == 400) return launch_variant<PcmT, 400, 160, 32, 16>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    return launch_variant<PcmT, 200, 80, 16, 16>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
 }
 
 template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *, cudaStream_t);

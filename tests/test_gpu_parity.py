@@ -181,7 +181,8 @@ def test_bad_calls_fail_loudly():
     assert api.Plan(config_a()).kernel_name.startswith("fused_sp_")
     assert api.Plan(config_b()).kernel_name.startswith("fused_sp_")
     assert api.Plan(config_a().copy(output=OUT_LOGMEL, lifter=22)).kernel_name.startswith("fused_sp_")
-    assert api.Plan(config_a().copy(n_mel=40)).kernel_name.startswith("fused_ct_")       # other filterbank structure
+    assert api.Plan(config_a().copy(n_mel=40)).kernel_name.startswith("fused_sp_")       # filterbank is data
+    assert api.Plan(config_a().copy(n_mel=40, n_cep=20)).kernel_name.startswith("fused_ct_")   # > 16 cepstra
     assert api.Plan(config_a(), kernel=KERNEL_FUSED_CT).kernel_name.startswith("fused_ct_")
     assert api.Plan(config_a().copy(hop_len=128)).kernel_name.startswith("fused_rt_")
     assert api.Plan(config_a(), kernel=KERNEL_FUSED_RT).kernel_name.startswith("fused_rt_")
