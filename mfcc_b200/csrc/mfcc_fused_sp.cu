@@ -61,7 +61,8 @@ struct Geo {
     static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
     static constexpr int WS = H * RA * 32 * 2;             // floats
     static constexpr int RAW = (TCEIL + 8) / 2;            // floats holding TCEIL + 8 int16 samples
-    static constexpr int HALF = UNION + WS + RAW + 4;      // + mbarrier (8 B in a 16-B slot)
+    static constexpr int DESC = 24;                        // two 40-byte tile descriptors (current, next)
+    static constexpr int HALF = UNION + WS + RAW + 4 + DESC;   // + mbarrier (8 B in a 16-B slot)
     // fixed part of the table blob (floats); the filterbank tables follow at run-time offsets
     static constexpr int T_WIN = 0;                        // [RA/2][NZP] float2
     static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;  // [RA][H] float2, slot k1 - 1
@@ -77,12 +78,16 @@ struct Geo {
 
 // Run-time part of the table blob (offsets in floats from its start).
 struct SpLayout {
-    int wseg;     // int2 per warp: first and last segment (inclusive) of the warp's filter group
-    int seg;      // int4 per segment: {first bin * 32, chunks, weight offset (floats from melw), 0}
-    int melw;     // per chunk: 4 rise weights then 4 fall weights (scaled by 1/NFFT, zero past the segment)
+    int wchunk;   // int2 per warp: its chunk records [first, last)
+    int wfilt;    // int2 per warp: its filters [first, last)
+    int chunk;    // records of kRec floats: 4 rise weights, 4 fall weights (scaled by 1/NFFT, zero past the
+                  // segment), descriptor = first bin * 32 | kRecEnd | kRecEmit | filter << 24, 3 unused
     int dct;      // [n_mel][KC]: DCT column of filter m, zero past n_cep
     int total;    // floats, multiple of 4
 };
+constexpr int kRec = 12;
+constexpr int kRecEnd = 1 << 16;    // last chunk of its segment
+constexpr int kRecEmit = 1 << 17;   // ... and that segment completes filter (descriptor >> 24) of this warp
 
 struct SpArgs {
     const Tile *tiles;
@@ -92,6 +97,7 @@ struct SpArgs {
     SpLayout lay;
     int n_mel, n_cep, logmel;
     int ls;               // log-mel staging row stride (n_mel | 1)
+    int est;              // scratch offset (floats) of the parked band energies [n_mel][32]
     int mel_magic;        // i / n_mel == (i * mel_magic) >> 20 for i < 32 * n_mel
     float preemph, log_floor;
 };
@@ -137,6 +143,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void half_sync(int half)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kHalfThreads) : "memory");
@@ -160,6 +171,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
     const int16_t *raw16 = reinterpret_cast<const int16_t *>(mine + G::UNION + G::WS);
     const uint32_t raw_s = smem_u32(raw16);
     const uint32_t bar = smem_u32(mine + G::UNION + G::WS + G::RAW);
+    const Tile *desc = reinterpret_cast<const Tile *>(mine + G::UNION + G::WS + G::RAW + 4);   // [2]
+    static_assert(sizeof(Tile) == 40, "descriptor copy assumes five 8-byte words");
+    // the tile table is read one tile ahead straight into shared memory (no registers held across the phases)
+    auto fetch_desc = [&](int slot, int64_t t) {
+        if (tid < 5) cp_async8(smem_u32(desc + slot) + tid * 8, reinterpret_cast<const char *>(a.tiles + t) + tid * 8);
+    };
 
     if (tid == 0) mbar_init(bar, 1);
     // slack rows of P: read with zero weights, so they must hold finite values (0 * NaN would turn a
@@ -168,9 +185,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
     for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW, *t_twh = tab + G::T_TWH;
-    const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
-    const int4 *t_seg = reinterpret_cast<const int4 *>(tab + a.lay.seg);
-    const float *t_melw = tab + a.lay.melw, *t_dct = tab + a.lay.dct;
+    const int2 *t_wchunk = reinterpret_cast<const int2 *>(tab + a.lay.wchunk);
+    const int2 *t_wfilt = reinterpret_cast<const int2 *>(tab + a.lay.wfilt);
+    const float *t_chunk = tab + a.lay.chunk, *t_dct = tab + a.lay.dct;
 
     // A tile takes the bulk-copy path when its samples are 16-byte aligned in HBM and lie inside
     // the utterance up to the staging granule (no zero fill needed).
@@ -187,21 +204,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         bulk_g2s(raw_s + (8 - lead) * 2, pcm + tl.first_sample - lead, bytes, bar);
     };
 
-    __syncthreads();   // mbarriers initialised, tables visible; from here on the halves only meet themselves
     const int64_t first = 2 * static_cast<int64_t>(blockIdx.x) + half, step = 2 * static_cast<int64_t>(gridDim.x);
-    Tile nt{};
-    bool nfast = false;
-    if (first < a.n_tiles) {
-        nt = a.tiles[first];
-        nfast = tile_fast(nt);
-        if (tid == 0 && nfast) issue_copy(nt);
+    if (first < a.n_tiles) fetch_desc(0, first);
+    cp_async_wait_all();
+    __syncthreads();   // mbarriers initialised, tables and first descriptors visible; from here on the halves only meet themselves
+    if (first < a.n_tiles && tid == 0) {
+        const Tile t0 = desc[0];
+        if (tile_fast(t0)) issue_copy(t0);
     }
     uint32_t phase = 0;
-    for (int64_t t = first; t < a.n_tiles; t += step) {
-        const Tile tile = nt;
-        const bool fast = nfast;
+    int cur = 0;
+    for (int64_t t = first; t < a.n_tiles; t += step, cur ^= 1) {
+        const Tile tile = desc[cur];
+        const bool fast = tile_fast(tile);
         const bool has_next = t + step < a.n_tiles;
-        if (has_next) nt = a.tiles[t + step];   // arrives while S0 runs
+        if (has_next) fetch_desc(cur ^ 1, t + step);   // lands while S0 runs
         const int n_frames = tile.n_frames;
         const int tc = G::tceil(n_frames);
 
@@ -240,11 +257,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
                 staged[G::padded(i)] = y;
             }
         }
-        half_sync(half);   // B1: staged complete; raw buffer and (previous tile's) scratch free
-        nfast = false;
-        if (has_next) {
-            nfast = tile_fast(nt);
-            if (tid == 0 && nfast) issue_copy(nt);
+        cp_async_wait_all();
+        half_sync(half);   // B1: staged complete; raw buffer and (previous tile's) scratch free; next descriptor visible
+        if (has_next && tid == 0) {
+            const Tile nt = desc[cur ^ 1];
+            if (tile_fast(nt)) issue_copy(nt);
         }
 
         // ---- S1: pass 1.  Warp = column pair (a, a + 1): windowed real DFT-RB over b, inter-pass twiddle ----
@@ -341,52 +358,76 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         }
         half_sync(half);   // B3: P complete, workspace free
 
-        // ---- S3: the warp's filter group.  Segment j = bins [b_j, b_j+1) rises into filter j and
-        // falls out of filter j - 1; filter m is complete after segment m + 1: log, then either the
-        // log-mel staging row or the filter's column of the DCT into 16 running cepstra. ----
+        // ---- S3: the warp's filter group, as a flat list of 4-bin chunks (host-built, duplicates the
+        // segment two neighbouring groups share).  Segment j = bins [b_j, b_j+1) rises into filter j and
+        // falls out of filter j - 1, so filter m is complete at the end of segment m + 1.  The loop is
+        // software-pipelined: chunk i + 1 is loaded before chunk i is summed.  Energies are parked in the
+        // thread's own scratch words, then a second loop takes logs and either stages log-mel rows or adds
+        // the filter's DCT column into 16 running cepstra. ----
         {
-            const int2 wr = t_wseg[warp];
-            float c[KC];
-#pragma unroll
-            for (int k = 0; k < KC; ++k) c[k] = 0.0f;
-            float r_prev = 0.0f;
+            const int2 wc = t_wchunk[warp];                 // chunk records [x, y)
+            const int2 wf = t_wfilt[warp];                  // filters [x, y)
+            float *est = scr + a.est + lane;                // E[m] of this lane at est[m * 32]
+            const int n = wc.y - wc.x;
+            if (n > 0) {
+                // two register sets (A, B) alternate, so the prefetch needs no register moves
+                struct Chunk { float4 wr, wf; int d; float p0, p1, p2, p3; };
+                auto load = [&](Chunk &c, const float *rec) {
+                    c.wr = lds_f4(rec);
+                    c.wf = lds_f4(rec + 4);
+                    c.d = __float_as_int(rec[8]);
+                    const float *p = pw + (c.d & 0xFFFF) + lane;
+                    c.p0 = p[0]; c.p1 = p[32]; c.p2 = p[64]; c.p3 = p[96];
+                };
+                float r0 = 0.0f, r1 = 0.0f, f0 = 0.0f, f1 = 0.0f, r_prev = 0.0f;
+                auto sum = [&](const Chunk &c) {
+                    r0 = fmaf(c.wr.x, c.p0, r0); f0 = fmaf(c.wf.x, c.p0, f0);
+                    r1 = fmaf(c.wr.y, c.p1, r1); f1 = fmaf(c.wf.y, c.p1, f1);
+                    r0 = fmaf(c.wr.z, c.p2, r0); f0 = fmaf(c.wf.z, c.p2, f0);
+                    r1 = fmaf(c.wr.w, c.p3, r1); f1 = fmaf(c.wf.w, c.p3, f1);
+                    if (c.d & kRecEnd) {
+                        if (c.d & kRecEmit) est[(c.d >> 24) * 32] = r_prev + (f0 + f1);
+                        r_prev = r0 + r1;
+                        r0 = r1 = f0 = f1 = 0.0f;
+                    }
+                };
+                const float *rec = t_chunk + wc.x * kRec;
+                Chunk A, B;
+                load(A, rec);
+                int left = n;   // chunks not yet summed, A holds the first of them
 #pragma unroll 1
-            for (int j = wr.x; j <= wr.y; ++j) {
-                const int4 sg = t_seg[j];
-                const float *p = pw + sg.x + lane;
-                const float *w = t_melw + sg.z;
-                float r0 = 0.0f, r1 = 0.0f, f0 = 0.0f, f1 = 0.0f;
-#pragma unroll 1
-                for (int ch = 0; ch < sg.y; ++ch) {
-                    const float4 wr4 = lds_f4(w), wf4 = lds_f4(w + 4);
-                    const float p0 = p[0], p1 = p[32], p2 = p[64], p3 = p[96];
-                    r0 = fmaf(wr4.x, p0, r0); f0 = fmaf(wf4.x, p0, f0);
-                    r1 = fmaf(wr4.y, p1, r1); f1 = fmaf(wf4.y, p1, f1);
-                    r0 = fmaf(wr4.z, p2, r0); f0 = fmaf(wf4.z, p2, f0);
-                    r1 = fmaf(wr4.w, p3, r1); f1 = fmaf(wf4.w, p3, f1);
-                    p += 128;
-                    w += 8;
+                while (true) {
+                    if (left > 1) load(B, rec + kRec);
+                    sum(A);
+                    if (left <= 1) break;
+                    if (left > 2) load(A, rec + 2 * kRec);
+                    sum(B);
+                    if (left <= 2) break;
+                    left -= 2;
+                    rec += 2 * kRec;
                 }
-                if (j > wr.x) {
-                    const int m = j - 1;
-                    const float lg = __logf(fmaxf(r_prev + (f0 + f1), a.log_floor));
-                    if (a.logmel) {
-                        scr[lane * a.ls + m] = lg;
-                    } else {
-                        const float *d = t_dct + m * KC;
+            }
+            if (a.logmel) {
+#pragma unroll 2
+                for (int m = wf.x; m < wf.y; ++m)
+                    scr[lane * a.ls + m] = __logf(fmaxf(est[m * 32], a.log_floor));
+            } else {
+                float c[KC];
 #pragma unroll
-                        for (int q = 0; q < KC; q += 4) {
-                            const float4 dv = lds_f4(d + q);
-                            c[q + 0] = fmaf(dv.x, lg, c[q + 0]);
-                            c[q + 1] = fmaf(dv.y, lg, c[q + 1]);
-                            c[q + 2] = fmaf(dv.z, lg, c[q + 2]);
-                            c[q + 3] = fmaf(dv.w, lg, c[q + 3]);
-                        }
+                for (int k = 0; k < KC; ++k) c[k] = 0.0f;
+#pragma unroll 2
+                for (int m = wf.x; m < wf.y; ++m) {
+                    const float lg = __logf(fmaxf(est[m * 32], a.log_floor));
+                    const float *dc = t_dct + m * KC;
+#pragma unroll
+                    for (int q = 0; q < KC; q += 4) {
+                        const float4 dv = lds_f4(dc + q);
+                        c[q + 0] = fmaf(dv.x, lg, c[q + 0]);
+                        c[q + 1] = fmaf(dv.y, lg, c[q + 1]);
+                        c[q + 2] = fmaf(dv.z, lg, c[q + 2]);
+                        c[q + 3] = fmaf(dv.w, lg, c[q + 3]);
                     }
                 }
-                r_prev = r0 + r1;
-            }
-            if (!a.logmel) {
                 float *dst = scr + (warp * 32 + lane) * PS;
 #pragma unroll
                 for (int k = 0; k < KC; ++k) dst[k] = c[k];
@@ -458,7 +499,8 @@ void variant_sizes(const SpVariant &v, int &tabf, int &half_floats)
 }
 
 // Chunks of 4 bins a segment needs.
-inline int seg_chunks(const HostTables &h, int j) { return (h.mel_bins[j + 1] - h.mel_bins[j] + 3) / 4; }
+// (an empty segment still gets one all-zero chunk: its end completes a filter)
+inline int seg_chunks(const HostTables &h, int j) { return std::max(1, (h.mel_bins[j + 1] - h.mel_bins[j] + 3) / 4); }
 
 // Contiguous split of the M filters over the warps that minimises the heaviest warp.  A warp owning
 // filters [m0, m1) walks segments m0 .. m1 (the boundary segment is walked by both neighbours).
@@ -467,8 +509,8 @@ std::vector<int> split_filters(const HostTables &h, int M)
     auto cost = [&](int m0, int m1) {   // instruction estimate of the S3 loop
         if (m1 <= m0) return 0;
         int c = 0;
-        for (int j = m0; j <= m1; ++j) c += 18 * seg_chunks(h, j) + 14;
-        return c + 30 * (m1 - m0);
+        for (int j = m0; j <= m1; ++j) c += 21 * seg_chunks(h, j) + 8;
+        return c + 28 * (m1 - m0);
     };
     const int INF = 1 << 30;
     std::vector<std::vector<int>> best(kWarps + 1, std::vector<int>(M + 1, INF)), arg(kWarps + 1, std::vector<int>(M + 1, 0));
@@ -498,11 +540,16 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
     // the run-time tables must fit next to the two halves
     int tabf = 0, half_floats = 0;
     variant_sizes(*v, tabf, half_floats);
+    const std::vector<int> beg = split_filters(h, p.n_mel);
     int chunks = 0;
-    for (int j = 0; j <= p.n_mel; ++j) chunks += seg_chunks(h, j);
-    const size_t total = tabf + 2 * kWarps + 4 * (p.n_mel + 1) + 8 * static_cast<size_t>(chunks) +
-                         static_cast<size_t>(KC) * p.n_mel + 16;
+    for (int w = 0; w < kWarps; ++w)
+        for (int j = beg[w]; beg[w + 1] > beg[w] && j <= beg[w + 1]; ++j) chunks += seg_chunks(h, j);
+    const size_t total = tabf + 4 * kWarps + kRec * static_cast<size_t>(chunks) + static_cast<size_t>(KC) * p.n_mel + 16;
     if ((total + 2 * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
+    // tail scratch (partial cepstra or log-mel rows, then the parked energies) must fit in the workspace
+    const size_t scratch = (p.output == MFCC_OUT_LOGMEL ? 32 * static_cast<size_t>(p.n_mel | 1) : kWarps * 32 * PS) +
+                           32 * static_cast<size_t>(p.n_mel);
+    if (scratch > static_cast<size_t>(v->rb / 2) * v->ra * 32 * 2) return nullptr;
     return v->name;
 }
 
@@ -541,38 +588,45 @@ int sp_prepare(mfcc_plan *plan)
     if (static_cast<int>(tab.size()) != tabf) return MFCC_ECUDA;   // layout drifted from Geo
 
     SpLayout lay{};
-    // warp -> segments
     const std::vector<int> beg = split_filters(h, M);
-    lay.wseg = static_cast<int>(tab.size());
+    // per-warp chunk records
+    std::vector<float> recs;
+    std::vector<int> wchunk;
+    const double scale = 1.0 / N;   // pass 2 leaves |X|^2
     for (int w = 0; w < kWarps; ++w) {
         const int m0 = beg[w], m1 = beg[w + 1];
-        push_int(m1 > m0 ? m0 : 1);    // empty group: first > last
-        push_int(m1 > m0 ? m1 : 0);
-    }
-    align4();
-    // segments and their chunk weights, pre-scaled by 1/N (pass 2 leaves |X|^2)
-    std::vector<float> melw;
-    lay.seg = static_cast<int>(tab.size());
-    const double scale = 1.0 / N;
-    for (int j = 0; j <= M; ++j) {
-        const int k0 = h.mel_bins[j], k1 = h.mel_bins[j + 1], chunks = seg_chunks(h, j);
-        push_int(k0 * 32);
-        push_int(chunks);
-        push_int(static_cast<int>(melw.size()));
-        push_int(0);
-        for (int c = 0; c < chunks; ++c) {
-            for (int e = 0; e < 4; ++e) {
-                const int k = k0 + 4 * c + e;
-                melw.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.rise[k]) * scale) : 0.0f);
-            }
-            for (int e = 0; e < 4; ++e) {
-                const int k = k0 + 4 * c + e;
-                melw.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.fall[k]) * scale) : 0.0f);
+        wchunk.push_back(static_cast<int>(recs.size()) / kRec);
+        for (int j = m0; m1 > m0 && j <= m1; ++j) {
+            const int k0 = h.mel_bins[j], k1 = h.mel_bins[j + 1], chunks = seg_chunks(h, j);
+            for (int c = 0; c < chunks; ++c) {
+                for (int e = 0; e < 4; ++e) {
+                    const int k = k0 + 4 * c + e;
+                    recs.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.rise[k]) * scale) : 0.0f);
+                }
+                for (int e = 0; e < 4; ++e) {
+                    const int k = k0 + 4 * c + e;
+                    recs.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.fall[k]) * scale) : 0.0f);
+                }
+                int d = std::min(k0 + 4 * c, N / 2) * 32;
+                if (c == chunks - 1) {
+                    d |= kRecEnd;
+                    if (j > m0) d |= kRecEmit | ((j - 1) << 24);
+                }
+                float f;
+                std::memcpy(&f, &d, 4);
+                recs.push_back(f);
+                recs.push_back(0.0f); recs.push_back(0.0f); recs.push_back(0.0f);
             }
         }
+        wchunk.push_back(static_cast<int>(recs.size()) / kRec);
     }
-    lay.melw = static_cast<int>(tab.size());
-    tab.insert(tab.end(), melw.begin(), melw.end());
+    lay.wchunk = static_cast<int>(tab.size());
+    for (int v : wchunk) push_int(v);
+    lay.wfilt = static_cast<int>(tab.size());
+    for (int w = 0; w < kWarps; ++w) { push_int(beg[w]); push_int(beg[w + 1]); }
+    align4();
+    lay.chunk = static_cast<int>(tab.size());
+    tab.insert(tab.end(), recs.begin(), recs.end());
     align4();
     // DCT columns, zero past n_cep
     lay.dct = static_cast<int>(tab.size());
@@ -592,6 +646,7 @@ int sp_prepare(mfcc_plan *plan)
     st->args.n_cep = p.n_cep;
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
     st->args.ls = M | 1;
+    st->args.est = p.output == MFCC_OUT_LOGMEL ? 32 * (M | 1) : kWarps * 32 * PS;
     st->args.mel_magic = (1 << 20) / M + 1;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
