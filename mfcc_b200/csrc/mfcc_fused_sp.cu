@@ -78,16 +78,12 @@ struct Geo {
 
 // Run-time part of the table blob (offsets in floats from its start).
 struct SpLayout {
-    int wchunk;   // int2 per warp: its chunk records [first, last)
+    int wseg;     // int2 per warp: its segments [first, last] (first > last: none)
     int wfilt;    // int2 per warp: its filters [first, last)
-    int chunk;    // records of kRec floats: 4 rise weights, 4 fall weights (scaled by 1/NFFT, zero past the
-                  // segment), descriptor = first bin * 32 | kRecEnd | kRecEmit | filter << 24, 3 unused
+    int seg;      // float4 per segment j: {first bin * 32 (int), width w (int), s = 1 / (w NFFT), s * w}
     int dct;      // [n_mel][KC]: DCT column of filter m, zero past n_cep
     int total;    // floats, multiple of 4
 };
-constexpr int kRec = 12;
-constexpr int kRecEnd = 1 << 16;    // last chunk of its segment
-constexpr int kRecEmit = 1 << 17;   // ... and that segment completes filter (descriptor >> 24) of this warp
 
 struct SpArgs {
     const Tile *tiles;
@@ -185,9 +181,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
     for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW, *t_twh = tab + G::T_TWH;
-    const int2 *t_wchunk = reinterpret_cast<const int2 *>(tab + a.lay.wchunk);
+    const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
     const int2 *t_wfilt = reinterpret_cast<const int2 *>(tab + a.lay.wfilt);
-    const float *t_chunk = tab + a.lay.chunk, *t_dct = tab + a.lay.dct;
+    const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
+    const float *t_dct = tab + a.lay.dct;
 
     // A tile takes the bulk-copy path when its samples are 16-byte aligned in HBM and lie inside
     // the utterance up to the staging granule (no zero fill needed).
@@ -358,54 +355,56 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         }
         half_sync(half);   // B3: P complete, workspace free
 
-        // ---- S3: the warp's filter group, as a flat list of 4-bin chunks (host-built, duplicates the
-        // segment two neighbouring groups share).  Segment j = bins [b_j, b_j+1) rises into filter j and
-        // falls out of filter j - 1, so filter m is complete at the end of segment m + 1.  The loop is
-        // software-pipelined: chunk i + 1 is loaded before chunk i is summed.  Energies are parked in the
-        // thread's own scratch words, then a second loop takes logs and either stages log-mel rows or adds
-        // the filter's DCT column into 16 running cepstra. ----
+        // ---- S3: the warp's filter group.  Segment j = bins [b_j, b_j + w) rises into filter j with weight
+        // i / w and falls out of filter j - 1 with weight (w - i) / w (i = bin - b_j), so two plain sums per
+        // segment, S = sum P and T = sum i P, give both: rise = s T, fall = s (w S - T), s = 1 / (w NFFT).
+        // No weight loads, and the P addresses do not depend on loaded data.  Filter m is complete at the end
+        // of segment m + 1; the segment two neighbouring groups share is walked by both.  Energies are parked
+        // in the thread's own scratch words, then a second loop takes logs and either stages log-mel rows or
+        // adds the filter's DCT column into 16 running cepstra. ----
         {
-            const int2 wc = t_wchunk[warp];                 // chunk records [x, y)
+            const int2 wsg = t_wseg[warp];                  // segments [x, y], empty when x > y
             const int2 wf = t_wfilt[warp];                  // filters [x, y)
             float *est = scr + a.est + lane;                // E[m] of this lane at est[m * 32]
-            const int n = wc.y - wc.x;
-            if (n > 0) {
-                // two register sets (A, B) alternate, so the prefetch needs no register moves
-                struct Chunk { float4 wr, wf; int d; float p0, p1, p2, p3; };
-                auto load = [&](Chunk &c, const float *rec) {
-                    c.wr = lds_f4(rec);
-                    c.wf = lds_f4(rec + 4);
-                    c.d = __float_as_int(rec[8]);
-                    const float *p = pw + (c.d & 0xFFFF) + lane;
-                    c.p0 = p[0]; c.p1 = p[32]; c.p2 = p[64]; c.p3 = p[96];
-                };
-                float r0 = 0.0f, r1 = 0.0f, f0 = 0.0f, f1 = 0.0f, r_prev = 0.0f;
-                auto sum = [&](const Chunk &c) {
-                    r0 = fmaf(c.wr.x, c.p0, r0); f0 = fmaf(c.wf.x, c.p0, f0);
-                    r1 = fmaf(c.wr.y, c.p1, r1); f1 = fmaf(c.wf.y, c.p1, f1);
-                    r0 = fmaf(c.wr.z, c.p2, r0); f0 = fmaf(c.wf.z, c.p2, f0);
-                    r1 = fmaf(c.wr.w, c.p3, r1); f1 = fmaf(c.wf.w, c.p3, f1);
-                    if (c.d & kRecEnd) {
-                        if (c.d & kRecEmit) est[(c.d >> 24) * 32] = r_prev + (f0 + f1);
-                        r_prev = r0 + r1;
-                        r0 = r1 = f0 = f1 = 0.0f;
-                    }
-                };
-                const float *rec = t_chunk + wc.x * kRec;
-                Chunk A, B;
-                load(A, rec);
-                int left = n;   // chunks not yet summed, A holds the first of them
+            float r_prev = 0.0f;
 #pragma unroll 1
-                while (true) {
-                    if (left > 1) load(B, rec + kRec);
-                    sum(A);
-                    if (left <= 1) break;
-                    if (left > 2) load(A, rec + 2 * kRec);
-                    sum(B);
-                    if (left <= 2) break;
-                    left -= 2;
-                    rec += 2 * kRec;
+            for (int j = wsg.x; j <= wsg.y; ++j) {
+                const float4 sg = t_seg[j];                 // {first bin * 32, w, s, s * w}
+                const float *p = pw + __float_as_int(sg.x) + lane;
+                const int w = __float_as_int(sg.y);
+                int c = w >> 2;
+                float S = 0.0f, T = 0.0f, i0 = 0.0f;
+#pragma unroll 1
+                for (; c >= 2; c -= 2) {
+                    const float a0 = p[0], a1 = p[32], a2 = p[64], a3 = p[96];
+                    const float b0 = p[128], b1 = p[160], b2 = p[192], b3 = p[224];
+                    const float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
+                    const float ta = fmaf(3.0f, a3, fmaf(2.0f, a2, a1)), tb = fmaf(3.0f, b3, fmaf(2.0f, b2, b1));
+                    T = fmaf(i0, sa, T) + ta;
+                    T = fmaf(i0 + 4.0f, sb, T) + tb;
+                    S += sa + sb;
+                    i0 += 8.0f;
+                    p += 256;
                 }
+                if (c) {
+                    const float a0 = p[0], a1 = p[32], a2 = p[64], a3 = p[96];
+                    const float sa = (a0 + a1) + (a2 + a3);
+                    T = fmaf(i0, sa, T) + fmaf(3.0f, a3, fmaf(2.0f, a2, a1));
+                    S += sa;
+                    i0 += 4.0f;
+                    p += 128;
+                }
+#pragma unroll 1
+                for (int e = w & 3; e > 0; --e) {
+                    const float a0 = p[0];
+                    T = fmaf(i0, a0, T);
+                    S += a0;
+                    i0 += 1.0f;
+                    p += 32;
+                }
+                const float r = sg.z * T;
+                if (j > wsg.x) est[(j - 1) * 32] = r_prev + fmaf(sg.w, S, -r);
+                r_prev = r;
             }
             if (a.logmel) {
 #pragma unroll 2
@@ -499,8 +498,12 @@ void variant_sizes(const SpVariant &v, int &tabf, int &half_floats)
 }
 
 // Chunks of 4 bins a segment needs.
-// (an empty segment still gets one all-zero chunk: its end completes a filter)
-inline int seg_chunks(const HostTables &h, int j) { return std::max(1, (h.mel_bins[j + 1] - h.mel_bins[j] + 3) / 4); }
+// Instruction estimate of one walk over segment j (S3): full 4-bin chunks, leftover bins, fixed part.
+inline int seg_cost(const HostTables &h, int j)
+{
+    const int w = h.mel_bins[j + 1] - h.mel_bins[j];
+    return 15 * (w / 4) + 6 * (w % 4) + 22;
+}
 
 // Contiguous split of the M filters over the warps that minimises the heaviest warp.  A warp owning
 // filters [m0, m1) walks segments m0 .. m1 (the boundary segment is walked by both neighbours).
@@ -509,7 +512,7 @@ std::vector<int> split_filters(const HostTables &h, int M)
     auto cost = [&](int m0, int m1) {   // instruction estimate of the S3 loop
         if (m1 <= m0) return 0;
         int c = 0;
-        for (int j = m0; j <= m1; ++j) c += 21 * seg_chunks(h, j) + 8;
+        for (int j = m0; j <= m1; ++j) c += seg_cost(h, j);
         return c + 28 * (m1 - m0);
     };
     const int INF = 1 << 30;
@@ -540,11 +543,7 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
     // the run-time tables must fit next to the two halves
     int tabf = 0, half_floats = 0;
     variant_sizes(*v, tabf, half_floats);
-    const std::vector<int> beg = split_filters(h, p.n_mel);
-    int chunks = 0;
-    for (int w = 0; w < kWarps; ++w)
-        for (int j = beg[w]; beg[w + 1] > beg[w] && j <= beg[w + 1]; ++j) chunks += seg_chunks(h, j);
-    const size_t total = tabf + 4 * kWarps + kRec * static_cast<size_t>(chunks) + static_cast<size_t>(KC) * p.n_mel + 16;
+    const size_t total = tabf + 4 * kWarps + 4 * static_cast<size_t>(p.n_mel + 1) + static_cast<size_t>(KC) * p.n_mel + 16;
     if ((total + 2 * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
     // tail scratch (partial cepstra or log-mel rows, then the parked energies) must fit in the workspace
     const size_t scratch = (p.output == MFCC_OUT_LOGMEL ? 32 * static_cast<size_t>(p.n_mel | 1) : kWarps * 32 * PS) +
@@ -589,44 +588,26 @@ int sp_prepare(mfcc_plan *plan)
 
     SpLayout lay{};
     const std::vector<int> beg = split_filters(h, M);
-    // per-warp chunk records
-    std::vector<float> recs;
-    std::vector<int> wchunk;
-    const double scale = 1.0 / N;   // pass 2 leaves |X|^2
+    lay.wseg = static_cast<int>(tab.size());
     for (int w = 0; w < kWarps; ++w) {
         const int m0 = beg[w], m1 = beg[w + 1];
-        wchunk.push_back(static_cast<int>(recs.size()) / kRec);
-        for (int j = m0; m1 > m0 && j <= m1; ++j) {
-            const int k0 = h.mel_bins[j], k1 = h.mel_bins[j + 1], chunks = seg_chunks(h, j);
-            for (int c = 0; c < chunks; ++c) {
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + 4 * c + e;
-                    recs.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.rise[k]) * scale) : 0.0f);
-                }
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + 4 * c + e;
-                    recs.push_back(k < k1 ? static_cast<float>(static_cast<double>(h.fall[k]) * scale) : 0.0f);
-                }
-                int d = std::min(k0 + 4 * c, N / 2) * 32;
-                if (c == chunks - 1) {
-                    d |= kRecEnd;
-                    if (j > m0) d |= kRecEmit | ((j - 1) << 24);
-                }
-                float f;
-                std::memcpy(&f, &d, 4);
-                recs.push_back(f);
-                recs.push_back(0.0f); recs.push_back(0.0f); recs.push_back(0.0f);
-            }
-        }
-        wchunk.push_back(static_cast<int>(recs.size()) / kRec);
+        push_int(m1 > m0 ? m0 : 1);
+        push_int(m1 > m0 ? m1 : 0);
     }
-    lay.wchunk = static_cast<int>(tab.size());
-    for (int v : wchunk) push_int(v);
     lay.wfilt = static_cast<int>(tab.size());
     for (int w = 0; w < kWarps; ++w) { push_int(beg[w]); push_int(beg[w + 1]); }
     align4();
-    lay.chunk = static_cast<int>(tab.size());
-    tab.insert(tab.end(), recs.begin(), recs.end());
+    // segments: the triangles are linear ramps over integer bins (mfcc_tables.cpp build_tables), so a
+    // segment is described by its first bin, its width and 1 / (w N) (pass 2 leaves |X|^2, hence the 1 / N)
+    lay.seg = static_cast<int>(tab.size());
+    for (int j = 0; j <= M; ++j) {
+        const int k0 = h.mel_bins[j], w = h.mel_bins[j + 1] - k0;
+        push_int(k0 * 32);
+        push_int(w);
+        const double sc = w > 0 ? 1.0 / (static_cast<double>(w) * N) : 0.0;
+        tab.push_back(static_cast<float>(sc));
+        tab.push_back(static_cast<float>(sc * w));
+    }
     align4();
     // DCT columns, zero past n_cep
     lay.dct = static_cast<int>(tab.size());
