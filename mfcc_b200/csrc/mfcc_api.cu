@@ -156,6 +156,9 @@ void mfcc_plan_destroy(mfcc_plan *plan)
         if (s) cudaStreamDestroy(s);
     if (plan->h2d_pcm) cudaFree(plan->h2d_pcm);
     if (plan->d2h_out) cudaFree(plan->d2h_out);
+    if (plan->d_tiles) cudaFree(plan->d_tiles);
+    if (plan->h_tiles) cudaFreeHost(plan->h_tiles);
+    if (plan->tiles_ready) cudaEventDestroy(plan->tiles_ready);
     if (plan->dev_blob) cudaFree(plan->dev_blob);
     mfcc::fused_release(plan);
     mfcc::ct_release(plan);
@@ -203,7 +206,8 @@ int64_t mfcc_plan_dct(const mfcc_plan *plan, float *dst)
     return static_cast<int64_t>(plan->host.dct.size());
 }
 
-int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out)
+// Host half of a batch: offsets -> frame rows -> tile table.  No CUDA calls.
+static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out)
 {
     if (out == nullptr) return MFCC_EINVAL;
     *out = nullptr;
@@ -243,7 +247,16 @@ int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n
     }
     b->total_frames = b->frame_offsets[n_utts];
     b->total_samples = n_utts > 0 ? b->offsets[n_utts] : 0;
+    *out = b;
+    return MFCC_OK;
+}
 
+int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out)
+{
+    mfcc_batch *b = nullptr;
+    const int rc = batch_build_host(plan, h_offsets, n_utts, &b);
+    if (out) *out = nullptr;
+    if (rc != MFCC_OK) return rc;
     DeviceGuard guard(plan->device);
     if (!guard.ok) { delete b; return MFCC_ECUDA; }
     const size_t tb = sizeof(Tile) * std::max<size_t>(b->tiles.size(), 1);
@@ -268,7 +281,7 @@ void mfcc_batch_destroy(mfcc_batch *b)
 {
     if (b == nullptr) return;
     DeviceGuard guard(b->device);
-    if (b->d_tiles) cudaFree(b->d_tiles);
+    if (b->d_tiles && !b->tiles_borrowed) cudaFree(b->d_tiles);
     if (b->d_frame_offsets) cudaFree(b->d_frame_offsets);
     delete b;
 }
@@ -317,7 +330,7 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
 {
     if (plan == nullptr || n_utts < 0) return MFCC_EINVAL;
     mfcc_batch *batch = nullptr;
-    int rc = mfcc_batch_create(plan, h_offsets, n_utts, &batch);
+    int rc = batch_build_host(plan, h_offsets, n_utts, &batch);   // no device allocation per call
     if (rc != MFCC_OK) return rc;
     if (h_frame_offsets) mfcc_batch_frame_offsets(batch, h_frame_offsets);
     if (batch->total_frames == 0) { mfcc_batch_destroy(batch); return MFCC_OK; }
@@ -326,20 +339,40 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
     DeviceGuard guard(plan->device);
     if (!guard.ok) { mfcc_batch_destroy(batch); return MFCC_ECUDA; }
     const int od = batch->out_dim;
+    const size_t tile_bytes = sizeof(Tile) * batch->tiles.size();
     rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(batch->total_samples));
     if (rc == MFCC_OK)
         rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(batch->total_frames) * od);
+    if (rc == MFCC_OK) rc = grow(&plan->d_tiles, &plan->d_tiles_bytes, tile_bytes);
+    if (rc == MFCC_OK && plan->h_tiles_bytes < tile_bytes) {   // pinned staging of the tile table
+        if (plan->h_tiles) cudaFreeHost(plan->h_tiles);
+        plan->h_tiles = nullptr;
+        plan->h_tiles_bytes = 0;
+        const size_t want = align_up(tile_bytes + tile_bytes / 8, 1 << 16);
+        if (cudaHostAlloc(&plan->h_tiles, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = MFCC_ENOMEM; }
+        else plan->h_tiles_bytes = want;
+    }
     for (auto &s : plan->streams)
         if (rc == MFCC_OK && s == nullptr && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess)
             rc = MFCC_ECUDA;
+    if (rc == MFCC_OK && plan->tiles_ready == nullptr &&
+        cudaEventCreateWithFlags(&plan->tiles_ready, cudaEventDisableTiming) != cudaSuccess)
+        rc = MFCC_ECUDA;
     if (rc != MFCC_OK) { mfcc_batch_destroy(batch); return rc; }
+    // the tile table goes up first, on stream 0; the other streams wait for it
+    std::memcpy(plan->h_tiles, batch->tiles.data(), tile_bytes);
+    batch->d_tiles = static_cast<Tile *>(plan->d_tiles);
+    batch->tiles_borrowed = true;
+    bool ok = cudaMemcpyAsync(plan->d_tiles, plan->h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[0]) ==
+              cudaSuccess;
+    ok = ok && cudaEventRecord(plan->tiles_ready, plan->streams[0]) == cudaSuccess;
+    for (int i = 1; i < 3 && ok; ++i) ok = cudaStreamWaitEvent(plan->streams[i], plan->tiles_ready, 0) == cudaSuccess;
 
     int16_t *d_pcm = static_cast<int16_t *>(plan->h2d_pcm);
     float *d_out = static_cast<float *>(plan->d2h_out);
     const int64_t chunk_samples = 16ll << 20;  // ~32 MiB of PCM per chunk
     int64_t u0 = 0;
     int c = 0;
-    bool ok = true;
     while (u0 < n_utts && ok) {
         int64_t u1 = u0 + 1;
         while (u1 < n_utts && batch->offsets[u1 + 1] - batch->offsets[u0] <= chunk_samples) ++u1;

@@ -75,6 +75,9 @@ struct mfcc_plan {
     // mfcc_compute_host state (grown on demand, reused across calls)
     void *h2d_pcm = nullptr;   size_t h2d_pcm_bytes = 0;
     void *d2h_out = nullptr;   size_t d2h_out_bytes = 0;
+    void *d_tiles = nullptr;   size_t d_tiles_bytes = 0;   // device tile table of the call in flight
+    void *h_tiles = nullptr;   size_t h_tiles_bytes = 0;   // its pinned staging copy
+    cudaEvent_t tiles_ready = nullptr;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -89,6 +92,7 @@ struct mfcc_batch {
     std::vector<mfcc::Tile> tiles;       // host copy
     std::vector<int64_t> utt_first_tile; // [n_utts + 1] tile index range per utterance
     mfcc::Tile *d_tiles = nullptr;
+    bool tiles_borrowed = false;         // d_tiles belongs to the plan (mfcc_compute_host)
     int64_t *d_frame_offsets = nullptr;
 };
 
