@@ -125,7 +125,9 @@ def run_reference(args, p, cfg_name, desc, n_utts, n_samp):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_utts = max(cores, min(n_utts, 64))
+    # one step = about 1 M frames of the workload (all of configs[1]); ~5 CPU-seconds of scalar C per step
+    frames_per_utt = max(1, 1 + (n_samp - p.frame_len) // p.hop_len)
+    sample_utts = max(cores, min(n_utts, -(-1_000_000 // frames_per_utt)))
     pcm, off = fast_fixed_batch(sample_utts, n_samp, seed=1000)
     import oracle
     oracle.mfcc_batch(p, pcm[:n_samp], off[:2], nthreads=1)
@@ -302,11 +304,11 @@ def main():
     cpu = None
     if not args.no_cpu and args.workload == "A":
         cores = os.cpu_count() or 1
-        n_s = max(cores, 32)
-        v, fr_s, dt = cpu_leg(p, pcm, off, n_s, cores)
-        v1, fr_1, dt1 = cpu_leg(p, pcm, off, 4, 1)
+        n_s = n_utts                       # the whole batch: ~5 CPU-seconds of scalar C per pass, best of 3
+        v, fr_s, dt = cpu_leg(p, pcm, off, n_s, cores, repeats=3)
+        v1, fr_1, dt1 = cpu_leg(p, pcm, off, 256, 1)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"first {n_s} utterances of the same batch ({fr_s} frames), {cores} pthreads, {dt:.2f} s",
+               "sample": f"all {n_s} utterances of the same batch ({fr_s} frames), {cores} pthreads, best of 3 passes, {dt:.2f} s; single thread: first 256 utterances, {dt1:.2f} s",
                "single_thread_value": v1,
                "note": "in-repo scalar C oracle (gcc -O2); simotin13/mfcc has no MFCC path to time"}
 
