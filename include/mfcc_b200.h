@@ -158,6 +158,25 @@ int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float
 int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst,
                      void *cuda_stream);
 
+/* Streaming / online front end.  One mfcc_stream is ONE audio stream fed in
+ * chunks of any size (host int16 PCM).  Row t it returns is bit-identical to row t of mfcc_compute over
+ * the concatenation of everything fed so far: the object carries the frame_len - hop_len unconsumed
+ * samples plus one sample of pre-emphasis history between calls, nothing else.
+ *   mfcc_stream_feed  : append n samples, write every frame that is now complete to `out`
+ *                       (capacity max_frames rows of out_dim floats; MFCC_EINVAL if too small — size it with
+ *                       mfcc_stream_pending), *n_frames = rows written.  One H2D, one kernel, one D2H.
+ *   mfcc_stream_flush : end of stream.  Under MFCC_PAD_ZERO_TAIL emits the zero-padded tail frame(s);
+ *                       under MFCC_PAD_NONE emits nothing.  Resets the stream for reuse.
+ *   mfcc_stream_pending: frames a feed of n_new more samples would return (n_new = 0 with
+ *                       at_flush != 0: frames a flush would return). */
+typedef struct mfcc_stream mfcc_stream;
+int mfcc_stream_create(mfcc_plan *plan, mfcc_stream **out);
+void mfcc_stream_destroy(mfcc_stream *stream);
+int64_t mfcc_stream_pending(const mfcc_stream *stream, int64_t n_new, int32_t at_flush);
+int mfcc_stream_feed(mfcc_stream *stream, const int16_t *pcm, int64_t n, float *out, int64_t max_frames,
+                     int64_t *n_frames);
+int mfcc_stream_flush(mfcc_stream *stream, float *out, int64_t max_frames, int64_t *n_frames);
+
 /* Pinned host memory helpers for the end-to-end path. */
 int mfcc_host_alloc(void **ptr, int64_t bytes);
 int mfcc_host_free(void *ptr);

@@ -52,6 +52,11 @@ ABI = {
     "mfcc_cmvn_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mfcc_delta_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "mfcc_decode_g711": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "mfcc_stream_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mfcc_stream_destroy": (None, [_vp]),
+    "mfcc_stream_pending": (_i64, [_vp, _i64, _i32]),
+    "mfcc_stream_feed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_i64)]),
+    "mfcc_stream_flush": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "mfcc_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "mfcc_host_free": (C.c_int, [_vp]),
     "mfcc_launch_count": (C.c_uint64, []),
@@ -241,6 +246,42 @@ class Plan:
         _check(load().mfcc_delta_batch(self._h, batch._h, feat.data_ptr(), window, d.data_ptr(),
                                        _stream_handle(stream)), "mfcc_delta_batch")
         return d
+
+
+class Stream:
+    """Online front end for one audio stream (``mfcc_stream_*``): feed chunks, get the frames that are complete."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        h = _vp()
+        _check(load().mfcc_stream_create(plan._h, C.byref(h)), "mfcc_stream_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and load is not None:
+            load().mfcc_stream_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def feed(self, pcm: np.ndarray) -> np.ndarray:
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        due = int(load().mfcc_stream_pending(self._h, pcm.size, 0))
+        if due < 0:
+            raise MfccError(due, "mfcc_stream_pending")
+        out = np.empty((due, self.plan.out_dim), np.float32)
+        got = _i64(0)
+        _check(load().mfcc_stream_feed(self._h, pcm.ctypes.data, pcm.size, out.ctypes.data, due, C.byref(got)),
+               "mfcc_stream_feed")
+        assert got.value == due
+        return out
+
+    def flush(self) -> np.ndarray:
+        due = max(int(load().mfcc_stream_pending(self._h, 0, 1)), 0)
+        out = np.empty((due, self.plan.out_dim), np.float32)
+        got = _i64(0)
+        _check(load().mfcc_stream_flush(self._h, out.ctypes.data, due, C.byref(got)), "mfcc_stream_flush")
+        return out[: got.value]
 
 
 def decode_g711(codes, alaw: bool = False, stream=None):

@@ -398,6 +398,165 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
     return MFCC_OK;
 }
 
+// ---- streaming ----
+}  // extern "C"
+
+struct mfcc_stream {
+    mfcc_plan *plan = nullptr;
+    std::vector<int16_t> buf;   // [history sample if any] + samples from the next frame's start on
+    bool has_history = false;   // buf[0] is the sample before the next frame's start
+    int64_t fed = 0;            // samples fed since the last reset
+    int64_t emitted = 0;        // frames returned since the last reset
+    int64_t skip = 0;           // incoming samples to drop first (hop_len > frame_len: gaps between frames)
+};
+
+namespace {
+
+// Frames of buf that are due: complete frames, or at flush the zero-padded tail the offline count implies.
+int64_t stream_due(const mfcc_stream *st, int64_t n_new, bool at_flush)
+{
+    const mfcc_params &p = st->plan->p;
+    const int64_t total = st->fed + n_new;
+    mfcc_params q = p;
+    q.pad_mode = at_flush ? p.pad_mode : MFCC_PAD_NONE;
+    return mfcc_num_frames(&q, total) - st->emitted;
+}
+
+// One utterance whose first `lead` samples are pre-emphasis history only; exactly n_frames frames
+// (zero fill past the end, as MFCC_PAD_ZERO_TAIL does).  H2D, kernel, D2H on the plan's stream 0.
+int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
+{
+    mfcc_plan *plan = st->plan;
+    const mfcc_params &p = plan->p;
+    const int lead = st->has_history ? 1 : 0;
+    const int64_t len = static_cast<int64_t>(st->buf.size());
+    const int od = plan->host.out_dim;
+    std::vector<Tile> tiles;
+    for (int64_t f = 0; f < n_frames; f += mfcc::kTileFrames) {
+        Tile t;
+        t.utt_begin = 0;
+        t.utt_end = len;
+        t.first_sample = lead + f * p.hop_len;
+        t.out_row = f;
+        t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, n_frames - f));
+        t.reserved = 0;
+        tiles.push_back(t);
+    }
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    int rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(len));
+    if (rc == MFCC_OK) rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(n_frames) * od);
+    if (rc == MFCC_OK) rc = grow(&plan->d_tiles, &plan->d_tiles_bytes, sizeof(Tile) * tiles.size());
+    if (rc == MFCC_OK && plan->streams[0] == nullptr &&
+        cudaStreamCreateWithFlags(&plan->streams[0], cudaStreamNonBlocking) != cudaSuccess)
+        rc = MFCC_ECUDA;
+    if (rc != MFCC_OK) return rc;
+    cudaStream_t s = plan->streams[0];
+    mfcc_batch b;
+    b.device = plan->device;
+    b.out_dim = od;
+    b.total_samples = len;
+    b.total_frames = n_frames;
+    b.d_tiles = static_cast<Tile *>(plan->d_tiles);
+    b.tiles_borrowed = true;
+    bool ok = cudaMemcpyAsync(plan->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice, s) ==
+              cudaSuccess;
+    ok = ok && cudaMemcpyAsync(plan->h2d_pcm, st->buf.data(), sizeof(int16_t) * len, cudaMemcpyHostToDevice, s) ==
+                   cudaSuccess;
+    ok = ok && compute_batch_impl<int16_t>(plan, &b, static_cast<const int16_t *>(plan->h2d_pcm),
+                                           static_cast<float *>(plan->d2h_out), 0,
+                                           static_cast<int64_t>(tiles.size()), s) == MFCC_OK;
+    ok = ok && cudaMemcpyAsync(out, plan->d2h_out, sizeof(float) * n_frames * od, cudaMemcpyDeviceToHost, s) ==
+                   cudaSuccess;
+    ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return MFCC_ECUDA; }
+    return MFCC_OK;
+}
+
+// Drop what the emitted frames consumed: keep one history sample and everything from the next frame's start.
+void stream_advance(mfcc_stream *st, int64_t n_frames)
+{
+    if (n_frames <= 0) return;
+    const int lead = st->has_history ? 1 : 0;
+    const int64_t next = lead + n_frames * st->plan->p.hop_len;   // index in buf of the next frame's start
+    const int64_t len = static_cast<int64_t>(st->buf.size());
+    if (next - 1 >= len) {          // the next frame's history sample has not arrived yet (hop > frame)
+        st->skip = next - 1 - len;
+        st->buf.clear();
+        st->has_history = true;     // the first sample kept after the skip is that history sample
+    } else {
+        st->buf.erase(st->buf.begin(), st->buf.begin() + (next - 1));
+        st->has_history = true;
+    }
+    st->emitted += n_frames;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mfcc_stream_create(mfcc_plan *plan, mfcc_stream **out)
+{
+    if (out == nullptr) return MFCC_EINVAL;
+    *out = nullptr;
+    if (plan == nullptr) return MFCC_EINVAL;
+    mfcc_stream *st = new (std::nothrow) mfcc_stream();
+    if (st == nullptr) return MFCC_ENOMEM;
+    st->plan = plan;
+    *out = st;
+    return MFCC_OK;
+}
+
+void mfcc_stream_destroy(mfcc_stream *st) { delete st; }
+
+int64_t mfcc_stream_pending(const mfcc_stream *st, int64_t n_new, int32_t at_flush)
+{
+    if (st == nullptr || n_new < 0) return MFCC_EINVAL;
+    return stream_due(st, n_new, at_flush != 0);
+}
+
+int mfcc_stream_feed(mfcc_stream *st, const int16_t *pcm, int64_t n, float *out, int64_t max_frames,
+                     int64_t *n_frames)
+{
+    if (st == nullptr || n < 0 || (n > 0 && pcm == nullptr)) return MFCC_EINVAL;
+    const int64_t due = stream_due(st, n, false);
+    if (due > max_frames || (due > 0 && out == nullptr)) return MFCC_EINVAL;
+    const int64_t drop = std::min(st->skip, n);
+    try {
+        st->buf.insert(st->buf.end(), pcm + drop, pcm + n);
+    } catch (const std::bad_alloc &) {
+        return MFCC_ENOMEM;
+    }
+    st->skip -= drop;
+    st->fed += n;
+    if (n_frames) *n_frames = 0;
+    if (due <= 0) return MFCC_OK;
+    const int rc = stream_run(st, due, out);
+    if (rc != MFCC_OK) return rc;
+    stream_advance(st, due);
+    if (n_frames) *n_frames = due;
+    return MFCC_OK;
+}
+
+int mfcc_stream_flush(mfcc_stream *st, float *out, int64_t max_frames, int64_t *n_frames)
+{
+    if (st == nullptr) return MFCC_EINVAL;
+    const int64_t due = stream_due(st, 0, true);
+    if (due > max_frames || (due > 0 && out == nullptr)) return MFCC_EINVAL;
+    if (n_frames) *n_frames = 0;
+    int rc = MFCC_OK;
+    if (due > 0) {
+        rc = stream_run(st, due, out);
+        if (rc == MFCC_OK && n_frames) *n_frames = due;
+    }
+    st->buf.clear();
+    st->has_history = false;
+    st->fed = 0;
+    st->emitted = 0;
+    st->skip = 0;
+    return rc;
+}
+
 int mfcc_compute(mfcc_plan *plan, const int16_t *pcm, int64_t n_samples, float *out, int64_t *n_frames)
 {
     if (plan == nullptr || n_samples < 0) return MFCC_EINVAL;

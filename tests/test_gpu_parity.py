@@ -267,3 +267,31 @@ def test_cmvn_delta_g711_on_device():
         for view in (codes, codes[1:]):   # aligned and misaligned starts
             got = api.decode_g711(torch.from_numpy(view.copy()).cuda()[...], alaw)
             assert np.array_equal(got.cpu().numpy(), oracle.decode_g711(view, alaw))   # bit-exact
+
+
+def test_streaming_feed_is_bit_identical_to_offline():
+    """mfcc_stream_*: any chunking of a clip gives the rows of the one-shot call, bit for bit;
+    zero-tail frames appear at flush; the object is reusable after flush."""
+    rng = np.random.default_rng(41)
+    for p in (config_a(), config_b(), config_a().copy(pad_mode=PAD_ZERO_TAIL), config_c(),
+              config_a().copy(hop_len=450)):      # hop > frame: gaps between frames
+        plan = api.Plan(p)
+        x = noise_utterance(5 * p.sample_rate // 2 + 123, seed=42)
+        full = plan.compute(x)
+        st = api.Stream(plan)
+        for trial in range(2):
+            rows, pos = [], 0
+            while pos < x.size:
+                n = int(rng.choice([1, 7, p.hop_len - 1, p.hop_len, p.frame_len, 1000, 4096, 40000]))
+                rows.append(st.feed(x[pos:pos + n]))
+                pos += n
+            rows.append(st.flush())
+            got = np.concatenate(rows)
+            assert got.shape == full.shape, (got.shape, full.shape, p.pad_mode)
+            assert np.array_equal(got, full)
+        # a stream shorter than one frame: nothing under PAD_NONE, one padded frame under ZERO_TAIL
+        assert st.feed(x[:10]).shape[0] == 0
+        tail = st.flush()
+        assert tail.shape[0] == (1 if p.pad_mode == PAD_ZERO_TAIL else 0)
+        if tail.shape[0]:
+            assert np.array_equal(tail, plan.compute(x[:10]))
