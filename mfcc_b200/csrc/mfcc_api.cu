@@ -83,6 +83,8 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     plan->fused = mfcc::find_fused(plan->p);
     const char *sp_name = (kernel == MFCC_KERNEL_AUTO || kernel == MFCC_KERNEL_FUSED)
                               ? mfcc::sp_match(plan->p, plan->host) : nullptr;
+    if (sp_name == nullptr && (kernel == MFCC_KERNEL_AUTO || kernel == MFCC_KERNEL_FUSED))
+        sp_name = mfcc::wide_match(plan->p, plan->host);
     const char *ct_name = kernel == MFCC_KERNEL_FUSED_RT ? nullptr : mfcc::ct_match(plan->p);
     const bool want_fused = kernel != MFCC_KERNEL_GENERIC;
     if (kernel >= MFCC_KERNEL_FUSED && plan->fused == nullptr && ct_name == nullptr && sp_name == nullptr) {
@@ -131,9 +133,10 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
 
     if (plan->kernel == MFCC_KERNEL_FUSED && sp_name != nullptr) {
         rc = mfcc::sp_prepare(plan);
+        if (rc == MFCC_ENOTSUP) rc = mfcc::wide_prepare(plan);
         if (rc != MFCC_OK && rc != MFCC_ENOTSUP) { mfcc_plan_destroy(plan); return rc; }
     }
-    if (plan->kernel == MFCC_KERNEL_FUSED && plan->sp_state == nullptr) {
+    if (plan->kernel == MFCC_KERNEL_FUSED && plan->sp_state == nullptr && plan->wide_state == nullptr) {
         rc = ct_name ? mfcc::ct_prepare(plan) : MFCC_ENOTSUP;
         if (rc == MFCC_ENOTSUP) {   // no compile-time variant (or its tables do not fit): runtime-geometry kernel
             if (plan->fused != nullptr) rc = mfcc::fused_prepare(plan);
@@ -142,7 +145,7 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
         if (rc != MFCC_OK) { mfcc_plan_destroy(plan); return rc; }
     }
     plan->kernel_name = plan->kernel != MFCC_KERNEL_FUSED ? "generic_radix2"
-                        : plan->sp_state ? sp_name
+                        : (plan->sp_state || plan->wide_state) ? sp_name
                         : plan->ct_state ? ct_name : mfcc::fused_name(plan->fused);
     *out = plan;
     return MFCC_OK;
@@ -163,6 +166,7 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     mfcc::fused_release(plan);
     mfcc::ct_release(plan);
     mfcc::sp_release(plan);
+    mfcc::wide_release(plan);
     delete plan;
 }
 

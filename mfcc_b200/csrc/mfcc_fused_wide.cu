@@ -1,0 +1,546 @@
+// mfcc_fused_wide.cu — fused tile kernel for the LARGE transform (BASELINE.json configs[3]: 48 kHz,
+// 1200-sample frames, 2048-point FFT, 80 mel bands, 40 cepstra): the "large-FFT, smem-pressure path".
+//
+// A 2048-point frame needs 8 KB of f32 workspace between the two FFT passes, so the 32-frames-per-tile,
+// lane = frame layout of mfcc_fused_sp.cu (64 KB for 512 points) cannot hold it.  Here a tile is F = 8
+// frames and a warp carries 4 work items at once: lane = sub * 8 + frame, sub = 0 .. 3.  Constants a
+// butterfly needs are then uniform per quarter-warp instead of per warp (shared-memory loads with 4
+// distinct addresses), every array is [...][8 frames], and the layouts are padded so that the four
+// quarter-warps of a load or store fall into different banks:
+//   staged  lane stride HOP + 4 words (= 4 mod 32): 8 frames x 2 column pairs x 8 bytes per half-warp
+//   ws      [row k1 - 1][column, bit 0 flipped when bit 1 is set][8] float2, rows padded by 16 words
+//   P       [bin][8]: four consecutive bins per warp store
+// One CTA per SM = two independent halves of 4 warps (named barriers), 16 work slots each:
+//   S0 stage     PCM -> f32 -> pre-emphasis -> staged (each sample read from HBM once per tile)
+//   S1 pass 1    16 slots = the 16 column pairs: windowed REAL DFT-64 over b (38 live rows), twiddle
+//   S2 pass 2    32 rows k1 = 1 .. 32 through a complex DFT-32, two rounds of 16 slots; row 0 (real)
+//                through a real DFT-32 by slot 0; |X|^2 -> P
+//   S3 tail      16 filter groups (one per slot): S/T sums per segment -> log -> partial DCT (40 cepstra)
+//   S4           add the 16 partial cepstra per frame, store
+// N = RB * RA = 64 * 32, n = a + 32 b, k = k1 + 64 k2 (mfcc_rfft.cuh; tests/codelets checks the data flow).
+//
+// No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mfcc_rfft.cuh"
+#include "mfcc_host.h"
+
+namespace mfcc {
+
+namespace {
+
+constexpr int F = 8;                      // frames per tile
+constexpr int SUBS = 32 / F;              // work items per warp
+constexpr int kWarps = 4;                 // per half
+constexpr int kSlots = kWarps * SUBS;     // 16
+constexpr int kHalfThreads = kWarps * 32;
+constexpr int kThreads = 2 * kHalfThreads;
+constexpr int kPad = 4;
+constexpr int KC = 40;                    // cepstra accumulated per frame (n_cep <= KC)
+constexpr int PS = KC + 1;
+constexpr size_t kSmemMax = 227 * 1024;
+
+template <int L_, int HOP_>
+struct Geo {
+    static constexpr int L = L_, HOP = HOP_, RB = 64, RA = 32;
+    static constexpr int NFFT = RB * RA, NB = NFFT / 2 + 1, H = RB / 2;
+    static constexpr int NZ = (L + RA - 1) / RA;
+    static constexpr int NZP = (NZ + 1) / 2 * 2;
+    static constexpr int STRIDE = HOP + kPad;
+    static constexpr int padded(int i) { return i + kPad * (i / HOP); }
+    static constexpr int SLACK = RA * NZ - L;
+    static constexpr int tceil(int n_frames) { return ((n_frames - 1) * HOP + L + SLACK + 7) / 8 * 8; }
+    static constexpr int TCEIL = tceil(F);
+    static constexpr int STAGED = padded(TCEIL) + 8;
+    static constexpr int PW = (NB + 7) * F;                 // 7 zeroed slack rows for the tail's 4-bin reads
+    static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
+    static constexpr int WSROW = RA * F * 2 + 16;           // floats per complex row, padded
+    static constexpr int WS = H * WSROW;                    // rows k1 = 1 .. H
+    static constexpr int R0 = RA * F;                       // row 0 (real)
+    static constexpr int HALF = UNION + WS + R0;
+    static constexpr int T_WIN = 0;                         // [RA/2][NZP] float2
+    static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;   // [RA][H] float2: W_N^(a k1), k1 = 1 .. H at slot k1 - 1
+    static constexpr int TABF = T_TW + RA * H * 2;
+    static constexpr int pcol(int c) { return c ^ ((c >> 1) & 1); }
+    static_assert(STRIDE % 32 == 4, "quarter-warp bank separation of the staged tile");
+    static_assert(HOP % 8 == 0 && HOP % RA == 0, "chunks and column pairs must not straddle a hop block");
+    static_assert(RA / 2 == kSlots, "one column pair per slot");
+    static_assert(H == 2 * kSlots, "two rounds of complex rows");
+    static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
+    static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0, "16-byte aligned regions");
+    static_assert(kSlots * F * PS + 128 * F <= WS, "tail scratch must fit in the workspace");
+};
+
+struct WideLayout {
+    int wseg;     // int2 per slot: its segments [first, last] (first > last: none)
+    int wfilt;    // int2 per slot: its filters [first, last)
+    int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), s * w}
+    int dct;      // [ceil(n_mel / 2)][KC]: DCT column of filter m < ceil(n_mel/2); column n_mel-1-m is (-1)^k times it
+    int total;
+};
+
+struct WideArgs {
+    const Tile *tiles;
+    int64_t n_tiles;
+    float *out;
+    const float *tab;
+    WideLayout lay;
+    int n_mel, n_cep, logmel;
+    int ls, est, mel_magic, half_mel;
+    float preemph, log_floor;
+};
+
+__device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+__device__ __forceinline__ float4 lds_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
+{
+    const uint32_t lo = ((w & 0xFFFFu) ^ 0x4B008000u);
+    const uint32_t hi = ((w >> 16) ^ 0x4B008000u);
+    return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
+}
+__device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ void half_sync(int half)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kHalfThreads) : "memory");
+}
+__device__ __forceinline__ float pwr(const rf::cplx &z) { return fmaf(z.re, z.re, z.im * z.im); }
+
+template <typename PcmT, int L_, int HOP_>
+__global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__restrict__ pcm, const WideArgs a)
+{
+    using G = Geo<L_, HOP_>;
+    constexpr int HOP = G::HOP, RB = G::RB, RA = G::RA, STRIDE = G::STRIDE, H = G::H, NZ = G::NZ;
+    extern __shared__ __align__(16) float smem[];
+    const int half = threadIdx.x / kHalfThreads, tid = threadIdx.x % kHalfThreads;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int f = lane % F, sub = lane / F, slot = warp * SUBS + sub;
+
+    float *tab = smem;
+    float *mine = smem + a.lay.total + half * G::HALF;
+    float *staged = mine;                 // S0-S1
+    float *pw = staged;                   // S2-S3 (aliases staged)
+    float *ws = mine + G::UNION;          // complex rows
+    float *r0row = ws + G::WS;            // row 0 (real) [RA][F]
+    float *scr = ws;                      // tail scratch (aliases ws)
+
+    for (int i = G::NB * F + tid; i < G::PW; i += kHalfThreads) pw[i] = 0.0f;   // slack rows stay zero
+    for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
+        *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
+    const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW;
+    const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
+    const int2 *t_wfilt = reinterpret_cast<const int2 *>(tab + a.lay.wfilt);
+    const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
+    const float *t_dct = tab + a.lay.dct;
+    __syncthreads();
+
+    // The batch's tile table holds 32-frame tiles (mfcc_host.h kTileFrames); a work unit here is a quarter of one.
+    constexpr int kQ = kTileFrames / F;
+    const int64_t n_units = a.n_tiles * kQ;
+    const int64_t first = 2 * static_cast<int64_t>(blockIdx.x) + half, step = 2 * static_cast<int64_t>(gridDim.x);
+    Tile nt{};
+    if (first < n_units) nt = a.tiles[first / kQ];
+    for (int64_t u = first; u < n_units; u += step) {
+        Tile tile = nt;
+        if (u + step < n_units) nt = a.tiles[(u + step) / kQ];   // arrives during the unit
+        const int q = static_cast<int>(u % kQ);
+        const int n_frames = min(F, tile.n_frames - q * F);
+        if (n_frames <= 0) continue;                              // (uniform for the half: no barrier is skipped by part of it)
+        tile.first_sample += static_cast<int64_t>(q) * F * HOP;
+        tile.out_row += q * F;
+        const int tc = G::tceil(n_frames);
+
+        // ---- S0: stage y[s] = x[s] - a x[s-1] once per sample, padded by kPad words per hop ----
+        {
+            bool fast = false;
+            if constexpr (sizeof(PcmT) == 2)
+                fast = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((tile.first_sample & 7) == 0) &&
+                       (tile.utt_end - tile.first_sample >= tc);
+            if (fast) {
+                const PcmT *x = pcm + tile.first_sample;
+                const bool at_start = tile.first_sample == tile.utt_begin;
+                const float na = -a.preemph;
+                for (int c = tid; c < (tc >> 3); c += kHalfThreads) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(x) + c);
+                    float xp = 0.0f;
+                    if (c > 0 || !at_start) xp = to_f32(x[8 * c - 1]);
+                    const float2 x01 = s16x2_to_f32(q.x), x23 = s16x2_to_f32(q.y);
+                    const float2 x45 = s16x2_to_f32(q.z), x67 = s16x2_to_f32(q.w);
+                    float *dst = staged + 8 * c + kPad * (c / (HOP / 8));
+                    *reinterpret_cast<float4 *>(dst) = make_float4(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y),
+                                                                    fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
+                    *reinterpret_cast<float4 *>(dst + 4) = make_float4(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y),
+                                                                        fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                }
+            } else {
+                const int64_t room_lo = tile.first_sample - tile.utt_begin;
+                const int64_t room_hi = tile.utt_end - tile.first_sample;
+                const PcmT *x = pcm + tile.first_sample;
+                for (int i = tid; i < tc; i += kHalfThreads) {
+                    float y = 0.0f;
+                    if (i < room_hi) {
+                        const float x0 = to_f32(x[i]);
+                        const float x1 = (i > -room_lo) ? to_f32(x[i - 1]) : 0.0f;
+                        y = fmaf(-a.preemph, x1, x0);
+                    }
+                    staged[G::padded(i)] = y;
+                }
+            }
+        }
+        half_sync(half);   // B1: staged complete; previous tile's scratch free
+
+        // ---- S1: pass 1.  Slot = column pair (a, a + 1): windowed real DFT-64 over b, inter-pass twiddle ----
+        {
+            const int pr = slot;
+            const float *base = staged + f * STRIDE + 2 * pr;
+            const float *wrow = t_win + pr * (2 * G::NZP);
+            float2 in[NZ];
+#pragma unroll
+            for (int b = 0; b < NZ; b += 2) {
+                const float4 w = lds_f4(wrow + 2 * b);
+                const float2 y0 = lds_f2(base + G::padded(RA * b));
+                in[b] = make_float2(y0.x * w.x, y0.y * w.y);
+                if (b + 1 < NZ) {
+                    const float2 y1 = lds_f2(base + G::padded(RA * (b + 1)));
+                    in[b + 1] = make_float2(y1.x * w.z, y1.y * w.w);
+                }
+            }
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                const int col = 2 * pr + hh;
+                float x[RB];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) x[b] = b < NZ ? (hh ? in[b < NZ ? b : 0].y : in[b < NZ ? b : 0].x) : 0.0f;
+                rf::cplx X[H + 1];
+                rf::rdft64<NZ>(x, X);
+                r0row[col * F + f] = X[0].re;
+                float *wsa = ws + ((col ^ ((col >> 1) & 1)) * F + f) * 2;   // column slot pcol(col)
+                const float *trow = t_tw + col * (2 * H);
+#pragma unroll
+                for (int k1 = 1; k1 <= H; k1 += 2) {
+                    const float4 tw = lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
+                    const rf::cplx v = rf::cmulc(X[k1], tw.x, tw.y);
+                    *reinterpret_cast<float2 *>(wsa + (k1 - 1) * G::WSROW) = make_float2(v.re, v.im);
+                    const rf::cplx u = rf::cmulc(X[k1 + 1], tw.z, tw.w);
+                    *reinterpret_cast<float2 *>(wsa + k1 * G::WSROW) = make_float2(u.re, u.im);
+                }
+            }
+        }
+        half_sync(half);   // B2
+
+        // ---- S2: pass 2.  Item = row k1 = 1 .. 32: complex DFT-32 over a gives bins k1 + 64 k2; power ----
+        {
+#pragma unroll 1
+            for (int round = 0; round < 2; ++round) {
+                const int k1 = round * kSlots + slot + 1;
+                const float *row = ws + (k1 - 1) * G::WSROW + f * 2;
+                rf::cplx z[RA];
+#pragma unroll
+                for (int c = 0; c < RA; ++c) {
+                    const float2 p = lds_f2(row + G::pcol(c) * F * 2);
+                    z[c] = rf::cplx{p.x, p.y};
+                }
+                rf::cdft32(z);
+                float *p_lo = pw + k1 * F + f;                    // bins k1 + 64 k2, k2 < 16
+#pragma unroll
+                for (int k2 = 0; k2 < RA / 2; ++k2) p_lo[RB * k2 * F] = pwr(z[k2]);
+                if (k1 < H) {                                     // row 32 mirrors onto itself
+                    float *p_hi = pw + (RB - k1) * F + f;         // N - k = (64 - k1) + 64 (31 - k2)
+#pragma unroll
+                    for (int k2 = RA / 2; k2 < RA; ++k2) p_hi[RB * (RA - 1 - k2) * F] = pwr(z[k2]);
+                }
+            }
+            if (slot == 0) {
+                // row 0 is real: real DFT-32 over a gives bins 64 k2, k2 = 0 .. 16
+                float x[RA];
+#pragma unroll
+                for (int c = 0; c < RA; ++c) x[c] = r0row[c * F + f];
+                rf::cplx X0[RA / 2 + 1];
+                rf::rdft32<32>(x, X0);
+                pw[f] = X0[0].re * X0[0].re;
+                pw[RB * (RA / 2) * F + f] = X0[RA / 2].re * X0[RA / 2].re;
+#pragma unroll
+                for (int k2 = 1; k2 < RA / 2; ++k2) pw[RB * k2 * F + f] = pwr(X0[k2]);
+            }
+        }
+        half_sync(half);   // B3: P complete, workspace free
+
+        // ---- S3: the slot's filter group (see mfcc_fused_sp.cu S3): per segment S = sum P, T = sum i P give
+        // rise = s T and fall = s (w S - T); filter m completes at the end of segment m + 1; then log and the
+        // filter's DCT column into 40 running cepstra.  Loop counts differ between the four slots of a warp:
+        // the warp runs the longest of them. ----
+        {
+            const int2 wsg = t_wseg[slot];
+            const int2 wf = t_wfilt[slot];
+            float *est = scr + a.est + f;                   // E[m] of this frame at est[m * F]
+            float r_prev = 0.0f;
+#pragma unroll 1
+            for (int j = wsg.x; j <= wsg.y; ++j) {
+                const float4 sg = t_seg[j];
+                const float *p = pw + __float_as_int(sg.x) + f;
+                const int w = __float_as_int(sg.y);
+                float S = 0.0f, T = 0.0f, i0 = 0.0f;
+#pragma unroll 1
+                for (int c = w >> 2; c > 0; --c) {
+                    const float a0 = p[0], a1 = p[F], a2 = p[2 * F], a3 = p[3 * F];
+                    const float sa = (a0 + a1) + (a2 + a3);
+                    T = fmaf(i0, sa, T) + fmaf(3.0f, a3, fmaf(2.0f, a2, a1));
+                    S += sa;
+                    i0 += 4.0f;
+                    p += 4 * F;
+                }
+#pragma unroll 1
+                for (int e = w & 3; e > 0; --e) {
+                    const float a0 = p[0];
+                    T = fmaf(i0, a0, T);
+                    S += a0;
+                    i0 += 1.0f;
+                    p += F;
+                }
+                const float r = sg.z * T;
+                if (j > wsg.x) est[(j - 1) * F] = r_prev + fmaf(sg.w, S, -r);
+                r_prev = r;
+            }
+            if (a.logmel) {
+#pragma unroll 1
+                for (int m = wf.x; m < wf.y; ++m) scr[f * a.ls + m] = __logf(fmaxf(est[m * F], a.log_floor));
+            } else {
+                float c[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) c[k] = 0.0f;
+#pragma unroll 1
+                for (int m = wf.x; m < wf.y; ++m) {
+                    const float lg = __logf(fmaxf(est[m * F], a.log_floor));
+                    const bool mirror = m >= a.half_mel;
+                    const float lo = mirror ? -lg : lg;          // odd cepstra change sign under m -> M - 1 - m
+                    const float *dc = t_dct + (mirror ? a.n_mel - 1 - m : m) * KC;
+#pragma unroll
+                    for (int q = 0; q < KC; q += 4) {
+                        const float4 dv = lds_f4(dc + q);
+                        c[q + 0] = fmaf(dv.x, lg, c[q + 0]);
+                        c[q + 1] = fmaf(dv.y, lo, c[q + 1]);
+                        c[q + 2] = fmaf(dv.z, lg, c[q + 2]);
+                        c[q + 3] = fmaf(dv.w, lo, c[q + 3]);
+                    }
+                }
+                float *dst = scr + (slot * F + f) * PS;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) dst[k] = c[k];
+            }
+        }
+        half_sync(half);   // B4
+
+        // ---- S4: add the 16 partial cepstra per frame and store (64 lanes per frame, n_cep of them live) ----
+        if (a.logmel) {
+            const int M = a.n_mel, total = n_frames * M;
+            float *o = a.out + tile.out_row * M;
+            for (int i = tid; i < total; i += kHalfThreads) {
+                const int fr = (i * a.mel_magic) >> 20, m = i - fr * M;
+                o[i] = scr[fr * a.ls + m];
+            }
+        } else {
+            const int k = tid & 63;
+#pragma unroll 1
+            for (int fr = tid >> 6; fr < n_frames; fr += kHalfThreads / 64) {
+                if (k < a.n_cep) {
+                    const float *src = scr + fr * PS + k;
+                    float s = src[0];
+#pragma unroll
+                    for (int sl = 1; sl < kSlots; ++sl) s += src[sl * F * PS];
+                    a.out[(tile.out_row + fr) * a.n_cep + k] = s;
+                }
+            }
+        }
+        // next S0 writes `staged` (nobody reads P any more); the scratch is next written by S1, after B1
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+constexpr int kL = 1200, kHop = 480;
+using G0 = Geo<kL, kHop>;
+
+struct WideState {
+    WideArgs args{};
+    float *d_tab = nullptr;
+    size_t smem = 0;
+    int sm_count = 0;
+};
+
+inline int seg_cost(const HostTables &h, int j)
+{
+    const int w = h.mel_bins[j + 1] - h.mel_bins[j];
+    return 15 * (w / 4) + 6 * (w % 4) + 22;
+}
+
+std::vector<int> split_filters(const HostTables &h, int M, int filter_cost)
+{
+    auto cost = [&](int m0, int m1) {
+        if (m1 <= m0) return 0;
+        int c = 0;
+        for (int j = m0; j <= m1; ++j) c += seg_cost(h, j);
+        return c + filter_cost * (m1 - m0);
+    };
+    const int INF = 1 << 30;
+    std::vector<std::vector<int>> best(kSlots + 1, std::vector<int>(M + 1, INF)), arg(kSlots + 1, std::vector<int>(M + 1, 0));
+    best[0][0] = 0;
+    for (int w = 1; w <= kSlots; ++w)
+        for (int m1 = 0; m1 <= M; ++m1)
+            for (int m0 = 0; m0 <= m1; ++m0) {
+                if (best[w - 1][m0] == INF) continue;
+                const int v = std::max(best[w - 1][m0], cost(m0, m1));
+                if (v < best[w][m1]) { best[w][m1] = v; arg[w][m1] = m0; }
+            }
+    std::vector<int> beg(kSlots + 1, 0);
+    beg[kSlots] = M;
+    for (int w = kSlots; w >= 1; --w) beg[w - 1] = arg[w][beg[w]];
+    return beg;
+}
+
+size_t table_floats(const mfcc_params &p)
+{
+    return G0::TABF + 4 * kSlots + 4 * static_cast<size_t>(p.n_mel + 1) + static_cast<size_t>(KC) * ((p.n_mel + 1) / 2) + 16;
+}
+
+}  // namespace
+
+const char *wide_match(const mfcc_params &p, const HostTables &h)
+{
+    if (p.frame_len != kL || p.hop_len != kHop || p.nfft != G0::NFFT) return nullptr;
+    if (p.output == MFCC_OUT_CEPSTRA && p.n_cep > KC) return nullptr;
+    for (int j = 0; j + 1 < static_cast<int>(h.mel_bins.size()); ++j)
+        if (h.mel_bins[j + 1] < h.mel_bins[j]) return nullptr;
+    if ((table_floats(p) + 2 * static_cast<size_t>(G0::HALF)) * sizeof(float) > kSmemMax) return nullptr;
+    const size_t scratch = (p.output == MFCC_OUT_LOGMEL ? F * static_cast<size_t>(p.n_mel | 1) : kSlots * F * PS) +
+                           F * static_cast<size_t>(p.n_mel);
+    if (scratch > static_cast<size_t>(G0::WS)) return nullptr;
+    return "fused_wide_tile8_L1200_H480_real64x32";
+}
+
+int wide_prepare(mfcc_plan *plan)
+{
+    const mfcc_params &p = plan->p;
+    const HostTables &h = plan->host;
+    if (wide_match(p, h) == nullptr) return MFCC_ENOTSUP;
+    constexpr int RA = G0::RA, N = G0::NFFT, H = G0::H, NZ = G0::NZ, NZP = G0::NZP;
+    const int M = p.n_mel;
+    std::vector<float> tab;
+    auto align4 = [&]() { while (tab.size() % 4) tab.push_back(0.0f); };
+    auto push_int = [&](int v) { float fl; std::memcpy(&fl, &v, 4); tab.push_back(fl); };
+    for (int pr = 0; pr < RA / 2; ++pr)
+        for (int b = 0; b < NZP; ++b)
+            for (int e = 0; e < 2; ++e) {
+                const int i = 2 * pr + e + RA * b;
+                tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
+            }
+    for (int col = 0; col < RA; ++col)
+        for (int sl = 0; sl < H; ++sl) {
+            const double ang = -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N;
+            tab.push_back(static_cast<float>(std::cos(ang)));
+            tab.push_back(static_cast<float>(std::sin(ang)));
+        }
+    if (static_cast<int>(tab.size()) != G0::TABF) return MFCC_ECUDA;
+
+    WideLayout lay{};
+    const std::vector<int> beg = split_filters(h, M, p.output == MFCC_OUT_LOGMEL ? 10 : 60);
+    lay.wseg = static_cast<int>(tab.size());
+    for (int w = 0; w < kSlots; ++w) {
+        const int m0 = beg[w], m1 = beg[w + 1];
+        push_int(m1 > m0 ? m0 : 1);
+        push_int(m1 > m0 ? m1 : 0);
+    }
+    lay.wfilt = static_cast<int>(tab.size());
+    for (int w = 0; w < kSlots; ++w) { push_int(beg[w]); push_int(beg[w + 1]); }
+    align4();
+    lay.seg = static_cast<int>(tab.size());
+    for (int j = 0; j <= M; ++j) {
+        const int k0 = h.mel_bins[j], w = h.mel_bins[j + 1] - k0;
+        push_int(k0 * F);
+        push_int(w);
+        const double sc = w > 0 ? 1.0 / (static_cast<double>(w) * N) : 0.0;
+        tab.push_back(static_cast<float>(sc));
+        tab.push_back(static_cast<float>(sc * w));
+    }
+    align4();
+    const int half_mel = (M + 1) / 2;
+    lay.dct = static_cast<int>(tab.size());
+    for (int m = 0; m < half_mel; ++m)
+        for (int k = 0; k < KC; ++k)
+            tab.push_back(p.output == MFCC_OUT_CEPSTRA && k < p.n_cep ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f);
+    align4();
+    lay.total = static_cast<int>(tab.size());
+
+    WideState *st = new WideState();
+    st->sm_count = plan->sm_count;
+    st->smem = sizeof(float) * (static_cast<size_t>(lay.total) + 2 * static_cast<size_t>(G0::HALF));
+    if (st->smem > kSmemMax) { delete st; return MFCC_ENOTSUP; }
+    st->args.lay = lay;
+    st->args.n_mel = M;
+    st->args.n_cep = p.n_cep;
+    st->args.logmel = p.output == MFCC_OUT_LOGMEL;
+    st->args.ls = M | 1;
+    st->args.est = p.output == MFCC_OUT_LOGMEL ? F * (M | 1) : kSlots * F * PS;
+    st->args.mel_magic = (1 << 20) / M + 1;
+    st->args.half_mel = half_mel;
+    st->args.preemph = p.preemph;
+    st->args.log_floor = p.log_floor;
+    if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
+        cudaGetLastError();
+        delete st;
+        return MFCC_ENOMEM;
+    }
+    if (cudaMemcpy(st->d_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(st->d_tab);
+        delete st;
+        return MFCC_ECUDA;
+    }
+    plan->wide_state = st;
+    return MFCC_OK;
+}
+
+void wide_release(mfcc_plan *plan)
+{
+    WideState *st = static_cast<WideState *>(plan->wide_state);
+    if (st == nullptr) return;
+    if (st->d_tab) cudaFree(st->d_tab);
+    delete st;
+    plan->wide_state = nullptr;
+}
+
+template <typename PcmT>
+int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
+                cudaStream_t stream)
+{
+    const WideState *st = static_cast<const WideState *>(plan->wide_state);
+    if (st == nullptr) return MFCC_ENOTSUP;
+    auto kern = fused_wide_kernel<PcmT, kL, kHop>;
+    static thread_local const void *configured = nullptr;
+    if (configured != reinterpret_cast<const void *>(kern)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return MFCC_ECUDA;
+        }
+        configured = reinterpret_cast<const void *>(kern);
+    }
+    WideArgs a = st->args;
+    a.tiles = d_tiles;
+    a.n_tiles = n_tiles;
+    a.out = d_out;
+    a.tab = st->d_tab;
+    const int64_t grid = std::min<int64_t>((n_tiles * (kTileFrames / F) + 1) / 2, st->sm_count);
+    kern<<<static_cast<unsigned>(grid), kThreads, st->smem, stream>>>(d_pcm, a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+template int wide_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *, cudaStream_t);
+template int wide_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *, cudaStream_t);
+
+}  // namespace mfcc

@@ -71,7 +71,8 @@ struct mfcc_plan {
     void *fused_blob = nullptr;         // device tables of the fused kernel
     void *fused_tables = nullptr;       // host struct of device pointers into fused_blob
     void *ct_state = nullptr;           // compile-time-geometry fused kernel state (mfcc_fused_ct.cu)
-    void *sp_state = nullptr;           // fully specialised fused kernel state (mfcc_fused_sp.cu)
+    void *sp_state = nullptr;           // streamlined fused kernel state (mfcc_fused_sp.cu)
+    void *wide_state = nullptr;         // large-transform fused kernel state (mfcc_fused_wide.cu)
     // mfcc_compute_host state (grown on demand, reused across calls)
     void *h2d_pcm = nullptr;   size_t h2d_pcm_bytes = 0;
     void *d2h_out = nullptr;   size_t d2h_out_bytes = 0;
@@ -126,6 +127,13 @@ void sp_release(mfcc_plan *plan);
 template <typename PcmT>
 int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
               cudaStream_t stream);
+// Large-transform variant (mfcc_fused_wide.cu): 2048-point frames, 8 frames per tile, 4 items per warp.
+const char *wide_match(const mfcc_params &p, const HostTables &h);
+int wide_prepare(mfcc_plan *plan);
+void wide_release(mfcc_plan *plan);
+template <typename PcmT>
+int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
+                cudaStream_t stream);
 // Upload whatever constant tables the fused kernel needs (called at plan creation).
 int fused_prepare(mfcc_plan *plan);
 void fused_release(mfcc_plan *plan);

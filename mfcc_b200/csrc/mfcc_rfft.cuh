@@ -228,12 +228,137 @@ MFCC_HD void rdft32(const float (&x)[32], cplx (&X)[17])
     X[3] = conj(u[7]);
 }
 
+
+// W32^j = exp(-2 pi i j / 32), j = 0 .. 21 (largest product nb * ka in cdft32), and W64^j, j = 0 .. 15.
+struct w2 { float re, im; };
+MFCC_HD w2 w32(int j)
+{
+    constexpr w2 t[22] = {
+    {1.0f, 0.0f},
+    {0.98078528040323043f, -0.19509032201612825f},
+    {0.92387953251128674f, -0.38268343236508978f},
+    {0.83146961230254524f, -0.55557023301960218f},
+    {0.70710678118654757f, -0.70710678118654746f},
+    {0.55557023301960229f, -0.83146961230254524f},
+    {0.38268343236508984f, -0.92387953251128674f},
+    {0.19509032201612833f, -0.98078528040323043f},
+    {0.0f, -1.0f},
+    {-0.19509032201612819f, -0.98078528040323043f},
+    {-0.38268343236508973f, -0.92387953251128674f},
+    {-0.55557023301960196f, -0.83146961230254546f},
+    {-0.70710678118654746f, -0.70710678118654757f},
+    {-0.83146961230254535f, -0.55557023301960218f},
+    {-0.92387953251128674f, -0.38268343236508989f},
+    {-0.98078528040323043f, -0.19509032201612861f},
+    {-1.0f, 0.0f},
+    {-0.98078528040323043f, 0.19509032201612836f},
+    {-0.92387953251128685f, 0.38268343236508967f},
+    {-0.83146961230254546f, 0.55557023301960196f},
+    {-0.70710678118654768f, 0.70710678118654746f},
+    {-0.55557023301960218f, 0.83146961230254524f}};
+    return t[j];
+}
+MFCC_HD w2 w64(int j)
+{
+    constexpr w2 t[16] = {
+    {1.0f, 0.0f},
+    {0.99518472667219693f, -0.098017140329560604f},
+    {0.98078528040323043f, -0.19509032201612825f},
+    {0.95694033573220882f, -0.29028467725446233f},
+    {0.92387953251128674f, -0.38268343236508978f},
+    {0.88192126434835505f, -0.47139673682599764f},
+    {0.83146961230254524f, -0.55557023301960218f},
+    {0.77301045336273699f, -0.63439328416364549f},
+    {0.70710678118654757f, -0.70710678118654746f},
+    {0.63439328416364549f, -0.77301045336273699f},
+    {0.55557023301960229f, -0.83146961230254524f},
+    {0.47139673682599781f, -0.88192126434835494f},
+    {0.38268343236508984f, -0.92387953251128674f},
+    {0.29028467725446233f, -0.95694033573220894f},
+    {0.19509032201612833f, -0.98078528040323043f},
+    {0.09801714032956077f, -0.99518472667219682f}};
+    return t[j];
+}
+
+// Forward 32-point DFT, natural order in and out: n = nb + 4 na (na < 8), k = ka + 8 kb (kb < 4).
+MFCC_HD void cdft32(cplx (&x)[32])
+{
+    cplx t[4][8];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+        for (int na = 0; na < 8; ++na) t[nb][na] = x[nb + 4 * na];
+        cdft8(t[nb]);
+    }
+#pragma unroll
+    for (int nb = 1; nb < 4; ++nb)
+#pragma unroll
+        for (int ka = 1; ka < 8; ++ka) {
+            const w2 w = w32(nb * ka);
+            t[nb][ka] = cmulc(t[nb][ka], w.re, w.im);
+        }
+#pragma unroll
+    for (int ka = 0; ka < 8; ++ka) {
+        cdft4(t[0][ka], t[1][ka], t[2][ka], t[3][ka]);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) x[ka + 8 * kb] = t[kb][ka];
+    }
+}
+
+// Real 64-point DFT of x[0 .. NZ) (the rest zero): X[0 .. 32], X[0].im = X[32].im = 0.
+// k = q + 4 r: bin q of the 4-point DFT over m of x[j + 16 m], times W64^(j q), through a 16-point DFT over j.
+template <int NZ>
+MFCC_HD void rdft64(const float (&x)[64], cplx (&X)[33])
+{
+    float t0[16], t2[16];
+    cplx u[16];
+#define MFCC_RS(j) rstage<live4(j, 16, NZ)>(x[j], x[j + 16], x[j + 32], x[j + 48], t0[j], t2[j], u[j])
+    MFCC_RS(0); MFCC_RS(1); MFCC_RS(2); MFCC_RS(3); MFCC_RS(4); MFCC_RS(5); MFCC_RS(6); MFCC_RS(7);
+    MFCC_RS(8); MFCC_RS(9); MFCC_RS(10); MFCC_RS(11); MFCC_RS(12); MFCC_RS(13); MFCC_RS(14); MFCC_RS(15);
+#undef MFCC_RS
+    {   // q = 0: real 16-point DFT of t0 -> X[4 r], r = 0 .. 8
+        cplx X0[9];
+        rdft16<16>(t0, X0);
+#pragma unroll
+        for (int r = 0; r <= 8; ++r) X[4 * r] = X0[r];
+        X[0].im = 0.0f;
+        X[32].im = 0.0f;
+    }
+    {   // q = 2: (t2[j] W32^j) through a complex 16-point DFT -> X[2 + 4 r], r = 0 .. 7
+        cplx z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const w2 w = w32(j);
+            z[j] = cplx{t2[j] * w.re, t2[j] * w.im};
+        }
+        cdft16(z);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) X[2 + 4 * r] = z[r];
+    }
+    {   // q = 1: (u[j] W64^j) through a complex 16-point DFT -> X[1 + 4 r]; r >= 8 gives the conjugates of X[3 + 4 r']
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+            const w2 w = w64(j);
+            u[j] = cmulc(u[j], w.re, w.im);
+        }
+        cdft16(u);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            X[1 + 4 * r] = u[r];
+            X[3 + 4 * r] = conj(u[15 - r]);
+        }
+    }
+}
+
 template <int RB> struct RDft;
 template <> struct RDft<16> {
     template <int NZ> static MFCC_HD void run(const float (&x)[16], cplx (&X)[9]) { rdft16<NZ>(x, X); }
 };
 template <> struct RDft<32> {
     template <int NZ> static MFCC_HD void run(const float (&x)[32], cplx (&X)[17]) { rdft32<NZ>(x, X); }
+};
+template <> struct RDft<64> {
+    template <int NZ> static MFCC_HD void run(const float (&x)[64], cplx (&X)[33]) { rdft64<NZ>(x, X); }
 };
 
 }  // namespace rf

@@ -112,6 +112,54 @@ static void check_two_pass(const char *name)
     }
 }
 
+// The wide kernel's data flow (mfcc_fused_wide.cu): N = 64 * 32, rows k1 = 1 .. 32 complex (row 32 is real
+// before its twiddle), row 0 real through a real DFT-32.
+template <int L>
+static void check_two_pass_wide(const char *name)
+{
+    constexpr int RB = 64, RA = 32, N = RB * RA, NZ = (L + RA - 1) / RA, H = RB / 2;
+    for (int rep = 0; rep < 3; ++rep) {
+        std::vector<float> y(N, 0.0f);
+        for (int i = 0; i < L; ++i) y[i] = (float)frand();
+        std::vector<cplx> ws(H * RA);            // rows k1 = 1 .. H at index k1 - 1
+        std::vector<float> r0(RA);
+        for (int a = 0; a < RA; ++a) {
+            float x[RB];
+            for (int b = 0; b < RB; ++b) x[b] = b < NZ ? y[a + RA * b] : 1e30f;
+            cplx X[H + 1];
+            rdft64<NZ>(x, X);
+            r0[a] = X[0].re;
+            for (int k1 = 1; k1 <= H; ++k1) {
+                const double ang = -2 * M_PI * a * k1 / N;
+                ws[(k1 - 1) * RA + a] = cmulc(X[k1], (float)std::cos(ang), (float)std::sin(ang));
+            }
+        }
+        std::vector<cplx> Xo(N / 2 + 1);
+        for (int k1 = 1; k1 <= H; ++k1) {
+            cplx z[32];
+            for (int a = 0; a < RA; ++a) z[a] = ws[(k1 - 1) * RA + a];
+            cdft32(z);
+            for (int k2 = 0; k2 < RA; ++k2) {
+                const int k = k1 + RB * k2;
+                if (k2 < RA / 2) Xo[k] = z[k2];
+                else if (k1 < H) Xo[N - k] = conj(z[k2]);
+            }
+        }
+        {
+            float x[32];
+            for (int a = 0; a < RA; ++a) x[a] = r0[a];
+            cplx X0[17];
+            rdft32<32>(x, X0);
+            for (int k2 = 0; k2 <= RA / 2; ++k2) Xo[RB * k2] = X0[k2];
+        }
+        for (int k = 0; k <= N / 2; ++k) {
+            double re = 0, im = 0;
+            for (int n = 0; n < L; ++n) { re += y[n] * std::cos(2 * M_PI * k * n / N); im -= y[n] * std::sin(2 * M_PI * k * n / N); }
+            expect(name, Xo[k].re, Xo[k].im, re, im, std::sqrt((double)N));
+        }
+    }
+}
+
 int main()
 {
     srand(12345);
@@ -123,6 +171,12 @@ int main()
     check_real<32, 32>("rdft32<32>", [](const float (&x)[32], cplx (&X)[17]) { rdft32<32>(x, X); });
     check_real<32, 25>("rdft32<25>", [](const float (&x)[32], cplx (&X)[17]) { rdft32<25>(x, X); });
     check_real<32, 19>("rdft32<19>", [](const float (&x)[32], cplx (&X)[17]) { rdft32<19>(x, X); });
+    check_cplx<32>("cdft32", [](cplx (&v)[32]) { cdft32(v); });
+    check_real<64, 64>("rdft64<64>", [](const float (&x)[64], cplx (&X)[33]) { rdft64<64>(x, X); });
+    check_real<64, 38>("rdft64<38>", [](const float (&x)[64], cplx (&X)[33]) { rdft64<38>(x, X); });
+    check_real<64, 17>("rdft64<17>", [](const float (&x)[64], cplx (&X)[33]) { rdft64<17>(x, X); });
+    check_two_pass_wide<1200>("two-pass 2048 (L=1200)");
+    check_two_pass_wide<2048>("two-pass 2048 (L=2048)");
     check_two_pass<32, 16, 400>("two-pass 512 (L=400)");
     check_two_pass<16, 16, 200>("two-pass 256 (L=200)");
     check_two_pass<32, 16, 512>("two-pass 512 (L=512)");
