@@ -10,9 +10,10 @@
 //     no LDG/LDL instructions, completion on an mbarrier.  Staging then converts 8 samples per
 //     thread (LDS.128) instead of 2.
 //   * tail: each warp OWNS a contiguous group of mel filters (balanced on the host), sums
-//     their bins from P, takes the log and accumulates its share of every cepstrum in
-//     registers; one barrier later the 8 partial cepstra per frame are added and stored
-//     coalesced.  4 barriers per tile instead of 7.
+//     their bins from P and leaves the log band energies lg[m][frame] in shared memory; one
+//     barrier later warp w forms cepstra w and w + 8 of every frame (26 conflict-free loads,
+//     DCT rows read as warp-uniform float4) and stores them straight to HBM.  4 barriers per
+//     tile instead of 7, no partial sums and no cross-warp reduction pass.
 //   * hot code stays under 32 KB: profiles/r1_v5_sp_unrolled_tail_A.md shows what happens when the
 //     tail is unrolled per warp (60 KB of code, 44 % of stall samples = no_instruction), so the
 //     tail is a table-driven loop shared by all warps.
@@ -41,8 +42,7 @@ constexpr int kWarps = 8;                 // per half
 constexpr int kHalfThreads = kWarps * 32;
 constexpr int kThreads = 2 * kHalfThreads;
 constexpr int kPad = 2;
-constexpr int KC = 16;                    // cepstra accumulated per frame (n_cep <= KC)
-constexpr int PS = KC + 1;                // partial-cepstra row stride (odd: conflict-free)
+constexpr int KC = 16;                    // cepstra per frame (n_cep <= KC): warp w forms k = w and k = w + 8
 constexpr size_t kSmemMax = 227 * 1024;
 
 template <int L_, int HOP_, int RB_, int RA_>
@@ -73,15 +73,14 @@ struct Geo {
     static_assert(RA == 2 * kWarps && RA == 16, "one column pair per warp, 16-point second pass");
     static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
     static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0 && RAW % 4 == 0, "16-byte aligned regions");
-    static_assert(kWarps * 32 * PS <= WS && 32 * 129 <= WS, "tail scratch must fit in the workspace");
+    static_assert(32 * 129 <= WS, "tail scratch must fit in the workspace");
 };
 
 // Run-time part of the table blob (offsets in floats from its start).
 struct SpLayout {
     int wseg;     // int2 per warp: its segments [first, last] (first > last: none)
-    int wfilt;    // int2 per warp: its filters [first, last)
     int seg;      // float4 per segment j: {first bin * 32 (int), width w (int), s = 1 / (w NFFT), s * w}
-    int dct;      // [n_mel][KC]: DCT column of filter m, zero past n_cep
+    int dct;      // [kWarps][n_mel] float2: DCT entries {d[w][m], d[w + 8][m]}, zero past n_cep (n_mel padded to even)
     int total;    // floats, multiple of 4
 };
 
@@ -93,7 +92,7 @@ struct SpArgs {
     SpLayout lay;
     int n_mel, n_cep, logmel;
     int ls;               // log-mel staging row stride (n_mel | 1)
-    int est;              // scratch offset (floats) of the parked band energies [n_mel][32]
+    int mp;               // n_mel rounded up to even (DCT row length in the table)
     int mel_magic;        // i / n_mel == (i * mel_magic) >> 20 for i < 32 * n_mel
     float preemph, log_floor;
 };
@@ -101,13 +100,23 @@ struct SpArgs {
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
 __device__ __forceinline__ float4 lds_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
-// int16 pair -> two exact floats without the XU pipe: (v ^ 0x8000) in the mantissa of 2^23.
+// int16 pair -> two exact floats without the XU pipe: (v ^ 0x8000) = v + 32768 sits in the mantissa of
+// 2^23 (bits 0x4B00xxxx); one XOR serves both halves, one byte permute (PRMT) builds each float.
 __device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
 {
-    const uint32_t lo = ((w & 0xFFFFu) ^ 0x4B008000u);
-    const uint32_t hi = ((w >> 16) ^ 0x4B008000u);
+    const uint32_t b = w ^ 0x80008000u;
+    const uint32_t lo = __byte_perm(b, 0x4B000000u, 0x7610);
+    const uint32_t hi = __byte_perm(b, 0x4B000000u, 0x7632);
     return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
 }
+// log2 of a NORMAL positive float (callers clamp to log_floor first): one MUFU.LG2, no denormal rescaling
+__device__ __forceinline__ float lg2_fast(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLn2 = 0.69314718055994531f;
 __device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
@@ -149,7 +158,8 @@ __device__ __forceinline__ void half_sync(int half)
     asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kHalfThreads) : "memory");
 }
 
-template <typename PcmT, int L_, int HOP_, int RB_, int RA_>
+// MEL > 0: the plan has exactly MEL filters and cepstral output, so the DCT loop of S4 is unrolled; MEL = 0: any plan.
+template <typename PcmT, int L_, int HOP_, int RB_, int RA_, int MEL>
 __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__restrict__ pcm, const SpArgs a)
 {
     using G = Geo<L_, HOP_, RB_, RA_>;
@@ -182,7 +192,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW, *t_twh = tab + G::T_TWH;
     const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
-    const int2 *t_wfilt = reinterpret_cast<const int2 *>(tab + a.lay.wfilt);
     const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
     const float *t_dct = tab + a.lay.dct;
 
@@ -226,19 +235,29 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
             const bool at_start = tile.first_sample == tile.utt_begin;
             const int nchunks = tc >> 3;
             const float na = -a.preemph;
-#pragma unroll 1
-            for (int c = tid; c < nchunks; c += kHalfThreads) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(raw16 + 8 + 8 * c);
-                const uint32_t pwd = *reinterpret_cast<const uint32_t *>(raw16 + 6 + 8 * c);
-                const float2 x01 = s16x2_to_f32(q.x), x23 = s16x2_to_f32(q.y);
-                const float2 x45 = s16x2_to_f32(q.z), x67 = s16x2_to_f32(q.w);
-                float xp = s16x2_to_f32(pwd).y;
-                if (c == 0 && at_start) xp = 0.0f;
-                float *dst = staged + 8 * c + kPad * (c / (HOP / 8));
-                *reinterpret_cast<float2 *>(dst + 0) = make_float2(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y));
-                *reinterpret_cast<float2 *>(dst + 2) = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
-                *reinterpret_cast<float2 *>(dst + 4) = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
-                *reinterpret_cast<float2 *>(dst + 6) = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+            // chunk c = 8 samples; the thread takes chunks tid, tid + 256, ...: all loads first, then the arithmetic
+            constexpr int NU = (G::TCEIL / 8 + kHalfThreads - 1) / kHalfThreads;
+            uint4 q[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int c = tid + u * kHalfThreads;
+                if (c < nchunks) q[u] = *reinterpret_cast<const uint4 *>(raw16 + 8 + 8 * c);
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int c = tid + u * kHalfThreads;
+                if (c < nchunks) {
+                    const uint32_t pv = static_cast<uint16_t>(raw16[7 + 8 * c]);   // the sample before the chunk; needed last
+                    const float2 x01 = s16x2_to_f32(q[u].x), x23 = s16x2_to_f32(q[u].y);
+                    const float2 x45 = s16x2_to_f32(q[u].z), x67 = s16x2_to_f32(q[u].w);
+                    float *dst = staged + 8 * c + kPad * (c / (HOP / 8));
+                    *reinterpret_cast<float2 *>(dst + 2) = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
+                    *reinterpret_cast<float2 *>(dst + 4) = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
+                    *reinterpret_cast<float2 *>(dst + 6) = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                    float xp = s16x2_to_f32(pv).x;
+                    if (u == 0 && c == 0 && at_start) xp = 0.0f;
+                    *reinterpret_cast<float2 *>(dst + 0) = make_float2(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y));
+                }
             }
         } else {
             const int64_t room_lo = tile.first_sample - tile.utt_begin;
@@ -359,13 +378,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         // i / w and falls out of filter j - 1 with weight (w - i) / w (i = bin - b_j), so two plain sums per
         // segment, S = sum P and T = sum i P, give both: rise = s T, fall = s (w S - T), s = 1 / (w NFFT).
         // No weight loads, and the P addresses do not depend on loaded data.  Filter m is complete at the end
-        // of segment m + 1; the segment two neighbouring groups share is walked by both.  Energies are parked
-        // in the thread's own scratch words, then a second loop takes logs and either stages log-mel rows or
-        // adds the filter's DCT column into 16 running cepstra. ----
+        // of segment m + 1; the segment two neighbouring groups share is walked by both.  The log of each
+        // finished band goes to lg[m][lane] (cepstra) or to the frame's log-mel row. ----
         {
             const int2 wsg = t_wseg[warp];                  // segments [x, y], empty when x > y
-            const int2 wf = t_wfilt[warp];                  // filters [x, y)
-            float *est = scr + a.est + lane;                // E[m] of this lane at est[m * 32]
+            const int lgs = a.logmel ? 1 : 32;              // stride between bands
+            float *lgw = (a.logmel ? scr + lane * a.ls : scr + lane) + wsg.x * lgs;   // band wsg.x is this warp's first
             float r_prev = 0.0f;
 #pragma unroll 1
             for (int j = wsg.x; j <= wsg.y; ++j) {
@@ -394,47 +412,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
                     i0 += 4.0f;
                     p += 128;
                 }
-#pragma unroll 1
-                for (int e = w & 3; e > 0; --e) {
-                    const float a0 = p[0];
-                    T = fmaf(i0, a0, T);
-                    S += a0;
-                    i0 += 1.0f;
-                    p += 32;
+                if (const int e = w & 3) {                  // 1..3 leftover bins, no loop: the rows past the segment are
+                    const float a0 = p[0];                  // finite (next segment or the zeroed slack rows) and deselected
+                    const float a1 = e > 1 ? p[32] : 0.0f;
+                    const float a2 = e > 2 ? p[64] : 0.0f;
+                    const float sa = (a0 + a1) + a2;
+                    T = fmaf(i0, sa, T) + fmaf(2.0f, a2, a1);
+                    S += sa;
                 }
                 const float r = sg.z * T;
-                if (j > wsg.x) est[(j - 1) * 32] = r_prev + fmaf(sg.w, S, -r);
+                if (j > wsg.x) {
+                    *lgw = kLn2 * lg2_fast(fmaxf(r_prev + fmaf(sg.w, S, -r), a.log_floor));
+                    lgw += lgs;
+                }
                 r_prev = r;
             }
-            if (a.logmel) {
-#pragma unroll 2
-                for (int m = wf.x; m < wf.y; ++m)
-                    scr[lane * a.ls + m] = __logf(fmaxf(est[m * 32], a.log_floor));
-            } else {
-                float c[KC];
-#pragma unroll
-                for (int k = 0; k < KC; ++k) c[k] = 0.0f;
-#pragma unroll 2
-                for (int m = wf.x; m < wf.y; ++m) {
-                    const float lg = __logf(fmaxf(est[m * 32], a.log_floor));
-                    const float *dc = t_dct + m * KC;
-#pragma unroll
-                    for (int q = 0; q < KC; q += 4) {
-                        const float4 dv = lds_f4(dc + q);
-                        c[q + 0] = fmaf(dv.x, lg, c[q + 0]);
-                        c[q + 1] = fmaf(dv.y, lg, c[q + 1]);
-                        c[q + 2] = fmaf(dv.z, lg, c[q + 2]);
-                        c[q + 3] = fmaf(dv.w, lg, c[q + 3]);
-                    }
-                }
-                float *dst = scr + (warp * 32 + lane) * PS;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) dst[k] = c[k];
-            }
         }
-        half_sync(half);   // B4
+        half_sync(half);   // B4: every band's log energy is in the scratch
 
-        // ---- S4: add the partial cepstra of the 8 warps and store (16 lanes per frame, n_cep of them live) ----
+        // ---- S4: log-mel rows are copied out coalesced; cepstra: warp w forms c[w] and c[w + 8] of frame = lane
+        // from the 26 log energies (conflict-free column reads, warp-uniform DCT entries) and stores them ----
         if (a.logmel) {
             const int M = a.n_mel, total = n_frames * M;
             float *o = a.out + tile.out_row * M;
@@ -442,18 +439,45 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
                 const int f = (i * a.mel_magic) >> 20, m = i - f * M;
                 o[i] = scr[f * a.ls + m];
             }
-        } else {
-            const int k = tid & (KC - 1);
+        } else if (warp < a.n_cep) {
+            const float *lg = scr + lane;
+            const float4 *dc = reinterpret_cast<const float4 *>(t_dct + warp * (2 * a.mp));   // {d[w][m], d[w+8][m], d[w][m+1], d[w+8][m+1]}
+            float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
+            if constexpr (MEL > 0) {
+                static_assert(MEL % 2 == 0, "unrolled DCT takes filters in pairs");
+                float l[MEL];
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int f = pass * (kHalfThreads / KC) + (tid >> 4);
-                if (f < n_frames && k < a.n_cep) {
-                    const float *src = scr + f * PS + k;
-                    float s = src[0];
+                for (int m = 0; m < MEL; ++m) l[m] = lg[m * 32];
 #pragma unroll
-                    for (int w = 1; w < kWarps; ++w) s += src[w * 32 * PS];
-                    a.out[(tile.out_row + f) * a.n_cep + k] = s;
+                for (int q = 0; q < MEL / 2; ++q) {
+                    const float4 d = dc[q];
+                    c0 = fmaf(d.x, l[2 * q], c0);
+                    c1 = fmaf(d.y, l[2 * q], c1);
+                    e0 = fmaf(d.z, l[2 * q + 1], e0);
+                    e1 = fmaf(d.w, l[2 * q + 1], e1);
                 }
+            } else {
+                const int M2 = a.n_mel >> 1;
+#pragma unroll 2
+                for (int q = 0; q < M2; ++q) {
+                    const float l0 = lg[(2 * q) * 32], l1 = lg[(2 * q + 1) * 32];
+                    const float4 d = dc[q];
+                    c0 = fmaf(d.x, l0, c0);
+                    c1 = fmaf(d.y, l0, c1);
+                    e0 = fmaf(d.z, l1, e0);
+                    e1 = fmaf(d.w, l1, e1);
+                }
+                if (a.n_mel & 1) {
+                    const float l0 = lg[(a.n_mel - 1) * 32];
+                    const float4 d = dc[M2];
+                    c0 = fmaf(d.x, l0, c0);
+                    c1 = fmaf(d.y, l0, c1);
+                }
+            }
+            if (lane < n_frames) {
+                float *o = a.out + (tile.out_row + lane) * a.n_cep + warp;
+                o[0] = c0 + e0;
+                if (warp + kWarps < a.n_cep) o[kWarps] = c1 + e1;
             }
         }
         // no barrier here: the next S0 writes `staged`, which nobody reads any more; the scratch is
@@ -538,16 +562,16 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
     const SpVariant *v = find_variant(p);
     if (v == nullptr) return nullptr;
     if (p.output == MFCC_OUT_CEPSTRA && p.n_cep > KC) return nullptr;
+    if (p.log_floor < 1.17549435e-38f) return nullptr;   // the tail takes lg2.approx.ftz of max(E, floor): floor must be a normal float
     for (int j = 0; j + 1 < static_cast<int>(h.mel_bins.size()); ++j)
         if (h.mel_bins[j + 1] < h.mel_bins[j]) return nullptr;
     // the run-time tables must fit next to the two halves
     int tabf = 0, half_floats = 0;
     variant_sizes(*v, tabf, half_floats);
-    const size_t total = tabf + 4 * kWarps + 4 * static_cast<size_t>(p.n_mel + 1) + static_cast<size_t>(KC) * p.n_mel + 16;
+    const size_t total = tabf + 4 * kWarps + 4 * static_cast<size_t>(p.n_mel + 1) + static_cast<size_t>(KC) * (p.n_mel + 1) + 16;
     if ((total + 2 * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
-    // tail scratch (partial cepstra or log-mel rows, then the parked energies) must fit in the workspace
-    const size_t scratch = (p.output == MFCC_OUT_LOGMEL ? 32 * static_cast<size_t>(p.n_mel | 1) : kWarps * 32 * PS) +
-                           32 * static_cast<size_t>(p.n_mel);
+    // tail scratch (log band energies [n_mel][32], or log-mel rows [32][n_mel | 1]) must fit in the workspace
+    const size_t scratch = 32 * static_cast<size_t>(p.n_mel | 1);
     if (scratch > static_cast<size_t>(v->rb / 2) * v->ra * 32 * 2) return nullptr;
     return v->name;
 }
@@ -594,8 +618,6 @@ int sp_prepare(mfcc_plan *plan)
         push_int(m1 > m0 ? m0 : 1);
         push_int(m1 > m0 ? m1 : 0);
     }
-    lay.wfilt = static_cast<int>(tab.size());
-    for (int w = 0; w < kWarps; ++w) { push_int(beg[w]); push_int(beg[w + 1]); }
     align4();
     // segments: the triangles are linear ramps over integer bins (mfcc_tables.cpp build_tables), so a
     // segment is described by its first bin, its width and 1 / (w N) (pass 2 leaves |X|^2, hence the 1 / N)
@@ -609,11 +631,17 @@ int sp_prepare(mfcc_plan *plan)
         tab.push_back(static_cast<float>(sc * w));
     }
     align4();
-    // DCT columns, zero past n_cep
+    // DCT entries for warp w: {d[w][m], d[w + 8][m]} per filter m, zero past n_cep; rows padded to even length
     lay.dct = static_cast<int>(tab.size());
-    for (int m = 0; m < M; ++m)
-        for (int k = 0; k < KC; ++k)
-            tab.push_back(p.output == MFCC_OUT_CEPSTRA && k < p.n_cep ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f);
+    const int MP = (M + 1) / 2 * 2;
+    auto dct_at = [&](int k, int m) {
+        return p.output == MFCC_OUT_CEPSTRA && k < p.n_cep && m < M ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f;
+    };
+    for (int w = 0; w < kWarps; ++w)
+        for (int m = 0; m < MP; ++m) {
+            tab.push_back(dct_at(w, m));
+            tab.push_back(dct_at(w + kWarps, m));
+        }
     align4();
     lay.total = static_cast<int>(tab.size());
 
@@ -627,7 +655,7 @@ int sp_prepare(mfcc_plan *plan)
     st->args.n_cep = p.n_cep;
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
     st->args.ls = M | 1;
-    st->args.est = p.output == MFCC_OUT_LOGMEL ? 32 * (M | 1) : kWarps * 32 * PS;
+    st->args.mp = MP;
     st->args.mel_magic = (1 << 20) / M + 1;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
@@ -654,11 +682,11 @@ void sp_release(mfcc_plan *plan)
     plan->sp_state = nullptr;
 }
 
-template <typename PcmT, int L, int HOP, int RB, int RA>
+template <typename PcmT, int L, int HOP, int RB, int RA, int MEL>
 static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
                           cudaStream_t stream)
 {
-    auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA>;
+    auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA, MEL>;
     static thread_local const void *configured = nullptr;
     if (configured != reinterpret_cast<const void *>(kern)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
@@ -685,8 +713,14 @@ int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const
 {
     const SpState *st = static_cast<const SpState *>(plan->sp_state);
     if (st == nullptr) return MFCC_ENOTSUP;
-    if (st->v->L == 400) return launch_variant<PcmT, 400, 160, 32, 16>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
-    return launch_variant<PcmT, 200, 80, 16, 16>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    // the BASELINE.json filter counts (26 at 16 kHz, 20 at 8 kHz) with cepstral output get the unrolled DCT
+    const bool cep = !st->args.logmel;
+    if (st->v->L == 400) {
+        if (cep && st->args.n_mel == 26) return launch_variant<PcmT, 400, 160, 32, 16, 26>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+        return launch_variant<PcmT, 400, 160, 32, 16, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    }
+    if (cep && st->args.n_mel == 20) return launch_variant<PcmT, 200, 80, 16, 16, 20>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    return launch_variant<PcmT, 200, 80, 16, 16, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
 }
 
 template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *, cudaStream_t);
