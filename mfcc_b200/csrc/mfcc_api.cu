@@ -240,11 +240,13 @@ static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int
                 t.first_sample = begin + f * p.hop_len;
                 t.out_row = b->frame_offsets[u] + f;
                 t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, nf - f));
-                t.reserved = 0;
+                t.flags = 0;
                 b->tiles.push_back(t);
             }
         }
         b->utt_first_tile[n_utts] = static_cast<int64_t>(b->tiles.size());
+        const int64_t total = n_utts > 0 ? b->offsets[n_utts] : 0;
+        for (Tile &t : b->tiles) t.flags = mfcc::tile_flags(p, t, total);
     } catch (const std::bad_alloc &) {
         delete b;
         return MFCC_ENOMEM;
@@ -443,7 +445,7 @@ int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
         t.first_sample = lead + f * p.hop_len;
         t.out_row = f;
         t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, n_frames - f));
-        t.reserved = 0;
+        t.flags = mfcc::tile_flags(p, t, len);
         tiles.push_back(t);
     }
     DeviceGuard guard(plan->device);

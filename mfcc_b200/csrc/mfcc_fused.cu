@@ -407,8 +407,8 @@ int launch_fused(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, co
                  float *d_out, cudaStream_t stream)
 {
     if (n_tiles <= 0) return MFCC_OK;
-    if (plan->sp_state != nullptr) return sp_launch<PcmT>(plan, d_tiles, n_tiles, d_pcm, d_out, stream);
-    if (plan->wide_state != nullptr) return wide_launch<PcmT>(plan, d_tiles, n_tiles, d_pcm, d_out, stream);
+    if (plan->sp_state != nullptr) return sp_launch<PcmT>(plan, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
+    if (plan->wide_state != nullptr) return wide_launch<PcmT>(plan, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
     if (plan->ct_state != nullptr) return ct_launch<PcmT>(plan, d_tiles, n_tiles, d_pcm, pcm_len, d_out, stream);
     if (plan->fused == nullptr || plan->fused_tables == nullptr) return MFCC_ENOTSUP;
     switch (plan->fused->g.nfft) {

@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "mfcc_rfft.cuh"
@@ -55,12 +56,13 @@ struct Geo {
     static constexpr int padded(int i) { return i + kPad * (i / HOP); }
     static constexpr int SLACK = RA * NZ - L;              // words past a frame's end read with a zero window
     static constexpr int tceil(int n_frames) { return ((n_frames - 1) * HOP + L + SLACK + 7) / 8 * 8; }
-    static constexpr int TCEIL = tceil(32);                // samples staged for a full tile
+    static constexpr int tceil_s(int n_frames, int shift) { return (shift + (n_frames - 1) * HOP + L + SLACK + 7) / 8 * 8; }
+    static constexpr int TCEIL = tceil(32) + 8;            // samples staged for a full tile (+ up to 7 of alignment shift)
     static constexpr int STAGED = padded(TCEIL) + 8;
     static constexpr int PW = (NB + 3) * 32;               // 3 zeroed slack rows: 4-bin chunks read past the last bin
     static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
     static constexpr int WS = H * RA * 32 * 2;             // floats
-    static constexpr int RAW = (TCEIL + 8) / 2;            // floats holding TCEIL + 8 int16 samples
+    static constexpr int RAW = (TCEIL + 16) / 2;           // floats holding 8 lead + TCEIL + 1 look-ahead int16 samples
     static constexpr int DESC = 24;                        // two 40-byte tile descriptors (current, next)
     static constexpr int HALF = UNION + WS + RAW + 4 + DESC;   // + mbarrier (8 B in a 16-B slot)
     // fixed part of the table blob (floats); the filterbank tables follow at run-time offsets
@@ -195,19 +197,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
     const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
     const float *t_dct = tab + a.lay.dct;
 
-    // A tile takes the bulk-copy path when its samples are 16-byte aligned in HBM and lie inside
-    // the utterance up to the staging granule (no zero fill needed).
-    auto tile_fast = [&](const Tile &tl) -> bool {
-        if constexpr (sizeof(PcmT) != 2) return false;
-        return ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((tl.first_sample & 7) == 0) &&
-               (tl.utt_end - tl.first_sample >= G::tceil(tl.n_frames));
-    };
-    // raw16[8 + i] = x[first_sample + i]; the 8 samples before the tile ride along when they exist
+    // A tile takes the bulk-copy path when the PCM array is 16-byte aligned, every frame lies inside the
+    // utterance (no zero fill) and the staged span stays inside the array (both checked on the host when the
+    // tile table is built: Tile::flags).  The utterance may start at ANY sample: the copy starts at the
+    // 8-sample boundary `o` below the tile's first sample and the shift s = first_sample - o (0..7) is
+    // absorbed by the staging (see S0).
+    const bool base_ok = sizeof(PcmT) == 2 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+    static_assert(G::SLACK + 8 <= kTileSpanSlack, "the host's span check must cover the staged span");
+    auto tile_fast = [&](const Tile &tl) -> bool { return base_ok && (tl.flags & kTileInside) != 0; };
+    // raw16[8 + i] = x[o + i]; the 8 samples before o ride along when they exist
     auto issue_copy = [&](const Tile &tl) {
-        const int lead = tl.first_sample >= 8 ? 8 : 0;
-        const uint32_t bytes = static_cast<uint32_t>(lead + G::tceil(tl.n_frames)) * 2u;
+        const int s = static_cast<int>(tl.first_sample & 7);
+        const int64_t o = tl.first_sample - s;
+        const int lead = o >= 8 ? 8 : 0;
+        const uint32_t bytes = static_cast<uint32_t>(lead + G::tceil_s(tl.n_frames, s)) * 2u;
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(raw_s + (8 - lead) * 2, pcm + tl.first_sample - lead, bytes, bar);
+        bulk_g2s(raw_s + (8 - lead) * 2, pcm + o - lead, bytes, bar);
     };
 
     const int64_t first = 2 * static_cast<int64_t>(blockIdx.x) + half, step = 2 * static_cast<int64_t>(gridDim.x);
@@ -227,13 +232,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         if (has_next) fetch_desc(cur ^ 1, t + step);   // lands while S0 runs
         const int n_frames = tile.n_frames;
         const int tc = G::tceil(n_frames);
+        // alignment shift of a bulk-copied tile: s = e + d, e even (absorbed as a word offset of the frame
+        // columns in the staged layout), d = 0/1 (absorbed by staging y one sample ahead of x)
+        const int sh = fast ? static_cast<int>(tile.first_sample & 7) : 0;
+        const int e = sh & 6, d = sh & 1;
 
-        // ---- S0: stage y[s] = x[s] - a x[s-1] once per sample, padded by kPad words per hop ----
+        // ---- S0: stage y[n] = x[n] - a x[n-1] once per sample: staged index i holds sample o + d + i (o = the
+        // 8-sample boundary below the tile), with kPad words inserted at i = e + k HOP, so that frame f starts
+        // at word e + f STRIDE ----
         if (fast) {
             mbar_wait(bar, phase);
             phase ^= 1u;
-            const bool at_start = tile.first_sample == tile.utt_begin;
-            const int nchunks = tc >> 3;
+            const int nchunks = G::tceil_s(n_frames, sh) >> 3;
             const float na = -a.preemph;
             // chunk c = 8 samples; the thread takes chunks tid, tid + 256, ...: all loads first, then the arithmetic
             constexpr int NU = (G::TCEIL / 8 + kHalfThreads - 1) / kHalfThreads;
@@ -247,16 +257,37 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
             for (int u = 0; u < NU; ++u) {
                 const int c = tid + u * kHalfThreads;
                 if (c < nchunks) {
-                    const uint32_t pv = static_cast<uint16_t>(raw16[7 + 8 * c]);   // the sample before the chunk; needed last
-                    const float2 x01 = s16x2_to_f32(q[u].x), x23 = s16x2_to_f32(q[u].y);
-                    const float2 x45 = s16x2_to_f32(q[u].z), x67 = s16x2_to_f32(q[u].w);
-                    float *dst = staged + 8 * c + kPad * (c / (HOP / 8));
-                    *reinterpret_cast<float2 *>(dst + 2) = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
-                    *reinterpret_cast<float2 *>(dst + 4) = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
-                    *reinterpret_cast<float2 *>(dst + 6) = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
-                    float xp = s16x2_to_f32(pv).x;
-                    if (u == 0 && c == 0 && at_start) xp = 0.0f;
-                    *reinterpret_cast<float2 *>(dst + 0) = make_float2(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y));
+                    // d = 0: the sample before the chunk; d = 1: the sample after it (low half-word of pv)
+                    uint32_t pv = static_cast<uint16_t>(raw16[7 + 9 * d + 8 * c]);
+                    uint32_t w0 = q[u].x, w1 = q[u].y, w2 = q[u].z, w3 = q[u].w;
+                    if (d) {   // odd shift: move the chunk down one half-word; its old first sample becomes the predecessor
+                        const uint32_t first = w0;
+                        w0 = __byte_perm(w0, w1, 0x5432);
+                        w1 = __byte_perm(w1, w2, 0x5432);
+                        w2 = __byte_perm(w2, w3, 0x5432);
+                        w3 = __byte_perm(w3, pv, 0x5432);
+                        pv = first;
+                    }
+                    const float2 x01 = s16x2_to_f32(w0), x23 = s16x2_to_f32(w1);
+                    const float2 x45 = s16x2_to_f32(w2), x67 = s16x2_to_f32(w3);
+                    // hop-block padding: block k = [e + k HOP, e + (k + 1) HOP).  Chunk c = (HOP / 8) k + m lies in
+                    // block k, except the words below e of the chunks with m = 0, which still belong to block k - 1.
+                    const int k = c / (HOP / 8);
+                    const int pad = kPad * k;
+                    const int pad_first = (c == k * (HOP / 8) && k > 0) ? pad - kPad : pad;
+                    float *dst = staged + 8 * c;
+                    float *d0 = dst + (0 < e ? pad_first : pad);
+                    float *d2 = dst + 2 + (2 < e ? pad_first : pad);
+                    float *d4 = dst + 4 + (4 < e ? pad_first : pad);
+                    float *d6 = dst + 6 + pad;
+                    *reinterpret_cast<float2 *>(d2) = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
+                    *reinterpret_cast<float2 *>(d4) = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
+                    *reinterpret_cast<float2 *>(d6) = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                    const float xe = s16x2_to_f32(pv).x;
+                    *reinterpret_cast<float2 *>(d0) = make_float2(fmaf(na, xe, x01.x), fmaf(na, x01.x, x01.y));
+                    // the utterance's first sample has no predecessor: y = x.  It is word e of chunk 0 (this
+                    // thread wrote it just above), sample raw16[8 + sh].
+                    if (u == 0 && c == 0 && tile.first_sample == tile.utt_begin) staged[e] = to_f32(raw16[8 + sh]);
                 }
             }
         } else {
@@ -283,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_sp_kernel(const PcmT *__res
         // ---- S1: pass 1.  Warp = column pair (a, a + 1): windowed real DFT-RB over b, inter-pass twiddle ----
         {
             const int pr = warp;
-            const float *base = staged + lane * STRIDE + 2 * pr;
+            const float *base = staged + e + lane * STRIDE + 2 * pr;
             const float *wrow = t_win + pr * (2 * G::NZP);
             float2 in[NZ];
 #pragma unroll
@@ -708,8 +739,8 @@ static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tile
 }
 
 template <typename PcmT>
-int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-              cudaStream_t stream)
+int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t /*pcm_len*/,
+              float *d_out, cudaStream_t stream)
 {
     const SpState *st = static_cast<const SpState *>(plan->sp_state);
     if (st == nullptr) return MFCC_ENOTSUP;
@@ -723,7 +754,7 @@ int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const
     return launch_variant<PcmT, 200, 80, 16, 16, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
 }
 
-template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *, cudaStream_t);
-template int sp_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *, cudaStream_t);
+template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *, cudaStream_t);
+template int sp_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, int64_t, float *, cudaStream_t);
 
 }  // namespace mfcc

@@ -55,7 +55,8 @@ struct Geo {
     static constexpr int padded(int i) { return i + kPad * (i / HOP); }
     static constexpr int SLACK = RA * NZ - L;
     static constexpr int tceil(int n_frames) { return ((n_frames - 1) * HOP + L + SLACK + 7) / 8 * 8; }
-    static constexpr int TCEIL = tceil(F);
+    static constexpr int tceil_s(int n_frames, int shift) { return (shift + (n_frames - 1) * HOP + L + SLACK + 7) / 8 * 8; }
+    static constexpr int TCEIL = tceil(F) + 8;              // + up to 7 samples of alignment shift
     static constexpr int STAGED = padded(TCEIL) + 8;
     static constexpr int PW = (NB + 7) * F;                 // 7 zeroed slack rows for the tail's 4-bin reads
     static constexpr int UNION = ((STAGED > PW ? STAGED : PW) + 3) / 4 * 4;
@@ -74,6 +75,7 @@ struct Geo {
     static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
     static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0, "16-byte aligned regions");
     static_assert(kSlots * F * PS + 128 * F <= WS, "tail scratch must fit in the workspace");
+    static_assert(SLACK + 8 <= kTileSpanSlack, "the host's span check (Tile::flags) must cover the staged span");
 };
 
 struct WideLayout {
@@ -97,10 +99,12 @@ struct WideArgs {
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
 __device__ __forceinline__ float4 lds_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+// int16 pair -> two exact floats: (v ^ 0x8000) = v + 32768 in the mantissa of 2^23; one XOR, one PRMT per float
 __device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
 {
-    const uint32_t lo = ((w & 0xFFFFu) ^ 0x4B008000u);
-    const uint32_t hi = ((w >> 16) ^ 0x4B008000u);
+    const uint32_t b = w ^ 0x80008000u;
+    const uint32_t lo = __byte_perm(b, 0x4B000000u, 0x7610);
+    const uint32_t hi = __byte_perm(b, 0x4B000000u, 0x7632);
     return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
 }
 __device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
@@ -155,27 +159,61 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         tile.out_row += q * F;
         const int tc = G::tceil(n_frames);
 
-        // ---- S0: stage y[s] = x[s] - a x[s-1] once per sample, padded by kPad words per hop ----
+        // ---- S0: stage y[n] = x[n] - a x[n-1] once per sample.  A tile whose frames lie inside the utterance is
+        // read with 16-byte loads from the 8-sample boundary o below its first sample, whatever the alignment of
+        // the utterance: the shift s = first_sample - o = e + d is absorbed by the layout (staged index i holds
+        // sample o + d + i, kPad words inserted at i = e + k HOP, so frame f starts at word e + f STRIDE) ----
+        int e = 0;
         {
             bool fast = false;
-            if constexpr (sizeof(PcmT) == 2)
-                fast = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((tile.first_sample & 7) == 0) &&
-                       (tile.utt_end - tile.first_sample >= tc);
+            const int sh = static_cast<int>(tile.first_sample & 7);
+            const int64_t o = tile.first_sample - sh;
+            if constexpr (sizeof(PcmT) == 2)   // frames inside the utterance, span inside the array: Tile::flags (host)
+                fast = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (tile.flags & kTileInside) != 0;
             if (fast) {
-                const PcmT *x = pcm + tile.first_sample;
-                const bool at_start = tile.first_sample == tile.utt_begin;
+                e = sh & 6;
+                const int d = sh & 1;
+                const PcmT *x = pcm + o;
                 const float na = -a.preemph;
-                for (int c = tid; c < (tc >> 3); c += kHalfThreads) {
+                const int nchunks = G::tceil_s(n_frames, sh) >> 3;
+                for (int c = tid; c < nchunks; c += kHalfThreads) {
                     const uint4 q = __ldg(reinterpret_cast<const uint4 *>(x) + c);
-                    float xp = 0.0f;
-                    if (c > 0 || !at_start) xp = to_f32(x[8 * c - 1]);
-                    const float2 x01 = s16x2_to_f32(q.x), x23 = s16x2_to_f32(q.y);
-                    const float2 x45 = s16x2_to_f32(q.z), x67 = s16x2_to_f32(q.w);
-                    float *dst = staged + 8 * c + kPad * (c / (HOP / 8));
-                    *reinterpret_cast<float4 *>(dst) = make_float4(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y),
-                                                                    fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
-                    *reinterpret_cast<float4 *>(dst + 4) = make_float4(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y),
-                                                                        fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                    // d = 0: the sample before the chunk; d = 1: the sample after it
+                    // (in bounds: only x[-1] of a tile at the very start of the array does not exist; the sample
+                    // after the last chunk lies inside the span the host checked, kTileSpanSlack)
+                    uint32_t pv = (d || c > 0 || o > 0) ? static_cast<uint16_t>(x[8 * c + (d ? 8 : -1)]) : 0u;
+                    uint32_t w0 = q.x, w1 = q.y, w2 = q.z, w3 = q.w;
+                    if (d) {   // odd shift: move the chunk down one half-word; its old first sample becomes the predecessor
+                        const uint32_t first = w0;
+                        w0 = __byte_perm(w0, w1, 0x5432);
+                        w1 = __byte_perm(w1, w2, 0x5432);
+                        w2 = __byte_perm(w2, w3, 0x5432);
+                        w3 = __byte_perm(w3, pv, 0x5432);
+                        pv = first;
+                    }
+                    const float xp = s16x2_to_f32(pv).x;
+                    const float2 x01 = s16x2_to_f32(w0), x23 = s16x2_to_f32(w1);
+                    const float2 x45 = s16x2_to_f32(w2), x67 = s16x2_to_f32(w3);
+                    const float4 lo4 = make_float4(fmaf(na, xp, x01.x), fmaf(na, x01.x, x01.y),
+                                                   fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
+                    const float4 hi4 = make_float4(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y),
+                                                   fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                    // chunk c = (HOP / 8) k + m lies in hop block k, except the words below e of the chunks with
+                    // m = 0, which still belong to block k - 1 (one chunk in HOP / 8 takes the split stores)
+                    const int k = c / (HOP / 8);
+                    float *dst = staged + 8 * c + kPad * k;
+                    if (e != 0 && k > 0 && c == k * (HOP / 8)) {
+                        float *dl = dst - kPad;
+                        *reinterpret_cast<float2 *>((0 < e ? dl : dst) + 0) = make_float2(lo4.x, lo4.y);
+                        *reinterpret_cast<float2 *>((2 < e ? dl : dst) + 2) = make_float2(lo4.z, lo4.w);
+                        *reinterpret_cast<float2 *>((4 < e ? dl : dst) + 4) = make_float2(hi4.x, hi4.y);
+                        *reinterpret_cast<float2 *>(dst + 6) = make_float2(hi4.z, hi4.w);
+                    } else {
+                        *reinterpret_cast<float4 *>(dst) = lo4;
+                        *reinterpret_cast<float4 *>(dst + 4) = hi4;
+                    }
+                    // the utterance's first sample has no predecessor: y = x (word e of chunk 0, written just above)
+                    if (c == 0 && tile.first_sample == tile.utt_begin) staged[e] = to_f32(x[sh]);
                 }
             } else {
                 const int64_t room_lo = tile.first_sample - tile.utt_begin;
@@ -197,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         // ---- S1: pass 1.  Slot = column pair (a, a + 1): windowed real DFT-64 over b, inter-pass twiddle ----
         {
             const int pr = slot;
-            const float *base = staged + f * STRIDE + 2 * pr;
+            const float *base = staged + e + f * STRIDE + 2 * pr;
             const float *wrow = t_win + pr * (2 * G::NZP);
             float2 in[NZ];
 #pragma unroll
@@ -514,8 +552,8 @@ void wide_release(mfcc_plan *plan)
 }
 
 template <typename PcmT>
-int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-                cudaStream_t stream)
+int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t /*pcm_len*/,
+                float *d_out, cudaStream_t stream)
 {
     const WideState *st = static_cast<const WideState *>(plan->wide_state);
     if (st == nullptr) return MFCC_ENOTSUP;
@@ -540,7 +578,7 @@ int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, con
     return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
 }
 
-template int wide_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *, cudaStream_t);
-template int wide_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *, cudaStream_t);
+template int wide_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *, cudaStream_t);
+template int wide_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, int64_t, float *, cudaStream_t);
 
 }  // namespace mfcc

@@ -23,8 +23,22 @@ struct Tile {
     int64_t first_sample;  // start of the tile's frame 0
     int64_t out_row;       // output row of the tile's frame 0
     int32_t n_frames;      // 1..kTileFrames
-    int32_t reserved;
+    int32_t flags;         // kTileInside | ...
 };
+
+// Tile::flags bit 0: every frame of the tile lies inside its utterance (no zero fill) and the span a fused
+// kernel stages for it — from the 8-sample boundary below first_sample to the last frame's end plus
+// kTileSpanSlack samples of transform slack and rounding — lies inside the batch's PCM array.  Such a tile can
+// be fetched by bulk copy / 16-byte loads whatever the alignment of its utterance.
+constexpr int32_t kTileInside = 1;
+constexpr int kTileSpanSlack = 64;
+inline int32_t tile_flags(const mfcc_params &p, const Tile &t, int64_t total_samples)
+{
+    const int64_t last_end = t.first_sample + static_cast<int64_t>(t.n_frames - 1) * p.hop_len + p.frame_len;
+    const int64_t o = t.first_sample & ~static_cast<int64_t>(7);
+    return (last_end <= t.utt_end && o + ((last_end - o + kTileSpanSlack + 7) & ~static_cast<int64_t>(7)) <= total_samples)
+               ? kTileInside : 0;
+}
 
 // Host-side tables, evaluated in double and rounded once to f32 (DESIGN.md "Tables").
 struct HostTables {
@@ -125,15 +139,15 @@ const char *sp_match(const mfcc_params &p, const HostTables &h);
 int sp_prepare(mfcc_plan *plan);
 void sp_release(mfcc_plan *plan);
 template <typename PcmT>
-int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-              cudaStream_t stream);
+int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
+              float *d_out, cudaStream_t stream);
 // Large-transform variant (mfcc_fused_wide.cu): 2048-point frames, 8 frames per tile, 4 items per warp.
 const char *wide_match(const mfcc_params &p, const HostTables &h);
 int wide_prepare(mfcc_plan *plan);
 void wide_release(mfcc_plan *plan);
 template <typename PcmT>
-int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-                cudaStream_t stream);
+int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
+                float *d_out, cudaStream_t stream);
 // Upload whatever constant tables the fused kernel needs (called at plan creation).
 int fused_prepare(mfcc_plan *plan);
 void fused_release(mfcc_plan *plan);

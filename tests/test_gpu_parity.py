@@ -113,6 +113,9 @@ def test_option_matrix_matches_oracle(kernel):
         base.copy(frame_len=512, hop_len=128), base.copy(frame_len=320, hop_len=100, preemph=0.95),
         base.copy(pad_mode=PAD_ZERO_TAIL, lifter=22), base.copy(output=OUT_LOGMEL, n_mel=80, n_cep=80),
         make_params(sample_rate=8000, frame_len=256, hop_len=64, nfft=256, n_mel=24, n_cep=12),
+        # cepstral counts around the 8-warp split of the DCT (warp w forms c[w] and c[w + 8])
+        base.copy(n_cep=5), base.copy(n_cep=8), base.copy(n_cep=9), base.copy(n_cep=16), base.copy(n_mel=25, n_cep=16),
+        config_b().copy(n_cep=1), config_b().copy(n_mel=21, n_cep=13, log_floor=1e-30),
     ]
     off = np.array([0, 5000, 5100, 12345, 12345, 20000], np.int64)
     pcm = noise_utterance(int(off[-1]), seed=22)
@@ -188,6 +191,29 @@ def test_bad_calls_fail_loudly():
     assert api.Plan(config_a(), kernel=KERNEL_FUSED_CT).kernel_name.startswith("fused_ct_")
     assert api.Plan(config_a().copy(hop_len=128)).kernel_name.startswith("fused_rt_")
     assert api.Plan(config_a(), kernel=KERNEL_FUSED_RT).kernel_name.startswith("fused_rt_")
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_every_start_alignment_takes_the_same_values(name):
+    """Utterances may start at any sample of the concatenated array: the bulk-copy staging absorbs the
+    shift (first_sample mod 8 = 0..7).  Same clip at 8 alignments -> bit-identical rows, and oracle parity."""
+    p = CFG[name]()
+    plan = api.Plan(p)
+    L, H = p.frame_len, p.hop_len
+    clip = noise_utterance(L + 75 * H + 3, seed=77)          # 76 frames: two full tiles and a partial one (A, B)
+    ref = oracle.mfcc(p, clip)
+    rows = []
+    for shift in range(8):
+        head = noise_utterance(8 * 50 + shift, seed=78)      # pushes the clip to alignment `shift`
+        tail = noise_utterance(1000, seed=79)                # keeps the staged span inside the array
+        off = np.cumsum([0, len(head), len(clip), len(tail)]).astype(np.int64)
+        got, fo = run_device(plan, np.concatenate([head, clip, tail]), off)
+        mine = got[fo[1]:fo[2]]
+        assert mine.shape == ref.shape
+        assert_parity(mine, ref, what=f"{name} shift {shift}")
+        rows.append(mine)
+    for shift in range(1, 8):
+        assert np.array_equal(rows[shift], rows[0]), f"alignment {shift} changed the values"
 
 
 # ---- BASELINE.json full sizes, through size-independent properties ----
