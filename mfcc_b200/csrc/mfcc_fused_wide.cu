@@ -63,7 +63,9 @@ struct Geo {
     static constexpr int WSROW = RA * F * 2 + 16;           // floats per complex row, padded
     static constexpr int WS = H * WSROW;                    // rows k1 = 1 .. H
     static constexpr int R0 = RA * F;                       // row 0 (real)
-    static constexpr int HALF = UNION + WS + R0;
+    static constexpr int RAWOFF = 8192;                     // raw PCM of the NEXT unit lands in the workspace past the tail scratch
+    static constexpr int RAW = (TCEIL + 16) / 2;            // floats holding 8 lead + TCEIL + 1 look-ahead int16 samples
+    static constexpr int HALF = UNION + WS + R0 + 4;        // + mbarrier (8 B in a 16-B slot)
     static constexpr int T_WIN = 0;                         // [RA/2][NZP] float2
     static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;   // [RA][H] float2: W_N^(a k1), k1 = 1 .. H at slot k1 - 1
     static constexpr int TABF = T_TW + RA * H * 2;
@@ -74,7 +76,8 @@ struct Geo {
     static_assert(H == 2 * kSlots, "two rounds of complex rows");
     static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
     static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0, "16-byte aligned regions");
-    static_assert(kSlots * F * PS + 128 * F <= WS, "tail scratch must fit in the workspace");
+    static_assert(kSlots * F * PS + 128 * F <= RAWOFF && RAWOFF + RAW <= WS && RAWOFF % 4 == 0,
+                  "tail scratch, then the raw PCM buffer, must fit in the workspace");
     static_assert(SLACK + 8 <= kTileSpanSlack, "the host's span check (Tile::flags) must cover the staged span");
 };
 
@@ -113,6 +116,36 @@ __device__ __forceinline__ void half_sync(int half)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kHalfThreads) : "memory");
 }
+// ---- mbarrier + bulk async copy (TMA engine, 1-D), as in mfcc_fused_sp.cu ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// orders the half's earlier generic-proxy accesses to the workspace before the async-proxy write of the copy
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float pwr(const rf::cplx &z) { return fmaf(z.re, z.re, z.im * z.im); }
 
 template <typename PcmT, int L_, int HOP_>
@@ -132,6 +165,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
     float *ws = mine + G::UNION;          // complex rows
     float *r0row = ws + G::WS;            // row 0 (real) [RA][F]
     float *scr = ws;                      // tail scratch (aliases ws)
+    // The NEXT unit's PCM is fetched by one bulk async copy into the part of the workspace the tail does not
+    // use, issued once pass 2 has released the workspace (B3) and consumed by the next S0 before S1 rewrites it.
+    const int16_t *raw16 = reinterpret_cast<const int16_t *>(ws + G::RAWOFF);
+    const uint32_t raw_s = smem_u32(raw16), bar = smem_u32(r0row + G::R0);
+    if (tid == 0) mbar_init(bar, 1);
 
     for (int i = G::NB * F + tid; i < G::PW; i += kHalfThreads) pw[i] = 0.0f;   // slack rows stay zero
     for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
@@ -147,17 +185,46 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
     constexpr int kQ = kTileFrames / F;
     const int64_t n_units = a.n_tiles * kQ;
     const int64_t first = 2 * static_cast<int64_t>(blockIdx.x) + half, step = 2 * static_cast<int64_t>(gridDim.x);
+    const bool base_ok = sizeof(PcmT) == 2 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+    // unit uu of tile tl: its first sample and frame count; "vector-loadable" = frames inside the utterance and
+    // staged span inside the array (Tile::flags, checked on the host), whatever the utterance's alignment
+    auto unit_geom = [&](const Tile &tl, int64_t uu, int64_t &fs, int &nf) -> bool {
+        const int qq = static_cast<int>(uu % kQ);
+        nf = min(F, tl.n_frames - qq * F);
+        fs = tl.first_sample + static_cast<int64_t>(qq) * F * HOP;
+        return base_ok && nf > 0 && (tl.flags & kTileInside) != 0;
+    };
+    // raw16[8 + i] = x[o + i], o = the 8-sample boundary below fs; the 8 samples before o ride along when they exist
+    auto issue_copy = [&](int64_t fs, int nf) {
+        const int s = static_cast<int>(fs & 7);
+        const int64_t o = fs - s;
+        const int lead = o >= 8 ? 8 : 0;
+        const uint32_t bytes = static_cast<uint32_t>(lead + G::tceil_s(nf, s)) * 2u;
+        fence_proxy_async();
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(raw_s + (8 - lead) * 2, pcm + o - lead, bytes, bar);
+    };
     Tile nt{};
-    if (first < n_units) nt = a.tiles[first / kQ];
+    bool copied = false;          // a bulk copy for the upcoming unit is in flight (same value in every thread of the half)
+    uint32_t phase = 0;
+    if (first < n_units) {
+        nt = a.tiles[first / kQ];
+        int64_t fs;
+        int nf;
+        copied = unit_geom(nt, first, fs, nf);
+        if (copied && tid == 0) issue_copy(fs, nf);
+    }
     for (int64_t u = first; u < n_units; u += step) {
         Tile tile = nt;
         if (u + step < n_units) nt = a.tiles[(u + step) / kQ];   // arrives during the unit
         const int q = static_cast<int>(u % kQ);
         const int n_frames = min(F, tile.n_frames - q * F);
-        if (n_frames <= 0) continue;                              // (uniform for the half: no barrier is skipped by part of it)
+        if (n_frames <= 0) continue;                              // (uniform for the half: no barrier is skipped by part of it; no copy was issued for it)
         tile.first_sample += static_cast<int64_t>(q) * F * HOP;
         tile.out_row += q * F;
         const int tc = G::tceil(n_frames);
+        const bool have_raw = copied;
+        copied = false;
 
         // ---- S0: stage y[n] = x[n] - a x[n-1] once per sample.  A tile whose frames lie inside the utterance is
         // read with 16-byte loads from the 8-sample boundary o below its first sample, whatever the alignment of
@@ -173,15 +240,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             if (fast) {
                 e = sh & 6;
                 const int d = sh & 1;
-                const PcmT *x = pcm + o;
+                // samples from o on: in the raw buffer when the copy was issued a unit ahead, else straight from HBM
+                if (have_raw) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                }
+                const int16_t *x = have_raw ? raw16 + 8 : reinterpret_cast<const int16_t *>(pcm) + o;
                 const float na = -a.preemph;
                 const int nchunks = G::tceil_s(n_frames, sh) >> 3;
                 for (int c = tid; c < nchunks; c += kHalfThreads) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(x) + c);
+                    const uint4 q = *(reinterpret_cast<const uint4 *>(x) + c);
                     // d = 0: the sample before the chunk; d = 1: the sample after it
                     // (in bounds: only x[-1] of a tile at the very start of the array does not exist; the sample
                     // after the last chunk lies inside the span the host checked, kTileSpanSlack)
-                    uint32_t pv = (d || c > 0 || o > 0) ? static_cast<uint16_t>(x[8 * c + (d ? 8 : -1)]) : 0u;
+                    uint32_t pv = (d || c > 0 || o > 0 || have_raw) ? static_cast<uint16_t>(x[8 * c + (d ? 8 : -1)]) : 0u;
                     uint32_t w0 = q.x, w1 = q.y, w2 = q.z, w3 = q.w;
                     if (d) {   // odd shift: move the chunk down one half-word; its old first sample becomes the predecessor
                         const uint32_t first = w0;
@@ -307,6 +379,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         }
         half_sync(half);   // B3: P complete, workspace free
+        if (u + step < n_units) {
+            int64_t fs;
+            int nf;
+            copied = unit_geom(nt, u + step, fs, nf);
+            if (copied && tid == 0) issue_copy(fs, nf);
+        }
 
         // ---- S3: the slot's filter group (see mfcc_fused_sp.cu S3): per segment S = sum P, T = sum i P give
         // rise = s T and fall = s (w S - T); filter m completes at the end of segment m + 1; then log and the
