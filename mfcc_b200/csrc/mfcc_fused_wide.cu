@@ -41,8 +41,7 @@ constexpr int kSlots = kWarps * SUBS;     // 16
 constexpr int kHalfThreads = kWarps * 32;
 constexpr int kThreads = 2 * kHalfThreads;
 constexpr int kPad = 4;
-constexpr int KC = 40;                    // cepstra accumulated per frame (n_cep <= KC)
-constexpr int PS = KC + 1;
+constexpr int KC = 40;                    // cepstra per frame (n_cep <= KC): thread (slot, frame) forms k = slot, slot + 16, slot + 32
 constexpr size_t kSmemMax = 227 * 1024;
 
 template <int L_, int HOP_>
@@ -76,16 +75,16 @@ struct Geo {
     static_assert(H == 2 * kSlots, "two rounds of complex rows");
     static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
     static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0, "16-byte aligned regions");
-    static_assert(kSlots * F * PS + 128 * F <= RAWOFF && RAWOFF + RAW <= WS && RAWOFF % 4 == 0,
+    static_assert(129 * F <= RAWOFF && RAWOFF + RAW <= WS && RAWOFF % 4 == 0,
                   "tail scratch, then the raw PCM buffer, must fit in the workspace");
     static_assert(SLACK + 8 <= kTileSpanSlack, "the host's span check (Tile::flags) must cover the staged span");
 };
 
 struct WideLayout {
     int wseg;     // int2 per slot: its segments [first, last] (first > last: none)
-    int wfilt;    // int2 per slot: its filters [first, last)
     int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), s * w}
-    int dct;      // [ceil(n_mel / 2)][KC]: DCT column of filter m < ceil(n_mel/2); column n_mel-1-m is (-1)^k times it
+    int dct;      // [16 slots][hmp / 2] float4 {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}, then [16][hmp / 2] float2
+                  // {d[s+32][m], d[s+32][m+1]}; m < hmp = ceil(n_mel / 2) rounded up to even; zero past n_cep
     int total;
 };
 
@@ -96,7 +95,7 @@ struct WideArgs {
     const float *tab;
     WideLayout lay;
     int n_mel, n_cep, logmel;
-    int ls, est, mel_magic, half_mel;
+    int ls, mel_magic, hmp;
     float preemph, log_floor;
 };
 
@@ -110,6 +109,14 @@ __device__ __forceinline__ float2 s16x2_to_f32(uint32_t w)
     const uint32_t hi = __byte_perm(b, 0x4B000000u, 0x7632);
     return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
 }
+// log2 of a NORMAL positive float (callers clamp to log_floor first): one MUFU.LG2, no denormal rescaling
+__device__ __forceinline__ float lg2_fast(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLn2 = 0.69314718055994531f;
 __device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ void half_sync(int half)
@@ -176,7 +183,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW;
     const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
-    const int2 *t_wfilt = reinterpret_cast<const int2 *>(tab + a.lay.wfilt);
     const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
     const float *t_dct = tab + a.lay.dct;
     __syncthreads();
@@ -387,13 +393,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         }
 
         // ---- S3: the slot's filter group (see mfcc_fused_sp.cu S3): per segment S = sum P, T = sum i P give
-        // rise = s T and fall = s (w S - T); filter m completes at the end of segment m + 1; then log and the
-        // filter's DCT column into 40 running cepstra.  Loop counts differ between the four slots of a warp:
-        // the warp runs the longest of them. ----
+        // rise = s T and fall = s (w S - T); filter m completes at the end of segment m + 1 and its log goes to
+        // lg[m][frame] (cepstra) or the frame's log-mel row.  Loop counts differ between the four slots of a
+        // warp: the warp runs the longest of them. ----
         {
             const int2 wsg = t_wseg[slot];
-            const int2 wf = t_wfilt[slot];
-            float *est = scr + a.est + f;                   // E[m] of this frame at est[m * F]
+            const int lgs = a.logmel ? 1 : F;               // stride between bands
+            float *lgw = (a.logmel ? scr + f * a.ls : scr + f) + wsg.x * lgs;   // band wsg.x is this slot's first
             float r_prev = 0.0f;
 #pragma unroll 1
             for (int j = wsg.x; j <= wsg.y; ++j) {
@@ -410,48 +416,27 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     i0 += 4.0f;
                     p += 4 * F;
                 }
-#pragma unroll 1
-                for (int e = w & 3; e > 0; --e) {
-                    const float a0 = p[0];
-                    T = fmaf(i0, a0, T);
-                    S += a0;
-                    i0 += 1.0f;
-                    p += F;
+                if (const int lo = w & 3) {                 // 1..3 leftover bins, no loop: the rows past the segment are
+                    const float a0 = p[0];                  // finite (next segment or the zeroed slack rows) and deselected
+                    const float a1 = lo > 1 ? p[F] : 0.0f;
+                    const float a2 = lo > 2 ? p[2 * F] : 0.0f;
+                    const float sa = (a0 + a1) + a2;
+                    T = fmaf(i0, sa, T) + fmaf(2.0f, a2, a1);
+                    S += sa;
                 }
                 const float r = sg.z * T;
-                if (j > wsg.x) est[(j - 1) * F] = r_prev + fmaf(sg.w, S, -r);
+                if (j > wsg.x) {
+                    *lgw = kLn2 * lg2_fast(fmaxf(r_prev + fmaf(sg.w, S, -r), a.log_floor));
+                    lgw += lgs;
+                }
                 r_prev = r;
             }
-            if (a.logmel) {
-#pragma unroll 1
-                for (int m = wf.x; m < wf.y; ++m) scr[f * a.ls + m] = __logf(fmaxf(est[m * F], a.log_floor));
-            } else {
-                float c[KC];
-#pragma unroll
-                for (int k = 0; k < KC; ++k) c[k] = 0.0f;
-#pragma unroll 1
-                for (int m = wf.x; m < wf.y; ++m) {
-                    const float lg = __logf(fmaxf(est[m * F], a.log_floor));
-                    const bool mirror = m >= a.half_mel;
-                    const float lo = mirror ? -lg : lg;          // odd cepstra change sign under m -> M - 1 - m
-                    const float *dc = t_dct + (mirror ? a.n_mel - 1 - m : m) * KC;
-#pragma unroll
-                    for (int q = 0; q < KC; q += 4) {
-                        const float4 dv = lds_f4(dc + q);
-                        c[q + 0] = fmaf(dv.x, lg, c[q + 0]);
-                        c[q + 1] = fmaf(dv.y, lo, c[q + 1]);
-                        c[q + 2] = fmaf(dv.z, lg, c[q + 2]);
-                        c[q + 3] = fmaf(dv.w, lo, c[q + 3]);
-                    }
-                }
-                float *dst = scr + (slot * F + f) * PS;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) dst[k] = c[k];
-            }
         }
-        half_sync(half);   // B4
+        half_sync(half);   // B4: every band's log energy is in the scratch
 
-        // ---- S4: add the 16 partial cepstra per frame and store (64 lanes per frame, n_cep of them live) ----
+        // ---- S4: log-mel rows are copied out coalesced.  Cepstra: thread (slot, frame) forms c[slot], c[slot + 16]
+        // and c[slot + 32] — all of one parity, so the DCT symmetry d[k][M-1-m] = (-1)^k d[k][m] folds the band
+        // pairs first: v[m] = lg[m] +- lg[M-1-m], then ceil(M/2) terms per cepstrum ----
         if (a.logmel) {
             const int M = a.n_mel, total = n_frames * M;
             float *o = a.out + tile.out_row * M;
@@ -459,17 +444,35 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 const int fr = (i * a.mel_magic) >> 20, m = i - fr * M;
                 o[i] = scr[fr * a.ls + m];
             }
-        } else {
-            const int k = tid & 63;
-#pragma unroll 1
-            for (int fr = tid >> 6; fr < n_frames; fr += kHalfThreads / 64) {
-                if (k < a.n_cep) {
-                    const float *src = scr + fr * PS + k;
-                    float s = src[0];
-#pragma unroll
-                    for (int sl = 1; sl < kSlots; ++sl) s += src[sl * F * PS];
-                    a.out[(tile.out_row + fr) * a.n_cep + k] = s;
+        } else if (slot < a.n_cep) {
+            const float *lg = scr + f, *lgm = scr + (a.n_mel - 1) * F + f;
+            const float sgn = (slot & 1) ? -1.0f : 1.0f;
+            const int hq = a.hmp >> 1;                       // band pairs are taken two at a time
+            const float4 *da = reinterpret_cast<const float4 *>(t_dct) + slot * hq;                     // {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}
+            const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * a.hmp * 2) + slot * hq; // {d[s+32][m], d[s+32][m+1]}, s < 8
+            const bool third = slot + 2 * kSlots < a.n_cep;  // uniform per warp (slots 4 w .. 4 w + 3)
+            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+#pragma unroll 4
+            for (int q2 = 0; q2 < hq; ++q2) {
+                const int m = 2 * q2;
+                const float v0 = fmaf(sgn, lgm[-m * F], lg[m * F]);
+                const float v1 = fmaf(sgn, lgm[-(m + 1) * F], lg[(m + 1) * F]);
+                const float4 d = da[q2];
+                c0 = fmaf(d.x, v0, c0);
+                c1 = fmaf(d.y, v0, c1);
+                e0 = fmaf(d.z, v1, e0);
+                e1 = fmaf(d.w, v1, e1);
+                if (third) {
+                    const float2 g = db[q2];
+                    c2 = fmaf(g.x, v0, c2);
+                    e2 = fmaf(g.y, v1, e2);
                 }
+            }
+            if (f < n_frames) {
+                float *o = a.out + (tile.out_row + f) * a.n_cep + slot;
+                o[0] = c0 + e0;
+                if (slot + kSlots < a.n_cep) o[kSlots] = c1 + e1;
+                if (third) o[2 * kSlots] = c2 + e2;
             }
         }
         // next S0 writes `staged` (nobody reads P any more); the scratch is next written by S1, after B1
@@ -521,7 +524,7 @@ std::vector<int> split_filters(const HostTables &h, int M, int filter_cost)
 
 size_t table_floats(const mfcc_params &p)
 {
-    return G0::TABF + 4 * kSlots + 4 * static_cast<size_t>(p.n_mel + 1) + static_cast<size_t>(KC) * ((p.n_mel + 1) / 2) + 16;
+    return G0::TABF + 2 * kSlots + 4 * static_cast<size_t>(p.n_mel + 1) + 3 * static_cast<size_t>(kSlots) * ((p.n_mel + 1) / 2 + 1) + 16;
 }
 
 }  // namespace
@@ -533,9 +536,9 @@ const char *wide_match(const mfcc_params &p, const HostTables &h)
     for (int j = 0; j + 1 < static_cast<int>(h.mel_bins.size()); ++j)
         if (h.mel_bins[j + 1] < h.mel_bins[j]) return nullptr;
     if ((table_floats(p) + 2 * static_cast<size_t>(G0::HALF)) * sizeof(float) > kSmemMax) return nullptr;
-    const size_t scratch = (p.output == MFCC_OUT_LOGMEL ? F * static_cast<size_t>(p.n_mel | 1) : kSlots * F * PS) +
-                           F * static_cast<size_t>(p.n_mel);
-    if (scratch > static_cast<size_t>(G0::WS)) return nullptr;
+    if (p.n_mel < 2 || p.log_floor < 1.17549435e-38f) return nullptr;   // band pairs; lg2.approx.ftz needs a normal floor
+    // tail scratch (log band energies [n_mel][F], or log-mel rows [F][n_mel | 1]) must stay below the raw PCM buffer
+    if (F * static_cast<size_t>(p.n_mel | 1) > static_cast<size_t>(G0::RAWOFF)) return nullptr;
     return "fused_wide_tile8_L1200_H480_real64x32";
 }
 
@@ -564,15 +567,13 @@ int wide_prepare(mfcc_plan *plan)
     if (static_cast<int>(tab.size()) != G0::TABF) return MFCC_ECUDA;
 
     WideLayout lay{};
-    const std::vector<int> beg = split_filters(h, M, p.output == MFCC_OUT_LOGMEL ? 10 : 60);
+    const std::vector<int> beg = split_filters(h, M, 10);
     lay.wseg = static_cast<int>(tab.size());
     for (int w = 0; w < kSlots; ++w) {
         const int m0 = beg[w], m1 = beg[w + 1];
         push_int(m1 > m0 ? m0 : 1);
         push_int(m1 > m0 ? m1 : 0);
     }
-    lay.wfilt = static_cast<int>(tab.size());
-    for (int w = 0; w < kSlots; ++w) { push_int(beg[w]); push_int(beg[w + 1]); }
     align4();
     lay.seg = static_cast<int>(tab.size());
     for (int j = 0; j <= M; ++j) {
@@ -584,11 +585,27 @@ int wide_prepare(mfcc_plan *plan)
         tab.push_back(static_cast<float>(sc * w));
     }
     align4();
-    const int half_mel = (M + 1) / 2;
+    // DCT entries by slot (see S4).  Band m pairs with M - 1 - m; for odd M the middle band pairs with itself,
+    // so its entry is halved (exact); the padding column of an odd half is zero.
+    const int half_mel = (M + 1) / 2, hmp = (half_mel + 1) / 2 * 2;
+    auto dct_at = [&](int k, int m) -> float {
+        if (p.output != MFCC_OUT_CEPSTRA || k >= p.n_cep || m >= half_mel) return 0.0f;
+        const float v = h.dct[static_cast<size_t>(k) * M + m];
+        return (M % 2 == 1 && m == half_mel - 1) ? 0.5f * v : v;
+    };
     lay.dct = static_cast<int>(tab.size());
-    for (int m = 0; m < half_mel; ++m)
-        for (int k = 0; k < KC; ++k)
-            tab.push_back(p.output == MFCC_OUT_CEPSTRA && k < p.n_cep ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f);
+    for (int sl = 0; sl < kSlots; ++sl)
+        for (int m = 0; m < hmp; m += 2) {
+            tab.push_back(dct_at(sl, m));
+            tab.push_back(dct_at(sl + kSlots, m));
+            tab.push_back(dct_at(sl, m + 1));
+            tab.push_back(dct_at(sl + kSlots, m + 1));
+        }
+    for (int sl = 0; sl < kSlots; ++sl)
+        for (int m = 0; m < hmp; m += 2) {
+            tab.push_back(dct_at(sl + 2 * kSlots, m));
+            tab.push_back(dct_at(sl + 2 * kSlots, m + 1));
+        }
     align4();
     lay.total = static_cast<int>(tab.size());
 
@@ -601,9 +618,8 @@ int wide_prepare(mfcc_plan *plan)
     st->args.n_cep = p.n_cep;
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
     st->args.ls = M | 1;
-    st->args.est = p.output == MFCC_OUT_LOGMEL ? F * (M | 1) : kSlots * F * PS;
     st->args.mel_magic = (1 << 20) / M + 1;
-    st->args.half_mel = half_mel;
+    st->args.hmp = hmp;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {

@@ -129,6 +129,30 @@ def test_option_matrix_matches_oracle(kernel):
         assert_parity(got, ref, what=f"{p.as_dict()}/{kernel}", truth=truth)
 
 
+def test_wide_kernel_option_matrix():
+    """2048-point geometry (configs[3]): band and cepstrum counts around the tail's pairing (band m with
+    M - 1 - m, cepstra slot, slot + 16, slot + 32), log-mel output, lifter, zero-tail padding."""
+    base = config_c()
+    variants = [base, base.copy(n_mel=41, n_cep=20), base.copy(n_mel=40, n_cep=40), base.copy(n_cep=7),
+                base.copy(n_cep=16), base.copy(n_cep=17), base.copy(n_cep=33), base.copy(n_mel=2, n_cep=2),
+                base.copy(output=OUT_LOGMEL, n_mel=64), base.copy(lifter=22, pad_mode=PAD_ZERO_TAIL),
+                base.copy(n_mel=128, n_cep=40, f_lo=20.0, f_hi=20000.0)]
+    off = np.array([0, 30000, 30007, 61234, 61234, 100001], np.int64)
+    pcm = noise_utterance(int(off[-1]), seed=23)
+    for p in variants:
+        plan = api.Plan(p)
+        assert plan.kernel_name.startswith("fused_wide"), plan.kernel_name
+        got, fo = run_device(plan, pcm, off)
+        ref, fo_ref = oracle.mfcc_batch(p, pcm, off)
+        assert np.array_equal(fo, fo_ref)
+        truth = np.concatenate([oracle.mfcc(p, pcm[off[u]:off[u + 1]], dtype=np.float64)
+                                for u in range(len(off) - 1)]).astype(np.float32)
+        # the stated tolerance is on plain cepstra; a lifter multiplies cepstrum k by up to 1 + Q/2 and the f32
+        # rounding noise with it (the f32 oracle itself is 2.3e-4 off the f64 truth for Q = 22, 80 bands)
+        gain = 1.0 + 0.5 * p.lifter
+        assert_parity(got, ref, abs_tol=1e-3 * gain, rel_tol=1e-4 * gain, what=f"{p.as_dict()}", truth=truth)
+
+
 def test_known_answers_on_device():
     p = config_a()
     plan = api.Plan(p)
