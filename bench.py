@@ -208,6 +208,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the MFCC path has no CPU fallback)")
     torch.cuda.set_device(local)
+    from mfcc_b200.sharding import bind_near_gpu
+    full_affinity = os.sched_getaffinity(0)
+    numa_cores = bind_near_gpu(local)   # pinned e2e buffers are first-touched on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -292,6 +295,7 @@ def main():
         e2e_dt = float(t.item())
     e2e_value = total_frames * args.e2e_steps / e2e_dt
     e2e_ok = bool(np.array_equal(h_out.array, d_out.cpu().numpy()))
+    os.sched_setaffinity(0, full_affinity)   # the CPU-baseline leg below uses every host core again
 
     if rank != 0:
         if world > 1:
@@ -356,6 +360,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "steps": args.e2e_steps, "step_ms": e2e_step_ms,
                 "api": "mfcc_compute_host (pinned host buffers, 3-stream chunk pipeline)",
+                "host_cores_bound": len(numa_cores) if numa_cores else None,
                 "matches_device_path": e2e_ok},
         "gpu_launches": launches,
         "roofline": roofline, "roofline_hbm": roofline_hbm,

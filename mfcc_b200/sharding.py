@@ -91,3 +91,29 @@ def gather_features(local_feat, local_rows: int, out_dim: int, group=None, dst: 
         if rank != dst:
             return None, counts
     return torch.cat([b[:c] for b, c in zip(blocks, counts)], dim=0), counts
+
+
+def bind_near_gpu(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA
+    node), so that the pinned host buffers allocated afterwards are first-touched next to the GPU's PCIe
+    root port.  With one process per GPU and host-resident audio (mfcc_compute_host) this keeps 8 concurrent
+    H2D streams off the inter-socket link.  Returns the core list, or None when NVML / affinity is unavailable
+    (nothing is changed then).  Honours CUDA_VISIBLE_DEVICES through the device's PCI bus id."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus_id = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

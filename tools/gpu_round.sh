@@ -29,3 +29,7 @@ for w in A C8; do
   echo "ncu $w rc=$?"; tail -2 gpurun_out/ncu_$w.log
 done
 fi
+# launch list of the default bench command (per-launch durations, cold-cache and serialised)
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "launch list rc=$?"
