@@ -327,8 +327,9 @@ def main():
     if os.path.exists(prof):
         try:
             t = json.load(open(prof)).get(plan.kernel_name)
-            if t:
-                roofline["traffic"] = roofline_hbm["traffic"] = t
+            if t:   # measured DRAM bytes per frame (one ncu --set full capture) x the frames of one launch
+                roofline["traffic"] = roofline_hbm["traffic"] = int(round(t["bytes_per_frame"] * frames_per_launch))
+                roofline["traffic_source"] = t["capture"]
         except Exception:
             pass
 
