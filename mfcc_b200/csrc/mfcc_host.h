@@ -93,7 +93,8 @@ struct mfcc_plan {
     void *d_tiles = nullptr;   size_t d_tiles_bytes = 0;   // device tile table of the call in flight
     void *h_tiles = nullptr;   size_t h_tiles_bytes = 0;   // its pinned staging copy
     cudaEvent_t tiles_ready = nullptr;
-    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> chunk_ready;   // one per H2D chunk of the call in flight (reused across calls)
+    cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};   // compute_host: two H2D queues, two compute + D2H queues
 };
 
 struct mfcc_batch {
