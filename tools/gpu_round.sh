@@ -22,7 +22,7 @@ for n in ("A", "B", "B3", "C8", "C"):
 PY
 timeout 300 python tools/tc_dft_bound.py > gpurun_out/tc_dft_bound.jsonl 2> gpurun_out/tc_dft_bound.err; echo "tc bound rc=$?"; cat gpurun_out/tc_dft_bound.jsonl
 if [ "$1" != "noncu" ]; then
-for w in A C8; do
+for w in A B3 C8; do
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --workload $w"
   $CMD > gpurun_out/plain_$w.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:fused -s 5 -c 1 -f -o gpurun_out/prof_$w $CMD > gpurun_out/ncu_$w.log 2>&1
