@@ -81,7 +81,6 @@ struct Geo {
 };
 
 struct WideLayout {
-    int wseg;     // int2 per slot: its segments [first, last] (first > last: none)
     int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), s * w}
     int dct;      // [16 slots][hmp / 2] float4 {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}, then [16][hmp / 2] float2
                   // {d[s+32][m], d[s+32][m+1]}; m < hmp = ceil(n_mel / 2) rounded up to even; zero past n_cep
@@ -96,6 +95,7 @@ struct WideArgs {
     WideLayout lay;
     int n_mel, n_cep, logmel;
     int ls, mel_magic, hmp;
+    int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 1][F] x 2
     float preemph, log_floor;
 };
 
@@ -155,7 +155,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float pwr(const rf::cplx &z) { return fmaf(z.re, z.re, z.im * z.im); }
 
-template <typename PcmT, int L_, int HOP_>
+// MEL > 0: the plan has exactly MEL (even) bands and cepstral output, so the DCT loop of S4 is unrolled; MEL = 0: any plan.
+template <typename PcmT, int L_, int HOP_, int MEL>
 __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__restrict__ pcm, const WideArgs a)
 {
     using G = Geo<L_, HOP_>;
@@ -182,7 +183,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
     for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW;
-    const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
     const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
     const float *t_dct = tab + a.lay.dct;
     __syncthreads();
@@ -392,17 +392,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             if (copied && tid == 0) issue_copy(fs, nf);
         }
 
-        // ---- S3: the slot's filter group (see mfcc_fused_sp.cu S3): per segment S = sum P, T = sum i P give
-        // rise = s T and fall = s (w S - T); filter m completes at the end of segment m + 1 and its log goes to
-        // lg[m][frame] (cepstra) or the frame's log-mel row.  Loop counts differ between the four slots of a
-        // warp: the warp runs the longest of them. ----
+        // ---- S3: filterbank sums (see mfcc_fused_sp.cu S3): per segment S = sum P, T = sum i P give the rise into
+        // filter j, s T, and the fall out of filter j - 1, s (w S - T).  Slot s takes segments s, s + 16, s + 32, ...:
+        // the four slots of a warp then walk NEIGHBOURING segments of nearly equal width in every round, so their
+        // loop counts agree (with a contiguous filter group per slot the warp ran the longest of four different
+        // walks).  rise[j][frame] and fall[j][frame] go through the scratch; S3b adds the two halves of each band. ----
         {
-            const int2 wsg = t_wseg[slot];
-            const int lgs = a.logmel ? 1 : F;               // stride between bands
-            float *lgw = (a.logmel ? scr + f * a.ls : scr + f) + wsg.x * lgs;   // band wsg.x is this slot's first
-            float r_prev = 0.0f;
+            float *rise = scr + a.rf + f, *fall = rise + (a.n_mel + 1) * F;
 #pragma unroll 1
-            for (int j = wsg.x; j <= wsg.y; ++j) {
+            for (int j = slot; j <= a.n_mel; j += kSlots) {
                 const float4 sg = t_seg[j];
                 const float *p = pw + __float_as_int(sg.x) + f;
                 const int w = __float_as_int(sg.y);
@@ -425,11 +423,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     S += sa;
                 }
                 const float r = sg.z * T;
-                if (j > wsg.x) {
-                    *lgw = kLn2 * lg2_fast(fmaxf(r_prev + fmaf(sg.w, S, -r), a.log_floor));
-                    lgw += lgs;
-                }
-                r_prev = r;
+                rise[j * F] = r;
+                fall[j * F] = fmaf(sg.w, S, -r);
+            }
+        }
+        half_sync(half);   // B4a: every segment's two sums are in the scratch
+        // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][frame] or the frame's log-mel row ----
+        {
+            const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 1) * F;
+            const int total = a.n_mel * F;
+            for (int i = tid; i < total; i += kHalfThreads) {
+                const int m = i / F, fr = i % F;
+                const float lg = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + F], a.log_floor));
+                if (a.logmel) scr[fr * a.ls + m] = lg;
+                else scr[i] = lg;
             }
         }
         half_sync(half);   // B4: every band's log energy is in the scratch
@@ -445,29 +452,31 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 o[i] = scr[fr * a.ls + m];
             }
         } else if (slot < a.n_cep) {
-            const float *lg = scr + f, *lgm = scr + (a.n_mel - 1) * F + f;
             const float sgn = (slot & 1) ? -1.0f : 1.0f;
-            const int hq = a.hmp >> 1;                       // band pairs are taken two at a time
-            const float4 *da = reinterpret_cast<const float4 *>(t_dct) + slot * hq;                     // {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}
-            const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * a.hmp * 2) + slot * hq; // {d[s+32][m], d[s+32][m+1]}, s < 8
             const bool third = slot + 2 * kSlots < a.n_cep;  // uniform per warp (slots 4 w .. 4 w + 3)
             float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+            auto dct_terms = [&](int hq, const float *lg, const float *lgm) {
+                const float4 *da = reinterpret_cast<const float4 *>(t_dct) + slot * hq;                     // {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}
+                const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * hq * 4) + slot * hq;   // {d[s+32][m], d[s+32][m+1]}, s < 8
 #pragma unroll 4
-            for (int q2 = 0; q2 < hq; ++q2) {
-                const int m = 2 * q2;
-                const float v0 = fmaf(sgn, lgm[-m * F], lg[m * F]);
-                const float v1 = fmaf(sgn, lgm[-(m + 1) * F], lg[(m + 1) * F]);
-                const float4 d = da[q2];
-                c0 = fmaf(d.x, v0, c0);
-                c1 = fmaf(d.y, v0, c1);
-                e0 = fmaf(d.z, v1, e0);
-                e1 = fmaf(d.w, v1, e1);
-                if (third) {
-                    const float2 g = db[q2];
-                    c2 = fmaf(g.x, v0, c2);
-                    e2 = fmaf(g.y, v1, e2);
+                for (int q2 = 0; q2 < hq; ++q2) {
+                    const int m = 2 * q2;
+                    const float v0 = fmaf(sgn, lgm[-m * F], lg[m * F]);
+                    const float v1 = fmaf(sgn, lgm[-(m + 1) * F], lg[(m + 1) * F]);
+                    const float4 d = da[q2];
+                    c0 = fmaf(d.x, v0, c0);
+                    c1 = fmaf(d.y, v0, c1);
+                    e0 = fmaf(d.z, v1, e0);
+                    e1 = fmaf(d.w, v1, e1);
+                    if (third) {
+                        const float2 g = db[q2];
+                        c2 = fmaf(g.x, v0, c2);
+                        e2 = fmaf(g.y, v1, e2);
+                    }
                 }
-            }
+            };
+            if constexpr (MEL > 0) dct_terms(MEL / 4, scr + f, scr + (MEL - 1) * F + f);   // band pairs two at a time: hmp / 2
+            else dct_terms(a.hmp >> 1, scr + f, scr + (a.n_mel - 1) * F + f);
             if (f < n_frames) {
                 float *o = a.out + (tile.out_row + f) * a.n_cep + slot;
                 o[0] = c0 + e0;
@@ -492,36 +501,6 @@ struct WideState {
     int sm_count = 0;
 };
 
-inline int seg_cost(const HostTables &h, int j)
-{
-    const int w = h.mel_bins[j + 1] - h.mel_bins[j];
-    return 15 * (w / 4) + 6 * (w % 4) + 22;
-}
-
-std::vector<int> split_filters(const HostTables &h, int M, int filter_cost)
-{
-    auto cost = [&](int m0, int m1) {
-        if (m1 <= m0) return 0;
-        int c = 0;
-        for (int j = m0; j <= m1; ++j) c += seg_cost(h, j);
-        return c + filter_cost * (m1 - m0);
-    };
-    const int INF = 1 << 30;
-    std::vector<std::vector<int>> best(kSlots + 1, std::vector<int>(M + 1, INF)), arg(kSlots + 1, std::vector<int>(M + 1, 0));
-    best[0][0] = 0;
-    for (int w = 1; w <= kSlots; ++w)
-        for (int m1 = 0; m1 <= M; ++m1)
-            for (int m0 = 0; m0 <= m1; ++m0) {
-                if (best[w - 1][m0] == INF) continue;
-                const int v = std::max(best[w - 1][m0], cost(m0, m1));
-                if (v < best[w][m1]) { best[w][m1] = v; arg[w][m1] = m0; }
-            }
-    std::vector<int> beg(kSlots + 1, 0);
-    beg[kSlots] = M;
-    for (int w = kSlots; w >= 1; --w) beg[w - 1] = arg[w][beg[w]];
-    return beg;
-}
-
 size_t table_floats(const mfcc_params &p)
 {
     return G0::TABF + 2 * kSlots + 4 * static_cast<size_t>(p.n_mel + 1) + 3 * static_cast<size_t>(kSlots) * ((p.n_mel + 1) / 2 + 1) + 16;
@@ -537,8 +516,9 @@ const char *wide_match(const mfcc_params &p, const HostTables &h)
         if (h.mel_bins[j + 1] < h.mel_bins[j]) return nullptr;
     if ((table_floats(p) + 2 * static_cast<size_t>(G0::HALF)) * sizeof(float) > kSmemMax) return nullptr;
     if (p.n_mel < 2 || p.log_floor < 1.17549435e-38f) return nullptr;   // band pairs; lg2.approx.ftz needs a normal floor
-    // tail scratch (log band energies [n_mel][F], or log-mel rows [F][n_mel | 1]) must stay below the raw PCM buffer
-    if (F * static_cast<size_t>(p.n_mel | 1) > static_cast<size_t>(G0::RAWOFF)) return nullptr;
+    // tail scratch (log band energies [n_mel][F] or log-mel rows [F][n_mel | 1], then the per-segment rise / fall
+    // sums [n_mel + 1][F] x 2) must stay below the raw PCM buffer
+    if (3 * F * static_cast<size_t>(p.n_mel + 2) > static_cast<size_t>(G0::RAWOFF)) return nullptr;
     return "fused_wide_tile8_L1200_H480_real64x32";
 }
 
@@ -567,13 +547,6 @@ int wide_prepare(mfcc_plan *plan)
     if (static_cast<int>(tab.size()) != G0::TABF) return MFCC_ECUDA;
 
     WideLayout lay{};
-    const std::vector<int> beg = split_filters(h, M, 10);
-    lay.wseg = static_cast<int>(tab.size());
-    for (int w = 0; w < kSlots; ++w) {
-        const int m0 = beg[w], m1 = beg[w + 1];
-        push_int(m1 > m0 ? m0 : 1);
-        push_int(m1 > m0 ? m1 : 0);
-    }
     align4();
     lay.seg = static_cast<int>(tab.size());
     for (int j = 0; j <= M; ++j) {
@@ -620,6 +593,7 @@ int wide_prepare(mfcc_plan *plan)
     st->args.ls = M | 1;
     st->args.mel_magic = (1 << 20) / M + 1;
     st->args.hmp = hmp;
+    st->args.rf = (F * (M | 1) + 3) / 4 * 4;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
@@ -651,15 +625,17 @@ int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, con
 {
     const WideState *st = static_cast<const WideState *>(plan->wide_state);
     if (st == nullptr) return MFCC_ENOTSUP;
-    auto kern = fused_wide_kernel<PcmT, kL, kHop>;
-    static thread_local const void *configured = nullptr;
-    if (configured != reinterpret_cast<const void *>(kern)) {
+    // the BASELINE.json band count (80) with cepstral output gets the unrolled DCT
+    const bool fixed = !st->args.logmel && st->args.n_mel == 80;
+    auto kern = fixed ? fused_wide_kernel<PcmT, kL, kHop, 80> : fused_wide_kernel<PcmT, kL, kHop, 0>;
+    static thread_local const void *configured[2] = {nullptr, nullptr};
+    if (configured[fixed] != reinterpret_cast<const void *>(kern)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
             cudaSuccess) {
             cudaGetLastError();
             return MFCC_ECUDA;
         }
-        configured = reinterpret_cast<const void *>(kern);
+        configured[fixed] = reinterpret_cast<const void *>(kern);
     }
     WideArgs a = st->args;
     a.tiles = d_tiles;
