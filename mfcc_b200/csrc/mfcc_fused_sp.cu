@@ -47,6 +47,7 @@ constexpr int kHalfThreads = kWarps * 32;
 // 64 registers: 2.52 G).
 constexpr int groups_for(int rb) { return rb >= 32 ? 2 : 3; }
 constexpr int kPad = 2;
+constexpr int kSegMax = 20;                // segments one warp may be given (n_mel + 1 <= 8 * kSegMax)
 constexpr int KC = 16;                    // cepstra per frame (n_cep <= KC): warp w forms k = w and k = w + 8
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -84,8 +85,8 @@ struct Geo {
 
 // Run-time part of the table blob (offsets in floats from its start).
 struct SpLayout {
-    int wseg;     // int2 per warp: its segments [first, last] (first > last: none)
-    int seg;      // float4 per segment j: {first bin * 32 (int), width w (int), s = 1 / (w NFFT), s * w}
+    int wseg;     // per warp: kSegMax segment descriptors in walk order, float4 {first bin * 32 (int), width w (int),
+                  // s = 1 / (w NFFT), segment index j (int)}; unused slots have j = -1
     int dct;      // [kWarps][n_mel] float2: DCT entries {d[w][m], d[w + 8][m]}, zero past n_cep (n_mel padded to even)
     int total;    // floats, multiple of 4
 };
@@ -98,6 +99,8 @@ struct SpArgs {
     SpLayout lay;
     int n_mel, n_cep, logmel;
     int ls;               // log-mel staging row stride (n_mel | 1)
+    int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 1][32] x 2
+    float inv_n;          // 1 / NFFT
     int mp;               // n_mel rounded up to even (DCT row length in the table)
     int mel_magic;        // i / n_mel == (i * mel_magic) >> 20 for i < 32 * n_mel
     float preemph, log_floor;
@@ -198,8 +201,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
         *reinterpret_cast<float4 *>(tab + i) = __ldg(reinterpret_cast<const float4 *>(a.tab + i));
     const float *t_win = tab + G::T_WIN, *t_tw = tab + G::T_TW, *t_twh = tab + G::T_TWH;
-    const int2 *t_wseg = reinterpret_cast<const int2 *>(tab + a.lay.wseg);
-    const float4 *t_seg = reinterpret_cast<const float4 *>(tab + a.lay.seg);
+    const float4 *t_wseg = reinterpret_cast<const float4 *>(tab + a.lay.wseg);
     const float *t_dct = tab + a.lay.dct;
 
     // A tile takes the bulk-copy path when the PCM array is 16-byte aligned, every frame lies inside the
@@ -410,22 +412,22 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         }
         half_sync(half);   // B3: P complete, workspace free
 
-        // ---- S3: the warp's filter group.  Segment j = bins [b_j, b_j + w) rises into filter j with weight
-        // i / w and falls out of filter j - 1 with weight (w - i) / w (i = bin - b_j), so two plain sums per
-        // segment, S = sum P and T = sum i P, give both: rise = s T, fall = s (w S - T), s = 1 / (w NFFT).
-        // No weight loads, and the P addresses do not depend on loaded data.  Filter m is complete at the end
-        // of segment m + 1; the segment two neighbouring groups share is walked by both.  The log of each
-        // finished band goes to lg[m][lane] (cepstra) or to the frame's log-mel row. ----
+        // ---- S3: filterbank sums.  Segment j = bins [b_j, b_j + w) rises into filter j with weight i / w and
+        // falls out of filter j - 1 with weight (w - i) / w (i = bin - b_j), so two plain sums per segment,
+        // S = sum P and T = sum i P, give both: rise = s T, fall = s (w S - T), s = 1 / (w NFFT).  No weight loads,
+        // and the P addresses do not depend on loaded data.  Every segment is walked ONCE, by the warp the host
+        // gave it to (longest-first assignment, so the eight walks cost the same); rise[j][lane] and fall[j][lane]
+        // go through the scratch and S3b adds the two halves of each band. ----
         {
-            const int2 wsg = t_wseg[warp];                  // segments [x, y], empty when x > y
-            const int lgs = a.logmel ? 1 : 32;              // stride between bands
-            float *lgw = (a.logmel ? scr + lane * a.ls : scr + lane) + wsg.x * lgs;   // band wsg.x is this warp's first
-            float r_prev = 0.0f;
+            const float4 *wd = t_wseg + warp * kSegMax;
+            float *rise = scr + a.rf + lane, *fall = rise + (a.n_mel + 1) * 32;
+            float4 nx = wd[0];                              // descriptors run one segment ahead of their use
 #pragma unroll 1
-            for (int j = wsg.x; j <= wsg.y; ++j) {
-                const float4 sg = t_seg[j];                 // {first bin * 32, w, s, s * w}
+            for (int q = 1; __float_as_int(nx.w) >= 0; ++q) {
+                const float4 sg = nx;                       // {first bin * 32, w, s, j}
+                nx = wd[q];                                 // (the list ends with a j = -1 entry)
                 const float *p = pw + __float_as_int(sg.x) + lane;
-                const int w = __float_as_int(sg.y);
+                const int w = __float_as_int(sg.y), j = __float_as_int(sg.w);
                 int c = w >> 2;
                 float S = 0.0f, T = 0.0f, i0 = 0.0f;
 #pragma unroll 1
@@ -457,11 +459,19 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     S += sa;
                 }
                 const float r = sg.z * T;
-                if (j > wsg.x) {
-                    *lgw = kLn2 * lg2_fast(fmaxf(r_prev + fmaf(sg.w, S, -r), a.log_floor));
-                    lgw += lgs;
-                }
-                r_prev = r;
+                rise[j * 32] = r;
+                fall[j * 32] = fmaf(a.inv_n, S, -r);
+            }
+        }
+        half_sync(half);   // B4a: every segment's two sums are in the scratch
+        // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][lane] or the frame's log-mel row ----
+        {
+            const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 1) * 32;
+            const int total = a.n_mel * 32;
+            for (int i = tid; i < total; i += kHalfThreads) {
+                const float lg = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + 32], a.log_floor));
+                if (a.logmel) scr[(i & 31) * a.ls + (i >> 5)] = lg;
+                else scr[i] = lg;
             }
         }
         half_sync(half);   // B4: every band's log energy is in the scratch
@@ -557,38 +567,35 @@ void variant_sizes(const SpVariant &v, int &tabf, int &half_floats)
     else geo_sizes<200, 80, 16, 16>(tabf, half_floats);
 }
 
-// Chunks of 4 bins a segment needs.
-// Instruction estimate of one walk over segment j (S3): full 4-bin chunks, leftover bins, fixed part.
+// Instruction estimate of one walk over segment j (S3): 8-bin chunk pairs, a 4-bin chunk, leftover bins, fixed part.
 inline int seg_cost(const HostTables &h, int j)
 {
     const int w = h.mel_bins[j + 1] - h.mel_bins[j];
-    return 15 * (w / 4) + 6 * (w % 4) + 22;
+    return 28 * (w / 8) + 14 * ((w / 4) & 1) + (w % 4 ? 11 : 0) + 30;
 }
 
-// Contiguous split of the M filters over the warps that minimises the heaviest warp.  A warp owning
-// filters [m0, m1) walks segments m0 .. m1 (the boundary segment is walked by both neighbours).
-std::vector<int> split_filters(const HostTables &h, int M)
+// Segments 0 .. M over the warps, longest first onto the least loaded warp.  Each warp's list is kept in
+// ascending segment order (the walk then moves forward through P).  Empty when a warp would need more than
+// kSegMax - 1 segments.
+std::vector<std::vector<int>> assign_segments(const HostTables &h, int M)
 {
-    auto cost = [&](int m0, int m1) {   // instruction estimate of the S3 loop
-        if (m1 <= m0) return 0;
-        int c = 0;
-        for (int j = m0; j <= m1; ++j) c += seg_cost(h, j);
-        return c + 28 * (m1 - m0);
-    };
-    const int INF = 1 << 30;
-    std::vector<std::vector<int>> best(kWarps + 1, std::vector<int>(M + 1, INF)), arg(kWarps + 1, std::vector<int>(M + 1, 0));
-    best[0][0] = 0;
-    for (int w = 1; w <= kWarps; ++w)
-        for (int m1 = 0; m1 <= M; ++m1)
-            for (int m0 = 0; m0 <= m1; ++m0) {
-                if (best[w - 1][m0] == INF) continue;
-                const int v = std::max(best[w - 1][m0], cost(m0, m1));
-                if (v < best[w][m1]) { best[w][m1] = v; arg[w][m1] = m0; }
-            }
-    std::vector<int> beg(kWarps + 1, 0);
-    beg[kWarps] = M;
-    for (int w = kWarps; w >= 1; --w) beg[w - 1] = arg[w][beg[w]];
-    return beg;
+    std::vector<int> order(M + 1);
+    for (int j = 0; j <= M; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seg_cost(h, x) > seg_cost(h, y); });
+    std::vector<std::vector<int>> lists(kWarps);
+    std::vector<int> load(kWarps, 0);
+    for (int j : order) {
+        int best = 0;
+        for (int w = 1; w < kWarps; ++w)
+            if (load[w] < load[best]) best = w;
+        lists[best].push_back(j);
+        load[best] += seg_cost(h, j);
+    }
+    for (auto &l : lists) {
+        if (static_cast<int>(l.size()) > kSegMax - 1) return {};
+        std::sort(l.begin(), l.end());
+    }
+    return lists;
 }
 
 }  // namespace
@@ -604,10 +611,12 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
     // the run-time tables must fit next to the two halves
     int tabf = 0, half_floats = 0;
     variant_sizes(*v, tabf, half_floats);
-    const size_t total = tabf + 4 * kWarps + 4 * static_cast<size_t>(p.n_mel + 1) + static_cast<size_t>(KC) * (p.n_mel + 1) + 16;
+    if (p.n_mel + 1 > kWarps * (kSegMax - 1) || assign_segments(h, p.n_mel).empty()) return nullptr;
+    const size_t total = tabf + 4 * static_cast<size_t>(kWarps) * kSegMax + static_cast<size_t>(KC) * (p.n_mel + 1) + 16;
     if ((total + groups_for(v->rb) * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
-    // tail scratch (log band energies [n_mel][32], or log-mel rows [32][n_mel | 1]) must fit in the workspace
-    const size_t scratch = 32 * static_cast<size_t>(p.n_mel | 1);
+    // tail scratch (log band energies [n_mel][32] or log-mel rows [32][n_mel | 1], then the per-segment rise / fall
+    // sums [n_mel + 1][32] x 2) must fit in the workspace
+    const size_t scratch = 3 * 32 * static_cast<size_t>(p.n_mel + 2);
     if (scratch > static_cast<size_t>(v->rb / 2) * v->ra * 32 * 2) return nullptr;
     return v->name;
 }
@@ -647,25 +656,27 @@ int sp_prepare(mfcc_plan *plan)
     if (static_cast<int>(tab.size()) != tabf) return MFCC_ECUDA;   // layout drifted from Geo
 
     SpLayout lay{};
-    const std::vector<int> beg = split_filters(h, M);
+    // per-warp segment walks.  The triangles are linear ramps over integer bins (mfcc_tables.cpp build_tables),
+    // so a segment is described by its first bin, its width and 1 / (w N) (pass 2 leaves |X|^2, hence the 1 / N).
+    const std::vector<std::vector<int>> lists = assign_segments(h, M);
+    if (lists.empty()) return MFCC_ENOTSUP;
     lay.wseg = static_cast<int>(tab.size());
-    for (int w = 0; w < kWarps; ++w) {
-        const int m0 = beg[w], m1 = beg[w + 1];
-        push_int(m1 > m0 ? m0 : 1);
-        push_int(m1 > m0 ? m1 : 0);
-    }
-    align4();
-    // segments: the triangles are linear ramps over integer bins (mfcc_tables.cpp build_tables), so a
-    // segment is described by its first bin, its width and 1 / (w N) (pass 2 leaves |X|^2, hence the 1 / N)
-    lay.seg = static_cast<int>(tab.size());
-    for (int j = 0; j <= M; ++j) {
-        const int k0 = h.mel_bins[j], w = h.mel_bins[j + 1] - k0;
-        push_int(k0 * 32);
-        push_int(w);
-        const double sc = w > 0 ? 1.0 / (static_cast<double>(w) * N) : 0.0;
-        tab.push_back(static_cast<float>(sc));
-        tab.push_back(static_cast<float>(sc * w));
-    }
+    for (int w = 0; w < kWarps; ++w)
+        for (int q = 0; q < kSegMax; ++q) {
+            if (q < static_cast<int>(lists[w].size())) {
+                const int j = lists[w][q];
+                const int k0 = h.mel_bins[j], wd = h.mel_bins[j + 1] - k0;
+                push_int(k0 * 32);
+                push_int(wd);
+                tab.push_back(wd > 0 ? static_cast<float>(1.0 / (static_cast<double>(wd) * N)) : 0.0f);
+                push_int(j);
+            } else {
+                push_int(0);
+                push_int(0);
+                tab.push_back(0.0f);
+                push_int(-1);
+            }
+        }
     align4();
     // DCT entries for warp w: {d[w][m], d[w + 8][m]} per filter m, zero past n_cep; rows padded to even length
     lay.dct = static_cast<int>(tab.size());
@@ -692,6 +703,8 @@ int sp_prepare(mfcc_plan *plan)
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
     st->args.ls = M | 1;
     st->args.mp = MP;
+    st->args.rf = (32 * (M | 1) + 3) / 4 * 4;
+    st->args.inv_n = static_cast<float>(1.0 / N);
     st->args.mel_magic = (1 << 20) / M + 1;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
