@@ -292,10 +292,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     *reinterpret_cast<float2 *>(d6) = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
                     const float xe = s16x2_to_f32(pv).x;
                     *reinterpret_cast<float2 *>(d0) = make_float2(fmaf(na, xe, x01.x), fmaf(na, x01.x, x01.y));
-                    // the utterance's first sample has no predecessor: y = x.  It is word e of chunk 0 (this
-                    // thread wrote it just above), sample raw16[8 + sh].
-                    if (u == 0 && c == 0 && tile.first_sample == tile.utt_begin) staged[e] = to_f32(raw16[8 + sh]);
                 }
+            }
+            // the utterance's first sample has no predecessor: y = x.  It is word e of chunk 0 (thread 0 wrote it
+            // just above), sample raw16[8 + sh].  A branch, not a predicate: one tile in 32 starts an utterance.
+            if (tile.first_sample == tile.utt_begin) {
+                if (tid == 0) staged[e] = to_f32(raw16[8 + sh]);
             }
         } else {
             const int64_t room_lo = tile.first_sample - tile.utt_begin;
