@@ -132,7 +132,11 @@ class Batch:
             load().mfcc_batch_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals (load, _lib) may already be gone
+            pass
 
 
 class Plan:
@@ -155,7 +159,11 @@ class Plan:
             load().mfcc_plan_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals (load, _lib) may already be gone
+            pass
 
     # ---- tables (host copies of what the kernels read) ----
     def window(self) -> np.ndarray:
@@ -262,7 +270,11 @@ class Stream:
             load().mfcc_stream_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals (load, _lib) may already be gone
+            pass
 
     def feed(self, pcm: np.ndarray) -> np.ndarray:
         pcm = np.ascontiguousarray(pcm, np.int16)
@@ -315,4 +327,8 @@ class PinnedBuffer:
             load().mfcc_host_free(self._p)
             self._p = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals (load, _lib) may already be gone
+            pass
