@@ -209,9 +209,13 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     // tile table is built: Tile::flags).  The utterance may start at ANY sample: the copy starts at the
     // 8-sample boundary `o` below the tile's first sample and the shift s = first_sample - o (0..7) is
     // absorbed by the staging (see S0).
-    const bool base_ok = sizeof(PcmT) == 2 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+    const bool base_ok = sizeof(PcmT) == 2 && base_aligned;
     static_assert(G::SLACK + 8 <= kTileSpanSlack, "the host's span check must cover the staged span");
     auto tile_fast = [&](const Tile &tl) -> bool { return base_ok && (tl.flags & kTileInside) != 0; };
+    // f32 PCM: same eligibility, but the samples are read straight from HBM with 16-byte loads in S0 (a raw f32
+    // buffer would need 21 KB per group, which the 512-point geometry does not have)
+    auto tile_vec = [&](const Tile &tl) -> bool { return sizeof(PcmT) == 4 && base_aligned && (tl.flags & kTileInside) != 0; };
     // raw16[8 + i] = x[o + i]; the 8 samples before o ride along when they exist
     auto issue_copy = [&](const Tile &tl) {
         const int s = static_cast<int>(tl.first_sample & 7);
@@ -234,14 +238,14 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     int cur = 0;
     for (int64_t t = first; t < a.n_tiles; t += step, cur ^= 1) {
         const Tile tile = desc[cur];
-        const bool fast = tile_fast(tile);
+        const bool fast = tile_fast(tile), vec = tile_vec(tile);
         const bool has_next = t + step < a.n_tiles;
         if (has_next) fetch_desc(cur ^ 1, t + step);   // lands while S0 runs
         const int n_frames = tile.n_frames;
         const int tc = G::tceil(n_frames);
         // alignment shift of a bulk-copied tile: s = e + d, e even (absorbed as a word offset of the frame
         // columns in the staged layout), d = 0/1 (absorbed by staging y one sample ahead of x)
-        const int sh = fast ? static_cast<int>(tile.first_sample & 7) : 0;
+        const int sh = (fast || vec) ? static_cast<int>(tile.first_sample & 7) : 0;
         const int e = sh & 6, d = sh & 1;
 
         // ---- S0: stage y[n] = x[n] - a x[n-1] once per sample: staged index i holds sample o + d + i (o = the
@@ -298,6 +302,34 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             // just above), sample raw16[8 + sh].  A branch, not a predicate: one tile in 32 starts an utterance.
             if (tile.first_sample == tile.utt_begin) {
                 if (tid == 0) staged[e] = to_f32(raw16[8 + sh]);
+            }
+        } else if (vec) {
+            if constexpr (sizeof(PcmT) == 4) {
+                const float *x = reinterpret_cast<const float *>(pcm) + (tile.first_sample - sh);   // x[i] = sample o + i
+                const bool has_before = tile.first_sample - sh > 0;
+                const int nchunks = G::tceil_s(n_frames, sh) >> 3;
+                const float na = -a.preemph;
+#pragma unroll 1
+                for (int c = tid; c < nchunks; c += kHalfThreads) {
+                    const float4 lo4 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * c);
+                    const float4 hi4 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * c + 1);
+                    // d = 0: the sample before the chunk; d = 1: the sample after it (inside the span the host checked)
+                    const float nb = (d || c > 0 || has_before) ? __ldg(x + 8 * c + (d ? 8 : -1)) : 0.0f;
+                    const float v0 = d ? lo4.x : nb, v1 = d ? lo4.y : lo4.x, v2 = d ? lo4.z : lo4.y, v3 = d ? lo4.w : lo4.z;
+                    const float v4 = d ? hi4.x : lo4.w, v5 = d ? hi4.y : hi4.x, v6 = d ? hi4.z : hi4.y, v7 = d ? hi4.w : hi4.z;
+                    const float v8 = d ? nb : hi4.w;        // staged word j = v[j + 1] - a v[j]
+                    const int k = c / (HOP / 8);
+                    const int pad = kPad * k;
+                    const int pad_first = (c == k * (HOP / 8) && k > 0) ? pad - kPad : pad;
+                    float *dst = staged + 8 * c;
+                    *reinterpret_cast<float2 *>(dst + (0 < e ? pad_first : pad)) = make_float2(fmaf(na, v0, v1), fmaf(na, v1, v2));
+                    *reinterpret_cast<float2 *>(dst + 2 + (2 < e ? pad_first : pad)) = make_float2(fmaf(na, v2, v3), fmaf(na, v3, v4));
+                    *reinterpret_cast<float2 *>(dst + 4 + (4 < e ? pad_first : pad)) = make_float2(fmaf(na, v4, v5), fmaf(na, v5, v6));
+                    *reinterpret_cast<float2 *>(dst + 6 + pad) = make_float2(fmaf(na, v6, v7), fmaf(na, v7, v8));
+                }
+                if (tile.first_sample == tile.utt_begin) {
+                    if (tid == 0) staged[e] = x[sh];   // the utterance's first sample has no predecessor: y = x
+                }
             }
         } else {
             const int64_t room_lo = tile.first_sample - tile.utt_begin;

@@ -231,11 +231,14 @@ def test_every_start_alignment_takes_the_same_values(name):
         head = noise_utterance(8 * 50 + shift, seed=78)      # pushes the clip to alignment `shift`
         tail = noise_utterance(1000, seed=79)                # keeps the staged span inside the array
         off = np.cumsum([0, len(head), len(clip), len(tail)]).astype(np.int64)
-        got, fo = run_device(plan, np.concatenate([head, clip, tail]), off)
+        batch = np.concatenate([head, clip, tail])
+        got, fo = run_device(plan, batch, off)
         mine = got[fo[1]:fo[2]]
         assert mine.shape == ref.shape
         assert_parity(mine, ref, what=f"{name} shift {shift}")
         rows.append(mine)
+        got32, _ = run_device(plan, batch.astype(np.float32), off)      # f32 PCM entry: 16-byte vector staging
+        assert np.array_equal(got32, got), f"f32 input differs from int16 input at alignment {shift}"
     for shift in range(1, 8):
         assert np.array_equal(rows[shift], rows[0]), f"alignment {shift} changed the values"
 
