@@ -293,6 +293,38 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     // the utterance's first sample has no predecessor: y = x (word e of chunk 0, written just above)
                     if (c == 0 && tile.first_sample == tile.utt_begin) staged[e] = to_f32(x[sh]);
                 }
+            } else if (sizeof(PcmT) == 4 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0 && (tile.flags & kTileInside) != 0) {
+                // f32 PCM: the same any-alignment staging with 16-byte loads straight from HBM (no raw buffer)
+                if constexpr (sizeof(PcmT) == 4) {
+                    e = sh & 6;
+                    const int d = sh & 1;
+                    const float *x = reinterpret_cast<const float *>(pcm) + o;   // x[i] = sample o + i
+                    const float na = -a.preemph;
+                    const int nchunks = G::tceil_s(n_frames, sh) >> 3;
+                    for (int c = tid; c < nchunks; c += kHalfThreads) {
+                        const float4 lo4 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * c);
+                        const float4 hi4 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * c + 1);
+                        const float nb = (d || c > 0 || o > 0) ? __ldg(x + 8 * c + (d ? 8 : -1)) : 0.0f;
+                        const float v0 = d ? lo4.x : nb, v1 = d ? lo4.y : lo4.x, v2 = d ? lo4.z : lo4.y, v3 = d ? lo4.w : lo4.z;
+                        const float v4 = d ? hi4.x : lo4.w, v5 = d ? hi4.y : hi4.x, v6 = d ? hi4.z : hi4.y, v7 = d ? hi4.w : hi4.z;
+                        const float v8 = d ? nb : hi4.w;    // staged word j = v[j + 1] - a v[j]
+                        const float4 y0 = make_float4(fmaf(na, v0, v1), fmaf(na, v1, v2), fmaf(na, v2, v3), fmaf(na, v3, v4));
+                        const float4 y1 = make_float4(fmaf(na, v4, v5), fmaf(na, v5, v6), fmaf(na, v6, v7), fmaf(na, v7, v8));
+                        const int k = c / (HOP / 8);
+                        float *dst = staged + 8 * c + kPad * k;
+                        if (e != 0 && k > 0 && c == k * (HOP / 8)) {
+                            float *dl = dst - kPad;
+                            *reinterpret_cast<float2 *>((0 < e ? dl : dst) + 0) = make_float2(y0.x, y0.y);
+                            *reinterpret_cast<float2 *>((2 < e ? dl : dst) + 2) = make_float2(y0.z, y0.w);
+                            *reinterpret_cast<float2 *>((4 < e ? dl : dst) + 4) = make_float2(y1.x, y1.y);
+                            *reinterpret_cast<float2 *>(dst + 6) = make_float2(y1.z, y1.w);
+                        } else {
+                            *reinterpret_cast<float4 *>(dst) = y0;
+                            *reinterpret_cast<float4 *>(dst + 4) = y1;
+                        }
+                        if (c == 0 && tile.first_sample == tile.utt_begin) staged[e] = x[sh];
+                    }
+                }
             } else {
                 const int64_t room_lo = tile.first_sample - tile.utt_begin;
                 const int64_t room_hi = tile.utt_end - tile.first_sample;

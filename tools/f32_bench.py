@@ -3,9 +3,10 @@ pointer by one sample so that the kernel falls back to its per-sample staging (w
 vector path existed)."""
 import sys, time, numpy as np, torch
 sys.path.insert(0, '.')
-from mfcc_b200 import api, config_a, config_b
+from mfcc_b200 import api, config_a, config_b, config_c
 from mfcc_b200.synth import fast_fixed_batch, ragged_batch
-for name, p, (pcm, off) in (("A", config_a(), fast_fixed_batch(1024, 160000, seed=1)), ("B3", config_b(), ragged_batch(16384, 4000, 24000, seed=3))):
+for name, p, (pcm, off) in (("A", config_a(), fast_fixed_batch(1024, 160000, seed=1)), ("B3", config_b(), ragged_batch(16384, 4000, 24000, seed=3)),
+                             ("C8", config_c(), fast_fixed_batch(8, 7200000, seed=4))):
     plan = api.Plan(p); b = plan.batch(off)
     for dt, mis in ((torch.int16, 0), (torch.float32, 0), (torch.float32, 1)):
         d = torch.from_numpy(np.concatenate([np.zeros(mis, pcm.dtype), pcm])).cuda().to(dt)[mis:]
