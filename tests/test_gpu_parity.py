@@ -298,6 +298,31 @@ def test_config4_long_stream():
     assert_parity(got, ref, what="config4")
 
 
+def test_config4_full_length_stream_properties():
+    """One full configs[3] stream: 10 min @ 48 kHz = 28.8 M samples, 59,998 frames, 7,500 work units of one utterance.
+    Frame count exact; windows of the result equal the oracle on the matching slice (the slice starts one hop early
+    and its first frame is dropped: it alone sees y[0] = x[0]); and the stream cut in two overlapping halves gives
+    the same rows bit for bit (tile decomposition independence)."""
+    p = config_c()
+    L, H = p.frame_len, p.hop_len
+    n = 28_800_000
+    x = fast_fixed_batch(1, n, seed=4000)[0]
+    plan = api.Plan(p)
+    off = np.array([0, n], np.int64)
+    got, fo = run_device(plan, x, off)
+    assert got.shape == (59_998, 40) and fo[-1] == 1 + (n - L) // H
+    assert np.isfinite(got).all()
+    for t0 in (1, 29_990, 59_900):
+        cnt = 64
+        s0 = (t0 - 1) * H
+        ref = oracle.mfcc(p, x[s0:s0 + (cnt) * H + L])      # frames t0-1 .. t0+cnt-1 of the stream
+        assert_parity(got[t0:t0 + cnt], ref[1:1 + cnt], what=f"stream window at frame {t0}")
+    # second half as its own utterance, starting one hop before frame 30,000
+    t1 = 30_000
+    g2, _ = run_device(plan, x[(t1 - 1) * H:], np.array([0, n - (t1 - 1) * H], np.int64))
+    assert np.array_equal(g2[1:], got[t1:])
+
+
 # ---- §8(f) widening ----
 def test_cmvn_delta_g711_on_device():
     p = config_a()
