@@ -318,7 +318,9 @@ def main():
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp32_peak, "traffic": None, "kernel": plan.kernel_name,
                 "algorithmic": f"2.5*N*log2(N) = {fft_flops(p.nfft):.0f} FLOP/frame x {frames_per_launch} frames/launch",
-                "peak_source": fp32_how}
+                "peak_source": fp32_how,
+                "note": "the path is FP32 CUDA-core bound (FFT FLOPs / stream bytes = 24-50 FLOP/B against a ridge of about 11), "
+                        "so the binding roofline is the measured FP32 FMA peak; the HBM view is in roofline_hbm"}
     roofline_hbm = {"bound": "hbm", "achieved": bytes_alg / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_alg / per_launch_s / 1e9 / hbm_peak, "traffic": None,
                     "algorithmic": f"{p.hop_len * 2 + plan.out_dim * 4} B/frame x {frames_per_launch} frames/launch",
