@@ -375,3 +375,20 @@ def test_streaming_feed_is_bit_identical_to_offline():
         assert tail.shape[0] == (1 if p.pad_mode == PAD_ZERO_TAIL else 0)
         if tail.shape[0]:
             assert np.array_equal(tail, plan.compute(x[:10]))
+
+
+def test_c_caller_runs_the_device_path(tmp_path):
+    """The plain C99 demo (tests/cabi/demo.c) through mfcc_compute on the GPU."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "demo")
+    libdir = os.path.join(root, "mfcc_b200")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cabi", "demo.c"), "-o", exe, "-L", libdir, "-lmfcc_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "mfcc_compute: ok, 98 frames" in r.stdout and "fused_sp" in r.stdout

@@ -87,3 +87,21 @@ def test_partition_balances_frames_and_covers_everything():
     assert sum(b - a for a, b in parts) == 3
     s0, s1, loc = sharding.local_slice(off, 10, 20)
     assert loc[0] == 0 and loc[-1] == s1 - s0 and np.array_equal(np.diff(loc), np.diff(off[10:21]))
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/mfcc_b200.h compiles as strict C99 and a C caller links against the shared library
+    (INTEGRATION.md §3).  Without a GPU the demo stops after the host-only calls (MFCC_ECUDA, no fallback)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "demo")
+    libdir = os.path.join(root, "mfcc_b200")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cabi", "demo.c"), "-o", exe, "-L", libdir, "-lmfcc_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "mfcc_b200" in r.stdout
