@@ -524,17 +524,28 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             const float4 *dc = reinterpret_cast<const float4 *>(t_dct + warp * (2 * a.mp));   // {d[w][m], d[w+8][m], d[w][m+1], d[w+8][m+1]}
             float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
             if constexpr (MEL > 0) {
-                static_assert(MEL % 2 == 0, "unrolled DCT takes filters in pairs");
+                // d[k][M - 1 - m] = (-1)^k d[k][m] and cepstra w, w + 8 have the same parity: fold the band pairs first,
+                // v[q] = lg[q] +- lg[M - 1 - q], then M / 2 terms per cepstrum (the table's first M / 2 entries)
+                static_assert(MEL % 2 == 0, "unrolled DCT takes the bands in mirrored pairs");
+                const float sgn = (warp & 1) ? -1.0f : 1.0f;
                 float l[MEL];
 #pragma unroll
                 for (int m = 0; m < MEL; ++m) l[m] = lg[m * 32];
 #pragma unroll
-                for (int q = 0; q < MEL / 2; ++q) {
-                    const float4 d = dc[q];
-                    c0 = fmaf(d.x, l[2 * q], c0);
-                    c1 = fmaf(d.y, l[2 * q], c1);
-                    e0 = fmaf(d.z, l[2 * q + 1], e0);
-                    e1 = fmaf(d.w, l[2 * q + 1], e1);
+                for (int q = 0; q + 1 < MEL / 2; q += 2) {
+                    const float4 d = dc[q / 2];
+                    const float v0 = fmaf(sgn, l[MEL - 1 - q], l[q]), v1 = fmaf(sgn, l[MEL - 2 - q], l[q + 1]);
+                    c0 = fmaf(d.x, v0, c0);
+                    c1 = fmaf(d.y, v0, c1);
+                    e0 = fmaf(d.z, v1, e0);
+                    e1 = fmaf(d.w, v1, e1);
+                }
+                if constexpr ((MEL / 2) % 2 == 1) {
+                    constexpr int q = MEL / 2 - 1;
+                    const float2 d = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(dc) + 2 * q);
+                    const float v0 = fmaf(sgn, l[MEL - 1 - q], l[q]);
+                    c0 = fmaf(d.x, v0, c0);
+                    c1 = fmaf(d.y, v0, c1);
                 }
             } else {
                 const int M2 = a.n_mel >> 1;
