@@ -49,6 +49,7 @@ constexpr int groups_for(int rb) { return rb >= 32 ? 2 : 3; }
 constexpr int kPad = 2;
 constexpr int kSegMax = 20;                // segments one warp may be given (n_mel + 1 <= 8 * kSegMax)
 constexpr int KC = 16;                    // cepstra per frame (n_cep <= KC): warp w forms k = w and k = w + 8
+constexpr int kFoldMax = 16;                // n_mel / 2 of a tail-warp variant (n_mel <= 32)
 constexpr size_t kSmemMax = 227 * 1024;
 
 template <int L_, int HOP_, int RB_, int RA_>
@@ -104,6 +105,10 @@ struct SpArgs {
     int mp;               // n_mel rounded up to even (DCT row length in the table)
     int mel_magic;        // i / n_mel == (i * mel_magic) >> 20 for i < 32 * n_mel
     float preemph, log_floor;
+    // tail-warp variants (MEL > 0): ln 2 * d[k][q] for q < MEL / 2 (the mirrored half follows from d[k][M - 1 - q] =
+    // (-1)^k d[k][q]).  Kernel parameters live in the constant bank, so with compile-time indices every entry is
+    // a uniform-register FFMA operand fetched four at a time (LDCU.128): no shared-memory loads in the DCT.
+    float4 dctc[KC][kFoldMax / 4];
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -167,8 +172,11 @@ __device__ __forceinline__ void half_sync(int half)
     asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kHalfThreads) : "memory");
 }
 
-// MEL > 0: the plan has exactly MEL filters and cepstral output, so the DCT loop of S4 is unrolled; MEL = 0: any plan.
-template <typename PcmT, int L_, int HOP_, int RB_, int RA_, int MEL>
+// MEL > 0: the plan has exactly MEL filters and CEP cepstra per frame.  Band assembly, log and DCT of tile t are then
+// done by ONE warp (the "tail warp", lane = frame, everything in registers, DCT entries as constant-bank operands)
+// while the other seven stage tile t + 1: 364 instructions per tile instead of the 1,400 of the all-warp S3b + S4,
+// and one barrier fewer.  MEL = 0: any plan (all-warp S3b + S4, table-driven DCT loop).
+template <typename PcmT, int L_, int HOP_, int RB_, int RA_, int MEL, int CEP>
 __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_kernel(const PcmT *__restrict__ pcm, const SpArgs a)
 {
     using G = Geo<L_, HOP_, RB_, RA_>;
@@ -226,6 +234,51 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         bulk_g2s(raw_s + (8 - lead) * 2, pcm + o - lead, bytes, bar);
     };
 
+    // staging threads of a group: all of it, or all but the tail warp
+    constexpr bool kTail = MEL > 0;
+    constexpr int kStage = kTail ? kHalfThreads - 32 : kHalfThreads;
+    const bool stager = !kTail || warp < kWarps - 1;
+    // tail warp: band m = rise of segment m + fall of segment m + 1, log2, mirrored-pair fold, DCT with constant-bank
+    // entries (ln 2 folded in on the host), CEP stores per frame
+    auto tail = [&](int64_t out_row, int nf) {
+        if constexpr (kTail) {
+            static_assert(MEL % 2 == 0 && MEL / 2 <= kFoldMax && CEP <= KC, "tail-warp variant limits");
+            const float *rise = scr + a.rf + lane, *fall = rise + (MEL + 1) * 32;
+            float l[MEL];
+#pragma unroll
+            for (int m = 0; m < MEL; ++m) l[m] = rise[m * 32] + fall[(m + 1) * 32];
+#pragma unroll
+            for (int m = 0; m < MEL; ++m) l[m] = lg2_fast(fmaxf(l[m], a.log_floor));
+            float ve[MEL / 2], vo[MEL / 2];
+#pragma unroll
+            for (int q = 0; q < MEL / 2; ++q) {
+                ve[q] = l[q] + l[MEL - 1 - q];
+                vo[q] = l[q] - l[MEL - 1 - q];
+            }
+            float c[CEP];
+#pragma unroll
+            for (int k = 0; k < CEP; ++k) c[k] = 0.0f;
+#pragma unroll
+            for (int q4 = 0; q4 < (MEL / 2 + 3) / 4; ++q4)
+#pragma unroll
+                for (int k = 0; k < CEP; ++k) {
+                    const float4 d = a.dctc[k][q4];   // one 16-byte uniform load from the parameter bank
+                    const float *v = (k & 1) ? vo : ve;
+                    c[k] = fmaf(d.x, v[4 * q4], c[k]);
+                    if (4 * q4 + 1 < MEL / 2) c[k] = fmaf(d.y, v[4 * q4 + 1], c[k]);
+                    if (4 * q4 + 2 < MEL / 2) c[k] = fmaf(d.z, v[4 * q4 + 2], c[k]);
+                    if (4 * q4 + 3 < MEL / 2) c[k] = fmaf(d.w, v[4 * q4 + 3], c[k]);
+                }
+            if (lane < nf) {
+                float *o = a.out + (out_row + lane) * CEP;
+#pragma unroll
+                for (int k = 0; k < CEP; ++k) o[k] = c[k];
+            }
+        }
+    };
+    int64_t prev_row = 0;
+    int prev_nf = 0;      // frames of the tile whose tail is still to be done (0: none)
+
     const int64_t first = GROUPS * static_cast<int64_t>(blockIdx.x) + half, step = GROUPS * static_cast<int64_t>(gridDim.x);
     if (first < a.n_tiles) fetch_desc(0, first);
     cp_async_wait_all();
@@ -236,7 +289,10 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     }
     uint32_t phase = 0;
     int cur = 0;
-    for (int64_t t = first; t < a.n_tiles; t += step, cur ^= 1) {
+    for (int64_t t = first;; t += step, cur ^= 1) {
+        // the previous tile's tail, concurrent with this tile's S0 (one call site: the tail is 300 instructions)
+        if (!stager && prev_nf > 0) tail(prev_row, prev_nf);
+        if (t >= a.n_tiles) break;
         const Tile tile = desc[cur];
         const bool fast = tile_fast(tile), vec = tile_vec(tile);
         const bool has_next = t + step < a.n_tiles;
@@ -251,22 +307,24 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         // ---- S0: stage y[n] = x[n] - a x[n-1] once per sample: staged index i holds sample o + d + i (o = the
         // 8-sample boundary below the tile), with kPad words inserted at i = e + k HOP, so that frame f starts
         // at word e + f STRIDE ----
-        if (fast) {
+        if (!stager) {
+            if (fast) phase ^= 1u;
+        } else if (fast) {
             mbar_wait(bar, phase);
             phase ^= 1u;
             const int nchunks = G::tceil_s(n_frames, sh) >> 3;
             const float na = -a.preemph;
             // chunk c = 8 samples; the thread takes chunks tid, tid + 256, ...: all loads first, then the arithmetic
-            constexpr int NU = (G::TCEIL / 8 + kHalfThreads - 1) / kHalfThreads;
+            constexpr int NU = (G::TCEIL / 8 + kStage - 1) / kStage;
             uint4 q[NU];
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
-                const int c = tid + u * kHalfThreads;
+                const int c = tid + u * kStage;
                 if (c < nchunks) q[u] = *reinterpret_cast<const uint4 *>(raw16 + 8 + 8 * c);
             }
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
-                const int c = tid + u * kHalfThreads;
+                const int c = tid + u * kStage;
                 if (c < nchunks) {
                     // d = 0: the sample before the chunk; d = 1: the sample after it (low half-word of pv)
                     uint32_t pv = static_cast<uint16_t>(raw16[7 + 9 * d + 8 * c]);
@@ -310,7 +368,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 const int nchunks = G::tceil_s(n_frames, sh) >> 3;
                 const float na = -a.preemph;
 #pragma unroll 1
-                for (int c = tid; c < nchunks; c += kHalfThreads) {
+                for (int c = tid; c < nchunks; c += kStage) {
                     const float4 lo4 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * c);
                     const float4 hi4 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * c + 1);
                     // d = 0: the sample before the chunk; d = 1: the sample after it (inside the span the host checked)
@@ -335,7 +393,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             const int64_t room_lo = tile.first_sample - tile.utt_begin;
             const int64_t room_hi = tile.utt_end - tile.first_sample;
             const PcmT *x = pcm + tile.first_sample;
-            for (int i = tid; i < tc; i += kHalfThreads) {
+            for (int i = tid; i < tc; i += kStage) {
                 float y = 0.0f;
                 if (i < room_hi) {
                     const float x0 = to_f32(x[i]);
@@ -498,6 +556,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             }
         }
         half_sync(half);   // B4a: every segment's two sums are in the scratch
+        if constexpr (kTail) {
+            // the tail warp takes it from here during the next tile's S0 (or after the loop): the scratch is next
+            // written by S1, after B1, which the tail warp joins only when it is done
+            prev_row = tile.out_row;
+            prev_nf = n_frames;
+        } else {
         // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][lane] or the frame's log-mel row ----
         {
             const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 1) * 32;
@@ -511,7 +575,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         half_sync(half);   // B4: every band's log energy is in the scratch
 
         // ---- S4: log-mel rows are copied out coalesced; cepstra: warp w forms c[w] and c[w + 8] of frame = lane
-        // from the 26 log energies (conflict-free column reads, warp-uniform DCT entries) and stores them ----
+        // from the log energies (conflict-free column reads, warp-uniform DCT entries) and stores them ----
         if (a.logmel) {
             const int M = a.n_mel, total = n_frames * M;
             float *o = a.out + tile.out_row * M;
@@ -523,53 +587,28 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             const float *lg = scr + lane;
             const float4 *dc = reinterpret_cast<const float4 *>(t_dct + warp * (2 * a.mp));   // {d[w][m], d[w+8][m], d[w][m+1], d[w+8][m+1]}
             float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
-            if constexpr (MEL > 0) {
-                // d[k][M - 1 - m] = (-1)^k d[k][m] and cepstra w, w + 8 have the same parity: fold the band pairs first,
-                // v[q] = lg[q] +- lg[M - 1 - q], then M / 2 terms per cepstrum (the table's first M / 2 entries)
-                static_assert(MEL % 2 == 0, "unrolled DCT takes the bands in mirrored pairs");
-                const float sgn = (warp & 1) ? -1.0f : 1.0f;
-                float l[MEL];
-#pragma unroll
-                for (int m = 0; m < MEL; ++m) l[m] = lg[m * 32];
-#pragma unroll
-                for (int q = 0; q + 1 < MEL / 2; q += 2) {
-                    const float4 d = dc[q / 2];
-                    const float v0 = fmaf(sgn, l[MEL - 1 - q], l[q]), v1 = fmaf(sgn, l[MEL - 2 - q], l[q + 1]);
-                    c0 = fmaf(d.x, v0, c0);
-                    c1 = fmaf(d.y, v0, c1);
-                    e0 = fmaf(d.z, v1, e0);
-                    e1 = fmaf(d.w, v1, e1);
-                }
-                if constexpr ((MEL / 2) % 2 == 1) {
-                    constexpr int q = MEL / 2 - 1;
-                    const float2 d = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(dc) + 2 * q);
-                    const float v0 = fmaf(sgn, l[MEL - 1 - q], l[q]);
-                    c0 = fmaf(d.x, v0, c0);
-                    c1 = fmaf(d.y, v0, c1);
-                }
-            } else {
-                const int M2 = a.n_mel >> 1;
+            const int M2 = a.n_mel >> 1;
 #pragma unroll 2
-                for (int q = 0; q < M2; ++q) {
-                    const float l0 = lg[(2 * q) * 32], l1 = lg[(2 * q + 1) * 32];
-                    const float4 d = dc[q];
-                    c0 = fmaf(d.x, l0, c0);
-                    c1 = fmaf(d.y, l0, c1);
-                    e0 = fmaf(d.z, l1, e0);
-                    e1 = fmaf(d.w, l1, e1);
-                }
-                if (a.n_mel & 1) {
-                    const float l0 = lg[(a.n_mel - 1) * 32];
-                    const float4 d = dc[M2];
-                    c0 = fmaf(d.x, l0, c0);
-                    c1 = fmaf(d.y, l0, c1);
-                }
+            for (int q = 0; q < M2; ++q) {
+                const float l0 = lg[(2 * q) * 32], l1 = lg[(2 * q + 1) * 32];
+                const float4 d = dc[q];
+                c0 = fmaf(d.x, l0, c0);
+                c1 = fmaf(d.y, l0, c1);
+                e0 = fmaf(d.z, l1, e0);
+                e1 = fmaf(d.w, l1, e1);
+            }
+            if (a.n_mel & 1) {
+                const float l0 = lg[(a.n_mel - 1) * 32];
+                const float4 d = dc[M2];
+                c0 = fmaf(d.x, l0, c0);
+                c1 = fmaf(d.y, l0, c1);
             }
             if (lane < n_frames) {
                 float *o = a.out + (tile.out_row + lane) * a.n_cep + warp;
                 o[0] = c0 + e0;
                 if (warp + kWarps < a.n_cep) o[kWarps] = c1 + e1;
             }
+        }
         }
         // no barrier here: the next S0 writes `staged`, which nobody reads any more; the scratch is
         // next written by S1, after B1.
@@ -753,6 +792,10 @@ int sp_prepare(mfcc_plan *plan)
     st->args.mel_magic = (1 << 20) / M + 1;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
+    if (p.output == MFCC_OUT_CEPSTRA && M % 2 == 0 && M / 2 <= kFoldMax)
+        for (int k = 0; k < p.n_cep && k < KC; ++k)
+            for (int q = 0; q < M / 2; ++q)
+                (&st->args.dctc[k][q / 4].x)[q % 4] = static_cast<float>(std::log(2.0) * static_cast<double>(h.dct[static_cast<size_t>(k) * M + q]));
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
         cudaGetLastError();
         delete st;
@@ -776,11 +819,11 @@ void sp_release(mfcc_plan *plan)
     plan->sp_state = nullptr;
 }
 
-template <typename PcmT, int L, int HOP, int RB, int RA, int MEL>
+template <typename PcmT, int L, int HOP, int RB, int RA, int MEL, int CEP>
 static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
                           cudaStream_t stream)
 {
-    auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA, MEL>;
+    auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA, MEL, CEP>;
     static thread_local const void *configured = nullptr;
     if (configured != reinterpret_cast<const void *>(kern)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
@@ -808,14 +851,14 @@ int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const
 {
     const SpState *st = static_cast<const SpState *>(plan->sp_state);
     if (st == nullptr) return MFCC_ENOTSUP;
-    // the BASELINE.json filter counts (26 at 16 kHz, 20 at 8 kHz) with cepstral output get the unrolled DCT
-    const bool cep = !st->args.logmel;
+    // the BASELINE.json shapes (26 filters at 16 kHz, 20 at 8 kHz, 13 cepstra) get the tail-warp variant
+    const bool cep13 = !st->args.logmel && st->args.n_cep == 13;
     if (st->v->L == 400) {
-        if (cep && st->args.n_mel == 26) return launch_variant<PcmT, 400, 160, 32, 16, 26>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
-        return launch_variant<PcmT, 400, 160, 32, 16, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+        if (cep13 && st->args.n_mel == 26) return launch_variant<PcmT, 400, 160, 32, 16, 26, 13>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+        return launch_variant<PcmT, 400, 160, 32, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
     }
-    if (cep && st->args.n_mel == 20) return launch_variant<PcmT, 200, 80, 16, 16, 20>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
-    return launch_variant<PcmT, 200, 80, 16, 16, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    if (cep13 && st->args.n_mel == 20) return launch_variant<PcmT, 200, 80, 16, 16, 20, 13>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+    return launch_variant<PcmT, 200, 80, 16, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
 }
 
 template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *, cudaStream_t);
