@@ -108,7 +108,7 @@ struct SpArgs {
     // tail-warp variants (MEL > 0): ln 2 * d[k][q] for q < MEL / 2 (the mirrored half follows from d[k][M - 1 - q] =
     // (-1)^k d[k][q]).  Kernel parameters live in the constant bank, so with compile-time indices every entry is
     // a uniform-register FFMA operand fetched four at a time (LDCU.128): no shared-memory loads in the DCT.
-    float4 dctc[KC][kFoldMax / 4];
+    float4 dctc[KC / 2][2][kFoldMax / 4];   // [k / 2][k & 1][q / 4]
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
 
     // staging threads of a group: all of it, or all but the tail warp
     constexpr bool kTail = MEL > 0;
-    constexpr int kStage = kTail ? kHalfThreads - 32 : kHalfThreads;
-    const bool stager = !kTail || warp < kWarps - 1;
+    constexpr int kTailWarps = 2;   // cepstra of even k on one, of odd k on the other
+    constexpr int kStage = kTail ? kHalfThreads - 32 * kTailWarps : kHalfThreads;
+    const bool stager = !kTail || warp < kWarps - kTailWarps;
     // tail warp: band m = rise of segment m + fall of segment m + 1, log2, mirrored-pair fold, DCT with constant-bank
     // entries (ln 2 folded in on the host), CEP stores per frame
     auto tail = [&](int64_t out_row, int nf) {
@@ -249,30 +250,31 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             for (int m = 0; m < MEL; ++m) l[m] = rise[m * 32] + fall[(m + 1) * 32];
 #pragma unroll
             for (int m = 0; m < MEL; ++m) l[m] = lg2_fast(fmaxf(l[m], a.log_floor));
-            float ve[MEL / 2], vo[MEL / 2];
+            // this warp's cepstra k = 2 kk + par all take v[q] = l[q] + (-1)^par l[M - 1 - q]
+            const int par = warp & 1;
+            const float sgn = par ? -1.0f : 1.0f;
+            float v[MEL / 2];
 #pragma unroll
-            for (int q = 0; q < MEL / 2; ++q) {
-                ve[q] = l[q] + l[MEL - 1 - q];
-                vo[q] = l[q] - l[MEL - 1 - q];
-            }
-            float c[CEP];
+            for (int q = 0; q < MEL / 2; ++q) v[q] = fmaf(sgn, l[MEL - 1 - q], l[q]);
+            constexpr int CH = (CEP + 1) / 2;
+            float c[CH];
 #pragma unroll
-            for (int k = 0; k < CEP; ++k) c[k] = 0.0f;
+            for (int kk = 0; kk < CH; ++kk) c[kk] = 0.0f;
 #pragma unroll
             for (int q4 = 0; q4 < (MEL / 2 + 3) / 4; ++q4)
 #pragma unroll
-                for (int k = 0; k < CEP; ++k) {
-                    const float4 d = a.dctc[k][q4];   // one 16-byte uniform load from the parameter bank
-                    const float *v = (k & 1) ? vo : ve;
-                    c[k] = fmaf(d.x, v[4 * q4], c[k]);
-                    if (4 * q4 + 1 < MEL / 2) c[k] = fmaf(d.y, v[4 * q4 + 1], c[k]);
-                    if (4 * q4 + 2 < MEL / 2) c[k] = fmaf(d.z, v[4 * q4 + 2], c[k]);
-                    if (4 * q4 + 3 < MEL / 2) c[k] = fmaf(d.w, v[4 * q4 + 3], c[k]);
+                for (int kk = 0; kk < CH; ++kk) {
+                    const float4 d = a.dctc[kk][par][q4];   // one 16-byte uniform load from the parameter bank (zeros past n_cep)
+                    c[kk] = fmaf(d.x, v[4 * q4], c[kk]);
+                    if (4 * q4 + 1 < MEL / 2) c[kk] = fmaf(d.y, v[4 * q4 + 1], c[kk]);
+                    if (4 * q4 + 2 < MEL / 2) c[kk] = fmaf(d.z, v[4 * q4 + 2], c[kk]);
+                    if (4 * q4 + 3 < MEL / 2) c[kk] = fmaf(d.w, v[4 * q4 + 3], c[kk]);
                 }
             if (lane < nf) {
-                float *o = a.out + (out_row + lane) * CEP;
+                float *o = a.out + (out_row + lane) * CEP + par;
 #pragma unroll
-                for (int k = 0; k < CEP; ++k) o[k] = c[k];
+                for (int kk = 0; kk < CH; ++kk)
+                    if (2 * kk + 1 < CEP || par == 0) o[2 * kk] = c[kk];
             }
         }
     };
@@ -795,7 +797,7 @@ int sp_prepare(mfcc_plan *plan)
     if (p.output == MFCC_OUT_CEPSTRA && M % 2 == 0 && M / 2 <= kFoldMax)
         for (int k = 0; k < p.n_cep && k < KC; ++k)
             for (int q = 0; q < M / 2; ++q)
-                (&st->args.dctc[k][q / 4].x)[q % 4] = static_cast<float>(std::log(2.0) * static_cast<double>(h.dct[static_cast<size_t>(k) * M + q]));
+                (&st->args.dctc[k / 2][k & 1][q / 4].x)[q % 4] = static_cast<float>(std::log(2.0) * static_cast<double>(h.dct[static_cast<size_t>(k) * M + q]));
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
         cudaGetLastError();
         delete st;
