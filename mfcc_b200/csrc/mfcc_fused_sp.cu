@@ -49,6 +49,7 @@ constexpr int groups_for(int rb) { return rb >= 32 ? 2 : 3; }
 constexpr int kPad = 2;
 constexpr int kSegMax = 20;                // segments one warp may be given (n_mel + 1 <= 8 * kSegMax)
 constexpr int KC = 16;                    // cepstra per frame (n_cep <= KC): warp w forms k = w and k = w + 8
+constexpr int kSegParam = 12;              // segments per warp (+ terminator) a tail-warp variant can take as parameters
 constexpr int kFoldMax = 16;                // n_mel / 2 of a tail-warp variant (n_mel <= 32)
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -109,6 +110,10 @@ struct SpArgs {
     // (-1)^k d[k][q]).  Kernel parameters live in the constant bank, so with compile-time indices every entry is
     // a uniform-register FFMA operand fetched four at a time (LDCU.128): no shared-memory loads in the DCT.
     float4 dctc[KC / 2][2][kFoldMax / 4];   // [k / 2][k & 1][q / 4]
+    // tail-warp variants: the segment walks of S3 as parameters too, {first bin * 128 (byte offset into P), width w,
+    // s = 1 / (w NFFT), segment index * 128 (byte offset into the rise / fall scratch; -1 ends the list)}: read with a
+    // warp-uniform index they arrive in uniform registers, so every branch of the walk is a uniform branch.
+    float4 useg[kWarps][kSegParam];
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -512,6 +517,59 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         // and the P addresses do not depend on loaded data.  Every segment is walked ONCE, by the warp the host
         // gave it to (longest-first assignment, so the eight walks cost the same); rise[j][lane] and fall[j][lane]
         // go through the scratch and S3b adds the two halves of each band. ----
+        if constexpr (kTail) {
+            // Forward walk with running sums: run_i = P_0 + .. + P_i and acc = run_0 + .. + run_(w-1) = sum (w - i) P_i,
+            // so fall = s acc and rise = S / NFFT - fall: one load and two additions per bin, no constants, no counter.
+            // The descriptors come from the parameter bank under a warp-uniform index (uniform registers, uniform
+            // branches); the width is taken apart in binary (8-bin loop, then 4, 2, 1).
+            const int uw = __shfl_sync(0xffffffffu, warp, 0);
+            const char *pl = reinterpret_cast<const char *>(pw + lane);
+            char *rl = reinterpret_cast<char *>(scr + a.rf + lane);
+#pragma unroll 1
+            for (int q = 0;; ++q) {
+                const float4 sg = a.useg[uw][q];
+                const int oo = __float_as_int(sg.w);
+                if (oo < 0) break;
+                const float *p = reinterpret_cast<const float *>(pl + __float_as_int(sg.x));
+                const int w = __float_as_int(sg.y);
+                float run = 0.0f, acc = 0.0f;
+#pragma unroll 1
+                for (int c = w >> 3; c > 0; --c) {
+                    const float a0 = p[0], a1 = p[32], a2 = p[64], a3 = p[96];
+                    const float a4 = p[128], a5 = p[160], a6 = p[192], a7 = p[224];
+                    run += a0; acc += run;
+                    run += a1; acc += run;
+                    run += a2; acc += run;
+                    run += a3; acc += run;
+                    run += a4; acc += run;
+                    run += a5; acc += run;
+                    run += a6; acc += run;
+                    run += a7; acc += run;
+                    p += 256;
+                }
+                if (w & 4) {
+                    const float a0 = p[0], a1 = p[32], a2 = p[64], a3 = p[96];
+                    run += a0; acc += run;
+                    run += a1; acc += run;
+                    run += a2; acc += run;
+                    run += a3; acc += run;
+                    p += 128;
+                }
+                if (w & 2) {
+                    const float a0 = p[0], a1 = p[32];
+                    run += a0; acc += run;
+                    run += a1; acc += run;
+                    p += 64;
+                }
+                if (w & 1) {
+                    run += p[0];
+                    acc += run;
+                }
+                const float f = sg.z * acc;
+                *reinterpret_cast<float *>(rl + oo) = fmaf(a.inv_n, run, -f);
+                *reinterpret_cast<float *>(rl + oo + (MEL + 1) * 128) = f;
+            }
+        } else
         {
             const float4 *wd = t_wseg + warp * kSegMax;
             float *rise = scr + a.rf + lane, *fall = rise + (a.n_mel + 1) * 32;
@@ -635,6 +693,7 @@ struct SpState {
     float *d_tab = nullptr;
     size_t smem = 0;
     int sm_count = 0;
+    bool useg_ok = false;      // every warp's segment list fits SpArgs::useg (tail-warp variants need it)
 };
 
 const SpVariant *find_variant(const mfcc_params &p)
@@ -653,11 +712,11 @@ void variant_sizes(const SpVariant &v, int &tabf, int &half_floats)
     else geo_sizes<200, 80, 16, 16>(tabf, half_floats);
 }
 
-// Instruction estimate of one walk over segment j (S3): 8-bin chunk pairs, a 4-bin chunk, leftover bins, fixed part.
+// Instruction estimate of one walk over segment j (S3): 8-bin chunks, then 4, 2, 1 bins, fixed part.
 inline int seg_cost(const HostTables &h, int j)
 {
     const int w = h.mel_bins[j + 1] - h.mel_bins[j];
-    return 28 * (w / 8) + 14 * ((w / 4) & 1) + (w % 4 ? 11 : 0) + 30;
+    return 28 * (w / 8) + 14 * ((w / 4) & 1) + 8 * ((w / 2) & 1) + 4 * (w & 1) + 18;
 }
 
 // Segments 0 .. M over the warps, longest first onto the least loaded warp.  Each warp's list is kept in
@@ -798,6 +857,27 @@ int sp_prepare(mfcc_plan *plan)
         for (int k = 0; k < p.n_cep && k < KC; ++k)
             for (int q = 0; q < M / 2; ++q)
                 (&st->args.dctc[k / 2][k & 1][q / 4].x)[q % 4] = static_cast<float>(std::log(2.0) * static_cast<double>(h.dct[static_cast<size_t>(k) * M + q]));
+    st->useg_ok = true;
+    for (int w = 0; w < kWarps; ++w) {
+        const int n = static_cast<int>(lists[w].size());
+        if (n > kSegParam - 1) st->useg_ok = false;
+        for (int q = 0; q < kSegParam; ++q) {
+            float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            int x = 0, y = 0, z = -1;
+            if (q < n && q < kSegParam - 1) {
+                const int j = lists[w][q];
+                const int k0 = h.mel_bins[j], wd = h.mel_bins[j + 1] - k0;
+                x = k0 * 128;
+                y = wd;
+                z = j * 128;
+                d.z = wd > 0 ? static_cast<float>(1.0 / (static_cast<double>(wd) * N)) : 0.0f;
+            }
+            std::memcpy(&d.x, &x, 4);
+            std::memcpy(&d.y, &y, 4);
+            std::memcpy(&d.w, &z, 4);
+            st->args.useg[w][q] = d;
+        }
+    }
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {
         cudaGetLastError();
         delete st;
@@ -854,7 +934,7 @@ int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const
     const SpState *st = static_cast<const SpState *>(plan->sp_state);
     if (st == nullptr) return MFCC_ENOTSUP;
     // the BASELINE.json shapes (26 filters at 16 kHz, 20 at 8 kHz, 13 cepstra) get the tail-warp variant
-    const bool cep13 = !st->args.logmel && st->args.n_cep == 13;
+    const bool cep13 = !st->args.logmel && st->args.n_cep == 13 && st->useg_ok;
     if (st->v->L == 400) {
         if (cep13 && st->args.n_mel == 26) return launch_variant<PcmT, 400, 160, 32, 16, 26, 13>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
         return launch_variant<PcmT, 400, 160, 32, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
