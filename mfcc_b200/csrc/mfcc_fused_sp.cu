@@ -35,6 +35,14 @@
 #include "mfcc_rfft.cuh"
 #include "mfcc_host.h"
 
+// Build-time switches for A/B measurements on one box (tools/variants_sp.py); the defaults are the measured winners.
+#ifndef MFCC_SP_TW2_16
+#define MFCC_SP_TW2_16 1
+#endif
+#ifndef MFCC_SP_TW2_32
+#define MFCC_SP_TW2_32 0
+#endif
+
 namespace mfcc {
 
 namespace {
@@ -74,7 +82,10 @@ struct Geo {
     static constexpr int HALF = UNION + WS + RAW + 4 + DESC;   // + mbarrier (8 B in a 16-B slot)
     // fixed part of the table blob (floats); the filterbank tables follow at run-time offsets
     static constexpr int T_WIN = 0;                        // [RA/2][NZP] float2
-    static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;  // [RA][H] float2, slot k1 - 1
+    // Where the inter-pass twiddle is applied.  16 x 16: pass 2 has one item per warp, seven plain rows and the longer
+    // special row, so the plain rows take the twiddle on load (measured +1.4 %); 32 x 16: pass 1 keeps it (-0.7 % moved).
+    static constexpr bool TW_IN_PASS2 = RB == 16 ? MFCC_SP_TW2_16 : MFCC_SP_TW2_32;
+    static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;  // TW_IN_PASS2 ? [H][RA] (row k1 - 1, column a) : [RA][H] float2
     static constexpr int T_TWH = T_TW + RA * H * 2;        // [RA] float2
     static constexpr int TABF = T_TWH + RA * 2;
     static_assert(HOP % 8 == 0, "an 8-sample chunk must not straddle a hop block");
@@ -443,15 +454,21 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 rf::RDft<RB>::template run<NZ>(x, X);
                 float2 *wsa = ws + col * 32 + lane;
                 wsa[(H - 1) * RA * 32] = make_float2(X[0].re, X[H].re);   // rows 0 and H are real here
-                const float *trow = t_tw + col * (2 * H);
+                if constexpr (G::TW_IN_PASS2) {
+                    // rows 1 .. H - 1 go out UNtwiddled: pass 2 applies the inter-pass twiddle on load
 #pragma unroll
-                for (int k1 = 1; k1 < H; k1 += 2) {
-                    const float4 tw = lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
-                    const rf::cplx v = rf::cmulc(X[k1], tw.x, tw.y);
-                    wsa[(k1 - 1) * RA * 32] = make_float2(v.re, v.im);
-                    if (k1 + 1 < H) {
-                        const rf::cplx u = rf::cmulc(X[k1 + 1], tw.z, tw.w);
-                        wsa[k1 * RA * 32] = make_float2(u.re, u.im);
+                    for (int k1 = 1; k1 < H; ++k1) wsa[(k1 - 1) * RA * 32] = make_float2(X[k1].re, X[k1].im);
+                } else {
+                    const float *trow = t_tw + col * (2 * H);
+#pragma unroll
+                    for (int k1 = 1; k1 < H; k1 += 2) {
+                        const float4 tw = lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
+                        const rf::cplx v = rf::cmulc(X[k1], tw.x, tw.y);
+                        wsa[(k1 - 1) * RA * 32] = make_float2(v.re, v.im);
+                        if (k1 + 1 < H) {
+                            const rf::cplx u = rf::cmulc(X[k1 + 1], tw.z, tw.w);
+                            wsa[k1 * RA * 32] = make_float2(u.re, u.im);
+                        }
                     }
                 }
             }
@@ -466,10 +483,21 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     const int k1 = it + 1;
                     const float2 *row = ws + (k1 - 1) * RA * 32 + lane;
                     rf::cplx z[RA];
+                    if constexpr (G::TW_IN_PASS2) {
+                        const float *trow = t_tw + (k1 - 1) * (2 * RA);      // W_N^(a k1), a = 0 .. RA - 1
 #pragma unroll
-                    for (int c = 0; c < RA; ++c) {
-                        const float2 p = row[c * 32];
-                        z[c] = rf::cplx{p.x, p.y};
+                        for (int c = 0; c < RA; c += 2) {
+                            const float4 tw = lds_f4(trow + 2 * c);
+                            const float2 p = row[c * 32], q = row[(c + 1) * 32];
+                            z[c] = c == 0 ? rf::cplx{p.x, p.y} : rf::cmulc(rf::cplx{p.x, p.y}, tw.x, tw.y);
+                            z[c + 1] = rf::cmulc(rf::cplx{q.x, q.y}, tw.z, tw.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < RA; ++c) {
+                            const float2 p = row[c * 32];
+                            z[c] = rf::cplx{p.x, p.y};
+                        }
                     }
                     rf::cdft16(z);
                     float *p_lo = pw + k1 * 32 + lane;            // bins k1 + RB k2, k2 < RA/2
@@ -787,12 +815,13 @@ int sp_prepare(mfcc_plan *plan)
                 const int i = 2 * pr + e + RA * b;
                 tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
             }
-    for (int col = 0; col < RA; ++col)
-        for (int sl = 0; sl < H; ++sl) {
-            const double ang = sl < H - 1 ? -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N : 0.0;
-            tab.push_back(static_cast<float>(std::cos(ang)));
-            tab.push_back(static_cast<float>(std::sin(ang)));
-        }
+    const bool tw_in_pass2 = RB == 16 ? MFCC_SP_TW2_16 : MFCC_SP_TW2_32;   // Geo::TW_IN_PASS2
+    for (int i = 0; i < RA * H; ++i) {
+        const int col = tw_in_pass2 ? i % RA : i / H, sl = tw_in_pass2 ? i / RA : i % H;
+        const double ang = sl < H - 1 ? -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N : 0.0;
+        tab.push_back(static_cast<float>(std::cos(ang)));
+        tab.push_back(static_cast<float>(std::sin(ang)));
+    }
     for (int col = 0; col < RA; ++col) {
         const double ang = -2.0 * M_PI * col / (2.0 * RA);
         tab.push_back(static_cast<float>(std::cos(ang)));
