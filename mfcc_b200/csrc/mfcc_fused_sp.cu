@@ -9,11 +9,16 @@
 //     into a raw int16 buffer while the current tile is transformed — no prefetch registers,
 //     no LDG/LDL instructions, completion on an mbarrier.  Staging then converts 8 samples per
 //     thread (LDS.128) instead of 2.
-//   * tail: each warp OWNS a contiguous group of mel filters (balanced on the host), sums
-//     their bins from P and leaves the log band energies lg[m][frame] in shared memory; one
-//     barrier later warp w forms cepstra w and w + 8 of every frame (26 conflict-free loads,
-//     DCT rows read as warp-uniform float4) and stores them straight to HBM.  4 barriers per
-//     tile instead of 7, no partial sums and no cross-warp reduction pass.
+//   * filterbank: a segment [b_j, b_j+1) rises into filter j and falls out of filter j - 1 with linear weights,
+//     so two running sums per segment give both halves; every segment is walked once, by the warp the host
+//     gave it to (cost-balanced lists).  In the tail-warp variants (the BASELINE filter / cepstrum counts) the
+//     segment descriptors are kernel PARAMETERS read under a warp-uniform index: uniform registers, uniform
+//     branches, one load and two additions per bin.
+//   * tail: band assembly + log + DCT of tile t run on TWO "tail warps" (lane = frame, everything in registers,
+//     DCT entries fetched from the parameter bank four at a time, even cepstra on one warp, odd on the other)
+//     WHILE the other six warps stage tile t + 1.  4 barriers per tile; the all-warp S3b + S4 of the generic
+//     variant (1,400 instructions per tile, 8 x redundant loads of the log energies) is gone from the hot path:
+//     1.545 -> 1.75 G frames/s on configs[1].
 //   * hot code stays under 32 KB: profiles/r1_v5_sp_unrolled_tail_A.md shows what happens when the
 //     tail is unrolled per warp (60 KB of code, 44 % of stall samples = no_instruction), so the
 //     tail is a table-driven loop shared by all warps.
@@ -41,6 +46,12 @@
 #endif
 #ifndef MFCC_SP_TW2_32
 #define MFCC_SP_TW2_32 0
+#endif
+// Phase ablation (timing only, results are wrong by construction; profiles/r1_ablation_sp_A.md): bit 0 S0 staging
+// arithmetic, 1 S1 pass 1, 2 S2 pass 2, 3 S3 filterbank sums, 4 tail (band assembly + log + DCT + store).  Barriers,
+// bulk copies and tile bookkeeping stay.
+#ifndef MFCC_SP_ABLATE
+#define MFCC_SP_ABLATE 0
 #endif
 
 namespace mfcc {
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     // tail warp: band m = rise of segment m + fall of segment m + 1, log2, mirrored-pair fold, DCT with constant-bank
     // entries (ln 2 folded in on the host), CEP stores per frame
     auto tail = [&](int64_t out_row, int nf) {
-        if constexpr (kTail) {
+        if constexpr (kTail && (MFCC_SP_ABLATE & 16) == 0) {
             static_assert(MEL % 2 == 0 && MEL / 2 <= kFoldMax && CEP <= KC, "tail-warp variant limits");
             const float *rise = scr + a.rf + lane, *fall = rise + (MEL + 1) * 32;
             float l[MEL];
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         } else if (fast) {
             mbar_wait(bar, phase);
             phase ^= 1u;
-            const int nchunks = G::tceil_s(n_frames, sh) >> 3;
+            const int nchunks = (MFCC_SP_ABLATE & 1) ? 0 : G::tceil_s(n_frames, sh) >> 3;
             const float na = -a.preemph;
             // chunk c = 8 samples; the thread takes chunks tid, tid + 256, ...: all loads first, then the arithmetic
             constexpr int NU = (G::TCEIL / 8 + kStage - 1) / kStage;
@@ -429,7 +440,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         }
 
         // ---- S1: pass 1.  Warp = column pair (a, a + 1): windowed real DFT-RB over b, inter-pass twiddle ----
-        {
+        if constexpr ((MFCC_SP_ABLATE & 2) == 0) {
             const int pr = warp;
             const float *base = staged + e + lane * STRIDE + 2 * pr;
             const float *wrow = t_win + pr * (2 * G::NZP);
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         half_sync(half);   // B2
 
         // ---- S2: pass 2.  Item = one row k1: complex DFT-RA over a gives bins k1 + RB k2; power ----
-        {
+        if constexpr ((MFCC_SP_ABLATE & 4) == 0) {
 #pragma unroll 1
             for (int it = warp; it < H; it += kWarps) {
                 if (it < H - 1) {
@@ -545,7 +556,8 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         // and the P addresses do not depend on loaded data.  Every segment is walked ONCE, by the warp the host
         // gave it to (longest-first assignment, so the eight walks cost the same); rise[j][lane] and fall[j][lane]
         // go through the scratch and S3b adds the two halves of each band. ----
-        if constexpr (kTail) {
+        if constexpr ((MFCC_SP_ABLATE & 8) != 0) {
+        } else if constexpr (kTail) {
             // Forward walk with running sums: run_i = P_0 + .. + P_i and acc = run_0 + .. + run_(w-1) = sum (w - i) P_i,
             // so fall = s acc and rise = S / NFFT - fall: one load and two additions per bin, no constants, no counter.
             // The descriptors come from the parameter bank under a warp-uniform index (uniform registers, uniform

@@ -33,3 +33,9 @@ fi
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
+# phase ablation of the A kernel (build-time switch MFCC_SP_ABLATE, rebuilt and timed on this box)
+if [ "$2" != "noablate" ]; then
+python tools/variants_sp.py --reps 1 --workloads A s0:"-DMFCC_SP_ABLATE=1" s1:"-DMFCC_SP_ABLATE=2" s2:"-DMFCC_SP_ABLATE=4" \
+  s3:"-DMFCC_SP_ABLATE=8" tail:"-DMFCC_SP_ABLATE=16" all:"-DMFCC_SP_ABLATE=31" > gpurun_out/ablate_sp.jsonl 2> gpurun_out/ablate_sp.err
+echo "ablation rc=$?"; tail -7 gpurun_out/ablate_sp.jsonl
+fi
