@@ -50,6 +50,13 @@
 // Phase ablation (timing only, results are wrong by construction; profiles/r1_ablation_sp_A.md): bit 0 S0 staging
 // arithmetic, 1 S1 pass 1, 2 S2 pass 2, 3 S3 filterbank sums, 4 tail (band assembly + log + DCT + store).  Barriers,
 // bulk copies and tile bookkeeping stay.
+// Groups per CTA (timing experiments: how much one group gains from its neighbours)
+#ifndef MFCC_SP_GROUPS_512
+#define MFCC_SP_GROUPS_512 2
+#endif
+#ifndef MFCC_SP_GROUPS_256
+#define MFCC_SP_GROUPS_256 3
+#endif
 #ifndef MFCC_SP_ABLATE
 #define MFCC_SP_ABLATE 0
 #endif
@@ -64,7 +71,7 @@ constexpr int kHalfThreads = kWarps * 32;
 // memory per group), 3 for the 256-point one (its codelets fit 80 registers and a group needs 55 KB), which buys
 // the latency-bound small-FFT path 24 resident warps instead of 16 (measured: 2.32 -> 2.61 G frames/s; 4 groups at
 // 64 registers: 2.52 G).
-constexpr int groups_for(int rb) { return rb >= 32 ? 2 : 3; }
+constexpr int groups_for(int rb) { return rb >= 32 ? MFCC_SP_GROUPS_512 : MFCC_SP_GROUPS_256; }
 constexpr int kPad = 2;
 constexpr int kSegMax = 20;                // segments one warp may be given (n_mel + 1 <= 8 * kSegMax)
 constexpr int KC = 16;                    // cepstra per frame (n_cep <= KC): warp w forms k = w and k = w + 8
