@@ -60,22 +60,83 @@ MFCC_HD void cdft4_01(cplx a0, cplx a1, cplx a2, cplx a3, cplx &y0, cplx &y1)
     y1 = cplx{d02.re + d13.im, d02.im - d13.re};
 }
 
-// Forward 8-point DFT, natural order in and out: n = nb + 2 na, k = ka + 4 kb.
-MFCC_HD void cdft8(cplx (&x)[8])
+// ---- FMA-fused twiddled butterflies (MFCC_RFFT_FUSED) ----
+// (a + w b, a - w b) for a COMPILE-TIME twiddle w = c + i s.  Multiplying first (2 FMUL + 2 FFMA) and adding after
+// (4 FADD) takes 8 instructions; factoring the larger of c, s out of w b leaves u = b (1 + i s/c) (2 FFMA) and four
+// FFMAs a +- c u: 6 instructions.  The ratio is folded by the compiler (the arguments are literals at every call
+// site); rounding is that of the product form to within one ulp of the factored-out component.
+#ifndef MFCC_RFFT_FUSED
+#define MFCC_RFFT_FUSED 0
+#endif
+MFCC_HD void bfly_tw(cplx a, cplx b, float c, float s, cplx &sum, cplx &dif)
 {
-    cdft4(x[0], x[2], x[4], x[6]);
-    cdft4(x[1], x[3], x[5], x[7]);
+    if (c == 0.0f && s == -1.0f) {             // w = -i: w b = (b.im, -b.re), no multiply at all
+        sum = cplx{a.re + b.im, a.im - b.re};
+        dif = cplx{a.re - b.im, a.im + b.re};
+    } else if (fabsf(c) >= fabsf(s)) {
+        const float r = s / c;                 // w b = c (b.re - r b.im, b.im + r b.re)
+        const float ur = fmaf(-r, b.im, b.re), ui = fmaf(r, b.re, b.im);
+        sum = cplx{fmaf(c, ur, a.re), fmaf(c, ui, a.im)};
+        dif = cplx{fmaf(-c, ur, a.re), fmaf(-c, ui, a.im)};
+    } else {
+        const float r = c / s;                 // w b = s (r b.re - b.im, r b.im + b.re)
+        const float ur = fmaf(r, b.re, -b.im), ui = fmaf(r, b.im, b.re);
+        sum = cplx{fmaf(s, ur, a.re), fmaf(s, ui, a.im)};
+        dif = cplx{fmaf(-s, ur, a.re), fmaf(-s, ui, a.im)};
+    }
+}
+// 4-point DFT of (x0, w1 x1, w2 x2, w3 x3), in place: 4 + 6 + 6 + 8 = 24 instructions against 12 + 16.
+MFCC_HD void cdft4_tw(cplx &x0, cplx &x1, cplx &x2, cplx &x3, float c1, float s1, float c2, float s2, float c3, float s3)
+{
+    cplx t0, t1, t2, t3;
+    bfly_tw(x0, x2, c2, s2, t0, t1);
+    bfly_tw(cmulc(x1, c1, s1), x3, c3, s3, t2, t3);
+    x0 = cplx{t0.re + t2.re, t0.im + t2.im};
+    x2 = cplx{t0.re - t2.re, t0.im - t2.im};
+    x1 = cplx{t1.re + t3.im, t1.im - t3.re};
+    x3 = cplx{t1.re - t3.im, t1.im + t3.re};
+}
+// Outputs 0 and 1 only of the 4-point DFT of (a0, w1 a1, w2 a2, w3 a3).
+MFCC_HD void cdft4_01_tw(cplx a0, cplx a1, cplx a2, cplx a3, float c1, float s1, float c2, float s2, float c3, float s3,
+                         cplx &y0, cplx &y1)
+{
+    cplx s02, d02, s13, d13;
+    bfly_tw(a0, a2, c2, s2, s02, d02);
+    bfly_tw(cmulc(a1, c1, s1), a3, c3, s3, s13, d13);
+    y0 = cplx{s02.re + s13.re, s02.im + s13.im};
+    y1 = cplx{d02.re + d13.im, d02.im - d13.re};
+}
+
+// Last stage of the 8-point DFT: x[2 ka + 1] *= W8^ka, then radix-2 over the pairs; natural order out.
+MFCC_HD void cdft8_last(cplx (&x)[8])
+{
+    cplx r[8];
+#if MFCC_RFFT_FUSED
+    r[0] = cplx{x[0].re + x[1].re, x[0].im + x[1].im};
+    r[4] = cplx{x[0].re - x[1].re, x[0].im - x[1].im};
+    bfly_tw(x[2], x[3], kH, -kH, r[1], r[5]);          // W8^1
+    bfly_tw(x[4], x[5], 0.0f, -1.0f, r[2], r[6]);      // W8^2 = -i
+    bfly_tw(x[6], x[7], -kH, -kH, r[3], r[7]);         // W8^3
+#else
     x[3] = cmulc(x[3], kH, -kH);             // W8^1
     x[5] = cplx{x[5].im, -x[5].re};          // W8^2 = -i
     x[7] = cmulc(x[7], -kH, -kH);            // W8^3
-    cplx r[8];
 #pragma unroll
     for (int ka = 0; ka < 4; ++ka) {
         r[ka] = cplx{x[2 * ka].re + x[2 * ka + 1].re, x[2 * ka].im + x[2 * ka + 1].im};
         r[ka + 4] = cplx{x[2 * ka].re - x[2 * ka + 1].re, x[2 * ka].im - x[2 * ka + 1].im};
     }
+#endif
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = r[i];
+}
+
+// Forward 8-point DFT, natural order in and out: n = nb + 2 na, k = ka + 4 kb.
+MFCC_HD void cdft8(cplx (&x)[8])
+{
+    cdft4(x[0], x[2], x[4], x[6]);
+    cdft4(x[1], x[3], x[5], x[7]);
+    cdft8_last(x);
 }
 
 // Forward 16-point DFT, natural order in and out: n = nb + 4 na, k = ka + 4 kb.
@@ -84,6 +145,12 @@ MFCC_HD void cdft16(cplx (&x)[16])
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) cdft4(x[nb], x[nb + 4], x[nb + 8], x[nb + 12]);
     // y[nb][ka] sits in x[nb + 4 ka]; multiply by W16^(nb ka)
+#if MFCC_RFFT_FUSED
+    cdft4(x[0], x[1], x[2], x[3]);
+    cdft4_tw(x[4], x[5], x[6], x[7], kC1, -kS1, kH, -kH, kS1, -kC1);
+    cdft4_tw(x[8], x[9], x[10], x[11], kH, -kH, 0.0f, -1.0f, -kH, -kH);
+    cdft4_tw(x[12], x[13], x[14], x[15], kS1, -kC1, -kH, -kH, -kC1, kS1);
+#else
     x[1 + 4 * 1] = cmulc(x[1 + 4 * 1], kC1, -kS1);
     x[1 + 4 * 2] = cmulc(x[1 + 4 * 2], kH, -kH);
     x[1 + 4 * 3] = cmulc(x[1 + 4 * 3], kS1, -kC1);
@@ -95,6 +162,7 @@ MFCC_HD void cdft16(cplx (&x)[16])
     x[3 + 4 * 3] = cmulc(x[3 + 4 * 3], -kC1, kS1);
 #pragma unroll
     for (int ka = 0; ka < 4; ++ka) cdft4(x[4 * ka], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);
+#endif
     // X[ka + 4 kb] sits in x[4 ka + kb]: transpose to natural order (register renaming)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -164,10 +232,14 @@ MFCC_HD void rdft16(const float (&x)[16], cplx (&X)[9])
         X[6] = cplx{fmaf(-kH, g, t2[0]), fmaf(-kH, s, t2[2])};
     }
     // q = 1: (u[j] W16^j) through a complex 4-point DFT -> X[1], X[5], X[9] = conj X[7], X[13] = conj X[3]
+#if MFCC_RFFT_FUSED
+    cdft4_tw(u[0], u[1], u[2], u[3], kC1, -kS1, kH, -kH, kS1, -kC1);
+#else
     u[1] = cmulc(u[1], kC1, -kS1);
     u[2] = cmulc(u[2], kH, -kH);
     u[3] = cmulc(u[3], kS1, -kC1);
     cdft4(u[0], u[1], u[2], u[3]);
+#endif
     X[1] = u[0];
     X[5] = u[1];
     X[7] = conj(u[2]);
@@ -198,18 +270,32 @@ MFCC_HD void rdft32(const float (&x)[32], cplx (&X)[17])
     {   // q = 2: X[2 + 4 r] = sum_{j<4} W16^(j (1 + 2 r)) (t2[j] - i (-1)^r t2[j + 4])
         // r even: outputs 0, 1 of the 4-point DFT of W16^j (t2[j], -t2[j+4])  -> X[2], X[10]
         const cplx a0{t2[0], -t2[4]};
+        // r odd: outputs 0, 1 of the 4-point DFT of W16^(3 j) (t2[j], +t2[j+4]) -> X[6], X[14]
+        const cplx b0{t2[0], t2[4]};
+#if MFCC_RFFT_FUSED
+        cdft4_01_tw(a0, cplx{t2[1], -t2[5]}, cplx{t2[2], -t2[6]}, cplx{t2[3], -t2[7]}, kC1, -kS1, kH, -kH, kS1, -kC1, X[2], X[10]);
+        cdft4_01_tw(b0, cplx{t2[1], t2[5]}, cplx{t2[2], t2[6]}, cplx{t2[3], t2[7]}, kS1, -kC1, -kH, -kH, -kC1, kS1, X[6], X[14]);
+#else
         const cplx a1 = cmulc(cplx{t2[1], -t2[5]}, kC1, -kS1);
         const cplx a2 = cmulc(cplx{t2[2], -t2[6]}, kH, -kH);
         const cplx a3 = cmulc(cplx{t2[3], -t2[7]}, kS1, -kC1);
         cdft4_01(a0, a1, a2, a3, X[2], X[10]);
-        // r odd: outputs 0, 1 of the 4-point DFT of W16^(3 j) (t2[j], +t2[j+4]) -> X[6], X[14]
-        const cplx b0{t2[0], t2[4]};
         const cplx b1 = cmulc(cplx{t2[1], t2[5]}, kS1, -kC1);    // W16^3
         const cplx b2 = cmulc(cplx{t2[2], t2[6]}, -kH, -kH);     // W16^6
         const cplx b3 = cmulc(cplx{t2[3], t2[7]}, -kC1, kS1);    // W16^9
         cdft4_01(b0, b1, b2, b3, X[6], X[14]);
+#endif
     }
     // q = 1: (u[j] W32^j) through a complex 8-point DFT -> X[1 + 4 r]; r >= 4 gives the conjugates of X[15], X[11], X[7], X[3]
+#if MFCC_RFFT_FUSED
+    // the W32^j twiddles ride on the first radix-4 stage of the 8-point DFT (even j on u0, u2, u4, u6; odd j on
+    // u1 W32^1 first, then u3, u5, u7)
+    cdft4_tw(u[0], u[2], u[4], u[6], kC1, -kS1, kH, -kH, kS1, -kC1);
+    u[1] = cmulc(u[1], 0.98078528040323044f, -0.19509032201612827f);
+    cdft4_tw(u[1], u[3], u[5], u[7], 0.83146961230254524f, -0.55557023301960222f, 0.55557023301960222f, -0.83146961230254524f,
+             0.19509032201612827f, -0.98078528040323044f);
+    cdft8_last(u);
+#else
     u[1] = cmulc(u[1], 0.98078528040323044f, -0.19509032201612827f);
     u[2] = cmulc(u[2], kC1, -kS1);
     u[3] = cmulc(u[3], 0.83146961230254524f, -0.55557023301960222f);
@@ -218,6 +304,7 @@ MFCC_HD void rdft32(const float (&x)[32], cplx (&X)[17])
     u[6] = cmulc(u[6], kS1, -kC1);
     u[7] = cmulc(u[7], 0.19509032201612827f, -0.98078528040323044f);
     cdft8(u);
+#endif
     X[1] = u[0];
     X[5] = u[1];
     X[9] = u[2];
