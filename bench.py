@@ -361,7 +361,7 @@ def main():
             pass
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
         cores = os.cpu_count() or 1
         # bounded sample: configs[1] is small enough to run whole (~5 CPU-seconds of scalar C per pass, best of 3);
         # the other workloads use the --impl reference step's sample of the same workload
