@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "fused_rt", "fused_ct"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -225,7 +225,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mfcc_b200 import api, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED, KERNEL_FUSED_RT, KERNEL_FUSED_CT
+    from mfcc_b200 import api, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,8 +239,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    kernel = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fused": KERNEL_FUSED, "fused_rt": KERNEL_FUSED_RT,
-              "fused_ct": KERNEL_FUSED_CT}[args.kernel]
+    kernel = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}[args.kernel]
     plan = api.Plan(p, device=local, kernel=kernel)
 
     # Synthetic batch, generated on the host, resident in HBM before timing.

@@ -52,9 +52,7 @@ extern "C" {
 
 #define MFCC_KERNEL_AUTO     0   /* fused tile kernel when the geometry has one, else generic */
 #define MFCC_KERNEL_GENERIC  1   /* one-frame-at-a-time shared-memory radix-2 kernel (any geometry) */
-#define MFCC_KERNEL_FUSED    2   /* fused 32-frame-tile kernel; plan creation fails if unavailable */
-#define MFCC_KERNEL_FUSED_RT 3   /* fused kernel with run-time geometry (skips the specialised variants) */
-#define MFCC_KERNEL_FUSED_CT 4   /* fused kernel with compile-time frame geometry, run-time filterbank */
+#define MFCC_KERNEL_FUSED    2   /* the fused tile kernel; plan creation fails with MFCC_ENOTSUP if the geometry has none */
 
 /* ---- parameters (all conventions explicit; see DESIGN.md "Spec") ---- */
 typedef struct mfcc_params {
@@ -74,8 +72,15 @@ typedef struct mfcc_params {
     int32_t output;       /* MFCC_OUT_* */
 } mfcc_params;
 
-typedef struct mfcc_plan  mfcc_plan;   /* immutable after creation; owns device tables */
-typedef struct mfcc_batch mfcc_batch;  /* the shape of one batch: offsets -> frame rows -> tiles */
+/* Threading.  A plan's parameters and device tables never change after creation, and mfcc_compute_batch(_f32),
+ * mfcc_cmvn_batch and mfcc_delta_batch touch nothing else: they are reentrant (any number of host threads, distinct
+ * streams).  The calls that take HOST buffers (mfcc_compute_host, mfcc_compute, mfcc_compute_host_g711 and every
+ * mfcc_stream_* / mfcc_stream_feed_many call on the plan) share plan-owned staging buffers, streams and events that
+ * grow on demand; they serialise on a mutex inside the plan, so they are safe to call from several threads but run
+ * one at a time per plan.  Use one plan per thread for concurrent host-buffer traffic. */
+typedef struct mfcc_plan  mfcc_plan;   /* owns device tables (immutable) and the host-path staging state (mutex-guarded) */
+typedef struct mfcc_batch mfcc_batch;  /* the shape of one batch: offsets -> frame rows -> tiles; tied to the framing
+                                          (frame_len, hop_len, pad_mode, out_dim) of the plan that created it */
 
 /* Fill *p with the repo defaults for a sample rate: 25 ms frame, 10 ms hop,
  * nfft = next power of two, 26 mel, 13 cepstra, preemph 0.97, Hamming,
@@ -144,10 +149,11 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
 int mfcc_compute(mfcc_plan *plan, const int16_t *pcm, int64_t n_samples,
                  float *out, int64_t *n_frames);
 
-/* Post-processing on the feature matrix in place on the device (SURVEY.md §8f
- * rank 2): per-utterance cepstral mean (and optionally variance)
- * normalisation, and delta / delta-delta regression (window N, HTK formula)
- * written to d_delta / d_delta2 (either may be NULL). */
+/* Post-processing on the feature matrix on the device:
+ * mfcc_cmvn_batch : per-utterance cepstral mean (norm_var != 0: and variance) normalisation of d_feat IN PLACE;
+ * mfcc_delta_batch: delta regression over +-window frames (HTK formula, edge frames replicated) of d_feat written to
+ *                   d_delta (same shape, must not alias d_feat; both required).  Delta-delta = a second call on the
+ *                   first call's output. */
 int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_feat,
                     int32_t norm_var, void *cuda_stream);
 int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat,

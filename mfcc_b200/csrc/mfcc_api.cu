@@ -36,10 +36,19 @@ template <typename PcmT>
 int compute_batch_impl(const mfcc_plan *plan, const mfcc_batch *batch, const PcmT *d_pcm, float *d_out,
                        int64_t tile0, int64_t n_tiles, cudaStream_t stream)
 {
-    if (plan->kernel == MFCC_KERNEL_FUSED)
-        return mfcc::launch_fused<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out,
-                                        stream);
+    if (plan->sp_state != nullptr)
+        return mfcc::sp_launch<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out, stream);
+    if (plan->wide_state != nullptr)
+        return mfcc::wide_launch<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out, stream);
     return mfcc::launch_generic<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, stream);
+}
+
+// A batch's tile table (frame starts, kTileInside flags) was computed for one framing: only plans with that framing
+// on that device may use it.
+bool batch_fits(const mfcc_plan *plan, const mfcc_batch *b)
+{
+    return plan != nullptr && b != nullptr && b->device == plan->device && b->out_dim == plan->host.out_dim &&
+           b->frame_len == plan->p.frame_len && b->hop_len == plan->p.hop_len && b->pad_mode == plan->p.pad_mode;
 }
 
 int grow(void **ptr, size_t *have, size_t need)
@@ -63,7 +72,7 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     if (out == nullptr) return MFCC_EINVAL;
     *out = nullptr;
     if (mfcc::validate_params(p) != MFCC_OK) return MFCC_EINVAL;
-    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED_CT) return MFCC_EINVAL;
+    if (kernel < MFCC_KERNEL_AUTO || kernel > MFCC_KERNEL_FUSED) return MFCC_EINVAL;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return MFCC_ECUDA; }
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MFCC_ECUDA;
@@ -80,20 +89,16 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     int rc = mfcc::build_tables(plan->p, plan->host);
     if (rc != MFCC_OK) { delete plan; return rc; }
 
-    // Kernel choice: fully specialised > compile-time-geometry fused > runtime-geometry fused > generic.
-    plan->fused = mfcc::find_fused(plan->p);
-    const char *sp_name = (kernel == MFCC_KERNEL_AUTO || kernel == MFCC_KERNEL_FUSED)
-                              ? mfcc::sp_match(plan->p, plan->host) : nullptr;
-    if (sp_name == nullptr && (kernel == MFCC_KERNEL_AUTO || kernel == MFCC_KERNEL_FUSED))
-        sp_name = mfcc::wide_match(plan->p, plan->host);
-    const char *ct_name = kernel == MFCC_KERNEL_FUSED_RT ? nullptr : mfcc::ct_match(plan->p);
+    // Kernel choice: the fused tile kernel of the geometry (512- / 256-point: mfcc_fused_sp.cu, 2048-point:
+    // mfcc_fused_wide.cu) when the plan has one, else the generic kernel.  MFCC_KERNEL_FUSED insists.
     const bool want_fused = kernel != MFCC_KERNEL_GENERIC;
-    if (kernel >= MFCC_KERNEL_FUSED && plan->fused == nullptr && ct_name == nullptr && sp_name == nullptr) {
-        delete plan;
-        return MFCC_ENOTSUP;
+    const char *fused_name = nullptr;
+    if (want_fused) {
+        fused_name = mfcc::sp_match(plan->p, plan->host);
+        if (fused_name == nullptr) fused_name = mfcc::wide_match(plan->p, plan->host);
     }
-    if (kernel == MFCC_KERNEL_FUSED_CT && ct_name == nullptr) { delete plan; return MFCC_ENOTSUP; }
-    plan->kernel = (want_fused && (plan->fused || ct_name || sp_name)) ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
+    if (kernel == MFCC_KERNEL_FUSED && fused_name == nullptr) { delete plan; return MFCC_ENOTSUP; }
+    plan->kernel = fused_name != nullptr ? MFCC_KERNEL_FUSED : MFCC_KERNEL_GENERIC;
 
     DeviceGuard guard(device);
     if (!guard.ok) { delete plan; return MFCC_ECUDA; }
@@ -132,22 +137,13 @@ int mfcc_plan_create(const mfcc_params *p, int32_t device, int32_t kernel, mfcc_
     plan->dev.rise = reinterpret_cast<const float *>(base + o_rise);
     plan->dev.fall = reinterpret_cast<const float *>(base + o_fall);
 
-    if (plan->kernel == MFCC_KERNEL_FUSED && sp_name != nullptr) {
+    if (plan->kernel == MFCC_KERNEL_FUSED) {
         rc = mfcc::sp_prepare(plan);
         if (rc == MFCC_ENOTSUP) rc = mfcc::wide_prepare(plan);
-        if (rc != MFCC_OK && rc != MFCC_ENOTSUP) { mfcc_plan_destroy(plan); return rc; }
-    }
-    if (plan->kernel == MFCC_KERNEL_FUSED && plan->sp_state == nullptr && plan->wide_state == nullptr) {
-        rc = ct_name ? mfcc::ct_prepare(plan) : MFCC_ENOTSUP;
-        if (rc == MFCC_ENOTSUP) {   // no compile-time variant (or its tables do not fit): runtime-geometry kernel
-            if (plan->fused != nullptr) rc = mfcc::fused_prepare(plan);
-            else if (kernel == MFCC_KERNEL_AUTO) { plan->kernel = MFCC_KERNEL_GENERIC; rc = MFCC_OK; }
-        }
+        if (rc == MFCC_ENOTSUP && kernel == MFCC_KERNEL_AUTO) { plan->kernel = MFCC_KERNEL_GENERIC; rc = MFCC_OK; }
         if (rc != MFCC_OK) { mfcc_plan_destroy(plan); return rc; }
     }
-    plan->kernel_name = plan->kernel != MFCC_KERNEL_FUSED ? "generic_radix2"
-                        : (plan->sp_state || plan->wide_state) ? sp_name
-                        : plan->ct_state ? ct_name : mfcc::fused_name(plan->fused);
+    plan->kernel_name = plan->kernel == MFCC_KERNEL_FUSED ? fused_name : "generic_radix2";
     *out = plan;
     return MFCC_OK;
 }
@@ -165,8 +161,6 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     if (plan->tiles_ready) cudaEventDestroy(plan->tiles_ready);
     for (cudaEvent_t e : plan->chunk_ready) cudaEventDestroy(e);
     if (plan->dev_blob) cudaFree(plan->dev_blob);
-    mfcc::fused_release(plan);
-    mfcc::ct_release(plan);
     mfcc::sp_release(plan);
     mfcc::wide_release(plan);
     delete plan;
@@ -224,6 +218,9 @@ static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int
     b->n_utts = n_utts;
     b->out_dim = plan->host.out_dim;
     const mfcc_params &p = plan->p;
+    b->frame_len = p.frame_len;
+    b->hop_len = p.hop_len;
+    b->pad_mode = p.pad_mode;
     try {
         b->offsets.assign(n_utts + 1, 0);
         b->frame_offsets.assign(n_utts + 1, 0);
@@ -307,8 +304,7 @@ int mfcc_batch_frame_offsets(const mfcc_batch *b, int64_t *dst)
 int mfcc_compute_batch(const mfcc_plan *plan, const mfcc_batch *batch, const int16_t *d_pcm, float *d_out,
                        void *cuda_stream)
 {
-    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
-    if (batch->out_dim != plan->host.out_dim) return MFCC_EINVAL;
+    if (!batch_fits(plan, batch)) return MFCC_EINVAL;
     if (batch->total_frames == 0) return MFCC_OK;
     if (d_pcm == nullptr || d_out == nullptr) return MFCC_EINVAL;
     DeviceGuard guard(plan->device);
@@ -320,8 +316,7 @@ int mfcc_compute_batch(const mfcc_plan *plan, const mfcc_batch *batch, const int
 int mfcc_compute_batch_f32(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_pcm, float *d_out,
                            void *cuda_stream)
 {
-    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
-    if (batch->out_dim != plan->host.out_dim) return MFCC_EINVAL;
+    if (!batch_fits(plan, batch)) return MFCC_EINVAL;
     if (batch->total_frames == 0) return MFCC_OK;
     if (d_pcm == nullptr || d_out == nullptr) return MFCC_EINVAL;
     DeviceGuard guard(plan->device);
@@ -367,6 +362,7 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
     }
     if (h_pcm == nullptr || h_out == nullptr) return MFCC_EINVAL;
 
+    std::lock_guard<std::mutex> lock(plan->host_mutex);
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
     const size_t tile_bytes = sizeof(Tile) * static_cast<size_t>(n_tiles);
@@ -509,6 +505,7 @@ int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
         t.flags = mfcc::tile_flags(p, t, len);
         tiles.push_back(t);
     }
+    std::lock_guard<std::mutex> lock(plan->host_mutex);
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
     int rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(len));
@@ -522,6 +519,9 @@ int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
     mfcc_batch b;
     b.device = plan->device;
     b.out_dim = od;
+    b.frame_len = p.frame_len;
+    b.hop_len = p.hop_len;
+    b.pad_mode = p.pad_mode;
     b.total_samples = len;
     b.total_frames = n_frames;
     b.d_tiles = static_cast<Tile *>(plan->d_tiles);
@@ -637,7 +637,7 @@ int mfcc_compute(mfcc_plan *plan, const int16_t *pcm, int64_t n_samples, float *
 int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_feat, int32_t norm_var,
                     void *cuda_stream)
 {
-    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
+    if (!batch_fits(plan, batch)) return MFCC_EINVAL;
     if (batch->total_frames == 0) return MFCC_OK;
     if (d_feat == nullptr) return MFCC_EINVAL;
     DeviceGuard guard(plan->device);
@@ -648,7 +648,7 @@ int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_fea
 int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t window,
                      float *d_delta, void *cuda_stream)
 {
-    if (plan == nullptr || batch == nullptr || batch->device != plan->device) return MFCC_EINVAL;
+    if (!batch_fits(plan, batch)) return MFCC_EINVAL;
     if (window < 1 || window > 8) return MFCC_EINVAL;
     if (batch->total_frames == 0) return MFCC_OK;
     if (d_feat == nullptr || d_delta == nullptr) return MFCC_EINVAL;

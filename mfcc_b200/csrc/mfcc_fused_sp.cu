@@ -77,7 +77,7 @@ constexpr int kHalfThreads = kWarps * 32;
 constexpr int groups_for(int rb) { return rb >= 32 ? MFCC_SP_GROUPS_512 : MFCC_SP_GROUPS_256; }
 constexpr int kPad = 2;
 constexpr int kSegMax = 20;                // segments one warp may be given (n_mel + 1 <= 8 * kSegMax)
-constexpr int KC = 16;                    // cepstra per frame (n_cep <= KC): warp w forms k = w and k = w + 8
+constexpr int KC = 16;                    // cepstra per DCT round: warp w forms k = w and k = w + 8 (tail-warp variants: n_cep <= KC)
 constexpr int kSegParam = 12;              // segments per warp (+ terminator) a tail-warp variant can take as parameters
 constexpr int kFoldMax = 16;                // n_mel / 2 of a tail-warp variant (n_mel <= 32)
 constexpr size_t kSmemMax = 227 * 1024;
@@ -121,7 +121,7 @@ struct Geo {
 struct SpLayout {
     int wseg;     // per warp: kSegMax segment descriptors in walk order, float4 {first bin * 32 (int), width w (int),
                   // s = 1 / (w NFFT), segment index j (int)}; unused slots have j = -1
-    int dct;      // [kWarps][n_mel] float2: DCT entries {d[w][m], d[w + 8][m]}, zero past n_cep (n_mel padded to even)
+    int dct;      // [rounds][kWarps][n_mel] float2: DCT entries {d[16 r + w][m], d[16 r + w + 8][m]}, zero past n_cep (n_mel padded to even)
     int total;    // floats, multiple of 4
 };
 
@@ -701,30 +701,34 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 const int f = (i * a.mel_magic) >> 20, m = i - f * M;
                 o[i] = scr[f * a.ls + m];
             }
-        } else if (warp < a.n_cep) {
-            const float *lg = scr + lane;
-            const float4 *dc = reinterpret_cast<const float4 *>(t_dct + warp * (2 * a.mp));   // {d[w][m], d[w+8][m], d[w][m+1], d[w+8][m+1]}
-            float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
-            const int M2 = a.n_mel >> 1;
+        } else {
+            // 16 cepstra per round: warp w forms c[kb + w] and c[kb + w + 8]
+#pragma unroll 1
+            for (int kb = 0; kb + warp < a.n_cep; kb += 2 * kWarps) {
+                const float *lg = scr + lane;
+                const float4 *dc = reinterpret_cast<const float4 *>(t_dct + ((kb >> 4) * kWarps + warp) * (2 * a.mp));   // {d[k][m], d[k+8][m], d[k][m+1], d[k+8][m+1]}
+                float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
+                const int M2 = a.n_mel >> 1;
 #pragma unroll 2
-            for (int q = 0; q < M2; ++q) {
-                const float l0 = lg[(2 * q) * 32], l1 = lg[(2 * q + 1) * 32];
-                const float4 d = dc[q];
-                c0 = fmaf(d.x, l0, c0);
-                c1 = fmaf(d.y, l0, c1);
-                e0 = fmaf(d.z, l1, e0);
-                e1 = fmaf(d.w, l1, e1);
-            }
-            if (a.n_mel & 1) {
-                const float l0 = lg[(a.n_mel - 1) * 32];
-                const float4 d = dc[M2];
-                c0 = fmaf(d.x, l0, c0);
-                c1 = fmaf(d.y, l0, c1);
-            }
-            if (lane < n_frames) {
-                float *o = a.out + (tile.out_row + lane) * a.n_cep + warp;
-                o[0] = c0 + e0;
-                if (warp + kWarps < a.n_cep) o[kWarps] = c1 + e1;
+                for (int q = 0; q < M2; ++q) {
+                    const float l0 = lg[(2 * q) * 32], l1 = lg[(2 * q + 1) * 32];
+                    const float4 d = dc[q];
+                    c0 = fmaf(d.x, l0, c0);
+                    c1 = fmaf(d.y, l0, c1);
+                    e0 = fmaf(d.z, l1, e0);
+                    e1 = fmaf(d.w, l1, e1);
+                }
+                if (a.n_mel & 1) {
+                    const float l0 = lg[(a.n_mel - 1) * 32];
+                    const float4 d = dc[M2];
+                    c0 = fmaf(d.x, l0, c0);
+                    c1 = fmaf(d.y, l0, c1);
+                }
+                if (lane < n_frames) {
+                    float *o = a.out + (tile.out_row + lane) * a.n_cep + kb + warp;
+                    o[0] = c0 + e0;
+                    if (kb + warp + kWarps < a.n_cep) o[kWarps] = c1 + e1;
+                }
             }
         }
         }
@@ -751,6 +755,7 @@ struct SpState {
     float *d_tab = nullptr;
     size_t smem = 0;
     int sm_count = 0;
+    int device = 0;
     bool useg_ok = false;      // every warp's segment list fits SpArgs::useg (tail-warp variants need it)
 };
 
@@ -807,7 +812,6 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
 {
     const SpVariant *v = find_variant(p);
     if (v == nullptr) return nullptr;
-    if (p.output == MFCC_OUT_CEPSTRA && p.n_cep > KC) return nullptr;
     if (p.log_floor < 1.17549435e-38f) return nullptr;   // the tail takes lg2.approx.ftz of max(E, floor): floor must be a normal float
     for (int j = 0; j + 1 < static_cast<int>(h.mel_bins.size()); ++j)
         if (h.mel_bins[j + 1] < h.mel_bins[j]) return nullptr;
@@ -815,7 +819,8 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
     int tabf = 0, half_floats = 0;
     variant_sizes(*v, tabf, half_floats);
     if (p.n_mel + 1 > kWarps * (kSegMax - 1) || assign_segments(h, p.n_mel).empty()) return nullptr;
-    const size_t total = tabf + 4 * static_cast<size_t>(kWarps) * kSegMax + static_cast<size_t>(KC) * (p.n_mel + 1) + 16;
+    const size_t rounds = p.output == MFCC_OUT_CEPSTRA ? (p.n_cep + KC - 1) / KC : 1;
+    const size_t total = tabf + 4 * static_cast<size_t>(kWarps) * kSegMax + rounds * KC * (p.n_mel + 1) + 16;
     if ((total + groups_for(v->rb) * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
     // tail scratch (log band energies [n_mel][32] or log-mel rows [32][n_mel | 1], then the per-segment rise / fall
     // sums [n_mel + 1][32] x 2) must fit in the workspace
@@ -888,17 +893,20 @@ int sp_prepare(mfcc_plan *plan)
     auto dct_at = [&](int k, int m) {
         return p.output == MFCC_OUT_CEPSTRA && k < p.n_cep && m < M ? h.dct[static_cast<size_t>(k) * M + m] : 0.0f;
     };
-    for (int w = 0; w < kWarps; ++w)
-        for (int m = 0; m < MP; ++m) {
-            tab.push_back(dct_at(w, m));
-            tab.push_back(dct_at(w + kWarps, m));
-        }
+    const int rounds = p.output == MFCC_OUT_CEPSTRA ? (p.n_cep + KC - 1) / KC : 1;
+    for (int r = 0; r < rounds; ++r)
+        for (int w = 0; w < kWarps; ++w)
+            for (int m = 0; m < MP; ++m) {
+                tab.push_back(dct_at(KC * r + w, m));
+                tab.push_back(dct_at(KC * r + w + kWarps, m));
+            }
     align4();
     lay.total = static_cast<int>(tab.size());
 
     SpState *st = new SpState();
     st->v = var;
     st->sm_count = plan->sm_count;
+    st->device = plan->device;
     st->smem = sizeof(float) * (static_cast<size_t>(lay.total) + groups_for(RB) * static_cast<size_t>(half_floats));
     if (st->smem > kSmemMax) { delete st; return MFCC_ENOTSUP; }
     st->args.lay = lay;
@@ -965,15 +973,8 @@ static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tile
                           cudaStream_t stream)
 {
     auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA, MEL, CEP>;
-    static thread_local const void *configured = nullptr;
-    if (configured != reinterpret_cast<const void *>(kern)) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
-            cudaSuccess) {
-            cudaGetLastError();
-            return MFCC_ECUDA;
-        }
-        configured = reinterpret_cast<const void *>(kern);
-    }
+    static std::atomic<uint64_t> optin{0};
+    if (ensure_smem_optin(kern, st->device, kSmemMax, optin) != MFCC_OK) return MFCC_ECUDA;
     SpArgs a = st->args;
     a.tiles = d_tiles;
     a.n_tiles = n_tiles;

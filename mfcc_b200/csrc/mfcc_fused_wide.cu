@@ -666,15 +666,8 @@ int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, con
     // the BASELINE.json band count (80) with cepstral output gets the unrolled DCT
     const bool fixed = !st->args.logmel && st->args.n_mel == 80;
     auto kern = fixed ? fused_wide_kernel<PcmT, kL, kHop, 80> : fused_wide_kernel<PcmT, kL, kHop, 0>;
-    static thread_local const void *configured[2] = {nullptr, nullptr};
-    if (configured[fixed] != reinterpret_cast<const void *>(kern)) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax)) !=
-            cudaSuccess) {
-            cudaGetLastError();
-            return MFCC_ECUDA;
-        }
-        configured[fixed] = reinterpret_cast<const void *>(kern);
-    }
+    static std::atomic<uint64_t> optin[2];
+    if (ensure_smem_optin(kern, plan->device, kSmemMax, optin[fixed]) != MFCC_OK) return MFCC_ECUDA;
     WideArgs a = st->args;
     a.tiles = d_tiles;
     a.n_tiles = n_tiles;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -68,8 +69,6 @@ struct DevTables {
     const float *fall;      // [nbins]
 };
 
-struct FusedKernel;  // opaque per-geometry launcher (mfcc_fused.cu)
-
 }  // namespace mfcc
 
 struct mfcc_plan {
@@ -81,13 +80,11 @@ struct mfcc_plan {
     mfcc::HostTables host;
     mfcc::DevTables dev{};
     void *dev_blob = nullptr;           // one allocation backing every DevTables pointer
-    const mfcc::FusedKernel *fused = nullptr;
-    void *fused_blob = nullptr;         // device tables of the fused kernel
-    void *fused_tables = nullptr;       // host struct of device pointers into fused_blob
-    void *ct_state = nullptr;           // compile-time-geometry fused kernel state (mfcc_fused_ct.cu)
-    void *sp_state = nullptr;           // streamlined fused kernel state (mfcc_fused_sp.cu)
+    void *sp_state = nullptr;           // 512- / 256-point fused tile kernel state (mfcc_fused_sp.cu)
     void *wide_state = nullptr;         // large-transform fused kernel state (mfcc_fused_wide.cu)
-    // mfcc_compute_host state (grown on demand, reused across calls)
+    // host-buffer entry points (mfcc_compute_host, mfcc_stream_*): state grown on demand and reused across calls,
+    // guarded by host_mutex — one such call at a time per plan
+    std::mutex host_mutex;
     void *h2d_pcm = nullptr;   size_t h2d_pcm_bytes = 0;
     void *d2h_out = nullptr;   size_t d2h_out_bytes = 0;
     void *d_tiles = nullptr;   size_t d_tiles_bytes = 0;   // device tile table of the call in flight
@@ -103,6 +100,7 @@ struct mfcc_batch {
     int64_t total_frames = 0;
     int64_t total_samples = 0;
     int out_dim = 0;
+    int frame_len = 0, hop_len = 0, pad_mode = 0;   // framing of the creating plan: the tile table is only valid for it
     std::vector<int64_t> offsets;        // [n_utts + 1]
     std::vector<int64_t> frame_offsets;  // [n_utts + 1]
     std::vector<mfcc::Tile> tiles;       // host copy
@@ -116,26 +114,29 @@ namespace mfcc {
 
 extern std::atomic<uint64_t> g_launches;
 
+// Function attributes belong to a device: the opt-in to more than 48 KB of dynamic shared memory is made once per
+// (kernel instantiation, device).  `done` is a per-instantiation bit mask over device ordinals (ordinals >= 64 opt in
+// on every launch).
+template <typename Kern>
+inline int ensure_smem_optin(Kern kern, int device, size_t bytes, std::atomic<uint64_t> &done)
+{
+    const uint64_t bit = device >= 0 && device < 64 ? 1ull << device : 0;
+    if (bit != 0 && (done.load(std::memory_order_acquire) & bit) != 0) return MFCC_OK;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) != cudaSuccess) {
+        cudaGetLastError();
+        return MFCC_ECUDA;
+    }
+    if (bit != 0) done.fetch_or(bit, std::memory_order_release);
+    return MFCC_OK;
+}
+
 // Kernel launchers.  `tile0`/`n_tiles` select a range of the batch's tile table;
 // d_pcm / d_out are the bases of the WHOLE batch arrays.
 template <typename PcmT>
 int launch_generic(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
                    float *d_out, cudaStream_t stream);
 
-// Returns nullptr when no fused kernel exists for the geometry.
-const FusedKernel *find_fused(const mfcc_params &p);
-const char *fused_name(const FusedKernel *k);
-template <typename PcmT>
-int launch_fused(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
-                 int64_t pcm_len, float *d_out, cudaStream_t stream);
-// Compile-time-geometry variant (mfcc_fused_ct.cu): name if the geometry has one, else nullptr.
-const char *ct_match(const mfcc_params &p);
-int ct_prepare(mfcc_plan *plan);
-void ct_release(mfcc_plan *plan);
-template <typename PcmT>
-int ct_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
-              float *d_out, cudaStream_t stream);
-// Fully specialised variant (mfcc_fused_sp.cu): geometry AND mel bin edges compile-time.
+// Fused tile kernel for the 512- and 256-point geometries (mfcc_fused_sp.cu): name if the plan has one, else nullptr.
 const char *sp_match(const mfcc_params &p, const HostTables &h);
 int sp_prepare(mfcc_plan *plan);
 void sp_release(mfcc_plan *plan);
@@ -149,10 +150,6 @@ void wide_release(mfcc_plan *plan);
 template <typename PcmT>
 int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
                 float *d_out, cudaStream_t stream);
-// Upload whatever constant tables the fused kernel needs (called at plan creation).
-int fused_prepare(mfcc_plan *plan);
-void fused_release(mfcc_plan *plan);
-
 int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s);
 int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
                  cudaStream_t s);

@@ -13,7 +13,7 @@ MFCC_OK, MFCC_EINVAL, MFCC_ENOMEM, MFCC_ECUDA, MFCC_ENOTSUP = 0, -1, -2, -3, -4
 WINDOW_RECT, WINDOW_HAMMING, WINDOW_HANN = 0, 1, 2
 PAD_NONE, PAD_ZERO_TAIL = 0, 1
 OUT_CEPSTRA, OUT_LOGMEL = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED, KERNEL_FUSED_RT, KERNEL_FUSED_CT = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 
 class MfccParams(C.Structure):

@@ -14,7 +14,7 @@ import pytest
 
 import oracle
 from mfcc_b200 import (api, config_a, config_b, config_c, make_params, KERNEL_GENERIC, KERNEL_FUSED,
-                       KERNEL_FUSED_RT, KERNEL_FUSED_CT, KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
+                       KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
 from mfcc_b200.synth import clip_config1, fast_fixed_batch, noise_utterance, ragged_batch
 from util import assert_parity, golden, parity_errors
 
@@ -22,17 +22,13 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 CFG = {"A": config_a, "B": config_b, "C": config_c}
-KERNELS = {"generic": KERNEL_GENERIC, "fused": KERNEL_FUSED, "fused_rt": KERNEL_FUSED_RT, "fused_ct": KERNEL_FUSED_CT}
-ALL_KERNELS = ["generic", "fused", "fused_ct", "fused_rt"]
+# "auto" is what a caller gets: the fused tile kernel of the geometry when there is one, else the generic kernel
+KERNELS = {"generic": KERNEL_GENERIC, "auto": KERNEL_AUTO}
+ALL_KERNELS = ["generic", "auto"]
 
 
 def make_plan(p, kernel):
-    try:
-        return api.Plan(p, kernel=KERNELS[kernel])
-    except api.MfccError as e:
-        if e.code == -4 and kernel.startswith("fused"):
-            pytest.skip("no fused kernel for this geometry yet")
-        raise
+    return api.Plan(p, kernel=KERNELS[kernel])
 
 
 def run_device(plan, pcm, offsets):
@@ -61,9 +57,8 @@ def test_ragged_batch_matches_oracle(name, kernel):
     assert_parity(got, ref, what=f"{name}/{kernel}")
 
 
-@pytest.mark.parametrize("kernel", ["fused", "fused_ct"])
 @pytest.mark.parametrize("name", ["A", "B"])
-def test_aligned_ragged_batch_takes_bulk_copy_path(name, kernel):
+def test_aligned_ragged_batch_takes_bulk_copy_path(name, kernel="auto"):
     """Utterances whose starts are multiples of 8 samples (16-byte aligned int16): the specialised
     kernel stages these tiles by bulk async copy; mixed with short, tile-boundary and tail tiles.
     Also an utterance that starts right after another one (the 8 lead samples belong to the
@@ -213,10 +208,11 @@ def test_bad_calls_fail_loudly():
     assert api.Plan(config_b()).kernel_name.startswith("fused_sp_")
     assert api.Plan(config_a().copy(output=OUT_LOGMEL, lifter=22)).kernel_name.startswith("fused_sp_")
     assert api.Plan(config_a().copy(n_mel=40)).kernel_name.startswith("fused_sp_")       # filterbank is data
-    assert api.Plan(config_a().copy(n_mel=40, n_cep=20)).kernel_name.startswith("fused_ct_")   # > 16 cepstra
-    assert api.Plan(config_a(), kernel=KERNEL_FUSED_CT).kernel_name.startswith("fused_ct_")
-    assert api.Plan(config_a().copy(hop_len=128)).kernel_name.startswith("fused_rt_")
-    assert api.Plan(config_a(), kernel=KERNEL_FUSED_RT).kernel_name.startswith("fused_rt_")
+    assert api.Plan(config_a().copy(n_mel=40, n_cep=20)).kernel_name.startswith("fused_sp_")   # > 16 cepstra: second DCT round
+    assert api.Plan(config_a().copy(hop_len=128)).kernel_name == "generic_radix2"
+    assert api.Plan(config_c()).kernel_name.startswith("fused_wide_")
+    with pytest.raises(api.MfccError):
+        api.Plan(config_a(), kernel=3)               # the selector is AUTO / GENERIC / FUSED, nothing else
 
 
 @pytest.mark.parametrize("name", ["A", "B", "C"])
