@@ -21,7 +21,9 @@ import numpy as np
 from .params import (MfccParams, KERNEL_AUTO, MFCC_OK)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfcc_b200.so")
+# MFCC_B200_LIB selects another BUILD of the same library (the poison build libmfcc_b200_poison.so of the tests);
+# it is never a fallback: whatever it names must exist and export the whole ABI.
+LIB_PATH = os.environ.get("MFCC_B200_LIB") or os.path.join(_HERE, "libmfcc_b200.so")
 _lib: Optional[C.CDLL] = None
 
 # name -> (restype, argtypes); every symbol include/mfcc_b200.h declares.

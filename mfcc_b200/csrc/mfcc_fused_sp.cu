@@ -63,6 +63,15 @@
 #ifndef MFCC_SP_ABLATE
 #define MFCC_SP_ABLATE 0
 #endif
+// Poison build (libmfcc_b200_poison.so, the compute-sanitizer substitute: the pool's boxes refuse the sanitizer).  The
+// kernel's buffers alias each other (staged / P, workspace / tail scratch, raw PCM refilled by the TMA engine); the
+// barrier reasoning in the comments says when each one is dead.  With MFCC_POISON every buffer is filled with NaN at
+// the point where it is said to be dead (one extra barrier each time), so any value that is read after its buffer
+// died, or before it was written for this tile, reaches the output as NaN.  tests/test_gpu_parity.py runs the
+// parity batches through this build.
+#ifndef MFCC_POISON
+#define MFCC_POISON 0
+#endif
 
 namespace mfcc {
 
@@ -239,6 +248,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         if (tid < 5) cp_async8(smem_u32(desc + slot) + tid * 8, reinterpret_cast<const char *>(a.tiles + t) + tid * 8);
     };
 
+    [[maybe_unused]] auto poison = [&](float *p, int n) {
+        for (int i = tid; i < n; i += kHalfThreads) p[i] = __int_as_float(0x7fc00000);
+    };
     if (tid == 0) mbar_init(bar, 1);
     // slack rows of P: read with zero weights, so they must hold finite values (0 * NaN would turn a
     // band into NaN and fmaxf would then silently replace it by the floor)
@@ -452,6 +464,11 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         }
         cp_async_wait_all();
         half_sync(half);   // B1: staged complete; raw buffer and (previous tile's) scratch free; next descriptor visible
+        if constexpr (MFCC_POISON) {   // the raw buffer is dead until the next bulk copy lands; so is the tail scratch
+            poison(mine + G::UNION + G::WS, G::RAW);
+            poison(scr, G::WS);
+            half_sync(half);
+        }
         if (has_next && tid == 0) {
             const Tile nt = desc[cur ^ 1];
             if (tile_fast(nt)) issue_copy(nt);
@@ -503,6 +520,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             }
         }
         half_sync(half);   // B2
+        if constexpr (MFCC_POISON) {   // the staged samples are dead: pass 2 writes P over them (slack rows stay zero)
+            poison(staged, G::UNION);
+            half_sync(half);
+            for (int i = G::NB * 32 + tid; i < G::PW; i += kHalfThreads) pw[i] = 0.0f;
+            half_sync(half);
+        }
 
         // ---- S2: pass 2.  Item = one row k1: complex DFT-RA over a gives bins k1 + RB k2; power ----
         if constexpr ((MFCC_SP_ABLATE & 4) == 0) {
@@ -567,6 +590,10 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             }
         }
         half_sync(half);   // B3: P complete, workspace free
+        if constexpr (MFCC_POISON) {   // the workspace is dead: S3 writes every segment's two sums into it
+            poison(scr, G::WS);
+            half_sync(half);
+        }
 
         // ---- S3: filterbank sums.  Segment j = bins [b_j, b_j + w) rises into filter j with weight i / w and
         // falls out of filter j - 1 with weight (w - i) / w (i = bin - b_j), so two plain sums per segment,
@@ -674,6 +701,10 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             }
         }
         half_sync(half);   // B4a: every segment's two sums are in the scratch
+        if constexpr (MFCC_POISON) {   // P is dead: the next S0 stages over it
+            poison(pw, G::NB * 32);
+            half_sync(half);
+        }
         if constexpr (kTail) {
             // the tail warp takes it from here during the next tile's S0 (or after the loop): the scratch is next
             // written by S1, after B1, which the tail warp joins only when it is done

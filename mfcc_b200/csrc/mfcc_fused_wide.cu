@@ -36,6 +36,11 @@
 #include "mfcc_rfft.cuh"
 #include "mfcc_host.h"
 
+// Poison build (see mfcc_fused_sp.cu): NaN-fill every aliased buffer at the point where the comments say it is dead.
+#ifndef MFCC_POISON
+#define MFCC_POISON 0
+#endif
+
 namespace mfcc {
 
 namespace {
@@ -184,6 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
     const int16_t *raw16 = reinterpret_cast<const int16_t *>(ws + G::RAWOFF);
     const uint32_t raw_s = smem_u32(raw16), bar = smem_u32(r0row + G::R0);
     if (tid == 0) mbar_init(bar, 1);
+    [[maybe_unused]] auto poison = [&](float *p, int n) {
+        for (int i = tid; i < n; i += kHalfThreads) p[i] = __int_as_float(0x7fc00000);
+    };
 
     for (int i = G::NB * F + tid; i < G::PW; i += kHalfThreads) pw[i] = 0.0f;   // slack rows stay zero
     for (int i = threadIdx.x * 4; i < a.lay.total; i += kThreads * 4)
@@ -347,6 +355,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         }
         half_sync(half);   // B1: staged complete; previous tile's scratch free
+        if constexpr (MFCC_POISON) {   // the raw PCM has been consumed and the tail scratch is dead: pass 1 rewrites the workspace
+            poison(ws, G::WS + G::R0);
+            half_sync(half);
+        }
 
         // ---- S1: pass 1.  Slot = column pair (a, a + 1): windowed real DFT-64 over b, inter-pass twiddle ----
         {
@@ -386,6 +398,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         }
         half_sync(half);   // B2
+        if constexpr (MFCC_POISON) {   // the staged samples are dead: pass 2 writes P over them (slack rows stay zero)
+            poison(staged, G::UNION);
+            half_sync(half);
+            for (int i = G::NB * F + tid; i < G::PW; i += kHalfThreads) pw[i] = 0.0f;
+            half_sync(half);
+        }
 
         // ---- S2: pass 2.  Item = row k1 = 1 .. 32: complex DFT-32 over a gives bins k1 + 64 k2; power ----
         {
@@ -423,6 +441,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         }
         half_sync(half);   // B3: P complete, workspace free
+        if constexpr (MFCC_POISON) {   // both the tail scratch and the raw buffer of the next unit start from dead memory
+            poison(ws, G::WS + G::R0);
+            half_sync(half);
+        }
         if (u + step < n_units) {
             int64_t fs;
             int nf;
@@ -466,6 +488,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         }
         half_sync(half);   // B4a: every segment's two sums are in the scratch
+        if constexpr (MFCC_POISON) {   // P is dead: the next S0 stages over it
+            poison(pw, G::NB * F);
+            half_sync(half);
+        }
         // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][frame] or the frame's log-mel row ----
         {
             const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 1) * F;

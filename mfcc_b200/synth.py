@@ -55,3 +55,29 @@ def ragged_batch(n_utts: int, min_len: int, max_len: int, seed: int = 3, sigma: 
     x = rng.standard_normal(int(offsets[-1]), dtype=np.float32) * np.float32(sigma)
     pcm = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
     return pcm, offsets
+
+
+HOSTILE_KINDS = ("silence_gaps", "dc_offset", "low_noise", "fullscale_tone", "clicks")
+
+
+def hostile_clip(kind: str, n: int, sr: int, seed: int = 7) -> np.ndarray:
+    """Inputs chosen to stress the places where a fast kernel and a plain loop can part ways:
+    the log floor (digital silence inside speech-level noise), pre-emphasis against a DC offset, the low end of the
+    int16 range (sigma = 3 LSB), FFT leakage under a full-scale tone, and flat spectra (single-sample clicks)."""
+    rng = np.random.default_rng(seed)
+    if kind == "silence_gaps":
+        x = rng.normal(0.0, 3000.0, n)
+        for lo, hi in ((n // 7, n // 7 + n // 5), (n // 2, n // 2 + n // 9), (n - n // 20, n)):
+            x[lo:hi] = 0.0
+    elif kind == "dc_offset":
+        x = rng.normal(0.0, 1000.0, n) + 2000.0
+    elif kind == "low_noise":
+        x = rng.normal(0.0, 3.0, n)
+    elif kind == "fullscale_tone":
+        x = 32767.0 * np.sin(2 * np.pi * 1000.0 * np.arange(n) / sr)
+    elif kind == "clicks":
+        x = np.zeros(n)
+        x[rng.integers(0, n, max(n // 900, 3))] = rng.choice([-20000.0, 15000.0, 32767.0], max(n // 900, 3))
+    else:
+        raise ValueError(kind)
+    return np.clip(np.rint(x), -32768, 32767).astype(np.int16)

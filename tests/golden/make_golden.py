@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(HERE, ".."))
 
 import np_ref  # noqa: E402
 from mfcc_b200 import config_a, config_b, config_c, OUT_LOGMEL, PAD_ZERO_TAIL  # noqa: E402
-from mfcc_b200.synth import clip_config1, noise_utterance  # noqa: E402
+from mfcc_b200.synth import clip_config1, noise_utterance, hostile_clip, HOSTILE_KINDS  # noqa: E402
 
 
 def main():
@@ -54,6 +54,23 @@ def main():
     np.savez_compressed(os.path.join(HERE, "g711_tables.npz"), ulaw=ulaw, alaw=alaw)
     for k, v in out.items():
         print(k, v.shape, v.dtype)
+
+    # Hostile inputs: every geometry x {cepstra, log-mel} x {no padding, zero tail}.  The PCM is
+    # regenerated from mfcc_b200.synth.hostile_clip by the tests (checked against the stored CRC), only the float64
+    # numpy results are stored, as float32.
+    import zlib
+    hostile = {}
+    for name, p in (("A", a), ("B", b), ("C", c)):
+        n = p.frame_len + 40 * p.hop_len + p.hop_len // 3          # 41 frames (42 with the zero tail)
+        for kind in HOSTILE_KINDS:
+            x = hostile_clip(kind, n, p.sample_rate)
+            hostile[f"{name}_{kind}_crc"] = np.array([zlib.crc32(x.tobytes())], np.uint32)
+            for oname, output in (("cep", 0), ("logmel", OUT_LOGMEL)):
+                for pname, pad in (("none", 0), ("tail", PAD_ZERO_TAIL)):
+                    q = p.copy(output=output, pad_mode=pad)
+                    hostile[f"{name}_{kind}_{oname}_{pname}"] = np_ref.mfcc(q, x).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "hostile_golden.npz"), **hostile)
+    print("hostile:", len(hostile), "arrays")
 
 
 if __name__ == "__main__":

@@ -15,8 +15,9 @@ import pytest
 import oracle
 from mfcc_b200 import (api, config_a, config_b, config_c, make_params, KERNEL_GENERIC, KERNEL_FUSED,
                        KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
-from mfcc_b200.synth import clip_config1, fast_fixed_batch, noise_utterance, ragged_batch
-from util import assert_parity, golden, parity_errors
+from mfcc_b200.synth import (clip_config1, fast_fixed_batch, noise_utterance, ragged_batch, hostile_clip,
+                             HOSTILE_KINDS)
+from util import assert_parity, golden, hostile_golden, lifter_gains, parity_errors
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -113,6 +114,7 @@ def test_option_matrix_matches_oracle(kernel):
         # cepstral counts around the 8-warp split of the DCT (warp w forms c[w] and c[w + 8])
         base.copy(n_cep=5), base.copy(n_cep=8), base.copy(n_cep=9), base.copy(n_cep=16), base.copy(n_mel=25, n_cep=16),
         config_b().copy(n_cep=1), config_b().copy(n_mel=21, n_cep=13, log_floor=1e-30),
+        config_b().copy(pad_mode=PAD_ZERO_TAIL), config_b().copy(pad_mode=PAD_ZERO_TAIL, output=OUT_LOGMEL),
     ]
     off = np.array([0, 5000, 5100, 12345, 12345, 20000], np.int64)
     pcm = noise_utterance(int(off[-1]), seed=22)
@@ -123,7 +125,11 @@ def test_option_matrix_matches_oracle(kernel):
         assert np.array_equal(fo, fo_ref)
         truth = np.concatenate([oracle.mfcc(p, pcm[off[u]:off[u + 1]], dtype=np.float64)
                                 for u in range(len(off) - 1)]).astype(np.float32)
-        assert_parity(got, ref, what=f"{p.as_dict()}/{kernel}", truth=truth)
+        # elements allowed to pass on the f64 criterion instead: the lowest band(s) of the 80-filter bank (one or two
+        # bins right above DC, 65 dB under the spectrum after pre-emphasis), nothing else
+        res = assert_parity(got, ref, what=f"{p.as_dict()}/{kernel}", truth=truth, col_scale=lifter_gains(p),
+                            max_escapes=(4 if p.n_mel >= 80 and p.output == OUT_LOGMEL else 0))   # measured: 1 of 9,440
+        assert all(c < 2 for c in res.where), res.where
 
 
 def test_wide_kernel_option_matrix():
@@ -144,10 +150,14 @@ def test_wide_kernel_option_matrix():
         assert np.array_equal(fo, fo_ref)
         truth = np.concatenate([oracle.mfcc(p, pcm[off[u]:off[u + 1]], dtype=np.float64)
                                 for u in range(len(off) - 1)]).astype(np.float32)
-        # the stated tolerance is on plain cepstra; a lifter multiplies cepstrum k by up to 1 + Q/2 and the f32
-        # rounding noise with it (the f32 oracle itself is 2.3e-4 off the f64 truth for Q = 22, 80 bands)
-        gain = 1.0 + 0.5 * p.lifter
-        assert_parity(got, ref, abs_tol=1e-3 * gain, rel_tol=1e-4 * gain, what=f"{p.as_dict()}", truth=truth)
+        # the stated tolerance is on plain cepstra; a lifter multiplies cepstrum k and its rounding noise by
+        # g_k = 1 + (Q/2) sin(pi k / Q): column k gets g_k times the tolerance (util.lifter_gains), not the largest
+        # gain for all.  Elements passing on the f64 criterion are bounded: the 80- and 128-filter banks have one or
+        # two filters on the bins right above DC (65 dB under the spectrum after pre-emphasis), which every cepstrum
+        # sees through the DCT.
+        noisy = p.n_mel >= 64
+        assert_parity(got, ref, what=f"{p.as_dict()}", truth=truth, col_scale=lifter_gains(p),
+                      max_escapes=(8 if noisy else 0))   # measured: none
 
 
 def test_known_answers_on_device():
@@ -241,6 +251,69 @@ def test_every_start_alignment_takes_the_same_values(name):
         assert np.array_equal(rows[shift], rows[0]), f"alignment {shift} changed the values"
 
 
+@pytest.mark.parametrize("kernel", ALL_KERNELS)
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_hostile_fixtures(name, kernel):
+    """Committed hostile inputs (tests/golden/hostile_golden.npz, numpy float64 results): digital silence inside
+    speech-level noise, DC offset, sigma = 3 LSB noise, a full-scale 1 kHz tone, single-sample clicks; cepstra and
+    log-mel, with and without the zero-padded tail.  Stated tolerance against the stored truth, nothing waved through."""
+    g = hostile_golden()
+    p0 = CFG[name]()
+    n = p0.frame_len + 40 * p0.hop_len + p0.hop_len // 3
+    for kind in HOSTILE_KINDS:
+        x = hostile_clip(kind, n, p0.sample_rate)
+        # as an utterance in the middle of a batch too (bulk-copy staging; neighbours are loud noise)
+        head, tail = noise_utterance(1003, seed=91), noise_utterance(2000, seed=92)
+        off = np.cumsum([0, head.size, x.size, tail.size]).astype(np.int64)
+        batch = np.concatenate([head, x, tail])
+        for oname, output in (("cep", 0), ("logmel", OUT_LOGMEL)):
+            for pname, pad in (("none", 0), ("tail", PAD_ZERO_TAIL)):
+                p = p0.copy(output=output, pad_mode=pad)
+                plan = make_plan(p, kernel)
+                ref = g[f"{name}_{kind}_{oname}_{pname}"]
+                got, fo = run_device(plan, batch, off)
+                assert_parity(got[fo[1]:fo[2]], ref, what=f"hostile {name}/{kind}/{oname}/{pname}/{kernel}")
+                alone, _ = run_device(plan, x, np.array([0, x.size], np.int64))
+                assert np.array_equal(alone, got[fo[1]:fo[2]])
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_bin_centred_tone_known_answer(name):
+    """SURVEY.md 8c known answer 3: a sinusoid exactly on bin k0 of a rectangular window without pre-emphasis.
+    (1) frame = NFFT (generic kernel): the energy sits in the <= 2 filters covering k0, every other band holds only
+    the int16 quantisation noise, > 60 dB down.  (2) the fused kernel's own frame length (L < NFFT, so the tone leaks
+    at the -13 dB level of the zero-padded rectangular window): tones on filter peaks and edges are where a
+    filterbank that forms one half of a triangle by subtraction (mfcc_fused_sp.cu S3: rise = S / N - fall) loses the
+    most — the bound is eps * w * P_peak / P_neighbour ~ 3e-5 relative for L / NFFT = 400 / 512 — so
+    every band must still match the dense-table oracle within the stated tolerance."""
+    base = CFG[name]()
+    N, M = base.nfft, base.n_mel
+    for L in (N, base.frame_len):
+        p = base.copy(frame_len=L, window=WINDOW_RECT, preemph=0.0, output=OUT_LOGMEL)
+        plan = api.Plan(p)
+        assert plan.kernel_name.startswith("fused_") == (L != N)
+        bins = oracle.mel_bins(p)
+        ks = sorted({int(bins[j]) for j in (1, 2, M // 2, M // 2 + 1, M - 1, M)} | {int(bins[M // 2]) + 1})
+        for k0 in ks:
+            if k0 <= 0 or k0 >= N // 2:
+                continue
+            nsamp = L + 40 * p.hop_len
+            x = np.rint(30000.0 * np.cos(2 * np.pi * k0 * np.arange(nsamp) / N + 0.3)).astype(np.int16)
+            got = plan.compute(x)
+            ref = oracle.mfcc(p, x)
+            truth = oracle.mfcc(p, x, np.float64)
+            what = f"tone {name} L={L} k0={k0} kernel={plan.kernel_name}"
+            if L == N:
+                # the quiet bands sit at the f32 FFT noise floor (the f32 oracle is 0.01 .. 0.2 off the f64 one there):
+                # parity on the loud bands, a level check on the quiet ones
+                loud = [m for m in range(M) if bins[m] < k0 < bins[m + 2]]
+                quiet = [m for m in range(M) if m not in loud]
+                assert_parity(got[:, loud], ref[:, loud], what=what)
+                assert got[:, loud].min() > got[:, quiet].max() + np.log(1e6), (k0, loud)
+            else:
+                assert_parity(got, ref, what=what, truth=truth)     # no element may need the f64 criterion
+
+
 # ---- BASELINE.json full sizes, through size-independent properties ----
 def test_config2_full_size_properties():
     """1,024 x 10 s @ 16 kHz: frame rows exact, fused == generic
@@ -260,9 +333,10 @@ def test_config2_full_size_properties():
     a, r = parity_errors(out.cpu().numpy(), out_g.cpu().numpy())
     assert a <= 1e-3 and r <= 1e-4, (a, r)
     o = out.cpu().numpy()
-    for u in (0, 1, 511, 1023):
-        ref = oracle.mfcc(p, pcm[off[u]:off[u + 1]])
-        assert_parity(o[b.frame_offsets[u]:b.frame_offsets[u + 1]], ref, what=f"utt {u}")
+    # every one of the 1,021,952 rows against the oracle (all host cores: a few seconds)
+    ref, fo_ref = oracle.mfcc_batch(p, pcm, off, nthreads=os.cpu_count() or 8)
+    assert np.array_equal(b.frame_offsets, fo_ref)
+    assert_parity(o, ref, what="configs[1], all rows")
     # drop the first hop of utterance 7: frame t of the shifted clip == frame t+1 of the original (t >= 1;
     # t = 0 differs through the pre-emphasis boundary y[0] = x[0])
     x = pcm[off[7]:off[8]]
@@ -388,3 +462,55 @@ def test_c_caller_runs_the_device_path(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "mfcc_compute: ok, 98 frames" in r.stdout and "fused_sp" in r.stdout
+
+
+POISON_SCRIPT = r"""
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import oracle
+from util import assert_parity
+from mfcc_b200 import api, config_a, config_b, config_c, OUT_LOGMEL, PAD_ZERO_TAIL
+from mfcc_b200.synth import ragged_batch, noise_utterance
+assert api.LIB_PATH.endswith("libmfcc_b200_poison.so"), api.LIB_PATH
+worst = {}
+cases = [("A", config_a()), ("B", config_b()), ("C", config_c()), ("A_logmel", config_a().copy(output=OUT_LOGMEL)),
+         ("B_40_20", config_b().copy(n_mel=24, n_cep=12)), ("A_tail", config_a().copy(pad_mode=PAD_ZERO_TAIL)),
+         ("C_logmel", config_c().copy(output=OUT_LOGMEL))]
+for name, p in cases:
+    plan = api.Plan(p)
+    assert plan.kernel_name.startswith("fused_"), plan.kernel_name
+    L, H = p.frame_len, p.hop_len
+    pcm, off = ragged_batch(700 if p.nfft < 2048 else 120, L // 2, L + 150 * H, seed=61)
+    b = plan.batch(off)
+    for dt in (torch.int16, torch.float32):
+        out = plan.compute_batch(b, torch.from_numpy(pcm).cuda().to(dt))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.isfinite(got).all(), f"{name}: NaN from a poisoned buffer reached the output"
+        ref, _ = oracle.mfcc_batch(p, pcm, off, nthreads=8)
+        truth = None
+        if p.nfft == 2048:   # 80 bands at 48 kHz: the band on the bins right above DC sits at the f32 noise floor
+            truth = np.concatenate([oracle.mfcc(p, pcm[off[u]:off[u + 1]], dtype=np.float64) for u in range(len(off) - 1)])
+        res = assert_parity(got, ref, what=name, truth=truth, max_escapes=got.size // 10000)
+        worst[name] = [res[0], res[1], res.escapes]
+print(json.dumps(worst))
+"""
+
+
+def test_poison_build_finds_no_stale_reads():
+    """The sanitizer substitute (compute-sanitizer is refused on the pool's boxes): libmfcc_b200_poison.so is the same
+    library built with -DMFCC_POISON=1, which NaN-fills every aliased shared-memory buffer (staged / P, workspace /
+    tail scratch, raw PCM) at the point where the kernels' barrier reasoning says it is dead.  A read of a dead or
+    not-yet-written value then reaches the output as NaN.  Ragged batches through both fused kernels, int16 and f32
+    entries, tail-warp and generic-tail variants: finite and within tolerance of the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "mfcc_b200", "libmfcc_b200_poison.so")
+    assert os.path.exists(lib), "poison build missing: make -C mfcc_b200/csrc poison (done by __graft_entry__.build())"
+    env = dict(os.environ, MFCC_B200_LIB=lib)
+    r = subprocess.run([sys.executable, "-c", POISON_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    print("poison build:", r.stdout.strip())

@@ -11,8 +11,8 @@ import np_ref
 import oracle
 from mfcc_b200 import (config_a, config_b, config_c, make_params, OUT_LOGMEL, PAD_ZERO_TAIL,
                        WINDOW_RECT, WINDOW_HANN)
-from mfcc_b200.synth import clip_config1, noise_utterance
-from util import assert_parity, golden
+from mfcc_b200.synth import clip_config1, noise_utterance, hostile_clip, HOSTILE_KINDS
+from util import assert_parity, golden, hostile_golden
 
 CFG = {"A": config_a, "B": config_b, "C": config_c}
 
@@ -218,3 +218,26 @@ def test_g711_tables_match_audioop():
     assert np.array_equal(oracle.decode_g711(codes, False), t["ulaw"])
     assert np.array_equal(oracle.decode_g711(codes, True), t["alaw"])
     assert oracle.decode_g711(np.array([0xFF, 0x00, 0x80], np.uint8), False).tolist() == [0, -32124, 32124]
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_hostile_golden_vectors(name):
+    """The committed hostile fixtures (tests/golden/make_golden.py: digital silence inside speech-level noise, DC
+    offset, sigma = 3 noise, full-scale 1 kHz tone, single-sample clicks; numpy float64 results stored as f32):
+    inputs regenerate bit for bit, the double oracle agrees to f32 storage precision, the float oracle to the
+    stated tolerance (elements that sit at the f32 noise floor are counted, not waved through)."""
+    import zlib
+    g = hostile_golden()
+    p0 = CFG[name]()
+    n = p0.frame_len + 40 * p0.hop_len + p0.hop_len // 3
+    for kind in HOSTILE_KINDS:
+        x = hostile_clip(kind, n, p0.sample_rate)
+        assert zlib.crc32(x.tobytes()) == int(g[f"{name}_{kind}_crc"][0])
+        for oname, output in (("cep", 0), ("logmel", OUT_LOGMEL)):
+            for pname, pad in (("none", 0), ("tail", PAD_ZERO_TAIL)):
+                ref = g[f"{name}_{kind}_{oname}_{pname}"]
+                p = p0.copy(output=output, pad_mode=pad)
+                f64 = oracle.mfcc(p, x, np.float64)
+                assert f64.shape == ref.shape == (41 + (pad == PAD_ZERO_TAIL), p.out_dim)
+                assert np.abs(f64 - ref).max() <= 4e-6 * max(1.0, np.abs(ref).max())
+                assert_parity(oracle.mfcc(p, x, np.float32), f64, what=f"{name}/{kind}/{oname}/{pname}")

@@ -22,25 +22,65 @@ def parity_errors(got, ref):
     return float(d.max()), float((d / np.maximum(np.abs(ref), 1.0)).max())
 
 
-def assert_parity(got, ref, abs_tol=ABS_TOL, rel_tol=REL_TOL, what="", truth=None):
-    """``got`` must match the f32 oracle ``ref`` within the tolerance.  With ``truth`` (the f64 oracle)
-    an element may instead be no further from the truth than twice the f32 oracle itself: a band
-    that sits at the fp32 FFT noise floor (e.g. the DC-only filter of an 80-band bank after
-    pre-emphasis, 65 dB under the spectrum) is not determined to 1e-4 by ANY f32 evaluation order —
-    the f32 oracle is off the truth by 1.4e-3 there — so "equal to the f32 oracle" is not a
-    meaningful bar for it, "as accurate as the f32 oracle" is."""
+class Parity(tuple):
+    """(max abs error, max rel error) with the escape-hatch bookkeeping attached."""
+    escapes = 0
+    where = ()
+
+
+# every assert_parity(truth=...) call appends {"what", "elements", "escapes", "columns"}: the GPU tests dump it to
+# gpurun_out/parity_escapes.json so that the number of elements that needed the f64 criterion is on record
+ESCAPE_LOG = []
+
+
+def assert_parity(got, ref, abs_tol=ABS_TOL, rel_tol=REL_TOL, what="", truth=None, max_escapes=0, col_scale=None):
+    """``got`` must match the f32 oracle ``ref`` within the tolerance.
+
+    ``col_scale`` (one factor per output column) widens the tolerance of column k by that factor: a lifter multiplies
+    cepstrum k — and every rounding error in it — by g_k = 1 + (Q/2) sin(pi k / Q), so the stated tolerance on plain
+    cepstra becomes g_k times that on liftered ones (column by column, not the largest gain for all).
+
+    With ``truth`` (the f64 oracle) an element may instead be no further from the truth than twice the f32 oracle
+    itself: a band that sits at the fp32 FFT noise floor (e.g. the DC-only filter of an 80-band bank after
+    pre-emphasis, 65 dB under the spectrum) is not determined to 1e-4 by ANY f32 evaluation order — the f32 oracle
+    is off the truth by 1.4e-3 there — so "equal to the f32 oracle" is not a meaningful bar for it, "as accurate as
+    the f32 oracle" is.  Such elements are COUNTED: at most ``max_escapes`` of them may exist (default none), and
+    the count and the columns they sit in are logged."""
     assert np.isfinite(np.asarray(got)).all(), f"{what}: non-finite output"
     a, r = parity_errors(got, ref)
-    if truth is None:
-        assert a <= abs_tol and r <= rel_tol, f"{what}: max abs {a:.3e} (tol {abs_tol}), max rel {r:.3e} (tol {rel_tol})"
-        return a, r
-    g, f32, f64 = (np.asarray(x, np.float64) for x in (got, ref, truth))
+    g, f32 = (np.asarray(x, np.float64) for x in (got, ref))
+    scale = np.ones(g.shape[-1] if g.ndim else 1) if col_scale is None else np.asarray(col_scale, np.float64)
     d = np.abs(g - f32)
-    ok = (d <= abs_tol) & (d / np.maximum(np.abs(f32), 1.0) <= rel_tol)
-    ok |= np.abs(g - f64) <= 2.0 * np.abs(f32 - f64) + 1e-6
-    assert ok.all(), (f"{what}: {int((~ok).sum())} elements off both the f32 oracle (max abs {a:.3e}, max rel {r:.3e}) "
-                      f"and the f64 truth")
-    return a, r
+    ok = (d <= abs_tol * scale) & (d / np.maximum(np.abs(f32), 1.0) <= rel_tol * scale)
+    res = Parity((a, r))
+    if truth is None:
+        assert ok.all(), (f"{what}: {int((~ok).sum())} of {ok.size} elements out of tolerance: max abs {a:.3e} "
+                          f"(tol {abs_tol}), max rel {r:.3e} (tol {rel_tol})")
+        return res
+    f64 = np.asarray(truth, np.float64)
+    hatch = ~ok & (np.abs(g - f64) <= 2.0 * np.abs(f32 - f64) + 1e-6)
+    bad = ~ok & ~hatch
+    res.escapes = int(hatch.sum())
+    res.where = tuple(sorted(set(np.nonzero(hatch)[-1].tolist()))) if hatch.any() else ()
+    ESCAPE_LOG.append({"what": what, "elements": int(ok.size), "escapes": res.escapes, "columns": list(res.where)})
+    assert not bad.any(), (f"{what}: {int(bad.sum())} elements off both the f32 oracle (max abs {a:.3e}, max rel {r:.3e}) "
+                           f"and the f64 truth")
+    assert res.escapes <= max_escapes, (f"{what}: {res.escapes} elements (columns {res.where}) needed the f64 criterion, "
+                                        f"at most {max_escapes} allowed")
+    return res
+
+
+def lifter_gains(p):
+    """Per-cepstrum lifter gain 1 + (Q/2) sin(pi k / Q) (ones without a lifter or for log-mel output)."""
+    dim = p.n_mel if p.output == 1 else p.n_cep
+    if p.lifter <= 0 or p.output == 1:
+        return np.ones(dim)
+    k = np.arange(dim)
+    return np.maximum(np.abs(1.0 + 0.5 * p.lifter * np.sin(np.pi * k / p.lifter)), 1.0)
+
+
+def hostile_golden():
+    return np.load(os.path.join(GOLDEN, "hostile_golden.npz"))
 
 
 def golden():
