@@ -113,18 +113,19 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
 
 
-def measured_fp32_peak():
-    """FP32 FMA peak in TFLOP/s measured live by tools/microbench (scalar FFMA line)."""
-    exe = os.path.join(ROOT, "tools", "microbench")
+def measured_fp32_peak(sm_mhz=None):
+    """FP32 FMA peak in TFLOP/s measured live by tools/fp32_peak (>= 5 ms per launch, 20 launches back to back between
+    two events); returns (TFLOP/s, how, details).  `sm_mhz` is the SM clock bench.py sampled under load: the tool then
+    also states measured / (SMs x 128 x 2 x that clock)."""
+    exe = os.path.join(ROOT, "tools", "fp32_peak")
+    derived = 148 * 128 * 2 * 1.965e9 / 1e12
     try:
-        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
-        for line in out.splitlines():
-            d = json.loads(line)
-            if d.get("bench", "").startswith("ffma_scalar"):
-                return 2.0 * d["fma_per_s"] / 1e12, "measured live: tools/microbench scalar FFMA, 32 warps/SM"
+        cmd = [exe] + (["--sm-mhz", str(sm_mhz)] if sm_mhz else [])
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        return float(d["tflops"]), "measured live: tools/fp32_peak (scalar FFMA, 32 warps/SM, 20 launches of >= 5 ms)", d
     except Exception:
-        pass
-    return 148 * 128 * 2 * 1.965e9 / 1e12, "derived 148 SM x 128 lanes x 2 x 1.965 GHz (microbench unavailable)"
+        return derived, "derived 148 SM x 128 lanes x 2 x 1.965 GHz (tools/fp32_peak unavailable)", None
 
 
 def cpu_leg(p, pcm, offsets, n_utts_sample, threads, repeats=1):
@@ -169,7 +170,7 @@ def run_reference(args, p, cfg_name, desc, ref_maker):
         "impl": "reference", "metric": "mfcc_frames_per_sec", "value": v, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "params": cfg_name},
+        "config": workload_config(args.workload, args.gpus),
         "audio_seconds_per_s": v * p.hop_len / p.sample_rate,
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "in-repo scalar C oracle; simotin13/mfcc has no MFCC path to time"},
@@ -203,46 +204,30 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
-def main():
-    claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+def workload_config(name, world):
+    """The `config` object of the JSON line: a function of the workload definition only, so that the two arms
+    (ours / --impl reference) print the same one."""
+    cfg_name, _, desc, _ = WORKLOADS[name]
+    return {"workload": desc, "params": cfg_name, "workload_key": name,
+            "l2": "input per step exceeds the 126 MB L2: every timed step re-reads it from HBM (no flush needed)",
+            "parallelism": f"utterance-sharded x{world}, no data-path collective"}
 
-    cfg_name, maker, desc, ref_maker = WORKLOADS[args.workload]
-    p = CONFIGS[cfg_name]()
-    if args.impl == "reference":
-        run_reference(args, p, cfg_name, desc, ref_maker)
-        return
 
+class Ctx:
+    pass
+
+
+def measure(ctx, name, steps, warmup, e2e_steps, with_cpu, peak=None):
+    """Device-timed steps, the e2e leg, rooflines and (N = 1) the CPU baseline of ONE workload."""
     import torch
     import torch.distributed as dist
-    from mfcc_b200 import api, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED
+    from mfcc_b200 import api
+    world, rank, local = ctx.world, ctx.rank, ctx.local
+    cfg_name, maker, desc, ref_maker = WORKLOADS[name]
+    p = CONFIGS[cfg_name]()
+    plan = api.Plan(p, device=local, kernel=ctx.kernel)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the MFCC path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    from mfcc_b200.sharding import bind_near_gpu
-    full_affinity = os.sched_getaffinity(0)
-    numa_cores = bind_near_gpu(local)   # pinned e2e buffers are first-touched on the GPU's NUMA node
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    kernel = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}[args.kernel]
-    plan = api.Plan(p, device=local, kernel=kernel)
-
-    # Synthetic batch, generated on the host, resident in HBM before timing.
+    # Synthetic batch (BASELINE.md 5), generated on the host, resident in HBM before timing.
     pcm, off = maker(1000 + rank)
     n_utts = len(off) - 1
     batch = plan.batch(off)
@@ -259,7 +244,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         plan.compute_batch(batch, d_pcm, d_out, stream)
     barrier()
     sampler = ClockSampler(local)
@@ -267,25 +252,26 @@ def main():
         sampler.start()
         time.sleep(0.25)
     # keep the GPU busy long enough for nvidia-smi to see load: untimed pre-roll, then the timed K steps
-    for _ in range(50):
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.05:
         plan.compute_batch(batch, d_pcm, d_out, stream)
+        torch.cuda.synchronize()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = api.launch_count()
     t_host0 = time.perf_counter()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         plan.compute_batch(batch, d_pcm, d_out, stream)
     ev1.record(stream)
     barrier()
-    t_host1 = time.perf_counter()
     launches = api.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     # hold the load a little longer so the sampler has rows inside the region even for short runs
     t_hold = time.perf_counter()
     while time.perf_counter() - t_hold < 0.6:
         plan.compute_batch(batch, d_pcm, d_out, stream)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
     clocks = sampler.stop(t_host0 - 0.3, time.perf_counter()) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -296,7 +282,7 @@ def main():
         total_frames = int(fr.item())
     else:
         total_frames = frames
-    value = total_frames * args.steps / (ms * 1e-3)
+    value = total_frames * steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through mfcc_compute_host (H2D + kernels + D2H inside the timed region) ----
     h_in = api.PinnedBuffer((pcm.size,), np.int16)
@@ -307,7 +293,7 @@ def main():
     barrier()
     e2e_step_ms = []
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         ts = time.perf_counter()
         plan.compute_host(h_in.array, off, h_out.array)   # returns with the features in h_out
         e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 3))
@@ -317,22 +303,27 @@ def main():
         t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
-    e2e_value = total_frames * args.e2e_steps / e2e_dt
+    e2e_value = total_frames * e2e_steps / e2e_dt
     e2e_ok = bool(np.array_equal(h_out.array, d_out.cpu().numpy()))
-    os.sched_setaffinity(0, full_affinity)   # the CPU-baseline leg below uses every host core again
-
+    kernel_name = plan.kernel_name
+    out_dim = plan.out_dim
+    h_in.close()
+    h_out.close()
+    del d_pcm, d_out, batch
+    plan.close()
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel (the only kernel in the step) ----
     per_launch_s = ms * 1e-3 / max(launches, 1)
     frames_per_launch = frames  # one launch covers the rank's whole batch
-    fp32_peak, fp32_how = measured_fp32_peak()
+    if peak is None:
+        peak = measured_fp32_peak(clocks.get("sm_mhz") if clocks else None)
+    fp32_peak, fp32_how, fp32_detail = peak
     flops = fft_flops(p.nfft) * frames_per_launch
     ach_tf = flops / per_launch_s / 1e12
-    bytes_alg = (p.hop_len * 2 + plan.out_dim * 4) * frames_per_launch
+    bytes_alg = (p.hop_len * 2 + out_dim * 4) * frames_per_launch
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -340,19 +331,19 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach_tf / fp32_peak, "traffic": None, "kernel": plan.kernel_name,
+                "frac": ach_tf / fp32_peak, "traffic": None, "kernel": kernel_name,
                 "algorithmic": f"2.5*N*log2(N) = {fft_flops(p.nfft):.0f} FLOP/frame x {frames_per_launch} frames/launch",
-                "peak_source": fp32_how,
+                "peak_source": fp32_how, "peak_detail": fp32_detail,
                 "note": "the path is FP32 CUDA-core bound (FFT FLOPs / stream bytes = 24-50 FLOP/B against a ridge of about 11), "
                         "so the binding roofline is the measured FP32 FMA peak; the HBM view is in roofline_hbm"}
     roofline_hbm = {"bound": "hbm", "achieved": bytes_alg / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_alg / per_launch_s / 1e9 / hbm_peak, "traffic": None,
-                    "algorithmic": f"{p.hop_len * 2 + plan.out_dim * 4} B/frame x {frames_per_launch} frames/launch",
+                    "algorithmic": f"{p.hop_len * 2 + out_dim * 4} B/frame x {frames_per_launch} frames/launch",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            t = json.load(open(prof)).get(plan.kernel_name)
+            t = json.load(open(prof)).get(kernel_name)
             if t:   # measured DRAM bytes per frame (one ncu --set full capture) x the frames of one launch
                 roofline["traffic"] = roofline_hbm["traffic"] = int(round(t["bytes_per_frame"] * frames_per_launch))
                 roofline["traffic_source"] = t["capture"]
@@ -360,11 +351,12 @@ def main():
             pass
 
     cpu = None
-    if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
+    if with_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
+        os.sched_setaffinity(0, ctx.full_affinity)   # this leg uses every host core
         cores = os.cpu_count() or 1
         # bounded sample: configs[1] is small enough to run whole (~5 CPU-seconds of scalar C per pass, best of 3);
         # the other workloads use the --impl reference step's sample of the same workload
-        pcm_r, off_r = (pcm, off) if args.workload == "A" else ref_maker(1000)
+        pcm_r, off_r = (pcm, off) if name == "A" else ref_maker(1000)
         n_s = len(off_r) - 1
         v, fr_s, dt = cpu_leg(p, pcm_r, off_r, n_s, cores, repeats=3)
         n_1 = max(1, n_s // 4)
@@ -374,26 +366,87 @@ def main():
                "single_thread_value": v1,
                "note": "in-repo scalar C oracle (gcc -O2); simotin13/mfcc has no MFCC path to time"}
 
-    line = {
-        "metric": "mfcc_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "params": cfg_name, "frames_per_step_per_gpu": frames,
-                   "kernel": plan.kernel_name, "l2": f"input {in_bytes / 1e6:.1f} MB per step > 126 MB L2 (no flush needed)",
-                   "utterances": n_utts,
-                   "parallelism": f"utterance-sharded x{world}, no data-path collective"},
+    return {
+        "value": value, "unit": "frames/s", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "config": workload_config(name, world),
+        "batch": {"frames_per_step_per_gpu": frames, "utterances": n_utts, "input_mb_per_step": round(in_bytes / 1e6, 1)},
+        "kernel": kernel_name,
         "audio_seconds_per_s": value * p.hop_len / p.sample_rate,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "steps": args.e2e_steps, "step_ms": e2e_step_ms,
-                "api": "mfcc_compute_host (pinned host buffers, 3-stream chunk pipeline)",
-                "host_cores_bound": len(numa_cores) if numa_cores else None,
+                "steps": e2e_steps, "step_ms": e2e_step_ms,
+                "api": "mfcc_compute_host (pinned host buffers, 4-stream chunk pipeline)",
+                "host_cores_bound": len(ctx.numa_cores) if ctx.numa_cores else None,
                 "matches_device_path": e2e_ok},
         "gpu_launches": launches,
         "roofline": roofline, "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,
+        "_peak": peak,
     }
-    emit(line)
+
+
+def main():
+    claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--extra", default=None,
+                    help="comma-separated workloads measured after the headline one and nested under `workloads` "
+                         "(default at N = 1 with the default workload: B3,C — BASELINE.json configs[2] and configs[3]; 'none' to skip)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    cfg_name, maker, desc, ref_maker = WORKLOADS[args.workload]
+    p = CONFIGS[cfg_name]()
+    if args.impl == "reference":
+        run_reference(args, p, cfg_name, desc, ref_maker)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mfcc_b200 import KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED
+
+    ctx = Ctx()
+    ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
+    ctx.local = local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the MFCC path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    from mfcc_b200.sharding import bind_near_gpu
+    ctx.full_affinity = os.sched_getaffinity(0)
+    ctx.numa_cores = bind_near_gpu(local)   # pinned e2e buffers are first-touched on the GPU's NUMA node
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx.kernel = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}[args.kernel]
+
+    res = measure(ctx, args.workload, args.steps, args.warmup, args.e2e_steps, not args.no_cpu)
+    extra = args.extra
+    if extra is None:
+        extra = "B3,C" if (world == 1 and args.workload == "A") else "none"
+    nested = {}
+    if extra != "none" and world == 1 and res is not None:
+        for name in extra.split(","):
+            # shorter step counts: these lines ride along with the headline one
+            r = measure(ctx, name, max(3, args.steps // 2), args.warmup, max(2, args.e2e_steps // 3), not args.no_cpu,
+                        peak=res["_peak"])
+            r.pop("_peak", None)
+            nested[name] = r
+    if rank == 0:
+        res.pop("_peak", None)
+        line = {"metric": "mfcc_frames_per_sec", "value": res.pop("value"), "unit": res.pop("unit"), "n_gpus": world,
+                "steps": res.pop("steps"), "warmup": res.pop("warmup"), "ms_per_step": res.pop("ms_per_step"),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        line.update(res)
+        if nested:
+            line["workloads"] = nested
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

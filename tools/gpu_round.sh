@@ -15,7 +15,7 @@ for n in ("A", "B", "B3", "C8", "C"):
     try:
         d = json.load(open(f"gpurun_out/bench_{n}.json"))
         c = d.get("cpu_baseline") or {}
-        print(n, f"{d['value']:.4g} frames/s", d["config"]["kernel"], f"e2e {d['e2e']['value']:.4g}", f"frac {d['roofline']['frac']:.3f}",
+        print(n, f"{d['value']:.4g} frames/s", d["kernel"], f"e2e {d['e2e']['value']:.4g}", f"frac {d['roofline']['frac']:.3f}",
               f"hbm {d['roofline_hbm']['frac']:.3f}", f"cpu {c.get('value', 0):.4g} x{c.get('cores')}", d["clocks"])
     except Exception as e:
         print(n, "parse failed", e)
