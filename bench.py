@@ -385,6 +385,101 @@ def measure(ctx, name, steps, warmup, e2e_steps, with_cpu, peak=None):
     }
 
 
+def run_shard(ctx, args):
+    """--shard: ONE ragged configs[2] batch (the same on every rank, as if read from shared storage), partitioned by
+    cumulative frame count (sharding.partition); every rank runs mfcc_compute_host on ITS slice (host buffers in, host
+    buffers out), then the optional feature gather over NCCL.  Strong scaling: the total work is fixed as N grows.
+    Reported: frames/s of the sharded compute (max over ranks), the gather time on a side stream, and the time of both
+    when the gather of chunk i overlaps nothing / runs after the compute (the collective is 52 B per frame)."""
+    import torch
+    import torch.distributed as dist
+    from mfcc_b200 import api
+    from mfcc_b200.sharding import partition, local_slice, gather_features, frame_counts
+    world, rank, local = ctx.world, ctx.rank, ctx.local
+    cfg_name, maker, desc, _ = WORKLOADS["B3"]
+    p = CONFIGS[cfg_name]()
+    plan = api.Plan(p, device=local, kernel=ctx.kernel)
+    pcm, off = maker(1000)                       # identical on every rank
+    parts = partition(p, off, world)
+    u0, u1 = parts[rank]
+    s0, s1, loc = local_slice(off, u0, u1)
+    rows = int(frame_counts(p, off)[u0:u1].sum())
+    total_rows = int(frame_counts(p, off).sum())
+    h_in = api.PinnedBuffer((max(s1 - s0, 1),), np.int16)
+    h_in.array[: s1 - s0] = pcm[s0:s1]
+    h_out = api.PinnedBuffer((max(rows, 1), plan.out_dim), np.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d_feat = torch.empty((max(rows, 1), plan.out_dim), dtype=torch.float32, device="cuda")
+    side = torch.cuda.Stream()
+    for _ in range(max(args.warmup, 2)):
+        plan.compute_host(h_in.array[: s1 - s0], loc, h_out.array)
+    # compute only
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        plan.compute_host(h_in.array[: s1 - s0], loc, h_out.array)
+    torch.cuda.synchronize()
+    dt_compute = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+    # gather only (device-resident rows, NCCL all_gather on a side stream), device-timed
+    gather_ms, full_ok = None, None
+    if world > 1:
+        d_feat[:rows].copy_(torch.from_numpy(h_out.array[:rows]))
+        for _ in range(2):
+            with torch.cuda.stream(side):
+                full, counts = gather_features(d_feat, rows, plan.out_dim)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(side):
+            e0.record(side)
+            for _ in range(args.e2e_steps):
+                full, counts = gather_features(d_feat, rows, plan.out_dim)
+            e1.record(side)
+        barrier()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1) / args.e2e_steps)
+        full_ok = bool(full.shape[0] == total_rows and sum(counts) == total_rows)
+        # compute + gather: the gather of step i runs on the side stream while step i + 1 computes
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            plan.compute_host(h_in.array[: s1 - s0], loc, h_out.array)
+            d_feat[:rows].copy_(torch.from_numpy(h_out.array[:rows]), non_blocking=True)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                full, counts = gather_features(d_feat, rows, plan.out_dim)
+        torch.cuda.synchronize()
+        dt_both = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+    else:
+        dt_both = dt_compute
+    if rank == 0:
+        emit({"metric": "mfcc_frames_per_sec", "mode": "shard", "value": total_rows / dt_compute, "unit": "frames/s",
+              "n_gpus": world, "steps": args.e2e_steps, "warmup": max(args.warmup, 2), "ms_per_step": dt_compute * 1e3,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": workload_config("B3", world),
+              "sharding": {"by": "cumulative frames, contiguous utterance ranges", "utterances_per_rank": [b - a for a, b in parts],
+                           "frames_total": total_rows, "frames_rank0": rows},
+              "collective": {"op": "NCCL all_gather of [rows_r, 13] f32 (padded to the largest block)", "ms": gather_ms,
+                             "bytes_total": total_rows * plan.out_dim * 4, "result_complete": full_ok,
+                             "compute_plus_gather_ms": dt_both * 1e3,
+                             "overlap": "gather of step i on a side stream under the compute of step i + 1"},
+              "value_with_gather": total_rows / dt_both,
+              "api": "mfcc_compute_host per rank on its slice (host buffers), sharding.partition / gather_features"})
+    h_in.close()
+    h_out.close()
+    plan.close()
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -396,6 +491,9 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", action="store_true",
+                    help="strong-scaling mode: ONE ragged configs[2] batch partitioned by frames over the ranks, "
+                         "mfcc_compute_host per rank, NCCL gather of the features timed beside it")
     ap.add_argument("--extra", default=None,
                     help="comma-separated workloads measured after the headline one and nested under `workloads` "
                          "(default at N = 1 with the default workload: B3,C — BASELINE.json configs[2] and configs[3]; 'none' to skip)")
@@ -426,6 +524,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx.kernel = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fused": KERNEL_FUSED}[args.kernel]
 
+    if args.shard:
+        run_shard(ctx, args)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     res = measure(ctx, args.workload, args.steps, args.warmup, args.e2e_steps, not args.no_cpu)
     extra = args.extra
     if extra is None:

@@ -164,6 +164,29 @@ int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float
 int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst,
                      void *cuda_stream);
 
+/* RIFF/WAVE header parsing on the host.  `data` is the whole file (or at least its header and
+ * as much of the data chunk as is present) in host memory; nothing is copied.  On MFCC_OK, info says which device
+ * entry takes the samples (MFCC_WAV_PCM16 -> mfcc_compute_batch, MFCC_WAV_MULAW / MFCC_WAV_ALAW ->
+ * mfcc_compute_batch_g711, MFCC_WAV_F32 -> mfcc_compute_batch_f32 after scaling by 32768) and where they are:
+ * data_offset bytes into the file, n_frames sample frames of `channels` interleaved samples.  A data chunk whose
+ * size field is 0 / 0xFFFFFFFF (streamed) or larger than the file (truncated) is taken to run to the end of `data`.
+ * MFCC_EINVAL: not a RIFF/WAVE file or malformed; MFCC_ENOTSUP: a sample format without a device entry
+ * (8 / 24 / 32-bit integer PCM, ADPCM, f64). */
+#define MFCC_WAV_PCM16  1
+#define MFCC_WAV_MULAW  2
+#define MFCC_WAV_ALAW   3
+#define MFCC_WAV_F32    4
+typedef struct mfcc_wav_info {
+    int32_t format;           /* MFCC_WAV_* */
+    int32_t channels;
+    int32_t sample_rate;
+    int32_t bits_per_sample;
+    int64_t data_offset;      /* byte offset of the first sample in the file */
+    int64_t data_bytes;       /* n_frames * channels * bytes per sample */
+    int64_t n_frames;         /* samples per channel */
+} mfcc_wav_info;
+int mfcc_wav_parse(const void *data, int64_t bytes, mfcc_wav_info *info);
+
 /* Streaming / online front end.  One mfcc_stream is ONE audio stream fed in
  * chunks of any size (host int16 PCM).  Row t it returns is bit-identical to row t of mfcc_compute over
  * the concatenation of everything fed so far: the object carries the frame_len - hop_len unconsumed

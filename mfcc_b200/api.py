@@ -54,6 +54,7 @@ ABI = {
     "mfcc_cmvn_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mfcc_delta_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "mfcc_decode_g711": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "mfcc_wav_parse": (C.c_int, [_vp, _i64, _vp]),
     "mfcc_stream_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "mfcc_stream_destroy": (None, [_vp]),
     "mfcc_stream_pending": (_i64, [_vp, _i64, _i32]),
@@ -65,6 +66,15 @@ ABI = {
     "mfcc_strerror": (C.c_char_p, [C.c_int]),
     "mfcc_version": (C.c_char_p, []),
 }
+
+
+class WavInfo(C.Structure):
+    """ctypes mirror of ``mfcc_wav_info``."""
+    _fields_ = [("format", _i32), ("channels", _i32), ("sample_rate", _i32), ("bits_per_sample", _i32),
+                ("data_offset", _i64), ("data_bytes", _i64), ("n_frames", _i64)]
+
+
+WAV_PCM16, WAV_MULAW, WAV_ALAW, WAV_F32 = 1, 2, 3, 4
 
 
 class MfccError(RuntimeError):
@@ -219,16 +229,21 @@ class Plan:
     def compute_host(self, pcm: np.ndarray, offsets: Sequence[int], out: Optional[np.ndarray] = None):
         pcm = np.ascontiguousarray(pcm, np.int16)
         offsets = np.ascontiguousarray(offsets, np.int64)
+        if offsets.ndim != 1 or offsets.size < 1:
+            raise ValueError("offsets must be a 1-D array of n_utts + 1 entries")
         n_utts = offsets.size - 1
+        if n_utts > 0 and (offsets[0] < 0 or (np.diff(offsets) < 0).any()):
+            raise MfccError(-1, "mfcc_compute_host (offsets must be non-negative and non-decreasing)")
+        if int(offsets[-1]) > pcm.size:
+            raise ValueError(f"offsets run to sample {int(offsets[-1])} but pcm holds {pcm.size}")
         fo = np.empty(n_utts + 1, np.int64)
+        from .sharding import frame_counts
+        total = int(frame_counts(self.params, offsets).sum())
         if out is None:
-            total = 0
-            for u in range(n_utts):
-                nf = num_frames(self.params, int(offsets[u + 1] - offsets[u]))
-                if nf < 0:
-                    raise MfccError(int(nf), "mfcc_num_frames")
-                total += nf
             out = np.empty((total, self.out_dim), np.float32)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags.c_contiguous
+              or out.size < total * self.out_dim):
+            raise ValueError(f"out must be a C-contiguous float32 array of at least {total} x {self.out_dim} elements")
         _check(load().mfcc_compute_host(self._h, pcm.ctypes.data, offsets.ctypes.data, n_utts,
                                         out.ctypes.data, fo.ctypes.data), "mfcc_compute_host")
         return out, fo
@@ -245,16 +260,29 @@ class Plan:
         return out
 
     # ---- §8(f) widening ----
+    def _check_feat(self, batch: Batch, feat, what: str):
+        import torch
+        if (not isinstance(feat, torch.Tensor) or not feat.is_cuda or feat.device.index != self.device
+                or feat.dtype != torch.float32 or not feat.is_contiguous()
+                or feat.numel() < batch.total_frames * self.out_dim):
+            raise ValueError(f"{what}: feat must be a contiguous float32 CUDA tensor on device {self.device} with at "
+                             f"least {batch.total_frames} x {self.out_dim} elements")
+
     def cmvn(self, batch: Batch, feat, norm_var: bool = False, stream=None):
-        _check(load().mfcc_cmvn_batch(self._h, batch._h, feat.data_ptr(), int(norm_var),
-                                      _stream_handle(stream)), "mfcc_cmvn_batch")
+        import torch
+        self._check_feat(batch, feat, "cmvn")
+        with torch.cuda.device(self.device):
+            _check(load().mfcc_cmvn_batch(self._h, batch._h, feat.data_ptr(), int(norm_var),
+                                          _stream_handle(stream)), "mfcc_cmvn_batch")
         return feat
 
     def delta(self, batch: Batch, feat, window: int = 2, stream=None):
         import torch
+        self._check_feat(batch, feat, "delta")
         d = torch.empty_like(feat)
-        _check(load().mfcc_delta_batch(self._h, batch._h, feat.data_ptr(), window, d.data_ptr(),
-                                       _stream_handle(stream)), "mfcc_delta_batch")
+        with torch.cuda.device(self.device):
+            _check(load().mfcc_delta_batch(self._h, batch._h, feat.data_ptr(), window, d.data_ptr(),
+                                           _stream_handle(stream)), "mfcc_delta_batch")
         return d
 
 
@@ -334,3 +362,20 @@ class PinnedBuffer:
             self.close()
         except Exception:   # interpreter shutdown: module globals (load, _lib) may already be gone
             pass
+
+
+def wav_parse(data) -> WavInfo:
+    """``mfcc_wav_parse`` over a bytes-like object holding a RIFF/WAVE file."""
+    buf = np.frombuffer(data, np.uint8)
+    info = WavInfo()
+    _check(load().mfcc_wav_parse(buf.ctypes.data if buf.size else None, buf.size, C.byref(info)), "mfcc_wav_parse")
+    return info
+
+
+def wav_samples(data):
+    """(info, samples): the data chunk viewed in place as [n_frames, channels] int16 (PCM16), uint8 (G.711 codes) or
+    float32 (IEEE float, full scale 1.0) — no conversion; pick the device entry by ``info.format``."""
+    info = wav_parse(data)
+    dt = {WAV_PCM16: "<i2", WAV_MULAW: np.uint8, WAV_ALAW: np.uint8, WAV_F32: "<f4"}[info.format]
+    a = np.frombuffer(data, dt, count=info.n_frames * info.channels, offset=info.data_offset)
+    return info, a.reshape(info.n_frames, info.channels)

@@ -65,3 +65,45 @@ def test_partition_with_more_ranks_than_utterances():
     parts = partition(p, off, 8)
     assert parts[0][0] == 0 and parts[-1][1] == 3
     assert all(a <= b for a, b in parts) and all(parts[i][1] == parts[i + 1][0] for i in range(7))
+
+
+def _gpu_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from mfcc_b200 import api
+        p = config_b()
+        pcm, off = ragged_batch(2000, 100, 24000, seed=13)          # same on every rank
+        plan = api.Plan(p, device=rank)
+        u0, u1 = partition(p, off, world)[rank]
+        s0, s1, loc = local_slice(off, u0, u1)
+        b = plan.batch(loc)
+        feat = plan.compute_batch(b, torch.from_numpy(pcm[s0:s1].copy()).cuda())
+        host, _ = plan.compute_host(pcm[s0:s1], loc)                 # the host-buffer entry on the slice
+        torch.cuda.synchronize()
+        assert np.array_equal(host, feat.cpu().numpy())
+        full, counts = gather_features(feat, b.total_frames, plan.out_dim)     # NCCL all_gather
+        assert sum(counts) == int(frame_counts(p, off).sum())
+        whole = plan.compute_batch(plan.batch(off), torch.from_numpy(pcm).cuda())
+        torch.cuda.synchronize()
+        assert full.shape == whole.shape and torch.equal(full, whole)   # sharded + gathered == one GPU, bit for bit
+        with open(f"{out_path}.{rank}", "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_batch_gathered_over_nccl_equals_single_gpu(tmp_path):
+    """SURVEY.md 8e on hardware: a ragged configs[2]-shaped batch partitioned by frames over every visible GPU, the fused
+    kernel per rank on its slice, NCCL all_gather of the feature rows; the gathered matrix equals the one-GPU result
+    bit for bit on every rank."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = min(n, 8)
+    out = str(tmp_path / "done")
+    mp.spawn(_gpu_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(os.path.exists(f"{out}.{r}") for r in range(world))

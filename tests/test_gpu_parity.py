@@ -223,6 +223,38 @@ def test_bad_calls_fail_loudly():
     assert api.Plan(config_c()).kernel_name.startswith("fused_wide_")
     with pytest.raises(api.MfccError):
         api.Plan(config_a(), kernel=3)               # the selector is AUTO / GENERIC / FUSED, nothing else
+    # host-buffer entry: offsets past the PCM, wrong dtype / short output
+    with pytest.raises(ValueError):
+        plan.compute_host(np.zeros(100, np.int16), np.array([0, 16000]))
+    with pytest.raises(ValueError):
+        plan.compute_host(np.zeros(16000, np.int16), np.array([0, 16000]), out=np.zeros((98, 13), np.float64))
+    with pytest.raises(ValueError):
+        plan.compute_host(np.zeros(16000, np.int16), np.array([0, 16000]), out=np.zeros((10, 13), np.float32))
+    with pytest.raises(ValueError):
+        plan.cmvn(b, torch.zeros((98, 13), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        plan.delta(b, torch.zeros((98, 13)))
+    # a batch built by a plan with another framing is refused: its tile table would be wrong for this plan
+    other = api.Plan(config_a().copy(pad_mode=PAD_ZERO_TAIL))
+    with pytest.raises(api.MfccError):
+        other.compute_batch(b, torch.zeros(16000, dtype=torch.int16, device="cuda"))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """One host thread, the same kernel instantiation on device 0 and then on device 1: the opt-in to > 48 KB of
+    dynamic shared memory is per device (it used to be cached per kernel pointer only)."""
+    p = config_a()
+    pcm, off = ragged_batch(50, 300, 9000, seed=9)
+    outs = []
+    for dev in (0, 1, 0):
+        plan = api.Plan(p, device=dev)
+        with torch.cuda.device(dev):
+            b = plan.batch(off)
+            o = plan.compute_batch(b, torch.from_numpy(pcm).to(f"cuda:{dev}"))
+            torch.cuda.synchronize(dev)
+            outs.append(o.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("name", ["A", "B", "C"])

@@ -105,3 +105,75 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "mfcc_b200" in r.stdout
+
+
+# ---- WAV header parsing ----
+def _riff(fmt_body: bytes, data: bytes, extra_chunks=(), data_size=None) -> bytes:
+    import struct
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt_body)) + fmt_body
+    for cid, payload in extra_chunks:
+        body += cid + struct.pack("<I", len(payload)) + payload + (b"\0" if len(payload) & 1 else b"")
+    body += b"data" + struct.pack("<I", len(data) if data_size is None else data_size) + data
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def _fmt(tag, channels, rate, bits, extensible_sub=None):
+    import struct
+    block = channels * bits // 8
+    base = struct.pack("<HHIIHH", 0xFFFE if extensible_sub is not None else tag, channels, rate, rate * block, block, bits)
+    if extensible_sub is None:
+        return base
+    guid_tail = bytes.fromhex("000000001000800000aa00389b71")
+    return base + struct.pack("<HHI", 22, bits, 0) + struct.pack("<H", extensible_sub) + guid_tail
+
+
+def test_wav_parse_pcm16_written_by_the_wave_module(tmp_path):
+    """An external writer (CPython's wave module) produces the file; the parser must find its samples."""
+    import wave
+    x = (np.random.default_rng(3).normal(0, 3000, (4000, 2))).astype("<i2")
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(16000)
+        w.writeframes(x.tobytes())
+    raw = open(path, "rb").read()
+    info, s = api.wav_samples(raw)
+    assert (info.format, info.channels, info.sample_rate, info.bits_per_sample) == (api.WAV_PCM16, 2, 16000, 16)
+    assert info.n_frames == 4000 and info.data_bytes == 16000 and np.array_equal(s, x)
+
+
+def test_wav_parse_formats_chunks_and_damage():
+    codes = bytes(range(256)) * 3 + b"\x7f"                      # odd length: the parser must not need the pad byte
+    # G.711 mu-law and A-law (tags 7 and 6), with LIST and odd-sized chunks before the data
+    for tag, fmt in ((7, api.WAV_MULAW), (6, api.WAV_ALAW)):
+        raw = _riff(_fmt(tag, 1, 8000, 8) + b"\0\0", codes, extra_chunks=[(b"LIST", b"INFOabc"), (b"fact", b"\1\2\3\4")])
+        info, s = api.wav_samples(raw)
+        assert (info.format, info.channels, info.sample_rate, info.n_frames) == (fmt, 1, 8000, len(codes))
+        assert s.tobytes() == codes
+        assert np.array_equal(oracle.decode_g711(s[:, 0], fmt == api.WAV_ALAW)[:4],
+                              oracle.decode_g711(np.frombuffer(codes, np.uint8), fmt == api.WAV_ALAW)[:4])
+    # IEEE float, plain tag 3 and WAVE_FORMAT_EXTENSIBLE with the float sub-format
+    f = np.linspace(-1, 1, 300, dtype="<f4")
+    for fmt_body in (_fmt(3, 1, 48000, 32), _fmt(0, 1, 48000, 32, extensible_sub=3)):
+        info, s = api.wav_samples(_riff(fmt_body, f.tobytes()))
+        assert (info.format, info.sample_rate, info.n_frames) == (api.WAV_F32, 48000, 300) and np.array_equal(s[:, 0], f)
+    # extensible PCM16
+    x = np.arange(-50, 50, dtype="<i2")
+    info, s = api.wav_samples(_riff(_fmt(0, 1, 16000, 16, extensible_sub=1), x.tobytes()))
+    assert info.format == api.WAV_PCM16 and np.array_equal(s[:, 0], x)
+    # streamed (size 0xFFFFFFFF / 0) and truncated data chunks run to the end of the buffer; partial frames are dropped
+    for claimed in (0xFFFFFFFF, 0, 10**6):
+        info = api.wav_parse(_riff(_fmt(1, 2, 16000, 16), x.tobytes() + b"\x01", data_size=claimed))
+        assert info.n_frames == 50 and info.data_bytes == 200
+    # unsupported sample formats say so; damage is EINVAL
+    for fmt_body in (_fmt(1, 1, 16000, 8), _fmt(1, 1, 16000, 24), _fmt(2, 1, 16000, 4), _fmt(3, 1, 16000, 64)):
+        with pytest.raises(api.MfccError) as e:
+            api.wav_parse(_riff(fmt_body, b"\0" * 64))
+        assert e.value.code == -4
+    good = _riff(_fmt(1, 1, 16000, 16), x.tobytes())
+    for bad in (b"", b"RIFF", good[:20], b"RIFX" + good[4:], good[:8] + b"AVI " + good[12:], good.replace(b"data", b"dat_"),
+                _riff(_fmt(1, 0, 16000, 16), x.tobytes()), b"RIFF\0\0\0\0WAVEdata\4\0\0\0abcd"):
+        with pytest.raises(api.MfccError) as e:
+            api.wav_parse(bad)
+        assert e.value.code == -1, bad[:24]
