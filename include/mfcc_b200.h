@@ -50,6 +50,12 @@ extern "C" {
 #define MFCC_OUT_CEPSTRA     0   /* [frames][n_cep]  DCT-II of log mel energies */
 #define MFCC_OUT_LOGMEL      1   /* [frames][n_mel]  log mel energies ("fbank") */
 
+#define MFCC_ENERGY_NONE        0
+#define MFCC_ENERGY_REPLACE_C0  1   /* cepstra only: c[0] = ln(max(E, log_floor)) instead of the DCT's c0 */
+#define MFCC_ENERGY_APPEND      2   /* one more column after the n_cep / n_mel ones: ln(max(E, log_floor)) */
+/* E = sum of the frame's one-sided power spectrum P[0 .. nfft/2] (the "appendEnergy" convention of the common Python
+ * front ends: total energy of the windowed, pre-emphasised frame as the filterbank sees it). */
+
 #define MFCC_KERNEL_AUTO     0   /* fused tile kernel when the geometry has one, else generic */
 #define MFCC_KERNEL_GENERIC  1   /* one-frame-at-a-time shared-memory radix-2 kernel (any geometry) */
 #define MFCC_KERNEL_FUSED    2   /* the fused tile kernel; plan creation fails with MFCC_ENOTSUP if the geometry has none */
@@ -70,6 +76,7 @@ typedef struct mfcc_params {
     int32_t lifter;       /* 0 = none; Q > 0: c[k] *= 1 + (Q/2) sin(pi k / Q) */
     int32_t pad_mode;     /* MFCC_PAD_* */
     int32_t output;       /* MFCC_OUT_* */
+    int32_t energy;       /* MFCC_ENERGY_* */
 } mfcc_params;
 
 /* Threading.  A plan's parameters and device tables never change after creation, and mfcc_compute_batch(_f32),
@@ -84,7 +91,7 @@ typedef struct mfcc_batch mfcc_batch;  /* the shape of one batch: offsets -> fra
 
 /* Fill *p with the repo defaults for a sample rate: 25 ms frame, 10 ms hop,
  * nfft = next power of two, 26 mel, 13 cepstra, preemph 0.97, Hamming,
- * f_lo 0, f_hi sr/2, floor 1e-10, no lifter, no padding, cepstra out. */
+ * f_lo 0, f_hi sr/2, floor 1e-10, no lifter, no padding, cepstra out, no energy term. */
 int mfcc_params_init(mfcc_params *p, int32_t sample_rate);
 
 /* 0 if the parameter set is usable, MFCC_EINVAL otherwise.  Pure host code. */
@@ -94,7 +101,7 @@ int mfcc_params_validate(const mfcc_params *p);
  * bit-exact framing contract).  Negative on bad parameters. */
 int64_t mfcc_num_frames(const mfcc_params *p, int64_t n_samples);
 
-/* Floats per output frame: n_cep or n_mel depending on p->output. */
+/* Floats per output frame: n_cep or n_mel depending on p->output, plus one under MFCC_ENERGY_APPEND. */
 int32_t mfcc_out_dim(const mfcc_params *p);
 
 /* Build window / mel / DCT / twiddle tables in double, round once to f32 and
@@ -137,12 +144,22 @@ int mfcc_compute_batch(const mfcc_plan *plan, const mfcc_batch *batch,
 int mfcc_compute_batch_f32(const mfcc_plan *plan, const mfcc_batch *batch,
                            const float *d_pcm, float *d_out, void *cuda_stream);
 
+/* Same for G.711 codes (1 byte per sample, alaw = 0: mu-law, != 0: A-law): the codes are expanded inside the fused
+ * kernel's staging, so telephony audio moves 1 byte per sample over PCIe and from HBM and never exists as int16
+ * (SURVEY.md §8f rank 3).  Values equal mfcc_decode_g711 followed by mfcc_compute_batch, bit for bit. */
+int mfcc_compute_batch_g711(const mfcc_plan *plan, const mfcc_batch *batch, const uint8_t *d_codes,
+                            int32_t alaw, float *d_out, void *cuda_stream);
+
 /* End-to-end call with HOST buffers: H2D copy of the PCM, the kernels, D2H
  * copy of the features, pipelined in chunks over internal streams; returns
  * after the features are in h_out.  Pinned host buffers (mfcc_host_alloc)
  * make the copies asynchronous.  h_frame_offsets may be NULL. */
 int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets,
                       int64_t n_utts, float *h_out, int64_t *h_frame_offsets);
+
+/* mfcc_compute_host for G.711 codes in host memory. */
+int mfcc_compute_host_g711(mfcc_plan *plan, const uint8_t *h_codes, int32_t alaw, const int64_t *h_offsets,
+                           int64_t n_utts, float *h_out, int64_t *h_frame_offsets);
 
 /* Single-clip convenience (the shape a C caller of an embedded MFCC routine
  * expects): n samples in, *n_frames rows of out_dim floats out. */

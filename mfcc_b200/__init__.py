@@ -6,6 +6,7 @@ it is missing (there is no CPU fallback).
 """
 from .params import (MfccParams, make_params, config_a, config_b, config_c, CONFIGS,  # noqa: F401
                      WINDOW_RECT, WINDOW_HAMMING, WINDOW_HANN, PAD_NONE, PAD_ZERO_TAIL,
-                     OUT_CEPSTRA, OUT_LOGMEL, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED)
+                     OUT_CEPSTRA, OUT_LOGMEL, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED,
+                     ENERGY_NONE, ENERGY_REPLACE_C0, ENERGY_APPEND)
 
 __version__ = "0.1.0"

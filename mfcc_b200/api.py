@@ -49,7 +49,9 @@ ABI = {
     "mfcc_batch_frame_offsets": (C.c_int, [_vp, _vp]),
     "mfcc_compute_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "mfcc_compute_batch_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mfcc_compute_batch_g711": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "mfcc_compute_host": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "mfcc_compute_host_g711": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "mfcc_compute": (C.c_int, [_vp, _vp, _i64, _vp, C.POINTER(_i64)]),
     "mfcc_cmvn_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mfcc_delta_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
@@ -202,9 +204,10 @@ class Plan:
     def batch(self, offsets: Sequence[int]) -> Batch:
         return Batch(self, offsets)
 
-    def compute_batch(self, batch: Batch, pcm, out=None, stream=None):
-        """``pcm``: torch CUDA tensor, int16 (or float32 scaled to int16 range), >= total_samples
-        elements.  Returns ``out`` [total_frames, out_dim] float32 on the same device.  Asynchronous."""
+    def compute_batch(self, batch: Batch, pcm, out=None, stream=None, alaw: bool = False):
+        """``pcm``: torch CUDA tensor, int16 (or float32 scaled to int16 range, or uint8 G.711 codes — mu-law unless
+        ``alaw``), >= total_samples elements.  Returns ``out`` [total_frames, out_dim] float32 on the same device.
+        Asynchronous."""
         import torch
         if not pcm.is_cuda or pcm.device.index != self.device or not pcm.is_contiguous():
             raise ValueError("pcm must be a contiguous CUDA tensor on the plan's device")
@@ -215,19 +218,27 @@ class Plan:
         elif (out.dtype != torch.float32 or not out.is_contiguous() or out.device != pcm.device
               or out.numel() < batch.total_frames * self.out_dim):
             raise ValueError("out must be a contiguous float32 CUDA tensor of total_frames * out_dim")
-        if pcm.dtype == torch.int16:
-            fn, where = load().mfcc_compute_batch, "mfcc_compute_batch"
-        elif pcm.dtype == torch.float32:
-            fn, where = load().mfcc_compute_batch_f32, "mfcc_compute_batch_f32"
-        else:
-            raise TypeError("pcm must be int16 or float32")
         with torch.cuda.device(self.device):
-            _check(fn(self._h, batch._h, pcm.data_ptr(), out.data_ptr(), _stream_handle(stream)), where)
+            if pcm.dtype == torch.int16:
+                _check(load().mfcc_compute_batch(self._h, batch._h, pcm.data_ptr(), out.data_ptr(),
+                                                 _stream_handle(stream)), "mfcc_compute_batch")
+            elif pcm.dtype == torch.float32:
+                _check(load().mfcc_compute_batch_f32(self._h, batch._h, pcm.data_ptr(), out.data_ptr(),
+                                                     _stream_handle(stream)), "mfcc_compute_batch_f32")
+            elif pcm.dtype == torch.uint8:
+                _check(load().mfcc_compute_batch_g711(self._h, batch._h, pcm.data_ptr(), int(alaw), out.data_ptr(),
+                                                      _stream_handle(stream)), "mfcc_compute_batch_g711")
+            else:
+                raise TypeError("pcm must be int16, float32 or uint8 (G.711 codes)")
         return out
 
     # ---- end to end with host buffers (H2D + kernels + D2H inside) ----
-    def compute_host(self, pcm: np.ndarray, offsets: Sequence[int], out: Optional[np.ndarray] = None):
-        pcm = np.ascontiguousarray(pcm, np.int16)
+    def compute_host(self, pcm: np.ndarray, offsets: Sequence[int], out: Optional[np.ndarray] = None,
+                     alaw: Optional[bool] = None):
+        """Host buffers in, host buffers out.  ``alaw`` given (False: mu-law, True: A-law): ``pcm`` holds G.711 codes
+        (uint8) and goes through ``mfcc_compute_host_g711`` — 1 byte per sample over PCIe."""
+        g711 = alaw is not None
+        pcm = np.ascontiguousarray(pcm, np.uint8 if g711 else np.int16)
         offsets = np.ascontiguousarray(offsets, np.int64)
         if offsets.ndim != 1 or offsets.size < 1:
             raise ValueError("offsets must be a 1-D array of n_utts + 1 entries")
@@ -244,8 +255,12 @@ class Plan:
         elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags.c_contiguous
               or out.size < total * self.out_dim):
             raise ValueError(f"out must be a C-contiguous float32 array of at least {total} x {self.out_dim} elements")
-        _check(load().mfcc_compute_host(self._h, pcm.ctypes.data, offsets.ctypes.data, n_utts,
-                                        out.ctypes.data, fo.ctypes.data), "mfcc_compute_host")
+        if g711:
+            _check(load().mfcc_compute_host_g711(self._h, pcm.ctypes.data, int(bool(alaw)), offsets.ctypes.data, n_utts,
+                                                 out.ctypes.data, fo.ctypes.data), "mfcc_compute_host_g711")
+        else:
+            _check(load().mfcc_compute_host(self._h, pcm.ctypes.data, offsets.ctypes.data, n_utts,
+                                            out.ctypes.data, fo.ctypes.data), "mfcc_compute_host")
         return out, fo
 
     def compute(self, pcm: np.ndarray) -> np.ndarray:

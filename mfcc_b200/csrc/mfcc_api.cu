@@ -32,15 +32,19 @@ struct DeviceGuard {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// PcmT = int16_t, float or uint8_t (G.711 codes, `alaw` selects the law).  The 2048-point kernel has no G.711 entry
+// (telephony codes at 48 kHz do not occur): such a plan takes the generic kernel for them.
 template <typename PcmT>
 int compute_batch_impl(const mfcc_plan *plan, const mfcc_batch *batch, const PcmT *d_pcm, float *d_out,
-                       int64_t tile0, int64_t n_tiles, cudaStream_t stream)
+                       int64_t tile0, int64_t n_tiles, cudaStream_t stream, int alaw = 0)
 {
     if (plan->sp_state != nullptr)
-        return mfcc::sp_launch<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out, stream);
-    if (plan->wide_state != nullptr)
-        return mfcc::wide_launch<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out, stream);
-    return mfcc::launch_generic<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, stream);
+        return mfcc::sp_launch<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out, alaw, stream);
+    if constexpr (sizeof(PcmT) != 1) {
+        if (plan->wide_state != nullptr)
+            return mfcc::wide_launch<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, batch->total_samples, d_out, stream);
+    }
+    return mfcc::launch_generic<PcmT>(plan, batch->d_tiles + tile0, n_tiles, d_pcm, d_out, alaw, stream);
 }
 
 // A batch's tile table (frame starts, kTileInside flags) was computed for one framing: only plans with that framing
@@ -340,7 +344,12 @@ int mfcc_compute_batch_f32(const mfcc_plan *plan, const mfcc_batch *batch, const
 //      input copy of that stream waits for the result copy, which costs 7 % on the ragged 8 kHz batch.
 // Chunks are 32 MiB of PCM, tapering geometrically over the last third of the batch so that the work left
 // after the last H2D byte (one kernel + one D2H of the LAST chunk) is small.
-int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets, int64_t n_utts,
+}  // extern "C"
+
+namespace {
+
+template <typename PcmT>
+int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_t *h_offsets, int64_t n_utts,
                       float *h_out, int64_t *h_frame_offsets)
 {
     if (plan == nullptr || n_utts < 0 || (n_utts > 0 && h_offsets == nullptr)) return MFCC_EINVAL;
@@ -366,7 +375,7 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
     const size_t tile_bytes = sizeof(Tile) * static_cast<size_t>(n_tiles);
-    int rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(total_samples));
+    int rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(PcmT) * static_cast<size_t>(total_samples));
     if (rc == MFCC_OK)
         rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(total_frames) * od);
     if (rc == MFCC_OK) rc = grow(&plan->d_tiles, &plan->d_tiles_bytes, tile_bytes);
@@ -389,7 +398,7 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
     // 2. chunk plan (utterance boundaries) and the whole H2D queue
     std::vector<int64_t> cut{0};
     try {
-        const int64_t full = 16ll << 20, least = 1ll << 20;   // samples: 32 MiB .. 2 MiB of PCM
+        const int64_t full = (32ll << 20) / static_cast<int64_t>(sizeof(PcmT)), least = full / 16;   // 32 MiB .. 2 MiB of PCM
         int64_t u0 = 0;
         while (u0 < n_utts) {
             const int64_t left = total_samples - h_offsets[u0];
@@ -406,14 +415,14 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return MFCC_ECUDA; }
         plan->chunk_ready.push_back(e);
     }
-    int16_t *d_pcm = static_cast<int16_t *>(plan->h2d_pcm);
+    PcmT *d_pcm = static_cast<PcmT *>(plan->h2d_pcm);
     float *d_out = static_cast<float *>(plan->d2h_out);
     bool ok = true;
     auto queue_h2d = [&](size_t c) {
         cudaStream_t copy = plan->streams[c & 1];
         const int64_t s0 = h_offsets[cut[c]], s1 = h_offsets[cut[c + 1]];
         if (s1 > s0)
-            ok = ok && cudaMemcpyAsync(d_pcm + s0, h_pcm + s0, sizeof(int16_t) * (s1 - s0), cudaMemcpyHostToDevice,
+            ok = ok && cudaMemcpyAsync(d_pcm + s0, h_pcm + s0, sizeof(PcmT) * (s1 - s0), cudaMemcpyHostToDevice,
                                        copy) == cudaSuccess;
         ok = ok && cudaEventRecord(plan->chunk_ready[c], copy) == cudaSuccess;
     };
@@ -449,7 +458,7 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
         const int64_t t0 = batch->utt_first_tile[u0], t1 = batch->utt_first_tile[u1];
         ok = cudaStreamWaitEvent(s, plan->chunk_ready[c], 0) == cudaSuccess;
         if (ok && t1 > t0)
-            ok = compute_batch_impl<int16_t>(plan, batch, d_pcm, d_out, t0, t1 - t0, s) == MFCC_OK;
+            ok = compute_batch_impl<PcmT>(plan, batch, d_pcm, d_out, t0, t1 - t0, s, alaw) == MFCC_OK;
         if (ok && f1 > f0)
             ok = cudaMemcpyAsync(h_out + f0 * od, d_out + f0 * od, sizeof(float) * (f1 - f0) * od,
                                  cudaMemcpyDeviceToHost, s) == cudaSuccess;
@@ -459,6 +468,35 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
     mfcc_batch_destroy(batch);
     if (!ok) { cudaGetLastError(); return MFCC_ECUDA; }
     return MFCC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets, int64_t n_utts,
+                      float *h_out, int64_t *h_frame_offsets)
+{
+    return compute_host_impl<int16_t>(plan, h_pcm, 0, h_offsets, n_utts, h_out, h_frame_offsets);
+}
+
+// G.711 bytes end to end: 1 byte per sample over PCIe and from HBM, expanded inside the fused kernel's staging.
+int mfcc_compute_host_g711(mfcc_plan *plan, const uint8_t *h_codes, int32_t alaw, const int64_t *h_offsets,
+                           int64_t n_utts, float *h_out, int64_t *h_frame_offsets)
+{
+    return compute_host_impl<uint8_t>(plan, h_codes, alaw != 0, h_offsets, n_utts, h_out, h_frame_offsets);
+}
+
+int mfcc_compute_batch_g711(const mfcc_plan *plan, const mfcc_batch *batch, const uint8_t *d_codes, int32_t alaw,
+                            float *d_out, void *cuda_stream)
+{
+    if (!batch_fits(plan, batch)) return MFCC_EINVAL;
+    if (batch->total_frames == 0) return MFCC_OK;
+    if (d_codes == nullptr || d_out == nullptr) return MFCC_EINVAL;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    return compute_batch_impl<uint8_t>(plan, batch, d_codes, d_out, 0, static_cast<int64_t>(batch->tiles.size()),
+                                       static_cast<cudaStream_t>(cuda_stream), alaw != 0);
 }
 
 // ---- streaming ----

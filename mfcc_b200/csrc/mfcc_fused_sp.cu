@@ -63,6 +63,11 @@
 #ifndef MFCC_SP_ABLATE
 #define MFCC_SP_ABLATE 0
 #endif
+// Which PCM entries this translation unit instantiates (the file is compiled once per input type so that the three sets
+// of kernel variants build in parallel): bit 0 int16 (+ the host half), bit 1 f32, bit 2 G.711 codes.
+#ifndef MFCC_SP_PCM_TYPES
+#define MFCC_SP_PCM_TYPES 7
+#endif
 // Poison build (libmfcc_b200_poison.so, the compute-sanitizer substitute: the pool's boxes refuse the sanitizer).  The
 // kernel's buffers alias each other (staged / P, workspace / tail scratch, raw PCM refilled by the TMA engine); the
 // barrier reasoning in the comments says when each one is dead.  With MFCC_POISON every buffer is filled with NaN at
@@ -88,7 +93,7 @@ constexpr int kPad = 2;
 constexpr int kSegMax = 20;                // segments one warp may be given (n_mel + 1 <= 8 * kSegMax)
 constexpr int KC = 16;                    // cepstra per DCT round: warp w forms k = w and k = w + 8 (tail-warp variants: n_cep <= KC)
 constexpr int kSegParam = 12;              // segments per warp (+ terminator) a tail-warp variant can take as parameters
-constexpr int kFoldMax = 16;                // n_mel / 2 of a tail-warp variant (n_mel <= 32)
+constexpr int kFoldMax = 20;                // ceil(n_mel / 2) of a tail-warp variant with cepstral output (n_mel <= 40)
 constexpr size_t kSmemMax = 227 * 1024;
 
 template <int L_, int HOP_, int RB_, int RA_>
@@ -141,16 +146,21 @@ struct SpArgs {
     const float *tab;     // global copy of the table blob
     SpLayout lay;
     int n_mel, n_cep, logmel;
-    int ls;               // log-mel staging row stride (n_mel | 1)
-    int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 1][32] x 2
+    int energy;           // MFCC_ENERGY_*: frame energy = sum of the one-sided power spectrum, taken from the segment sums
+    int od;               // floats per output row (n_cep or n_mel, + 1 under MFCC_ENERGY_APPEND)
+    int alaw;             // G.711 entry (uint8 codes): 0 mu-law, 1 A-law
+    int ls;               // log-mel staging row stride (odd, >= od)
+    int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 3][32] x 2 (segments 0 .. n_mel, then the two
+                          // pseudo-segments below / above the filterbank that only the energy term reads)
+    int ef;               // scratch offset of the log frame energy [32] (generic tail)
     float inv_n;          // 1 / NFFT
     int mp;               // n_mel rounded up to even (DCT row length in the table)
-    int mel_magic;        // i / n_mel == (i * mel_magic) >> 20 for i < 32 * n_mel
+    int mel_magic;        // i / od == (i * mel_magic) >> 20 for i < 32 * od
     float preemph, log_floor;
     // tail-warp variants (MEL > 0): ln 2 * d[k][q] for q < MEL / 2 (the mirrored half follows from d[k][M - 1 - q] =
     // (-1)^k d[k][q]).  Kernel parameters live in the constant bank, so with compile-time indices every entry is
     // a uniform-register FFMA operand fetched four at a time (LDCU.128): no shared-memory loads in the DCT.
-    float4 dctc[KC / 2][2][kFoldMax / 4];   // [k / 2][k & 1][q / 4]
+    float4 dctc[KC / 2][2][kFoldMax / 4];   // [k / 2][k & 1][q / 4]; odd n_mel: the middle band pairs with itself, its entry is halved
     // tail-warp variants: the segment walks of S3 as parameters too, {first bin * 128 (byte offset into P), width w,
     // s = 1 / (w NFFT), segment index * 128 (byte offset into the rise / fall scratch; -1 ends the list)}: read with a
     // warp-uniform index they arrive in uniform registers, so every branch of the walk is a uniform branch.
@@ -177,8 +187,26 @@ __device__ __forceinline__ float lg2_fast(float x)
     return y;
 }
 constexpr float kLn2 = 0.69314718055994531f;
-__device__ __forceinline__ float to_f32(int16_t v) { return static_cast<float>(v); }
-__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(int16_t v, int) { return static_cast<float>(v); }
+__device__ __forceinline__ float to_f32(float v, int) { return v; }
+// G.711 code -> linear PCM value as an exact float, integer pipe only (no I2F): the magnitude (< 2^15) is dropped into
+// the mantissa of 2^23, the sign is XORed in.  Same arithmetic as g711_kernel (mfcc_generic.cu) / ITU-T G.711 tables.
+__device__ __forceinline__ float g711_to_f32(uint32_t b, int alaw)
+{
+    uint32_t mag, neg;
+    if (alaw) {
+        const uint32_t a = b ^ 0x55u, seg = (a >> 4) & 7u, man = a & 0x0Fu;
+        mag = seg == 0 ? (man << 4) + 8u : ((man << 4) + 0x108u) << (seg - 1);
+        neg = (~a) & 0x80u;
+    } else {
+        const uint32_t u = (~b) & 0xFFu;
+        mag = ((((u & 0x0Fu) << 3) + 0x84u) << ((u >> 4) & 7u)) - 0x84u;
+        neg = u & 0x80u;
+    }
+    const float f = __uint_as_float(0x4B000000u | mag) - 8388608.0f;
+    return __uint_as_float(__float_as_uint(f) ^ (neg << 24));
+}
+__device__ __forceinline__ float to_f32(uint8_t v, int alaw) { return g711_to_f32(v, alaw); }
 
 // ---- mbarrier + bulk async copy (TMA engine, 1-D) + named barrier ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -267,8 +295,8 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     // 8-sample boundary `o` below the tile's first sample and the shift s = first_sample - o (0..7) is
     // absorbed by the staging (see S0).
     const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
-    const bool base_ok = sizeof(PcmT) == 2 && base_aligned;
-    static_assert(G::SLACK + 8 <= kTileSpanSlack, "the host's span check must cover the staged span");
+    const bool base_ok = sizeof(PcmT) <= 2 && base_aligned;   // int16 PCM and G.711 codes arrive by bulk copy
+    static_assert(G::SLACK + 16 <= kTileSpanSlack, "the host's span check must cover the staged span (16-byte units of 1-byte codes included)");
     auto tile_fast = [&](const Tile &tl) -> bool { return base_ok && (tl.flags & kTileInside) != 0; };
     // f32 PCM: same eligibility, but the samples are read straight from HBM with 16-byte loads in S0 (a raw f32
     // buffer would need 21 KB per group, which the 512-point geometry does not have)
@@ -276,11 +304,22 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     // raw16[8 + i] = x[o + i]; the 8 samples before o ride along when they exist
     auto issue_copy = [&](const Tile &tl) {
         const int s = static_cast<int>(tl.first_sample & 7);
-        const int64_t o = tl.first_sample - s;
-        const int lead = o >= 8 ? 8 : 0;
-        const uint32_t bytes = static_cast<uint32_t>(lead + G::tceil_s(tl.n_frames, s)) * 2u;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(raw_s + (8 - lead) * 2, pcm + o - lead, bytes, bar);
+        if constexpr (sizeof(PcmT) == 1) {
+            // G.711 codes: 16-byte units are 16 samples, so the copy starts at the 16-sample boundary o16 below the tile
+            // (raw bytes [16 + i] = code of sample o16 + i, the 16 codes before o16 ride along when they exist)
+            const int64_t o16 = tl.first_sample & ~static_cast<int64_t>(15);
+            const int lead = o16 >= 16 ? 16 : 0;
+            const int span = (static_cast<int>(tl.first_sample) & 8) + G::tceil_s(tl.n_frames, s);
+            const uint32_t bytes = static_cast<uint32_t>(lead + ((span + 15) & ~15));
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(raw_s + (16 - lead), pcm + o16 - lead, bytes, bar);
+        } else {
+            const int64_t o = tl.first_sample - s;
+            const int lead = o >= 8 ? 8 : 0;
+            const uint32_t bytes = static_cast<uint32_t>(lead + G::tceil_s(tl.n_frames, s)) * 2u;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(raw_s + (8 - lead) * 2, pcm + o - lead, bytes, bar);
+        }
     };
 
     // staging threads of a group: all of it, or all but the tail warp
@@ -290,40 +329,67 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     const bool stager = !kTail || warp < kWarps - kTailWarps;
     // tail warp: band m = rise of segment m + fall of segment m + 1, log2, mirrored-pair fold, DCT with constant-bank
     // entries (ln 2 folded in on the host), CEP stores per frame
+    // CEP > 0: cepstra (even k on one tail warp, odd k on the other); CEP == 0: log-mel rows (even bands on one, odd on the
+    // other).  The frame energy (MFCC_ENERGY_*) is the sum of ALL segment sums: every band, plus the fall of segment 0
+    // and the rise of segment M (the two half-triangles that belong to no band), plus the two pseudo-segments that
+    // cover the bins below and above the filterbank.
     auto tail = [&](int64_t out_row, int nf) {
         if constexpr (kTail && (MFCC_SP_ABLATE & 16) == 0) {
-            static_assert(MEL % 2 == 0 && MEL / 2 <= kFoldMax && CEP <= KC, "tail-warp variant limits");
-            const float *rise = scr + a.rf + lane, *fall = rise + (MEL + 1) * 32;
+            constexpr int HM = (MEL + 1) / 2;
+            static_assert((CEP == 0 || HM <= kFoldMax) && CEP <= KC, "tail-warp variant limits");
+            const float *rise = scr + a.rf + lane, *fall = rise + (MEL + 3) * 32;
+            const int par = warp & 1;
             float l[MEL];
 #pragma unroll
             for (int m = 0; m < MEL; ++m) l[m] = rise[m * 32] + fall[(m + 1) * 32];
+            float le = 0.0f;
+            if (a.energy != MFCC_ENERGY_NONE) {   // uniform branch
+                float e0 = fall[0] + rise[MEL * 32], e1 = rise[(MEL + 1) * 32] + fall[(MEL + 1) * 32];
+                e1 += rise[(MEL + 2) * 32] + fall[(MEL + 2) * 32];
+#pragma unroll
+                for (int m = 0; m + 1 < MEL; m += 2) { e0 += l[m]; e1 += l[m + 1]; }
+                if (MEL & 1) e0 += l[MEL - 1];
+                le = kLn2 * lg2_fast(fmaxf(e0 + e1, a.log_floor));
+            }
 #pragma unroll
             for (int m = 0; m < MEL; ++m) l[m] = lg2_fast(fmaxf(l[m], a.log_floor));
-            // this warp's cepstra k = 2 kk + par all take v[q] = l[q] + (-1)^par l[M - 1 - q]
-            const int par = warp & 1;
-            const float sgn = par ? -1.0f : 1.0f;
-            float v[MEL / 2];
+            if constexpr (CEP == 0) {
+                if (lane < nf) {
+                    float *o = a.out + (out_row + lane) * a.od;
 #pragma unroll
-            for (int q = 0; q < MEL / 2; ++q) v[q] = fmaf(sgn, l[MEL - 1 - q], l[q]);
-            constexpr int CH = (CEP + 1) / 2;
-            float c[CH];
-#pragma unroll
-            for (int kk = 0; kk < CH; ++kk) c[kk] = 0.0f;
-#pragma unroll
-            for (int q4 = 0; q4 < (MEL / 2 + 3) / 4; ++q4)
-#pragma unroll
-                for (int kk = 0; kk < CH; ++kk) {
-                    const float4 d = a.dctc[kk][par][q4];   // one 16-byte uniform load from the parameter bank (zeros past n_cep)
-                    c[kk] = fmaf(d.x, v[4 * q4], c[kk]);
-                    if (4 * q4 + 1 < MEL / 2) c[kk] = fmaf(d.y, v[4 * q4 + 1], c[kk]);
-                    if (4 * q4 + 2 < MEL / 2) c[kk] = fmaf(d.z, v[4 * q4 + 2], c[kk]);
-                    if (4 * q4 + 3 < MEL / 2) c[kk] = fmaf(d.w, v[4 * q4 + 3], c[kk]);
+                    for (int m = 0; m < MEL; ++m)
+                        if ((m & 1) == par) o[m] = kLn2 * l[m];
+                    if (par == 1 && a.energy == MFCC_ENERGY_APPEND) o[MEL] = le;
                 }
-            if (lane < nf) {
-                float *o = a.out + (out_row + lane) * CEP + par;
+            } else {
+                // this warp's cepstra k = 2 kk + par all take v[q] = l[q] + (-1)^par l[M - 1 - q]; DCT entries from the constant
+                // bank (ln 2 folded in on the host; odd M: the middle band meets itself, its entry is halved)
+                const float sgn = par ? -1.0f : 1.0f;
+                float v[HM];
 #pragma unroll
-                for (int kk = 0; kk < CH; ++kk)
-                    if (2 * kk + 1 < CEP || par == 0) o[2 * kk] = c[kk];
+                for (int q = 0; q < HM; ++q) v[q] = fmaf(sgn, l[MEL - 1 - q], l[q]);
+                constexpr int CH = (CEP + 1) / 2;
+                float c[CH];
+#pragma unroll
+                for (int kk = 0; kk < CH; ++kk) c[kk] = 0.0f;
+#pragma unroll
+                for (int q4 = 0; q4 < (HM + 3) / 4; ++q4)
+#pragma unroll
+                    for (int kk = 0; kk < CH; ++kk) {
+                        const float4 d = a.dctc[kk][par][q4];   // one 16-byte uniform load from the parameter bank (zeros past n_cep)
+                        c[kk] = fmaf(d.x, v[4 * q4], c[kk]);
+                        if (4 * q4 + 1 < HM) c[kk] = fmaf(d.y, v[4 * q4 + 1], c[kk]);
+                        if (4 * q4 + 2 < HM) c[kk] = fmaf(d.z, v[4 * q4 + 2], c[kk]);
+                        if (4 * q4 + 3 < HM) c[kk] = fmaf(d.w, v[4 * q4 + 3], c[kk]);
+                    }
+                if (par == 0 && a.energy == MFCC_ENERGY_REPLACE_C0) c[0] = le;
+                if (lane < nf) {
+                    float *o = a.out + (out_row + lane) * a.od + par;
+#pragma unroll
+                    for (int kk = 0; kk < CH; ++kk)
+                        if (2 * kk + 1 < CEP || par == 0) o[2 * kk] = c[kk];
+                    if (par == 1 && a.energy == MFCC_ENERGY_APPEND) o[CEP - 1] = le;
+                }
             }
         }
     };
@@ -368,6 +434,43 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         // at word e + f STRIDE ----
         if (!stager) {
             if (fast) phase ^= 1u;
+        } else if (fast && sizeof(PcmT) == 1) {
+            // G.711 codes (mu-law / A-law bytes): expanded here, on the way from the raw buffer to the staged tile — the
+            // PCM never exists as int16 anywhere (1 byte per sample over PCIe and from HBM)
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            const uint8_t *raw8 = reinterpret_cast<const uint8_t *>(raw16) + 16 + (static_cast<int>(tile.first_sample) & 8);   // raw8[i] = code of sample o + i
+            const int nchunks = G::tceil_s(n_frames, sh) >> 3;
+            const float na = -a.preemph;
+            const int alaw = a.alaw;
+#pragma unroll 1
+            for (int c = tid; c < nchunks; c += kStage) {
+                const uint2 q = *reinterpret_cast<const uint2 *>(raw8 + 8 * c);
+                uint32_t pv = raw8[8 * c + (d ? 8 : -1)];      // d = 0: the code before the chunk; d = 1: the code after it
+                uint32_t w0 = q.x, w1 = q.y;
+                if (d) {   // odd shift: move the chunk down one byte; its old first code becomes the predecessor
+                    const uint32_t first = w0 & 0xFFu;
+                    w0 = __funnelshift_r(w0, w1, 8);
+                    w1 = __funnelshift_r(w1, pv, 8);
+                    pv = first;
+                }
+                const float xe = g711_to_f32(pv, alaw);
+                const float x0 = g711_to_f32(w0 & 0xFFu, alaw), x1 = g711_to_f32((w0 >> 8) & 0xFFu, alaw);
+                const float x2 = g711_to_f32((w0 >> 16) & 0xFFu, alaw), x3 = g711_to_f32(w0 >> 24, alaw);
+                const float x4 = g711_to_f32(w1 & 0xFFu, alaw), x5 = g711_to_f32((w1 >> 8) & 0xFFu, alaw);
+                const float x6 = g711_to_f32((w1 >> 16) & 0xFFu, alaw), x7 = g711_to_f32(w1 >> 24, alaw);
+                const int k = c / (HOP / 8);
+                const int pad = kPad * k;
+                const int pad_first = (c == k * (HOP / 8) && k > 0) ? pad - kPad : pad;
+                float *dst = staged + 8 * c;
+                *reinterpret_cast<float2 *>(dst + (0 < e ? pad_first : pad)) = make_float2(fmaf(na, xe, x0), fmaf(na, x0, x1));
+                *reinterpret_cast<float2 *>(dst + 2 + (2 < e ? pad_first : pad)) = make_float2(fmaf(na, x1, x2), fmaf(na, x2, x3));
+                *reinterpret_cast<float2 *>(dst + 4 + (4 < e ? pad_first : pad)) = make_float2(fmaf(na, x3, x4), fmaf(na, x4, x5));
+                *reinterpret_cast<float2 *>(dst + 6 + pad) = make_float2(fmaf(na, x5, x6), fmaf(na, x6, x7));
+            }
+            if (tile.first_sample == tile.utt_begin) {
+                if (tid == 0) staged[e] = g711_to_f32(raw8[sh], alaw);   // the utterance's first sample has no predecessor: y = x
+            }
         } else if (fast) {
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -418,7 +521,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             // the utterance's first sample has no predecessor: y = x.  It is word e of chunk 0 (thread 0 wrote it
             // just above), sample raw16[8 + sh].  A branch, not a predicate: one tile in 32 starts an utterance.
             if (tile.first_sample == tile.utt_begin) {
-                if (tid == 0) staged[e] = to_f32(raw16[8 + sh]);
+                if (tid == 0) staged[e] = static_cast<float>(raw16[8 + sh]);
             }
         } else if (vec) {
             if constexpr (sizeof(PcmT) == 4) {
@@ -455,8 +558,8 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             for (int i = tid; i < tc; i += kStage) {
                 float y = 0.0f;
                 if (i < room_hi) {
-                    const float x0 = to_f32(x[i]);
-                    const float x1 = (i > -room_lo) ? to_f32(x[i - 1]) : 0.0f;
+                    const float x0 = to_f32(x[i], a.alaw);
+                    const float x1 = (i > -room_lo) ? to_f32(x[i - 1], a.alaw) : 0.0f;
                     y = fmaf(-a.preemph, x1, x0);
                 }
                 staged[G::padded(i)] = y;
@@ -652,12 +755,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 }
                 const float f = sg.z * acc;
                 *reinterpret_cast<float *>(rl + oo) = fmaf(a.inv_n, run, -f);
-                *reinterpret_cast<float *>(rl + oo + (MEL + 1) * 128) = f;
+                *reinterpret_cast<float *>(rl + oo + (MEL + 3) * 128) = f;
             }
         } else
         {
             const float4 *wd = t_wseg + warp * kSegMax;
-            float *rise = scr + a.rf + lane, *fall = rise + (a.n_mel + 1) * 32;
+            float *rise = scr + a.rf + lane, *fall = rise + (a.n_mel + 3) * 32;
             float4 nx = wd[0];                              // descriptors run one segment ahead of their use
 #pragma unroll 1
             for (int q = 1; __float_as_int(nx.w) >= 0; ++q) {
@@ -713,12 +816,23 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         } else {
         // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][lane] or the frame's log-mel row ----
         {
-            const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 1) * 32;
+            const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 3) * 32;
             const int total = a.n_mel * 32;
             for (int i = tid; i < total; i += kHalfThreads) {
                 const float lg = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + 32], a.log_floor));
                 if (a.logmel) scr[(i & 31) * a.ls + (i >> 5)] = lg;
                 else scr[i] = lg;
+            }
+            // frame energy: all segment sums of the frame (lane = frame), the last warp's job
+            if (a.energy != MFCC_ENERGY_NONE && warp == kWarps - 1) {
+                float e0 = 0.0f, e1 = 0.0f;
+                for (int j = 0; j < a.n_mel + 3; ++j) {
+                    e0 += rise[j * 32 + lane];
+                    e1 += fall[j * 32 + lane];
+                }
+                const float le = kLn2 * lg2_fast(fmaxf(e0 + e1, a.log_floor));
+                if (a.logmel) scr[lane * a.ls + a.n_mel] = le;
+                else scr[a.ef + lane] = le;
             }
         }
         half_sync(half);   // B4: every band's log energy is in the scratch
@@ -726,7 +840,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         // ---- S4: log-mel rows are copied out coalesced; cepstra: warp w forms c[w] and c[w + 8] of frame = lane
         // from the log energies (conflict-free column reads, warp-uniform DCT entries) and stores them ----
         if (a.logmel) {
-            const int M = a.n_mel, total = n_frames * M;
+            const int M = a.od, total = n_frames * M;     // n_mel columns, + the energy column under MFCC_ENERGY_APPEND
             float *o = a.out + tile.out_row * M;
             for (int i = tid; i < total; i += kHalfThreads) {
                 const int f = (i * a.mel_magic) >> 20, m = i - f * M;
@@ -756,10 +870,15 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     c1 = fmaf(d.y, l0, c1);
                 }
                 if (lane < n_frames) {
-                    float *o = a.out + (tile.out_row + lane) * a.n_cep + kb + warp;
+                    float *o = a.out + (tile.out_row + lane) * a.od + kb + warp;
                     o[0] = c0 + e0;
                     if (kb + warp + kWarps < a.n_cep) o[kWarps] = c1 + e1;
                 }
+            }
+            // energy term: warp 0 formed c[0] of its frames above (same thread, program order), so it replaces it here
+            if (a.energy != MFCC_ENERGY_NONE && warp == 0 && lane < n_frames) {
+                float *o = a.out + (tile.out_row + lane) * a.od;
+                o[a.energy == MFCC_ENERGY_REPLACE_C0 ? 0 : a.n_cep] = scr[a.ef + lane];
             }
         }
         }
@@ -806,39 +925,62 @@ void variant_sizes(const SpVariant &v, int &tabf, int &half_floats)
     else geo_sizes<200, 80, 16, 16>(tabf, half_floats);
 }
 
-// Instruction estimate of one walk over segment j (S3): 8-bin chunks, then 4, 2, 1 bins, fixed part.
-inline int seg_cost(const HostTables &h, int j)
+// One walk of S3: bins [k0, k0 + w) summed into scratch row j.  Rows 0 .. M are the filterbank's segments; rows M + 1 and
+// M + 2 are the pseudo-segments below and above the filterbank (s = 0: plain sums), walked only when the plan has an
+// energy term.
+struct Seg {
+    int k0, w, row;
+    float s;        // 1 / (w NFFT): pass 2 leaves |X|^2, hence the 1 / N
+};
+
+std::vector<Seg> plan_segments(const mfcc_params &p, const HostTables &h)
 {
-    const int w = h.mel_bins[j + 1] - h.mel_bins[j];
-    return 28 * (w / 8) + 14 * ((w / 4) & 1) + 8 * ((w / 2) & 1) + 4 * (w & 1) + 18;
+    const int M = p.n_mel, N = p.nfft;
+    std::vector<Seg> segs;
+    for (int j = 0; j <= M; ++j) {
+        const int k0 = h.mel_bins[j], w = h.mel_bins[j + 1] - k0;
+        segs.push_back({k0, w, j, w > 0 ? static_cast<float>(1.0 / (static_cast<double>(w) * N)) : 0.0f});
+    }
+    if (p.energy != MFCC_ENERGY_NONE) {
+        segs.push_back({0, h.mel_bins[0], M + 1, 0.0f});
+        segs.push_back({h.mel_bins[M + 1], h.nbins - h.mel_bins[M + 1], M + 2, 0.0f});
+    }
+    return segs;
 }
 
-// Segments 0 .. M over the warps, longest first onto the least loaded warp.  Each warp's list is kept in
-// ascending segment order (the walk then moves forward through P).  Empty when a warp would need more than
-// kSegMax - 1 segments.
-std::vector<std::vector<int>> assign_segments(const HostTables &h, int M)
+// Instruction estimate of one walk (S3): 8-bin chunks, then 4, 2, 1 bins, fixed part.
+inline int seg_cost(const Seg &g) { return 28 * (g.w / 8) + 14 * ((g.w / 4) & 1) + 8 * ((g.w / 2) & 1) + 4 * (g.w & 1) + 18; }
+
+// Segments over the warps, longest first onto the least loaded warp.  Each warp's list is kept in ascending bin order
+// (the walk then moves forward through P).  Empty when a warp would need more than kSegMax - 1 segments.
+std::vector<std::vector<Seg>> assign_segments(const std::vector<Seg> &segs)
 {
-    std::vector<int> order(M + 1);
-    for (int j = 0; j <= M; ++j) order[j] = j;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seg_cost(h, x) > seg_cost(h, y); });
-    std::vector<std::vector<int>> lists(kWarps);
+    std::vector<int> order(segs.size());
+    for (size_t j = 0; j < segs.size(); ++j) order[j] = static_cast<int>(j);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seg_cost(segs[x]) > seg_cost(segs[y]); });
+    std::vector<std::vector<Seg>> lists(kWarps);
     std::vector<int> load(kWarps, 0);
     for (int j : order) {
         int best = 0;
         for (int w = 1; w < kWarps; ++w)
             if (load[w] < load[best]) best = w;
-        lists[best].push_back(j);
-        load[best] += seg_cost(h, j);
+        lists[best].push_back(segs[j]);
+        load[best] += seg_cost(segs[j]);
     }
     for (auto &l : lists) {
         if (static_cast<int>(l.size()) > kSegMax - 1) return {};
-        std::sort(l.begin(), l.end());
+        std::sort(l.begin(), l.end(), [](const Seg &x, const Seg &y) { return x.k0 != y.k0 ? x.k0 < y.k0 : x.row < y.row; });
     }
     return lists;
 }
 
+inline int out_stride(const mfcc_params &p) { return (p.output == MFCC_OUT_LOGMEL ? p.n_mel : p.n_cep) + (p.energy == MFCC_ENERGY_APPEND ? 1 : 0); }
+inline int logmel_stride(const mfcc_params &p) { return out_stride(p) | 1; }
+inline int scratch_rf(const mfcc_params &p) { return (32 * std::max(logmel_stride(p), p.n_mel) + 3) / 4 * 4; }
+
 }  // namespace
 
+#if MFCC_SP_PCM_TYPES & 1   // the host half is compiled once, with the int16 entry
 const char *sp_match(const mfcc_params &p, const HostTables &h)
 {
     const SpVariant *v = find_variant(p);
@@ -849,13 +991,13 @@ const char *sp_match(const mfcc_params &p, const HostTables &h)
     // the run-time tables must fit next to the two halves
     int tabf = 0, half_floats = 0;
     variant_sizes(*v, tabf, half_floats);
-    if (p.n_mel + 1 > kWarps * (kSegMax - 1) || assign_segments(h, p.n_mel).empty()) return nullptr;
+    if (p.n_mel + 3 > kWarps * (kSegMax - 1) || assign_segments(plan_segments(p, h)).empty()) return nullptr;
     const size_t rounds = p.output == MFCC_OUT_CEPSTRA ? (p.n_cep + KC - 1) / KC : 1;
     const size_t total = tabf + 4 * static_cast<size_t>(kWarps) * kSegMax + rounds * KC * (p.n_mel + 1) + 16;
     if ((total + groups_for(v->rb) * static_cast<size_t>(half_floats)) * sizeof(float) > kSmemMax) return nullptr;
-    // tail scratch (log band energies [n_mel][32] or log-mel rows [32][n_mel | 1], then the per-segment rise / fall
-    // sums [n_mel + 1][32] x 2) must fit in the workspace
-    const size_t scratch = 3 * 32 * static_cast<size_t>(p.n_mel + 2);
+    // tail scratch (log band energies [n_mel][32] or log-mel rows [32][ls], then the per-segment rise / fall sums
+    // [n_mel + 3][32] x 2, then the log frame energy [32]) must fit in the workspace
+    const size_t scratch = static_cast<size_t>(scratch_rf(p)) + 2 * 32 * static_cast<size_t>(p.n_mel + 3) + 32;
     if (scratch > static_cast<size_t>(v->rb / 2) * v->ra * 32 * 2) return nullptr;
     return v->name;
 }
@@ -897,19 +1039,18 @@ int sp_prepare(mfcc_plan *plan)
 
     SpLayout lay{};
     // per-warp segment walks.  The triangles are linear ramps over integer bins (mfcc_tables.cpp build_tables),
-    // so a segment is described by its first bin, its width and 1 / (w N) (pass 2 leaves |X|^2, hence the 1 / N).
-    const std::vector<std::vector<int>> lists = assign_segments(h, M);
+    // so a segment is described by its first bin, its width and 1 / (w N).
+    const std::vector<std::vector<Seg>> lists = assign_segments(plan_segments(p, h));
     if (lists.empty()) return MFCC_ENOTSUP;
     lay.wseg = static_cast<int>(tab.size());
     for (int w = 0; w < kWarps; ++w)
         for (int q = 0; q < kSegMax; ++q) {
             if (q < static_cast<int>(lists[w].size())) {
-                const int j = lists[w][q];
-                const int k0 = h.mel_bins[j], wd = h.mel_bins[j + 1] - k0;
-                push_int(k0 * 32);
-                push_int(wd);
-                tab.push_back(wd > 0 ? static_cast<float>(1.0 / (static_cast<double>(wd) * N)) : 0.0f);
-                push_int(j);
+                const Seg &g = lists[w][q];
+                push_int(g.k0 * 32);
+                push_int(g.w);
+                tab.push_back(g.s);
+                push_int(g.row);
             } else {
                 push_int(0);
                 push_int(0);
@@ -944,17 +1085,25 @@ int sp_prepare(mfcc_plan *plan)
     st->args.n_mel = M;
     st->args.n_cep = p.n_cep;
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
-    st->args.ls = M | 1;
+    st->args.energy = p.energy;
+    st->args.od = out_stride(p);
+    st->args.alaw = 0;
+    st->args.ls = logmel_stride(p);
     st->args.mp = MP;
-    st->args.rf = (32 * (M | 1) + 3) / 4 * 4;
+    st->args.rf = scratch_rf(p);
+    st->args.ef = st->args.rf + 2 * 32 * (M + 3);
     st->args.inv_n = static_cast<float>(1.0 / N);
-    st->args.mel_magic = (1 << 20) / M + 1;
+    st->args.mel_magic = (1 << 20) / st->args.od + 1;
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
-    if (p.output == MFCC_OUT_CEPSTRA && M % 2 == 0 && M / 2 <= kFoldMax)
+    const int HM = (M + 1) / 2;
+    if (p.output == MFCC_OUT_CEPSTRA && HM <= kFoldMax)
         for (int k = 0; k < p.n_cep && k < KC; ++k)
-            for (int q = 0; q < M / 2; ++q)
-                (&st->args.dctc[k / 2][k & 1][q / 4].x)[q % 4] = static_cast<float>(std::log(2.0) * static_cast<double>(h.dct[static_cast<size_t>(k) * M + q]));
+            for (int q = 0; q < HM; ++q) {
+                double d = std::log(2.0) * static_cast<double>(h.dct[static_cast<size_t>(k) * M + q]);
+                if ((M & 1) && q == HM - 1) d *= 0.5;   // the middle band of an odd bank is folded onto itself
+                (&st->args.dctc[k / 2][k & 1][q / 4].x)[q % 4] = static_cast<float>(d);
+            }
     st->useg_ok = true;
     for (int w = 0; w < kWarps; ++w) {
         const int n = static_cast<int>(lists[w].size());
@@ -963,12 +1112,11 @@ int sp_prepare(mfcc_plan *plan)
             float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             int x = 0, y = 0, z = -1;
             if (q < n && q < kSegParam - 1) {
-                const int j = lists[w][q];
-                const int k0 = h.mel_bins[j], wd = h.mel_bins[j + 1] - k0;
-                x = k0 * 128;
-                y = wd;
-                z = j * 128;
-                d.z = wd > 0 ? static_cast<float>(1.0 / (static_cast<double>(wd) * N)) : 0.0f;
+                const Seg &g = lists[w][q];
+                x = g.k0 * 128;
+                y = g.w;
+                z = g.row * 128;
+                d.z = g.s;
             }
             std::memcpy(&d.x, &x, 4);
             std::memcpy(&d.y, &y, 4);
@@ -998,10 +1146,11 @@ void sp_release(mfcc_plan *plan)
     delete st;
     plan->sp_state = nullptr;
 }
+#endif
 
 template <typename PcmT, int L, int HOP, int RB, int RA, int MEL, int CEP>
 static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, float *d_out,
-                          cudaStream_t stream)
+                          int alaw, cudaStream_t stream)
 {
     auto kern = fused_sp_kernel<PcmT, L, HOP, RB, RA, MEL, CEP>;
     static std::atomic<uint64_t> optin{0};
@@ -1011,6 +1160,7 @@ static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tile
     a.n_tiles = n_tiles;
     a.out = d_out;
     a.tab = st->d_tab;
+    a.alaw = alaw;
     constexpr int GROUPS = groups_for(RB);
     const int64_t grid = std::min<int64_t>((n_tiles + GROUPS - 1) / GROUPS, st->sm_count);
     kern<<<static_cast<unsigned>(grid), GROUPS * kHalfThreads, st->smem, stream>>>(d_pcm, a);
@@ -1018,23 +1168,38 @@ static int launch_variant(const SpState *st, const Tile *d_tiles, int64_t n_tile
     return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
 }
 
+// Tail-warp variants (band assembly + log + DCT / log-mel rows on two tail warps, everything in registers) exist for the
+// filter / cepstrum counts front ends actually use; everything else takes the generic tail (MEL = 0).  CEP = 0: log-mel.
+#define MFCC_SP_SHAPES_512(X) X(26, 13) X(40, 13) X(23, 13) X(26, 0) X(40, 0) X(80, 0)
+#define MFCC_SP_SHAPES_256(X) X(20, 13) X(23, 13) X(20, 0) X(40, 0)
+
 template <typename PcmT>
 int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t /*pcm_len*/,
-              float *d_out, cudaStream_t stream)
+              float *d_out, int alaw, cudaStream_t stream)
 {
     const SpState *st = static_cast<const SpState *>(plan->sp_state);
     if (st == nullptr) return MFCC_ENOTSUP;
-    // the BASELINE.json shapes (26 filters at 16 kHz, 20 at 8 kHz, 13 cepstra) get the tail-warp variant
-    const bool cep13 = !st->args.logmel && st->args.n_cep == 13 && st->useg_ok;
+    const int mel = st->useg_ok ? st->args.n_mel : -1, cep = st->args.logmel ? 0 : st->args.n_cep;
     if (st->v->L == 400) {
-        if (cep13 && st->args.n_mel == 26) return launch_variant<PcmT, 400, 160, 32, 16, 26, 13>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
-        return launch_variant<PcmT, 400, 160, 32, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+#define X(M_, C_) if (mel == M_ && cep == C_) return launch_variant<PcmT, 400, 160, 32, 16, M_, C_>(st, d_tiles, n_tiles, d_pcm, d_out, alaw, stream);
+        MFCC_SP_SHAPES_512(X)
+#undef X
+        return launch_variant<PcmT, 400, 160, 32, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, alaw, stream);
     }
-    if (cep13 && st->args.n_mel == 20) return launch_variant<PcmT, 200, 80, 16, 16, 20, 13>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
-    return launch_variant<PcmT, 200, 80, 16, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, stream);
+#define X(M_, C_) if (mel == M_ && cep == C_) return launch_variant<PcmT, 200, 80, 16, 16, M_, C_>(st, d_tiles, n_tiles, d_pcm, d_out, alaw, stream);
+    MFCC_SP_SHAPES_256(X)
+#undef X
+    return launch_variant<PcmT, 200, 80, 16, 16, 0, 0>(st, d_tiles, n_tiles, d_pcm, d_out, alaw, stream);
 }
 
-template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *, cudaStream_t);
-template int sp_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, int64_t, float *, cudaStream_t);
+#if MFCC_SP_PCM_TYPES & 1
+template int sp_launch<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, int64_t, float *, int, cudaStream_t);
+#endif
+#if MFCC_SP_PCM_TYPES & 2
+template int sp_launch<float>(const mfcc_plan *, const Tile *, int64_t, const float *, int64_t, float *, int, cudaStream_t);
+#endif
+#if MFCC_SP_PCM_TYPES & 4
+template int sp_launch<uint8_t>(const mfcc_plan *, const Tile *, int64_t, const uint8_t *, int64_t, float *, int, cudaStream_t);
+#endif
 
 }  // namespace mfcc

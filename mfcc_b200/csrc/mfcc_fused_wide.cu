@@ -105,8 +105,11 @@ struct WideArgs {
     const float *tab;
     WideLayout lay;
     int n_mel, n_cep, logmel;
+    int energy, od;       // MFCC_ENERGY_*; floats per output row
+    int nseg;             // segments walked: n_mel + 1, + the two pseudo-segments outside the filterbank when the energy term is on
     int ls, mel_magic, hmp;
-    int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 1][F] x 2
+    int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 3][F] x 2
+    int ef;               // scratch offset of the log frame energy [F]
     float preemph, log_floor;
 };
 
@@ -458,9 +461,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         // loop counts agree (with a contiguous filter group per slot the warp ran the longest of four different
         // walks).  rise[j][frame] and fall[j][frame] go through the scratch; S3b adds the two halves of each band. ----
         {
-            float *rise = scr + a.rf + f, *fall = rise + (a.n_mel + 1) * F;
+            float *rise = scr + a.rf + f, *fall = rise + (a.n_mel + 3) * F;
 #pragma unroll 1
-            for (int j = slot; j <= a.n_mel; j += kSlots) {
+            for (int j = slot; j < a.nseg; j += kSlots) {
                 const float4 sg = t_seg[j];
                 const float *p = pw + __float_as_int(sg.x) + f;
                 const int w = __float_as_int(sg.y);
@@ -494,13 +497,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         }
         // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][frame] or the frame's log-mel row ----
         {
-            const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 1) * F;
+            const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 3) * F;
             const int total = a.n_mel * F;
             for (int i = tid; i < total; i += kHalfThreads) {
                 const int m = i / F, fr = i % F;
                 const float lg = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + F], a.log_floor));
                 if (a.logmel) scr[fr * a.ls + m] = lg;
                 else scr[i] = lg;
+            }
+            // frame energy = all segment sums of the frame (the filterbank's and the two pseudo-segments outside it)
+            if (a.energy != MFCC_ENERGY_NONE && tid >= kHalfThreads - F) {
+                const int fr = tid - (kHalfThreads - F);
+                float e0 = 0.0f, e1 = 0.0f;
+                for (int j = 0; j < a.n_mel + 3; ++j) {
+                    e0 += rise[j * F + fr];
+                    e1 += fall[j * F + fr];
+                }
+                const float le = kLn2 * lg2_fast(fmaxf(e0 + e1, a.log_floor));
+                if (a.logmel) scr[fr * a.ls + a.n_mel] = le;
+                else scr[a.ef + fr] = le;
             }
         }
         half_sync(half);   // B4: every band's log energy is in the scratch
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         // and c[slot + 32] — all of one parity, so the DCT symmetry d[k][M-1-m] = (-1)^k d[k][m] folds the band
         // pairs first: v[m] = lg[m] +- lg[M-1-m], then ceil(M/2) terms per cepstrum ----
         if (a.logmel) {
-            const int M = a.n_mel, total = n_frames * M;
+            const int M = a.od, total = n_frames * M;
             float *o = a.out + tile.out_row * M;
             for (int i = tid; i < total; i += kHalfThreads) {
                 const int fr = (i * a.mel_magic) >> 20, m = i - fr * M;
@@ -542,11 +557,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             if constexpr (MEL > 0) dct_terms(MEL / 4, scr + f, scr + (MEL - 1) * F + f);   // band pairs two at a time: hmp / 2
             else dct_terms(a.hmp >> 1, scr + f, scr + (a.n_mel - 1) * F + f);
             if (f < n_frames) {
-                float *o = a.out + (tile.out_row + f) * a.n_cep + slot;
+                float *o = a.out + (tile.out_row + f) * a.od + slot;
                 o[0] = c0 + e0;
                 if (slot + kSlots < a.n_cep) o[kSlots] = c1 + e1;
                 if (third) o[2 * kSlots] = c2 + e2;
             }
+        }
+        if (!a.logmel && a.energy != MFCC_ENERGY_NONE && slot == 0 && f < n_frames) {
+            // slot 0 formed c[0] of its frame above (same thread, program order): replace it, or append after the cepstra
+            float *o = a.out + (tile.out_row + f) * a.od;
+            o[a.energy == MFCC_ENERGY_REPLACE_C0 ? 0 : a.n_cep] = scr[a.ef + f];
         }
         // next S0 writes `staged` (nobody reads P any more); the scratch is next written by S1, after B1
     }
@@ -567,7 +587,7 @@ struct WideState {
 
 size_t table_floats(const mfcc_params &p)
 {
-    return G0::TABF + 2 * kSlots + 4 * static_cast<size_t>(p.n_mel + 1) + 3 * static_cast<size_t>(kSlots) * ((p.n_mel + 1) / 2 + 1) + 16;
+    return G0::TABF + 2 * kSlots + 4 * static_cast<size_t>(p.n_mel + 3) + 3 * static_cast<size_t>(kSlots) * ((p.n_mel + 1) / 2 + 1) + 16;
 }
 
 }  // namespace
@@ -582,7 +602,7 @@ const char *wide_match(const mfcc_params &p, const HostTables &h)
     if (p.n_mel < 2 || p.log_floor < 1.17549435e-38f) return nullptr;   // band pairs; lg2.approx.ftz needs a normal floor
     // tail scratch (log band energies [n_mel][F] or log-mel rows [F][n_mel | 1], then the per-segment rise / fall
     // sums [n_mel + 1][F] x 2) must stay below the raw PCM buffer
-    if (3 * F * static_cast<size_t>(p.n_mel + 2) > static_cast<size_t>(G0::RAWOFF)) return nullptr;
+    if (3 * F * static_cast<size_t>(p.n_mel + 4) + F > static_cast<size_t>(G0::RAWOFF)) return nullptr;
     return "fused_wide_tile8_L1200_H480_real64x32";
 }
 
@@ -621,6 +641,14 @@ int wide_prepare(mfcc_plan *plan)
         tab.push_back(static_cast<float>(sc));
         tab.push_back(static_cast<float>(sc * w));
     }
+    // pseudo-segments below and above the filterbank (energy term only): plain sums, s = 0 and s w = 1 / N
+    const int below[2] = {0, h.mel_bins[0]}, above[2] = {h.mel_bins[M + 1], h.nbins - h.mel_bins[M + 1]};
+    for (const int *g : {below, above}) {
+        push_int(g[0] * F);
+        push_int(g[1]);
+        tab.push_back(0.0f);
+        tab.push_back(static_cast<float>(1.0 / N));
+    }
     align4();
     // DCT entries by slot (see S4).  Band m pairs with M - 1 - m; for odd M the middle band pairs with itself,
     // so its entry is halved (exact); the padding column of an odd half is zero.
@@ -654,10 +682,14 @@ int wide_prepare(mfcc_plan *plan)
     st->args.n_mel = M;
     st->args.n_cep = p.n_cep;
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
-    st->args.ls = M | 1;
-    st->args.mel_magic = (1 << 20) / M + 1;
+    st->args.energy = p.energy;
+    st->args.od = h.out_dim;
+    st->args.nseg = M + 1 + (p.energy != MFCC_ENERGY_NONE ? 2 : 0);
+    st->args.ls = h.out_dim | 1;
+    st->args.mel_magic = (1 << 20) / h.out_dim + 1;
     st->args.hmp = hmp;
-    st->args.rf = (F * (M | 1) + 3) / 4 * 4;
+    st->args.rf = (F * std::max(h.out_dim | 1, M) + 3) / 4 * 4;
+    st->args.ef = st->args.rf + 2 * F * (M + 3);
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
     if (cudaMalloc(&st->d_tab, sizeof(float) * tab.size()) != cudaSuccess) {

@@ -22,22 +22,29 @@ namespace {
 
 constexpr int kGenericThreads = 128;
 
-__device__ __forceinline__ float load_sample(const int16_t *p, int64_t i) { return static_cast<float>(p[i]); }
-__device__ __forceinline__ float load_sample(const float *p, int64_t i) { return p[i]; }
+__device__ __forceinline__ int ulaw_expand(unsigned b);
+__device__ __forceinline__ int alaw_expand(unsigned b);
+__device__ __forceinline__ float load_sample(const int16_t *p, int64_t i, int) { return static_cast<float>(p[i]); }
+__device__ __forceinline__ float load_sample(const float *p, int64_t i, int) { return p[i]; }
+__device__ __forceinline__ float load_sample(const uint8_t *p, int64_t i, int alaw)   // G.711 code -> linear PCM
+{
+    return static_cast<float>(alaw ? alaw_expand(p[i]) : ulaw_expand(p[i]));
+}
 
 template <typename PcmT>
 __global__ void __launch_bounds__(kGenericThreads)
 generic_radix2_kernel(const Tile *__restrict__ tiles, const PcmT *__restrict__ pcm,
                       float *__restrict__ out, DevTables tb, int frame_len, int hop, int nfft,
-                      int log2n, int n_mel, int n_cep, int logmel, float preemph, float log_floor)
+                      int log2n, int n_mel, int n_cep, int logmel, int energy, int alaw, float preemph, float log_floor)
 {
     extern __shared__ float smem[];
     float *re = smem;                 // [nfft]
     float *im = re + nfft;            // [nfft]
     float *pw = im + nfft;            // [nfft/2 + 1]
-    float *lg = pw + (nfft / 2 + 1);  // [n_mel]
+    float *lg = pw + (nfft / 2 + 1);  // [n_mel] log band energies, then the log frame energy
     const int nbins = nfft / 2 + 1;
-    const int out_dim = logmel ? n_mel : n_cep;
+    const int base_dim = logmel ? n_mel : n_cep;
+    const int out_dim = base_dim + (energy == MFCC_ENERGY_APPEND ? 1 : 0);
     const Tile tile = tiles[blockIdx.x];
     const float inv_n = 1.0f / static_cast<float>(nfft);
 
@@ -48,8 +55,8 @@ generic_radix2_kernel(const Tile *__restrict__ tiles, const PcmT *__restrict__ p
             float v = 0.0f;
             const int64_t s = s0 + i;
             if (i < frame_len && s < tile.utt_end) {
-                const float x0 = load_sample(pcm, s);
-                const float x1 = s > tile.utt_begin ? load_sample(pcm, s - 1) : 0.0f;
+                const float x0 = load_sample(pcm, s, alaw);
+                const float x1 = s > tile.utt_begin ? load_sample(pcm, s - 1, alaw) : 0.0f;
                 v = __fmul_rn(__fsub_rn(x0, __fmul_rn(preemph, x1)), tb.window[i]);
             }
             const int r = static_cast<int>(__brev(static_cast<unsigned>(i)) >> (32 - log2n));
@@ -74,7 +81,13 @@ generic_radix2_kernel(const Tile *__restrict__ tiles, const PcmT *__restrict__ p
         for (int k = threadIdx.x; k < nbins; k += kGenericThreads)
             pw[k] = __fmul_rn(__fadd_rn(__fmul_rn(re[k], re[k]), __fmul_rn(im[k], im[k])), inv_n);
         __syncthreads();
-        for (int m = threadIdx.x; m < n_mel; m += kGenericThreads) {
+        for (int m = threadIdx.x; m < n_mel + (energy != MFCC_ENERGY_NONE ? 1 : 0); m += kGenericThreads) {
+            if (m == n_mel) {   // frame energy: the one-sided power spectrum summed in ascending-bin order
+                float e = 0.0f;
+                for (int k = 0; k < nbins; ++k) e = __fadd_rn(e, pw[k]);
+                lg[m] = logf(fmaxf(e, log_floor));
+                continue;
+            }
             const float *w = tb.mel_w + static_cast<size_t>(m) * nbins;
             int k1 = tb.mel_bins[m + 2];
             if (k1 > nbins - 1) k1 = nbins - 1;
@@ -85,7 +98,9 @@ generic_radix2_kernel(const Tile *__restrict__ tiles, const PcmT *__restrict__ p
         __syncthreads();
         float *o = out + (tile.out_row + f) * out_dim;
         for (int k = threadIdx.x; k < out_dim; k += kGenericThreads) {
-            if (logmel) {
+            if (k == base_dim || (k == 0 && energy == MFCC_ENERGY_REPLACE_C0)) {
+                o[k] = lg[n_mel];
+            } else if (logmel) {
                 o[k] = lg[k];
             } else {
                 const float *d = tb.dct + static_cast<size_t>(k) * n_mel;
@@ -223,29 +238,31 @@ g711_kernel(const uint8_t *__restrict__ src, int64_t n, int alaw, int16_t *__res
 
 template <typename PcmT>
 int launch_generic(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
-                   float *d_out, cudaStream_t stream)
+                   float *d_out, int alaw, cudaStream_t stream)
 {
     if (n_tiles <= 0) return MFCC_OK;
     const mfcc_params &p = plan->p;
     int log2n = 0;
     while ((1 << log2n) < p.nfft) ++log2n;
-    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(p.nfft) + p.nfft / 2 + 1 + p.n_mel);
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(p.nfft) + p.nfft / 2 + 1 + p.n_mel + 1);
     int64_t done = 0;
     while (done < n_tiles) {  // gridDim.x limit is 2^31-1; chunk anyway
         const int64_t n = n_tiles - done > (1 << 30) ? (1 << 30) : n_tiles - done;
         generic_radix2_kernel<PcmT><<<static_cast<unsigned>(n), kGenericThreads, smem, stream>>>(
             d_tiles + done, d_pcm, d_out, plan->dev, p.frame_len, p.hop_len, p.nfft, log2n, p.n_mel,
-            p.n_cep, p.output == MFCC_OUT_LOGMEL, p.preemph, p.log_floor);
+            p.n_cep, p.output == MFCC_OUT_LOGMEL, p.energy, alaw, p.preemph, p.log_floor);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         done += n;
     }
     return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
 }
 
-template int launch_generic<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *,
+template int launch_generic<int16_t>(const mfcc_plan *, const Tile *, int64_t, const int16_t *, float *, int,
                                      cudaStream_t);
-template int launch_generic<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *,
+template int launch_generic<float>(const mfcc_plan *, const Tile *, int64_t, const float *, float *, int,
                                    cudaStream_t);
+template int launch_generic<uint8_t>(const mfcc_plan *, const Tile *, int64_t, const uint8_t *, float *, int,
+                                     cudaStream_t);
 
 int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s)
 {

@@ -132,9 +132,10 @@ inline int ensure_smem_optin(Kern kern, int device, size_t bytes, std::atomic<ui
 
 // Kernel launchers.  `tile0`/`n_tiles` select a range of the batch's tile table;
 // d_pcm / d_out are the bases of the WHOLE batch arrays.
+// PcmT: int16_t, float (scaled to the int16 range) or uint8_t (G.711 codes; `alaw` selects the law, ignored otherwise)
 template <typename PcmT>
 int launch_generic(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm,
-                   float *d_out, cudaStream_t stream);
+                   float *d_out, int alaw, cudaStream_t stream);
 
 // Fused tile kernel for the 512- and 256-point geometries (mfcc_fused_sp.cu): name if the plan has one, else nullptr.
 const char *sp_match(const mfcc_params &p, const HostTables &h);
@@ -142,7 +143,7 @@ int sp_prepare(mfcc_plan *plan);
 void sp_release(mfcc_plan *plan);
 template <typename PcmT>
 int sp_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
-              float *d_out, cudaStream_t stream);
+              float *d_out, int alaw, cudaStream_t stream);
 // Large-transform variant (mfcc_fused_wide.cu): 2048-point frames, 8 frames per tile, 4 items per warp.
 const char *wide_match(const mfcc_params &p, const HostTables &h);
 int wide_prepare(mfcc_plan *plan);

@@ -25,6 +25,8 @@ int validate_params(const mfcc_params *p)
     }
     if (p->pad_mode != MFCC_PAD_NONE && p->pad_mode != MFCC_PAD_ZERO_TAIL) return MFCC_EINVAL;
     if (p->output != MFCC_OUT_CEPSTRA && p->output != MFCC_OUT_LOGMEL) return MFCC_EINVAL;
+    if (p->energy < MFCC_ENERGY_NONE || p->energy > MFCC_ENERGY_APPEND) return MFCC_EINVAL;
+    if (p->energy == MFCC_ENERGY_REPLACE_C0 && p->output != MFCC_OUT_CEPSTRA) return MFCC_EINVAL;
     if (p->lifter < 0) return MFCC_EINVAL;
     if (!(p->log_floor > 0.0f) || !std::isfinite(p->log_floor)) return MFCC_EINVAL;
     if (!(p->preemph >= 0.0f && p->preemph <= 1.0f)) return MFCC_EINVAL;
@@ -42,7 +44,7 @@ int build_tables(const mfcc_params &p, HostTables &t)
     if (validate_params(&p) != MFCC_OK) return MFCC_EINVAL;
     const int L = p.frame_len, N = p.nfft, M = p.n_mel, nb = N / 2 + 1;
     t.nbins = nb;
-    t.out_dim = p.output == MFCC_OUT_LOGMEL ? M : p.n_cep;
+    t.out_dim = (p.output == MFCC_OUT_LOGMEL ? M : p.n_cep) + (p.energy == MFCC_ENERGY_APPEND ? 1 : 0);
 
     // Window.
     t.window.resize(L);
@@ -136,6 +138,7 @@ int mfcc_params_init(mfcc_params *p, int32_t sample_rate)
     p->lifter = 0;
     p->pad_mode = MFCC_PAD_NONE;
     p->output = MFCC_OUT_CEPSTRA;
+    p->energy = MFCC_ENERGY_NONE;
     return mfcc::validate_params(p);
 }
 
@@ -153,7 +156,7 @@ int64_t mfcc_num_frames(const mfcc_params *p, int64_t n)
 int32_t mfcc_out_dim(const mfcc_params *p)
 {
     if (mfcc::validate_params(p) != MFCC_OK) return MFCC_EINVAL;
-    return p->output == MFCC_OUT_LOGMEL ? p->n_mel : p->n_cep;
+    return (p->output == MFCC_OUT_LOGMEL ? p->n_mel : p->n_cep) + (p->energy == MFCC_ENERGY_APPEND ? 1 : 0);
 }
 
 const char *mfcc_strerror(int err)

@@ -14,6 +14,7 @@ WINDOW_RECT, WINDOW_HAMMING, WINDOW_HANN = 0, 1, 2
 PAD_NONE, PAD_ZERO_TAIL = 0, 1
 OUT_CEPSTRA, OUT_LOGMEL = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
+ENERGY_NONE, ENERGY_REPLACE_C0, ENERGY_APPEND = 0, 1, 2
 
 
 class MfccParams(C.Structure):
@@ -32,6 +33,7 @@ class MfccParams(C.Structure):
         ("lifter", C.c_int32),
         ("pad_mode", C.c_int32),
         ("output", C.c_int32),
+        ("energy", C.c_int32),
     ]
 
     def copy(self, **kw) -> "MfccParams":
@@ -44,7 +46,7 @@ class MfccParams(C.Structure):
 
     @property
     def out_dim(self) -> int:
-        return self.n_mel if self.output == OUT_LOGMEL else self.n_cep
+        return (self.n_mel if self.output == OUT_LOGMEL else self.n_cep) + (1 if self.energy == ENERGY_APPEND else 0)
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -52,9 +54,9 @@ class MfccParams(C.Structure):
 
 def make_params(sample_rate=16000, frame_len=400, hop_len=160, nfft=512, n_mel=26, n_cep=13,
                 preemph=0.97, window=WINDOW_HAMMING, f_lo=0.0, f_hi=0.0, log_floor=1e-10,
-                lifter=0, pad_mode=PAD_NONE, output=OUT_CEPSTRA) -> MfccParams:
+                lifter=0, pad_mode=PAD_NONE, output=OUT_CEPSTRA, energy=ENERGY_NONE) -> MfccParams:
     return MfccParams(sample_rate, frame_len, hop_len, nfft, n_mel, n_cep, preemph, window,
-                      f_lo, f_hi, log_floor, lifter, pad_mode, output)
+                      f_lo, f_hi, log_floor, lifter, pad_mode, output, energy)
 
 
 def config_a() -> MfccParams:

@@ -147,8 +147,16 @@ static void FN(one_frame)(const mfcc_params *p, FN(tables) *t, const int16_t *pc
         if (tap_mel) tap_mel[m] = e;
         t->loge[m] = (REAL)LOGFN(e > flo ? e : flo);
     }
+    /* Frame energy term (MFCC_ENERGY_*): E = sum of the one-sided power spectrum, ascending k. */
+    REAL log_energy = 0;
+    if (p->energy != MFCC_ENERGY_NONE) {
+        REAL e = 0;
+        for (int k = 0; k < t->nbins; ++k) e += t->pw[k];
+        log_energy = (REAL)LOGFN(e > flo ? e : flo);
+    }
     if (p->output == MFCC_OUT_LOGMEL) {
         for (int m = 0; m < p->n_mel; ++m) out[m] = t->loge[m];
+        if (p->energy == MFCC_ENERGY_APPEND) out[p->n_mel] = log_energy;
         return;
     }
     /* DCT-II (orthonormal; lifter already folded into the rows). */
@@ -158,6 +166,8 @@ static void FN(one_frame)(const mfcc_params *p, FN(tables) *t, const int16_t *pc
         for (int m = 0; m < p->n_mel; ++m) c += d[m] * t->loge[m];
         out[k] = c;
     }
+    if (p->energy == MFCC_ENERGY_REPLACE_C0) out[0] = log_energy;
+    if (p->energy == MFCC_ENERGY_APPEND) out[p->n_cep] = log_energy;
 }
 
 /* Whole utterance: returns the frame count (>= 0) or a negative error.
@@ -171,7 +181,7 @@ int64_t FN(oracle_mfcc)(const mfcc_params *p, const int16_t *pcm, int64_t n, REA
     FN(tables) t;
     int rc = FN(tables_init)(&t, p);
     if (rc != 0) { FN(tables_free)(&t); return rc; }
-    const int od = p->output == MFCC_OUT_LOGMEL ? p->n_mel : p->n_cep;
+    const int od = ORACLE_OUT_DIM(p);
     for (int64_t f = 0; f < nf; ++f)
         FN(one_frame)(p, &t, pcm, n, f * (int64_t)p->hop_len, out + f * od, NULL, NULL, NULL);
     FN(tables_free)(&t);
@@ -189,7 +199,7 @@ int FN(oracle_stages)(const mfcc_params *p, const int16_t *pcm, int64_t n, int64
     FN(tables) t;
     int rc = FN(tables_init)(&t, p);
     if (rc != 0) { FN(tables_free)(&t); return rc; }
-    const int od = p->output == MFCC_OUT_LOGMEL ? p->n_mel : p->n_cep;
+    const int od = ORACLE_OUT_DIM(p);
     REAL *tmp = (REAL *)malloc(sizeof(REAL) * (size_t)od);
     FN(one_frame)(p, &t, pcm, n, frame * (int64_t)p->hop_len, out ? out : tmp, framed, power, mel);
     free(tmp);

@@ -57,7 +57,7 @@ def mfcc(p, pcm: np.ndarray) -> np.ndarray:
     n = x.size
     nf = num_frames(p, n)
     if nf == 0:
-        return np.zeros((0, p.n_mel if p.output == 1 else p.n_cep))
+        return np.zeros((0, (p.n_mel if p.output == 1 else p.n_cep) + (getattr(p, "energy", 0) == 2)))
     y = x.copy()
     y[1:] -= float(np.float32(p.preemph)) * x[:-1]
     need = (nf - 1) * p.hop_len + p.frame_len
@@ -68,11 +68,18 @@ def mfcc(p, pcm: np.ndarray) -> np.ndarray:
     spec = np.fft.rfft(frames, n=p.nfft, axis=1)
     power = (spec.real ** 2 + spec.imag ** 2) / p.nfft
     E = power @ mel_weights(p).T
-    L = np.log(np.maximum(E, float(np.float32(p.log_floor))))
+    floor = float(np.float32(p.log_floor))
+    L = np.log(np.maximum(E, floor))
+    energy = getattr(p, "energy", 0)
+    log_e = np.log(np.maximum(power.sum(axis=1), floor))[:, None]      # total of the one-sided power spectrum
     if p.output == 1:
-        return L
+        return np.concatenate([L, log_e], axis=1) if energy == 2 else L
     c = scipy.fft.dct(L, type=2, norm="ortho", axis=1)[:, : p.n_cep]
     if p.lifter > 0:
         k = np.arange(p.n_cep)
         c = c * (1.0 + 0.5 * p.lifter * np.sin(np.pi * k / p.lifter))[None, :]
+    if energy == 1:
+        c[:, :1] = log_e
+    elif energy == 2:
+        c = np.concatenate([c, log_e], axis=1)
     return c

@@ -14,7 +14,8 @@ import pytest
 
 import oracle
 from mfcc_b200 import (api, config_a, config_b, config_c, make_params, KERNEL_GENERIC, KERNEL_FUSED,
-                       KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT)
+                       KERNEL_AUTO, OUT_LOGMEL, PAD_ZERO_TAIL, WINDOW_HANN, WINDOW_RECT, ENERGY_APPEND,
+                       ENERGY_REPLACE_C0)
 from mfcc_b200.synth import (clip_config1, fast_fixed_batch, noise_utterance, ragged_batch, hostile_clip,
                              HOSTILE_KINDS)
 from util import assert_parity, golden, hostile_golden, lifter_gains, parity_errors
@@ -428,6 +429,72 @@ def test_config4_full_length_stream_properties():
 
 
 # ---- §8(f) widening ----
+@pytest.mark.parametrize("kernel", ALL_KERNELS)
+def test_energy_term_and_front_end_shapes(kernel):
+    """append-energy / c0 replacement on every geometry and output, and the filter / cepstrum
+    counts that have a tail-warp variant of the 512- / 256-point kernel (26/13, 40/13, 23/13 — an odd bank —, log-mel
+    26 / 40 / 80; 8 kHz: 20/13, 23/13, log-mel 20 / 40) next to ones that take the generic tail."""
+    a, b, c = config_a(), config_b(), config_c()
+    variants = [
+        a.copy(energy=ENERGY_REPLACE_C0), a.copy(energy=ENERGY_APPEND), a.copy(energy=ENERGY_APPEND, output=OUT_LOGMEL),
+        a.copy(energy=ENERGY_REPLACE_C0, lifter=22, pad_mode=PAD_ZERO_TAIL), a.copy(energy=ENERGY_APPEND, f_lo=300.0, f_hi=3400.0),
+        a.copy(n_mel=40), a.copy(n_mel=23, f_lo=20.0, f_hi=7800.0), a.copy(n_mel=23, energy=ENERGY_APPEND),
+        a.copy(output=OUT_LOGMEL), a.copy(output=OUT_LOGMEL, n_mel=40), a.copy(output=OUT_LOGMEL, n_mel=80, n_cep=80, f_lo=40.0),
+        a.copy(output=OUT_LOGMEL, n_mel=80, n_cep=80, f_lo=40.0, energy=ENERGY_APPEND),
+        a.copy(n_mel=30, n_cep=12, energy=ENERGY_REPLACE_C0), a.copy(n_mel=31, output=OUT_LOGMEL, energy=ENERGY_APPEND),
+        b.copy(energy=ENERGY_REPLACE_C0), b.copy(energy=ENERGY_APPEND), b.copy(n_mel=23), b.copy(output=OUT_LOGMEL),
+        b.copy(output=OUT_LOGMEL, n_mel=40, n_cep=40, energy=ENERGY_APPEND), b.copy(n_mel=23, f_lo=100.0, f_hi=3800.0, energy=ENERGY_REPLACE_C0),
+        c.copy(energy=ENERGY_REPLACE_C0), c.copy(energy=ENERGY_APPEND), c.copy(energy=ENERGY_APPEND, output=OUT_LOGMEL),
+        c.copy(energy=ENERGY_APPEND, n_mel=41, n_cep=13, f_lo=60.0, f_hi=20000.0),
+    ]
+    for p in variants:
+        plan = make_plan(p, kernel)
+        L, H = p.frame_len, p.hop_len
+        lens = [L + 70 * H + 3, 5, L, L + 31 * H, 0, L + 33 * H + 1]
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        pcm = noise_utterance(int(off[-1]), seed=24)
+        got, fo = run_device(plan, pcm, off)
+        ref, fo_ref = oracle.mfcc_batch(p, pcm, off)
+        assert np.array_equal(fo, fo_ref) and got.shape == ref.shape == (fo[-1], p.out_dim)
+        truth = np.concatenate([oracle.mfcc(p, pcm[off[u]:off[u + 1]], dtype=np.float64) for u in range(len(off) - 1)])
+        assert_parity(got, ref, what=f"{p.as_dict()}/{kernel}/{plan.kernel_name}", truth=truth, col_scale=lifter_gains(p),
+                      max_escapes=(4 if p.n_mel >= 80 and p.f_lo < 20 else 0))
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_g711_codes_are_expanded_inside_the_kernel(name):
+    """mfcc_compute_batch_g711 / mfcc_compute_host_g711: mu-law and A-law bytes in, the same rows as decoding to
+    int16 first (mfcc_decode_g711, itself bit-exact against the ITU tables) and calling mfcc_compute_batch — bit for
+    bit, for every start alignment (the 1-byte codes are bulk-copied in 16-sample units)."""
+    p = CFG[name]()
+    if name == "C":
+        p = p.copy(f_lo=60.0)     # two kernels are compared here: keep the bank off the noise-floor bins right above DC
+    plan = api.Plan(p)
+    L, H = p.frame_len, p.hop_len
+    rng = np.random.default_rng(15)
+    lens = [int(v) for v in rng.integers(1, 40 * H, 60)] + [L + 64 * H, 0, 3, L, L + 31 * H + 1]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    codes = rng.integers(0, 256, int(off[-1])).astype(np.uint8)
+    b = plan.batch(off)
+    for alaw in (False, True):
+        lin = oracle.decode_g711(codes, alaw)
+        want = plan.compute_batch(b, torch.from_numpy(lin).cuda())
+        got = plan.compute_batch(b, torch.from_numpy(codes).cuda(), alaw=alaw)
+        torch.cuda.synchronize()
+        if plan.kernel_name.startswith("fused_sp"):
+            assert torch.equal(got, want)            # same kernel, the codes expanded in its staging
+        else:                                        # 2048-point plans take the generic kernel for G.711 codes
+            assert_parity(got.cpu().numpy(), want.cpu().numpy(), what=f"g711 {name} vs int16 entry")
+        ref, _ = oracle.mfcc_batch(p, lin, off)
+        assert_parity(got.cpu().numpy(), ref, what=f"g711 {name} alaw={alaw}")
+        host, fo = plan.compute_host(codes, off, alaw=alaw)
+        assert np.array_equal(host, got.cpu().numpy()) and np.array_equal(fo, b.frame_offsets)
+        # a device view that starts at an odd byte: no tile may take the bulk-copy path, same values
+        shifted = torch.from_numpy(np.concatenate([[0], codes]).astype(np.uint8)).cuda()[1:]
+        assert torch.equal(plan.compute_batch(b, shifted, alaw=alaw), got)
+
+
+
 def test_cmvn_delta_g711_on_device():
     p = config_a()
     plan = api.Plan(p)
@@ -507,16 +574,29 @@ from mfcc_b200 import api, config_a, config_b, config_c, OUT_LOGMEL, PAD_ZERO_TA
 from mfcc_b200.synth import ragged_batch, noise_utterance
 assert api.LIB_PATH.endswith("libmfcc_b200_poison.so"), api.LIB_PATH
 worst = {}
-cases = [("A", config_a()), ("B", config_b()), ("C", config_c()), ("A_logmel", config_a().copy(output=OUT_LOGMEL)),
-         ("B_40_20", config_b().copy(n_mel=24, n_cep=12)), ("A_tail", config_a().copy(pad_mode=PAD_ZERO_TAIL)),
-         ("C_logmel", config_c().copy(output=OUT_LOGMEL))]
+# (48 kHz cases: f_lo = 60 Hz keeps the bank off the one or two bins right above DC, which sit at the f32 noise floor)
+cases = [("A", config_a()), ("B", config_b()), ("C", config_c().copy(f_lo=60.0)), ("A_logmel", config_a().copy(output=OUT_LOGMEL)),
+         ("B_24_12", config_b().copy(n_mel=24, n_cep=12)), ("A_tail", config_a().copy(pad_mode=PAD_ZERO_TAIL)),
+         ("A_energy", config_a().copy(energy=2)), ("B_30_energy", config_b().copy(n_mel=30, energy=1, f_lo=100.0)),
+         ("C_logmel", config_c().copy(output=OUT_LOGMEL, f_lo=60.0, energy=2))]
 for name, p in cases:
     plan = api.Plan(p)
     assert plan.kernel_name.startswith("fused_"), plan.kernel_name
     L, H = p.frame_len, p.hop_len
     pcm, off = ragged_batch(700 if p.nfft < 2048 else 120, L // 2, L + 150 * H, seed=61)
     b = plan.batch(off)
-    for dt in (torch.int16, torch.float32):
+    for dt in (torch.int16, torch.float32, torch.uint8):
+        if dt == torch.uint8:     # G.711 entry: the PCM's low bytes as mu-law codes, against their own expansion
+            if not plan.kernel_name.startswith("fused_sp"):
+                continue
+            codes = pcm.view(np.uint8)[::2].copy()
+            out = plan.compute_batch(b, torch.from_numpy(codes).cuda())
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            ref, _ = oracle.mfcc_batch(p, oracle.decode_g711(codes, False), off, nthreads=8)
+            assert np.isfinite(got).all()
+            assert_parity(got, ref, what=name + "/g711")
+            continue
         out = plan.compute_batch(b, torch.from_numpy(pcm).cuda().to(dt))
         torch.cuda.synchronize()
         got = out.cpu().numpy()

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_params_struct_layout_matches_header():
-    assert C.sizeof(MfccParams) == 14 * 4
+    assert C.sizeof(MfccParams) == 15 * 4
     p = MfccParams()
     assert api.load().mfcc_params_init(C.byref(p), 16000) == 0
     a = config_a()
@@ -51,7 +51,8 @@ def test_num_frames_and_validation_agree_with_oracle():
         assert lib.mfcc_out_dim(C.byref(p)) == p.out_dim
     bad = [dict(nfft=500), dict(frame_len=600), dict(n_cep=27), dict(n_mel=0), dict(hop_len=0),
            dict(window=7), dict(log_floor=0.0), dict(f_hi=9000.0), dict(f_lo=8000.0), dict(lifter=-1),
-           dict(preemph=1.5), dict(pad_mode=3), dict(output=2)]
+           dict(preemph=1.5), dict(pad_mode=3), dict(output=2),
+           dict(energy=3), dict(energy=-1), dict(energy=1, output=1)]
     for kw in bad:
         q = make_params(**kw)
         assert lib.mfcc_params_validate(C.byref(q)) == -1, kw

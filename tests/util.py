@@ -71,12 +71,15 @@ def assert_parity(got, ref, abs_tol=ABS_TOL, rel_tol=REL_TOL, what="", truth=Non
 
 
 def lifter_gains(p):
-    """Per-cepstrum lifter gain 1 + (Q/2) sin(pi k / Q) (ones without a lifter or for log-mel output)."""
-    dim = p.n_mel if p.output == 1 else p.n_cep
-    if p.lifter <= 0 or p.output == 1:
-        return np.ones(dim)
-    k = np.arange(dim)
-    return np.maximum(np.abs(1.0 + 0.5 * p.lifter * np.sin(np.pi * k / p.lifter)), 1.0)
+    """Per-column lifter gain 1 + (Q/2) sin(pi k / Q) (ones without a lifter, for log-mel output and for the energy column)."""
+    dim = p.out_dim
+    g = np.ones(dim)
+    if p.lifter > 0 and p.output == 0:
+        k = np.arange(p.n_cep)
+        g[: p.n_cep] = np.maximum(np.abs(1.0 + 0.5 * p.lifter * np.sin(np.pi * k / p.lifter)), 1.0)
+        if getattr(p, "energy", 0) == 1:
+            g[0] = 1.0
+    return g
 
 
 def hostile_golden():
