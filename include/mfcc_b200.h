@@ -222,6 +222,13 @@ int64_t mfcc_stream_pending(const mfcc_stream *stream, int64_t n_new, int32_t at
 int mfcc_stream_feed(mfcc_stream *stream, const int16_t *pcm, int64_t n, float *out, int64_t max_frames,
                      int64_t *n_frames);
 int mfcc_stream_flush(mfcc_stream *stream, float *out, int64_t max_frames, int64_t *n_frames);
+/* Serving form: n_streams live streams of ONE plan fed in one call — stream i gets n[i] samples from pcm[i] and writes
+ * its complete frames to out[i] (capacity max_frames[i] rows; NULL allowed when nothing is due), n_frames[i] = rows
+ * written.  The streams' pending samples are packed into one pinned staging array: ONE host->device copy, ONE kernel
+ * launch over all streams' tiles, ONE device->host copy, whatever n_streams is.  Row for row identical to feeding the
+ * streams one by one.  The call is all-or-nothing: on MFCC_EINVAL no stream has been fed. */
+int mfcc_stream_feed_many(mfcc_stream *const *streams, int64_t n_streams, const int16_t *const *pcm, const int64_t *n,
+                          float *const *out, const int64_t *max_frames, int64_t *n_frames);
 
 /* Pinned host memory helpers for the end-to-end path. */
 int mfcc_host_alloc(void **ptr, int64_t bytes);

@@ -62,6 +62,7 @@ ABI = {
     "mfcc_stream_pending": (_i64, [_vp, _i64, _i32]),
     "mfcc_stream_feed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_i64)]),
     "mfcc_stream_flush": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "mfcc_stream_feed_many": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mfcc_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "mfcc_host_free": (C.c_int, [_vp]),
     "mfcc_launch_count": (C.c_uint64, []),
@@ -339,6 +340,47 @@ class Stream:
         got = _i64(0)
         _check(load().mfcc_stream_flush(self._h, out.ctypes.data, due, C.byref(got)), "mfcc_stream_flush")
         return out[: got.value]
+
+
+class StreamGroup:
+    """S live streams of one plan fed together (``mfcc_stream_feed_many``): one staging copy, one launch, one read-back
+    per call whatever S is.  ``feed(chunks)`` takes either a [S, n] int16 array (every stream gets n samples) or a
+    list of S 1-D arrays; it returns (rows [S, cap, out_dim] float32, counts [S]) — stream i's new frames are
+    ``rows[i, :counts[i]]``."""
+
+    def __init__(self, plan: Plan, n_streams: int, max_frames_per_feed: int = 64):
+        self.plan, self.n = plan, int(n_streams)
+        self.streams = [Stream(plan) for _ in range(self.n)]
+        self._handles = (C.c_void_p * self.n)(*[st._h.value for st in self.streams])
+        self.cap = int(max_frames_per_feed)
+        self.rows = np.zeros((self.n, self.cap, plan.out_dim), np.float32)
+        stride = self.rows.strides[0]
+        self._out = (self.rows.ctypes.data + stride * np.arange(self.n, dtype=np.uint64)).astype(np.uint64)
+        self._cap = np.full(self.n, self.cap, np.int64)
+        self.counts = np.zeros(self.n, np.int64)
+
+    def feed(self, chunks):
+        if isinstance(chunks, np.ndarray) and chunks.ndim == 2:
+            if chunks.dtype != np.int16 or chunks.shape[0] != self.n or chunks.strides[1] != 2:
+                raise ValueError("chunks must be [n_streams, n] int16 with contiguous rows")
+            ptrs = (chunks.ctypes.data + chunks.strides[0] * np.arange(self.n, dtype=np.uint64)).astype(np.uint64)
+            lens = np.full(self.n, chunks.shape[1], np.int64)
+            keep = chunks
+        else:
+            keep = [np.ascontiguousarray(c, np.int16) for c in chunks]
+            if len(keep) != self.n:
+                raise ValueError("one chunk per stream")
+            ptrs = np.array([c.ctypes.data for c in keep], np.uint64)
+            lens = np.array([c.size for c in keep], np.int64)
+        _check(load().mfcc_stream_feed_many(C.addressof(self._handles), self.n, ptrs.ctypes.data, lens.ctypes.data,
+                                            self._out.ctypes.data, self._cap.ctypes.data, self.counts.ctypes.data),
+               "mfcc_stream_feed_many")
+        del keep
+        return self.rows, self.counts
+
+    def close(self):
+        for st in self.streams:
+            st.close()
 
 
 def decode_g711(codes, alaw: bool = False, stream=None):

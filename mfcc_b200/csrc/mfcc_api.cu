@@ -162,6 +162,8 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     if (plan->d2h_out) cudaFree(plan->d2h_out);
     if (plan->d_tiles) cudaFree(plan->d_tiles);
     if (plan->h_tiles) cudaFreeHost(plan->h_tiles);
+    if (plan->h_stage_pcm) cudaFreeHost(plan->h_stage_pcm);
+    if (plan->h_stage_out) cudaFreeHost(plan->h_stage_out);
     if (plan->tiles_ready) cudaEventDestroy(plan->tiles_ready);
     for (cudaEvent_t e : plan->chunk_ready) cudaEventDestroy(e);
     if (plan->dev_blob) cudaFree(plan->dev_blob);
@@ -523,36 +525,73 @@ int64_t stream_due(const mfcc_stream *st, int64_t n_new, bool at_flush)
     return mfcc_num_frames(&q, total) - st->emitted;
 }
 
-// One utterance whose first `lead` samples are pre-emphasis history only; exactly n_frames frames
-// (zero fill past the end, as MFCC_PAD_ZERO_TAIL does).  H2D, kernel, D2H on the plan's stream 0.
-int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
+int grow_pinned(void **ptr, size_t *have, size_t need)
 {
-    mfcc_plan *plan = st->plan;
+    if (*have >= need) return MFCC_OK;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    const size_t want = align_up(need + need / 4, 1 << 16);
+    if (cudaHostAlloc(ptr, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MFCC_ENOMEM; }
+    *have = want;
+    return MFCC_OK;
+}
+
+// One launch for any number of live streams of ONE plan.  Stream i contributes due[i] frames of its buffer (whose first
+// sample is pre-emphasis history when has_history is set; zero fill past the end, as MFCC_PAD_ZERO_TAIL does).  The
+// buffers are packed into ONE pinned staging array (each starting on a 16-byte boundary, so the tiles stay eligible for
+// the bulk-copy path), the tile table into another: two H2D copies, one kernel, one D2H into pinned memory, then the
+// rows are handed out to the callers' buffers.  All on the plan's stream 0, under the plan's mutex.
+int streams_run(mfcc_plan *plan, mfcc_stream *const *sts, int64_t n_streams, const int64_t *due, float *const *outs)
+{
     const mfcc_params &p = plan->p;
-    const int lead = st->has_history ? 1 : 0;
-    const int64_t len = static_cast<int64_t>(st->buf.size());
     const int od = plan->host.out_dim;
-    std::vector<Tile> tiles;
-    for (int64_t f = 0; f < n_frames; f += mfcc::kTileFrames) {
-        Tile t;
-        t.utt_begin = 0;
-        t.utt_end = len;
-        t.first_sample = lead + f * p.hop_len;
-        t.out_row = f;
-        t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, n_frames - f));
-        t.flags = mfcc::tile_flags(p, t, len);
-        tiles.push_back(t);
+    std::vector<int64_t> base(n_streams + 1, 0), row0(n_streams + 1, 0);
+    int64_t n_tiles = 0;
+    for (int64_t i = 0; i < n_streams; ++i) {
+        const int64_t len = due[i] > 0 ? static_cast<int64_t>(sts[i]->buf.size()) : 0;
+        base[i + 1] = base[i] + ((len + 7) & ~static_cast<int64_t>(7));
+        row0[i + 1] = row0[i] + std::max<int64_t>(due[i], 0);
+        n_tiles += (std::max<int64_t>(due[i], 0) + mfcc::kTileFrames - 1) / mfcc::kTileFrames;
     }
+    const int64_t total_samples = base[n_streams] + mfcc::kTileSpanSlack + 16, total_rows = row0[n_streams];
+    if (total_rows == 0) return MFCC_OK;
+
     std::lock_guard<std::mutex> lock(plan->host_mutex);
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
-    int rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(len));
-    if (rc == MFCC_OK) rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(n_frames) * od);
-    if (rc == MFCC_OK) rc = grow(&plan->d_tiles, &plan->d_tiles_bytes, sizeof(Tile) * tiles.size());
+    int rc = grow(&plan->h2d_pcm, &plan->h2d_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(total_samples));
+    if (rc == MFCC_OK) rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(total_rows) * od);
+    if (rc == MFCC_OK) rc = grow(&plan->d_tiles, &plan->d_tiles_bytes, sizeof(Tile) * static_cast<size_t>(n_tiles));
+    if (rc == MFCC_OK) rc = grow_pinned(&plan->h_tiles, &plan->h_tiles_bytes, sizeof(Tile) * static_cast<size_t>(n_tiles));
+    if (rc == MFCC_OK) rc = grow_pinned(&plan->h_stage_pcm, &plan->h_stage_pcm_bytes, sizeof(int16_t) * static_cast<size_t>(total_samples));
+    if (rc == MFCC_OK) rc = grow_pinned(&plan->h_stage_out, &plan->h_stage_out_bytes, sizeof(float) * static_cast<size_t>(total_rows) * od);
     if (rc == MFCC_OK && plan->streams[0] == nullptr &&
         cudaStreamCreateWithFlags(&plan->streams[0], cudaStreamNonBlocking) != cudaSuccess)
         rc = MFCC_ECUDA;
     if (rc != MFCC_OK) return rc;
+
+    int16_t *stage = static_cast<int16_t *>(plan->h_stage_pcm);
+    Tile *tiles = static_cast<Tile *>(plan->h_tiles);
+    int64_t t = 0;
+    for (int64_t i = 0; i < n_streams; ++i) {
+        if (due[i] <= 0) continue;
+        const mfcc_stream *st = sts[i];
+        const int64_t len = static_cast<int64_t>(st->buf.size());
+        std::memcpy(stage + base[i], st->buf.data(), sizeof(int16_t) * len);
+        if (base[i + 1] > base[i] + len) std::memset(stage + base[i] + len, 0, sizeof(int16_t) * (base[i + 1] - base[i] - len));
+        const int lead = st->has_history ? 1 : 0;
+        for (int64_t f = 0; f < due[i]; f += mfcc::kTileFrames) {
+            Tile &tl = tiles[t++];
+            tl.utt_begin = base[i];
+            tl.utt_end = base[i] + len;
+            tl.first_sample = base[i] + lead + f * p.hop_len;
+            tl.out_row = row0[i] + f;
+            tl.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, due[i] - f));
+            tl.flags = mfcc::tile_flags(p, tl, total_samples);
+        }
+    }
+    std::memset(stage + base[n_streams], 0, sizeof(int16_t) * (total_samples - base[n_streams]));
     cudaStream_t s = plan->streams[0];
     mfcc_batch b;
     b.device = plan->device;
@@ -560,22 +599,29 @@ int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
     b.frame_len = p.frame_len;
     b.hop_len = p.hop_len;
     b.pad_mode = p.pad_mode;
-    b.total_samples = len;
-    b.total_frames = n_frames;
+    b.total_samples = total_samples;
+    b.total_frames = total_rows;
     b.d_tiles = static_cast<Tile *>(plan->d_tiles);
     b.tiles_borrowed = true;
-    bool ok = cudaMemcpyAsync(plan->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice, s) ==
-              cudaSuccess;
-    ok = ok && cudaMemcpyAsync(plan->h2d_pcm, st->buf.data(), sizeof(int16_t) * len, cudaMemcpyHostToDevice, s) ==
-                   cudaSuccess;
+    bool ok = cudaMemcpyAsync(plan->d_tiles, tiles, sizeof(Tile) * static_cast<size_t>(n_tiles), cudaMemcpyHostToDevice, s) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(plan->h2d_pcm, stage, sizeof(int16_t) * static_cast<size_t>(total_samples), cudaMemcpyHostToDevice, s) == cudaSuccess;
     ok = ok && compute_batch_impl<int16_t>(plan, &b, static_cast<const int16_t *>(plan->h2d_pcm),
-                                           static_cast<float *>(plan->d2h_out), 0,
-                                           static_cast<int64_t>(tiles.size()), s) == MFCC_OK;
-    ok = ok && cudaMemcpyAsync(out, plan->d2h_out, sizeof(float) * n_frames * od, cudaMemcpyDeviceToHost, s) ==
-                   cudaSuccess;
+                                           static_cast<float *>(plan->d2h_out), 0, n_tiles, s) == MFCC_OK;
+    ok = ok && cudaMemcpyAsync(plan->h_stage_out, plan->d2h_out, sizeof(float) * static_cast<size_t>(total_rows) * od,
+                               cudaMemcpyDeviceToHost, s) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
     if (!ok) { cudaGetLastError(); return MFCC_ECUDA; }
+    const float *res = static_cast<const float *>(plan->h_stage_out);
+    for (int64_t i = 0; i < n_streams; ++i)
+        if (due[i] > 0) std::memcpy(outs[i], res + row0[i] * od, sizeof(float) * static_cast<size_t>(due[i]) * od);
     return MFCC_OK;
+}
+
+int stream_run(mfcc_stream *st, int64_t n_frames, float *out)
+{
+    mfcc_stream *one[1] = {st};
+    float *outs[1] = {out};
+    return streams_run(st->plan, one, 1, &n_frames, outs);
 }
 
 // Drop what the emitted frames consumed: keep one history sample and everything from the next frame's start.
@@ -640,6 +686,44 @@ int mfcc_stream_feed(mfcc_stream *st, const int16_t *pcm, int64_t n, float *out,
     if (rc != MFCC_OK) return rc;
     stream_advance(st, due);
     if (n_frames) *n_frames = due;
+    return MFCC_OK;
+}
+
+int mfcc_stream_feed_many(mfcc_stream *const *streams, int64_t n_streams, const int16_t *const *pcm, const int64_t *n,
+                          float *const *out, const int64_t *max_frames, int64_t *n_frames)
+{
+    if (n_streams < 0 || (n_streams > 0 && (streams == nullptr || pcm == nullptr || n == nullptr || out == nullptr ||
+                                            max_frames == nullptr))) return MFCC_EINVAL;
+    if (n_streams == 0) return MFCC_OK;
+    // validate everything before touching any stream: the call either feeds all of them or none
+    std::vector<int64_t> due(n_streams);
+    for (int64_t i = 0; i < n_streams; ++i) {
+        mfcc_stream *st = streams[i];
+        if (st == nullptr || st->plan != streams[0]->plan || n[i] < 0 || (n[i] > 0 && pcm[i] == nullptr)) return MFCC_EINVAL;
+        for (int64_t k = 0; k < i && n_streams <= 64; ++k)
+            if (streams[k] == st) return MFCC_EINVAL;   // (a stream twice in one call; checked for small calls)
+        due[i] = stream_due(st, n[i], false);
+        if (due[i] > max_frames[i] || (due[i] > 0 && out[i] == nullptr)) return MFCC_EINVAL;
+    }
+    try {
+        for (int64_t i = 0; i < n_streams; ++i) {
+            mfcc_stream *st = streams[i];
+            const int64_t drop = std::min(st->skip, n[i]);
+            st->buf.insert(st->buf.end(), pcm[i] + drop, pcm[i] + n[i]);
+            st->skip -= drop;
+            st->fed += n[i];
+            if (n_frames) n_frames[i] = 0;
+        }
+    } catch (const std::bad_alloc &) {
+        return MFCC_ENOMEM;
+    }
+    const int rc = streams_run(streams[0]->plan, streams, n_streams, due.data(), out);
+    if (rc != MFCC_OK) return rc;
+    for (int64_t i = 0; i < n_streams; ++i) {
+        if (due[i] <= 0) continue;
+        stream_advance(streams[i], due[i]);
+        if (n_frames) n_frames[i] = due[i];
+    }
     return MFCC_OK;
 }
 

@@ -89,6 +89,8 @@ struct mfcc_plan {
     void *d2h_out = nullptr;   size_t d2h_out_bytes = 0;
     void *d_tiles = nullptr;   size_t d_tiles_bytes = 0;   // device tile table of the call in flight
     void *h_tiles = nullptr;   size_t h_tiles_bytes = 0;   // its pinned staging copy
+    void *h_stage_pcm = nullptr; size_t h_stage_pcm_bytes = 0;   // streaming: pinned staging of the packed stream buffers
+    void *h_stage_out = nullptr; size_t h_stage_out_bytes = 0;   // streaming: pinned landing area of the feature rows
     cudaEvent_t tiles_ready = nullptr;
     std::vector<cudaEvent_t> chunk_ready;   // one per H2D chunk of the call in flight (reused across calls)
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};   // compute_host: two H2D queues, two compute + D2H queues

@@ -546,6 +546,91 @@ def test_streaming_feed_is_bit_identical_to_offline():
             assert np.array_equal(tail, plan.compute(x[:10]))
 
 
+def test_feed_many_streams_in_one_launch():
+    """mfcc_stream_feed_many: S live streams, ragged chunk sizes, ONE launch per call; every stream's rows equal the
+    offline rows of its own audio, bit for bit, and equal feeding the streams one at a time."""
+    rng = np.random.default_rng(51)
+    for p in (config_b(), config_a().copy(pad_mode=PAD_ZERO_TAIL), config_c()):
+        plan = api.Plan(p)
+        S = 37
+        clips = [noise_utterance(int(rng.integers(p.frame_len // 2, 4 * p.sample_rate // 10)), seed=500 + i) for i in range(S)]
+        want = [plan.compute(c) for c in clips]
+        grp = api.StreamGroup(plan, S, max_frames_per_feed=64)
+        pos = [0] * S
+        got = [[] for _ in range(S)]
+        calls = 0
+        while any(pos[i] < clips[i].size for i in range(S)):
+            chunks = []
+            for i in range(S):
+                n = int(rng.choice([0, 1, p.hop_len - 1, p.hop_len, 2 * p.hop_len, p.frame_len + 3, 20 * p.hop_len]))
+                chunks.append(clips[i][pos[i]:pos[i] + n])
+                pos[i] += n
+            l0 = api.launch_count()
+            rows, counts = grp.feed(chunks)
+            assert api.launch_count() - l0 <= 1
+            calls += 1
+            for i in range(S):
+                got[i].append(rows[i, :counts[i]].copy())
+        for i in range(S):
+            tail = grp.streams[i].flush()
+            g = np.concatenate(got[i] + [tail])
+            assert g.shape == want[i].shape, (i, g.shape, want[i].shape)
+            assert np.array_equal(g, want[i])
+        # uniform chunks as one [S, n] array (the serving shape: 20 ms per stream per call)
+        n = 2 * p.hop_len
+        audio = np.stack([noise_utterance(10 * n + p.frame_len, seed=900 + i) for i in range(S)])
+        ref = [plan.compute(audio[i]) for i in range(S)]
+        acc = [[] for _ in range(S)]
+        for k in range(audio.shape[1] // n):
+            rows, counts = grp.feed(np.ascontiguousarray(audio[:, k * n:(k + 1) * n]))
+            for i in range(S):
+                acc[i].append(rows[i, :counts[i]].copy())
+        for i in range(S):
+            g = np.concatenate(acc[i])
+            assert np.array_equal(g, ref[i][:g.shape[0]]) and g.shape[0] >= ref[i].shape[0] - 3
+        # all-or-nothing: a capacity that is too small for one stream feeds none of them
+        grp2 = api.StreamGroup(plan, 2, max_frames_per_feed=1)
+        with pytest.raises(api.MfccError):
+            grp2.feed([clips[0][:p.hop_len], noise_utterance(p.frame_len + 5 * p.hop_len, seed=1)])
+        rows, counts = grp2.feed([clips[0][:p.frame_len], np.zeros(0, np.int16)])
+        assert counts.tolist() == [1, 0] and np.array_equal(rows[0, :1], plan.compute(clips[0][:p.frame_len]))
+
+
+def test_torch_custom_op_and_dlpack_entry():
+    """torch.ops.mfcc_b200.compute_batch: runs on the CURRENT stream (a side stream here), passes torch's op checks
+    (schema, fake tensor shape), traces through torch.compile as an opaque call, and takes DLPack capsules."""
+    import mfcc_b200.torch_ops as ops
+    p = config_a()
+    pcm, off = ragged_batch(64, 300, 30000, seed=71)
+    h = ops.Handle(p, off)
+    d = torch.from_numpy(pcm).cuda()
+    want = h.plan.compute_batch(h.batch, d)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        got = torch.ops.mfcc_b200.compute_batch(d, h.id)
+    side.synchronize()
+    assert torch.equal(got, want) and got.shape == h.shape
+    torch.library.opcheck(torch.ops.mfcc_b200.compute_batch.default, (d, h.id), test_utils=("test_schema", "test_faketensor"))
+
+    @torch.compile(fullgraph=True)
+    def front_end(x):
+        return torch.ops.mfcc_b200.compute_batch(x, h.id) * 2.0
+    assert torch.equal(front_end(d), want * 2.0)
+    # DLPack in (a capsule from another owner of the memory), DLPack out
+    cap = torch.utils.dlpack.to_dlpack(d.float())
+    class Foreign:          # an object that only speaks the protocol
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, stream=None): return self.t.__dlpack__(stream=stream)
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+    out = ops.mfcc_from_dlpack(Foreign(d.float()), h)
+    assert torch.equal(out, want)
+    back = torch.from_dlpack(out)
+    assert back.data_ptr() == out.data_ptr()
+    del cap
+    h.close()
+
+
 def test_c_caller_runs_the_device_path(tmp_path):
     """The plain C99 demo (tests/cabi/demo.c) through mfcc_compute on the GPU."""
     import shutil
