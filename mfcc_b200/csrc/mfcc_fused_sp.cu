@@ -63,6 +63,32 @@
 #ifndef MFCC_SP_ABLATE
 #define MFCC_SP_ABLATE 0
 #endif
+// Mutual exclusion of the groups of a CTA on a span of phases: 10 * from + to, the lock is taken before barrier B<from> and
+// released after barrier B<to> (B1 | S1 | B2 | S2 | B3 | S3 | B4): 12 = pass 1 exclusive, 23 = pass 2 exclusive, 0 = none.
+// Inside a phase the 8 warps of a group do the same thing at the same time (a burst of shared-memory loads, FP32, a burst
+// of stores); with the FFT pass of one group always running over the latency-bound phases of the others (S3, S0, tail) the
+// issue slots and the shared-memory port are shared better than when the groups drift freely.  Measured on one box
+// (tools/time_variants.py, profiles/r2_phase_lock.md), against no lock: 512-point S3 exclusive +2.5 % (S2 +1.7 %, S1 +1.4 %,
+// any two of them together less than either alone, S1 + S2 as one section -17 %); 256-point (three groups) S1 exclusive
+// +2.5 % (S2 -2.5 %, S3 -7 %, S0 -11 %).  The winners keep two latency-bound phases from coinciding (512-point: both
+// groups walking the filterbank leaves the SM idle) or the FP32-heaviest phase from tripling up (256-point).
+#ifndef MFCC_SP_LOCK_512
+#define MFCC_SP_LOCK_512 34
+#endif
+#ifndef MFCC_SP_LOCK_256
+#define MFCC_SP_LOCK_256 12
+#endif
+#ifndef MFCC_SP_LOCK_NS
+#define MFCC_SP_LOCK_NS 32
+#endif
+// S0 of bulk-copied int16 tiles, second form: the predecessor sample loaded with the chunk, the rare split-pad chunk on a
+// branch instead of four selects per chunk; MFCC_SP_I2F: int16 -> f32 on the conversion pipe (one I2F per sample).
+#ifndef MFCC_SP_S0V2
+#define MFCC_SP_S0V2 0
+#endif
+#ifndef MFCC_SP_I2F
+#define MFCC_SP_I2F 0
+#endif
 // Which PCM entries this translation unit instantiates (the file is compiled once per input type so that the three sets
 // of kernel variants build in parallel): bit 0 int16 (+ the host half), bit 1 f32, bit 2 G.711 codes.
 #ifndef MFCC_SP_PCM_TYPES
@@ -257,6 +283,31 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     constexpr int GROUPS = groups_for(RB_), kThreads = GROUPS * kHalfThreads;
     constexpr int HOP = G::HOP, RB = G::RB, RA = G::RA, STRIDE = G::STRIDE, H = G::H, NZ = G::NZ;
     extern __shared__ __align__(16) float smem[];
+    // (two words next to group 0's mbarrier, which uses 8 bytes of its 16-byte slot)
+    [[maybe_unused]] int *phase_lock = reinterpret_cast<int *>(smem + a.lay.total + Geo<L_, HOP_, RB_, RA_>::UNION + Geo<L_, HOP_, RB_, RA_>::WS + Geo<L_, HOP_, RB_, RA_>::RAW + 2);
+    // up to two independent locks, two digits each (from, to): the group is held at barrier B<from> until it owns the lock and
+    // gives it back after barrier B<to> (to < from: the span wraps around the tile loop, e.g. 41 = S0 exclusive)
+    constexpr int kLock = groups_for(RB_) > 1 ? (RB_ >= 32 ? MFCC_SP_LOCK_512 : MFCC_SP_LOCK_256) : 0;
+    constexpr int kLockFrom[2] = {(kLock % 100) / 10, kLock / 1000}, kLockTo[2] = {kLock % 10, (kLock / 100) % 10};
+    constexpr bool kLockOn[2] = {kLock % 100 != 0, kLock / 100 != 0};
+    if (kLock != 0 && threadIdx.x < 2) phase_lock[threadIdx.x] = 0;
+    bool held[2] = {false, false};
+    [[maybe_unused]] auto lock_at = [&](int point) {      // before barrier B<point> (0: before S0)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (kLockOn[i] && point == kLockFrom[i] && threadIdx.x % kHalfThreads == 0) {
+                while (atomicCAS(&phase_lock[i], 0, 1) != 0) __nanosleep(MFCC_SP_LOCK_NS);
+                held[i] = true;
+            }
+    };
+    [[maybe_unused]] auto unlock_at = [&](int point) {    // after barrier B<point>
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (kLockOn[i] && point == kLockTo[i] && held[i]) {
+                atomicExch(&phase_lock[i], 0);
+                held[i] = false;
+            }
+    };
     const int half = threadIdx.x >> 8, tid = threadIdx.x & (kHalfThreads - 1);
     const int lane = tid & 31, warp = tid >> 5;
 
@@ -471,6 +522,79 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             if (tile.first_sample == tile.utt_begin) {
                 if (tid == 0) staged[e] = g711_to_f32(raw8[sh], alaw);   // the utterance's first sample has no predecessor: y = x
             }
+#if MFCC_SP_S0V2
+        } else if (fast) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            const int nchunks = (MFCC_SP_ABLATE & 1) ? 0 : G::tceil_s(n_frames, sh) >> 3;
+            const float na = -a.preemph;
+            // chunk c = 8 samples; the thread takes chunks tid, tid + kStage, ...: all loads first, then the arithmetic
+            constexpr int NU = (G::TCEIL / 8 + kStage - 1) / kStage;
+            uint4 q[NU];
+            uint32_t pvs[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int c = tid + u * kStage;
+                if (c < nchunks) {
+                    q[u] = *reinterpret_cast<const uint4 *>(raw16 + 8 + 8 * c);
+                    pvs[u] = static_cast<uint16_t>(raw16[7 + 9 * d + 8 * c]);   // d = 0: the sample before the chunk; d = 1: the sample after it
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int c = tid + u * kStage;
+                if (c < nchunks) {
+                    uint32_t pv = pvs[u];
+                    uint32_t w0 = q[u].x, w1 = q[u].y, w2 = q[u].z, w3 = q[u].w;
+                    if (d) {   // odd shift (uniform): move the chunk down one half-word; its old first sample becomes the predecessor
+                        const uint32_t first = w0;
+                        w0 = __byte_perm(w0, w1, 0x5432);
+                        w1 = __byte_perm(w1, w2, 0x5432);
+                        w2 = __byte_perm(w2, w3, 0x5432);
+                        w3 = __byte_perm(w3, pv, 0x5432);
+                        pv = first;
+                    }
+#if MFCC_SP_I2F
+                    // conversion pipe: one I2F per sample (16 lanes/clk, otherwise idle) instead of XOR/2 + PRMT + FADD
+                    const float2 x01 = make_float2(static_cast<float>(static_cast<int16_t>(w0)), static_cast<float>(static_cast<int32_t>(w0) >> 16));
+                    const float2 x23 = make_float2(static_cast<float>(static_cast<int16_t>(w1)), static_cast<float>(static_cast<int32_t>(w1) >> 16));
+                    const float2 x45 = make_float2(static_cast<float>(static_cast<int16_t>(w2)), static_cast<float>(static_cast<int32_t>(w2) >> 16));
+                    const float2 x67 = make_float2(static_cast<float>(static_cast<int16_t>(w3)), static_cast<float>(static_cast<int32_t>(w3) >> 16));
+                    const float xe = static_cast<float>(static_cast<int16_t>(pv));
+#else
+                    const float2 x01 = s16x2_to_f32(w0), x23 = s16x2_to_f32(w1);
+                    const float2 x45 = s16x2_to_f32(w2), x67 = s16x2_to_f32(w3);
+                    const float xe = s16x2_to_f32(pv).x;
+#endif
+                    const float2 y0 = make_float2(fmaf(na, xe, x01.x), fmaf(na, x01.x, x01.y));
+                    const float2 y2 = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
+                    const float2 y4 = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
+                    const float2 y6 = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                    // hop-block padding: block k = [e + k HOP, e + (k + 1) HOP).  Chunk c = (HOP / 8) k + m lies in
+                    // block k, except the words below e of the chunks with m = 0, which still belong to block k - 1:
+                    // one chunk in HOP / 8, and only when the tile is shifted (e != 0) — a branch, not four selects
+                    const int k = c / (HOP / 8);
+                    float *dst = staged + 8 * c + kPad * k;
+                    if (e != 0 && c == k * (HOP / 8) && k > 0) {
+                        float *dl = dst - kPad;
+                        *reinterpret_cast<float2 *>(0 < e ? dl : dst) = y0;
+                        *reinterpret_cast<float2 *>((2 < e ? dl : dst) + 2) = y2;
+                        *reinterpret_cast<float2 *>((4 < e ? dl : dst) + 4) = y4;
+                        *reinterpret_cast<float2 *>(dst + 6) = y6;
+                    } else {
+                        *reinterpret_cast<float2 *>(dst) = y0;
+                        *reinterpret_cast<float2 *>(dst + 2) = y2;
+                        *reinterpret_cast<float2 *>(dst + 4) = y4;
+                        *reinterpret_cast<float2 *>(dst + 6) = y6;
+                    }
+                }
+            }
+            // the utterance's first sample has no predecessor: y = x.  It is word e of chunk 0 (thread 0 wrote it
+            // just above), sample raw16[8 + sh].  A branch, not a predicate: one tile in 32 starts an utterance.
+            if (tile.first_sample == tile.utt_begin) {
+                if (tid == 0) staged[e] = static_cast<float>(raw16[8 + sh]);
+            }
+#else
         } else if (fast) {
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -523,6 +647,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             if (tile.first_sample == tile.utt_begin) {
                 if (tid == 0) staged[e] = static_cast<float>(raw16[8 + sh]);
             }
+#endif
         } else if (vec) {
             if constexpr (sizeof(PcmT) == 4) {
                 const float *x = reinterpret_cast<const float *>(pcm) + (tile.first_sample - sh);   // x[i] = sample o + i
@@ -566,7 +691,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
             }
         }
         cp_async_wait_all();
+        lock_at(1);
         half_sync(half);   // B1: staged complete; raw buffer and (previous tile's) scratch free; next descriptor visible
+        unlock_at(1);
         if constexpr (MFCC_POISON) {   // the raw buffer is dead until the next bulk copy lands; so is the tail scratch
             poison(mine + G::UNION + G::WS, G::RAW);
             poison(scr, G::WS);
@@ -622,7 +749,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 }
             }
         }
+        lock_at(2);
         half_sync(half);   // B2
+        unlock_at(2);
         if constexpr (MFCC_POISON) {   // the staged samples are dead: pass 2 writes P over them (slack rows stay zero)
             poison(staged, G::UNION);
             half_sync(half);
@@ -692,7 +821,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 }
             }
         }
+        lock_at(3);
         half_sync(half);   // B3: P complete, workspace free
+        unlock_at(3);
         if constexpr (MFCC_POISON) {   // the workspace is dead: S3 writes every segment's two sums into it
             poison(scr, G::WS);
             half_sync(half);
@@ -803,7 +934,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 fall[j * 32] = fmaf(a.inv_n, S, -r);
             }
         }
+        lock_at(4);
         half_sync(half);   // B4a: every segment's two sums are in the scratch
+        unlock_at(4);
         if constexpr (MFCC_POISON) {   // P is dead: the next S0 stages over it
             poison(pw, G::NB * 32);
             half_sync(half);
@@ -885,6 +1018,9 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         // no barrier here: the next S0 writes `staged`, which nobody reads any more; the scratch is
         // next written by S1, after B1.
     }
+    // a lock whose span wraps around the loop is still held after the last tile
+    for (int i = 0; i < 2; ++i)
+        if (held[i]) atomicExch(&phase_lock[i], 0);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -7,16 +7,19 @@
 // butterfly needs are then uniform per quarter-warp instead of per warp (shared-memory loads with 4
 // distinct addresses), every array is [...][8 frames], and the layouts are padded so that the four
 // quarter-warps of a load or store fall into different banks:
-//   staged  lane stride HOP + 4 words (= 4 mod 32): 8 frames x 2 column pairs x 8 bytes per half-warp
+//   staged  lane stride HOP + 4 words (= 4 mod 32): 8 frames x 4 consecutive columns = 32 distinct banks per scalar load
 //   ws      [row k1 - 1][column, bit 0 flipped when bit 1 is set][8] float2, rows padded by 16 words
 //   P       [bin][8]: four consecutive bins per warp store
-// One CTA per SM = two independent halves of 4 warps (named barriers), 16 work slots each:
-//   S0 stage     PCM -> f32 -> pre-emphasis -> staged (each sample read from HBM once per tile)
-//   S1 pass 1    16 slots = the 16 column pairs: windowed REAL DFT-64 over b (38 live rows), twiddle
-//   S2 pass 2    32 rows k1 = 1 .. 32 through a complex DFT-32, two rounds of 16 slots; row 0 (real)
-//                through a real DFT-32 by slot 0; |X|^2 -> P
-//   S3 tail      16 filter groups (one per slot): S/T sums per segment -> log -> partial DCT (40 cepstra)
-//   S4           add the 16 partial cepstra per frame, store
+// One CTA per SM = two independent halves of 8 warps (named barriers, 128 registers, 16 resident warps), 32 work
+// slots each (slot = warp * 4 + sub):
+//   S0 stage     PCM -> f32 -> pre-emphasis -> staged (each sample read from HBM once per tile; the next unit's PCM
+//                arrives by bulk async copy into the idle part of the workspace)
+//   S1 pass 1    slot = column a: windowed REAL DFT-64 over b (38 live rows), inter-pass twiddle
+//   S2 pass 2    slot = row k1 - 1, k1 = 1 .. 32: complex DFT-32 over a; row 0 (real) through a real DFT-32 by
+//                slot 0; |X|^2 -> P
+//   S3           slot s walks mel segments s, s + 32, s + 64: S / T sums per segment -> rise / fall halves
+//   S3b          band = rise + fall of the neighbouring segments -> log (and the frame energy term)
+//   S4           thread (slot, frame) forms cepstra slot and slot + 32 from the mirrored band pairs; store
 // N = RB * RA = 64 * 32, n = a + 32 b, k = k1 + 64 k2 (mfcc_rfft.cuh; tests/codelets checks the data flow).
 //
 // No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
@@ -36,6 +39,13 @@
 #include "mfcc_rfft.cuh"
 #include "mfcc_host.h"
 
+// Mutual exclusion of the two halves of a CTA on a span of phases (see MFCC_SP_LOCK_* in mfcc_fused_sp.cu): 10 * from + to,
+// the half is held at barrier B<from> (1 = B1, 2 = B2, 3 = B3, 4 = B4a, 5 = B4) until it owns the lock and gives it back
+// after barrier B<to>; 0 = none.  Measured with 16 warps (one box, tools/time_variants.py): pass 1 exclusive (12) +6.3 %,
+// pass 2 exclusive (23) +4.6 %, S3 (34) +3.0 %, S4 + S0 (51) +3.5 %.
+#ifndef MFCC_WIDE_LOCK
+#define MFCC_WIDE_LOCK 12
+#endif
 // Poison build (see mfcc_fused_sp.cu): NaN-fill every aliased buffer at the point where the comments say it is dead.
 #ifndef MFCC_POISON
 #define MFCC_POISON 0
@@ -47,12 +57,16 @@ namespace {
 
 constexpr int F = 8;                      // frames per tile
 constexpr int SUBS = 32 / F;              // work items per warp
-constexpr int kWarps = 4;                 // per half
-constexpr int kSlots = kWarps * SUBS;     // 16
+// 8 warps per half = 32 slots: a slot carries ONE column in pass 1 and ONE row in pass 2, so the codelets fit 128 registers
+// (the 64-point real and the 32-point complex transform compile to 72 and 128 registers on their own) and the SM holds 16
+// warps.  Round 1 had 4 warps per half, a column PAIR and two rows per slot: 255 registers, 8 resident warps, issue 53 % —
+// 275.6 M against 310.1 M frames/s on the same box (profiles/r2_wide_16warps.md).
+constexpr int kWarps = 8;                 // per half
+constexpr int kSlots = kWarps * SUBS;     // 32
 constexpr int kHalfThreads = kWarps * 32;
 constexpr int kThreads = 2 * kHalfThreads;
 constexpr int kPad = 4;
-constexpr int KC = 40;                    // cepstra per frame (n_cep <= KC): thread (slot, frame) forms k = slot, slot + 16, slot + 32
+constexpr int KC = 64;                    // cepstra per frame (n_cep <= KC): thread (slot, frame) forms k = slot and k = slot + 32
 constexpr size_t kSmemMax = 227 * 1024;
 
 template <int L_, int HOP_>
@@ -60,7 +74,7 @@ struct Geo {
     static constexpr int L = L_, HOP = HOP_, RB = 64, RA = 32;
     static constexpr int NFFT = RB * RA, NB = NFFT / 2 + 1, H = RB / 2;
     static constexpr int NZ = (L + RA - 1) / RA;
-    static constexpr int NZP = (NZ + 1) / 2 * 2;
+    static constexpr int NZP = (NZ + 3) / 4 * 4;            // window rows per column, padded for 16-byte loads
     static constexpr int STRIDE = HOP + kPad;
     static constexpr int padded(int i) { return i + kPad * (i / HOP); }
     static constexpr int SLACK = RA * NZ - L;
@@ -76,14 +90,14 @@ struct Geo {
     static constexpr int RAWOFF = 8192;                     // raw PCM of the NEXT unit lands in the workspace past the tail scratch
     static constexpr int RAW = (TCEIL + 16) / 2;            // floats holding 8 lead + TCEIL + 1 look-ahead int16 samples
     static constexpr int HALF = UNION + WS + R0 + 4;        // + mbarrier (8 B in a 16-B slot)
-    static constexpr int T_WIN = 0;                         // [RA/2][NZP] float2
-    static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;   // [RA][H] float2: W_N^(a k1), k1 = 1 .. H at slot k1 - 1
+    static constexpr int T_WIN = 0;                         // [RA][NZP] float: the window values of column a, row b
+    static constexpr int T_TW = T_WIN + RA * NZP;           // [RA][H] float2: W_N^(a k1), k1 = 1 .. H at slot k1 - 1
     static constexpr int TABF = T_TW + RA * H * 2;
     static constexpr int pcol(int c) { return c ^ ((c >> 1) & 1); }
     static_assert(STRIDE % 32 == 4, "quarter-warp bank separation of the staged tile");
     static_assert(HOP % 8 == 0 && HOP % RA == 0, "chunks and column pairs must not straddle a hop block");
-    static_assert(RA / 2 == kSlots, "one column pair per slot");
-    static_assert(H == 2 * kSlots, "two rounds of complex rows");
+    static_assert(RA == kSlots, "one column per slot");
+    static_assert(H == kSlots, "one complex row per slot");
     static_assert(L <= NFFT && NZ <= RB, "frame does not fit the transform");
     static_assert(TABF % 4 == 0 && UNION % 4 == 0 && WS % 4 == 0, "16-byte aligned regions");
     static_assert(129 * F <= RAWOFF && RAWOFF + RAW <= WS && RAWOFF % 4 == 0,
@@ -93,8 +107,8 @@ struct Geo {
 
 struct WideLayout {
     int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), s * w}
-    int dct;      // [16 slots][hmp / 2] float4 {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}, then [16][hmp / 2] float2
-                  // {d[s+32][m], d[s+32][m+1]}; m < hmp = ceil(n_mel / 2) rounded up to even; zero past n_cep
+    int dct;      // [32 slots][hmp] d[s][m], then [n2 slots][hmp] d[s + 32][m]; m < hmp = ceil(n_mel / 2) rounded up to
+                  // even (the mirrored half follows from the symmetry); zero past n_cep
     int total;
 };
 
@@ -108,6 +122,7 @@ struct WideArgs {
     int energy, od;       // MFCC_ENERGY_*; floats per output row
     int nseg;             // segments walked: n_mel + 1, + the two pseudo-segments outside the filterbank when the energy term is on
     int ls, mel_magic, hmp;
+    int n2;               // slots that form a second cepstrum (k = slot + 32): n_cep - 32 rounded up to a multiple of 4, or 0
     int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 3][F] x 2
     int ef;               // scratch offset of the log frame energy [F]
     float preemph, log_floor;
@@ -192,6 +207,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
     const int16_t *raw16 = reinterpret_cast<const int16_t *>(ws + G::RAWOFF);
     const uint32_t raw_s = smem_u32(raw16), bar = smem_u32(r0row + G::R0);
     if (tid == 0) mbar_init(bar, 1);
+    constexpr int kLockFrom = MFCC_WIDE_LOCK / 10, kLockTo = MFCC_WIDE_LOCK % 10;
+    // (one word next to half 0's mbarrier, which uses 8 bytes of its 16-byte slot)
+    [[maybe_unused]] int *phase_lock = reinterpret_cast<int *>(smem + a.lay.total + G::UNION + G::WS + G::R0 + 2);
+    if (MFCC_WIDE_LOCK != 0 && threadIdx.x == 0) *phase_lock = 0;
+    bool held = false;
+    [[maybe_unused]] auto lock_at = [&](int point) {
+        if (MFCC_WIDE_LOCK != 0 && point == kLockFrom && tid == 0) {
+            while (atomicCAS(phase_lock, 0, 1) != 0) __nanosleep(32);
+            held = true;
+        }
+    };
+    [[maybe_unused]] auto unlock_at = [&](int point) {
+        if (MFCC_WIDE_LOCK != 0 && point == kLockTo && held) {
+            atomicExch(phase_lock, 0);
+            held = false;
+        }
+    };
     [[maybe_unused]] auto poison = [&](float *p, int n) {
         for (int i = tid; i < n; i += kHalfThreads) p[i] = __int_as_float(0x7fc00000);
     };
@@ -357,34 +389,35 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 }
             }
         }
+        lock_at(1);
         half_sync(half);   // B1: staged complete; previous tile's scratch free
+        unlock_at(1);
         if constexpr (MFCC_POISON) {   // the raw PCM has been consumed and the tail scratch is dead: pass 1 rewrites the workspace
             poison(ws, G::WS + G::R0);
             half_sync(half);
         }
 
-        // ---- S1: pass 1.  Slot = column pair (a, a + 1): windowed real DFT-64 over b, inter-pass twiddle ----
+        // ---- S1: pass 1.  Slot = column a: windowed real DFT-64 over b, inter-pass twiddle ----
         {
-            const int pr = slot;
-            const float *base = staged + e + f * STRIDE + 2 * pr;
-            const float *wrow = t_win + pr * (2 * G::NZP);
-            float2 in[NZ];
-#pragma unroll
-            for (int b = 0; b < NZ; b += 2) {
-                const float4 w = lds_f4(wrow + 2 * b);
-                const float2 y0 = lds_f2(base + G::padded(RA * b));
-                in[b] = make_float2(y0.x * w.x, y0.y * w.y);
-                if (b + 1 < NZ) {
-                    const float2 y1 = lds_f2(base + G::padded(RA * (b + 1)));
-                    in[b + 1] = make_float2(y1.x * w.z, y1.y * w.w);
-                }
-            }
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-                const int col = 2 * pr + hh;
+            {
+                // 38 scalar loads (lane stride 4 words + the slot: 32 distinct banks), window from the
+                // column's own row of the table (four rows per 16-byte load)
+                const int col = slot;
+                const float *base = staged + e + f * STRIDE + col;
+                const float *wrow = t_win + col * G::NZP;
                 float x[RB];
 #pragma unroll
-                for (int b = 0; b < RB; ++b) x[b] = b < NZ ? (hh ? in[b < NZ ? b : 0].y : in[b < NZ ? b : 0].x) : 0.0f;
+                for (int b = 0; b < RB; b += 4) {
+                    if (b < NZ) {
+                        const float4 w = lds_f4(wrow + b);
+                        x[b] = base[G::padded(RA * b)] * w.x;
+                        x[b + 1] = b + 1 < NZ ? base[G::padded(RA * (b + 1))] * w.y : 0.0f;
+                        x[b + 2] = b + 2 < NZ ? base[G::padded(RA * (b + 2))] * w.z : 0.0f;
+                        x[b + 3] = b + 3 < NZ ? base[G::padded(RA * (b + 3))] * w.w : 0.0f;
+                    } else {
+                        x[b] = x[b + 1] = x[b + 2] = x[b + 3] = 0.0f;
+                    }
+                }
                 rf::cplx X[H + 1];
                 rf::rdft64<NZ>(x, X);
                 r0row[col * F + f] = X[0].re;
@@ -400,7 +433,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 }
             }
         }
+        lock_at(2);
         half_sync(half);   // B2
+        unlock_at(2);
         if constexpr (MFCC_POISON) {   // the staged samples are dead: pass 2 writes P over them (slack rows stay zero)
             poison(staged, G::UNION);
             half_sync(half);
@@ -411,8 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         // ---- S2: pass 2.  Item = row k1 = 1 .. 32: complex DFT-32 over a gives bins k1 + 64 k2; power ----
         {
 #pragma unroll 1
-            for (int round = 0; round < 2; ++round) {
-                const int k1 = round * kSlots + slot + 1;
+            {
+                const int k1 = slot + 1;
                 const float *row = ws + (k1 - 1) * G::WSROW + f * 2;
                 rf::cplx z[RA];
 #pragma unroll
@@ -443,7 +478,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 for (int k2 = 1; k2 < RA / 2; ++k2) pw[RB * k2 * F + f] = pwr(X0[k2]);
             }
         }
+        lock_at(3);
         half_sync(half);   // B3: P complete, workspace free
+        unlock_at(3);
         if constexpr (MFCC_POISON) {   // both the tail scratch and the raw buffer of the next unit start from dead memory
             poison(ws, G::WS + G::R0);
             half_sync(half);
@@ -490,7 +527,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 fall[j * F] = fmaf(sg.w, S, -r);
             }
         }
+        lock_at(4);
         half_sync(half);   // B4a: every segment's two sums are in the scratch
+        unlock_at(4);
         if constexpr (MFCC_POISON) {   // P is dead: the next S0 stages over it
             poison(pw, G::NB * F);
             half_sync(half);
@@ -518,7 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 else scr[a.ef + fr] = le;
             }
         }
+        lock_at(5);
         half_sync(half);   // B4: every band's log energy is in the scratch
+        unlock_at(5);
 
         // ---- S4: log-mel rows are copied out coalesced.  Cepstra: thread (slot, frame) forms c[slot], c[slot + 16]
         // and c[slot + 32] — all of one parity, so the DCT symmetry d[k][M-1-m] = (-1)^k d[k][m] folds the band
@@ -532,25 +573,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         } else if (slot < a.n_cep) {
             const float sgn = (slot & 1) ? -1.0f : 1.0f;
-            const bool third = slot + 2 * kSlots < a.n_cep;  // uniform per warp (slots 4 w .. 4 w + 3)
-            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+            const bool second = slot < a.n2;               // this thread also forms c[slot + 32] (uniform per warp when n2 is a multiple of 4)
+            float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
             auto dct_terms = [&](int hq, const float *lg, const float *lgm) {
-                const float4 *da = reinterpret_cast<const float4 *>(t_dct) + slot * hq;                     // {d[s][m], d[s+16][m], d[s][m+1], d[s+16][m+1]}
-                const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * hq * 4) + slot * hq;   // {d[s+32][m], d[s+32][m+1]}, s < 8
+                const float2 *da = reinterpret_cast<const float2 *>(t_dct) + slot * hq;                    // {d[s][m], d[s][m+1]}
+                const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * hq * 2) + slot * hq;  // {d[s+32][m], d[s+32][m+1]}, s < n2
 #pragma unroll 4
                 for (int q2 = 0; q2 < hq; ++q2) {
                     const int m = 2 * q2;
                     const float v0 = fmaf(sgn, lgm[-m * F], lg[m * F]);
                     const float v1 = fmaf(sgn, lgm[-(m + 1) * F], lg[(m + 1) * F]);
-                    const float4 d = da[q2];
+                    const float2 d = da[q2];
                     c0 = fmaf(d.x, v0, c0);
-                    c1 = fmaf(d.y, v0, c1);
-                    e0 = fmaf(d.z, v1, e0);
-                    e1 = fmaf(d.w, v1, e1);
-                    if (third) {
+                    e0 = fmaf(d.y, v1, e0);
+                    if (second) {
                         const float2 g = db[q2];
-                        c2 = fmaf(g.x, v0, c2);
-                        e2 = fmaf(g.y, v1, e2);
+                        c1 = fmaf(g.x, v0, c1);
+                        e1 = fmaf(g.y, v1, e1);
                     }
                 }
             };
@@ -560,7 +599,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 float *o = a.out + (tile.out_row + f) * a.od + slot;
                 o[0] = c0 + e0;
                 if (slot + kSlots < a.n_cep) o[kSlots] = c1 + e1;
-                if (third) o[2 * kSlots] = c2 + e2;
             }
         }
         if (!a.logmel && a.energy != MFCC_ENERGY_NONE && slot == 0 && f < n_frames) {
@@ -570,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         }
         // next S0 writes `staged` (nobody reads P any more); the scratch is next written by S1, after B1
     }
+    if (held) atomicExch(phase_lock, 0);   // a span that wraps around the loop is still held after the last unit
 }
 
 // ---------------------------------------------------------------------------------------
@@ -587,7 +626,8 @@ struct WideState {
 
 size_t table_floats(const mfcc_params &p)
 {
-    return G0::TABF + 2 * kSlots + 4 * static_cast<size_t>(p.n_mel + 3) + 3 * static_cast<size_t>(kSlots) * ((p.n_mel + 1) / 2 + 1) + 16;
+    const size_t second = p.output == MFCC_OUT_CEPSTRA && p.n_cep > kSlots ? static_cast<size_t>((p.n_cep - kSlots + 3) / 4 * 4) : 0;
+    return G0::TABF + 2 * kSlots + 4 * static_cast<size_t>(p.n_mel + 3) + (kSlots + second) * ((p.n_mel + 1) / 2 + 1) + 16;
 }
 
 }  // namespace
@@ -616,12 +656,11 @@ int wide_prepare(mfcc_plan *plan)
     std::vector<float> tab;
     auto align4 = [&]() { while (tab.size() % 4) tab.push_back(0.0f); };
     auto push_int = [&](int v) { float fl; std::memcpy(&fl, &v, 4); tab.push_back(fl); };
-    for (int pr = 0; pr < RA / 2; ++pr)
-        for (int b = 0; b < NZP; ++b)
-            for (int e = 0; e < 2; ++e) {
-                const int i = 2 * pr + e + RA * b;
-                tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
-            }
+    for (int col = 0; col < RA; ++col)
+        for (int b = 0; b < NZP; ++b) {
+            const int i = col + RA * b;
+            tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
+        }
     for (int col = 0; col < RA; ++col)
         for (int sl = 0; sl < H; ++sl) {
             const double ang = -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N;
@@ -659,18 +698,11 @@ int wide_prepare(mfcc_plan *plan)
         return (M % 2 == 1 && m == half_mel - 1) ? 0.5f * v : v;
     };
     lay.dct = static_cast<int>(tab.size());
+    const int n2 = p.output == MFCC_OUT_CEPSTRA && p.n_cep > kSlots ? (p.n_cep - kSlots + 3) / 4 * 4 : 0;
     for (int sl = 0; sl < kSlots; ++sl)
-        for (int m = 0; m < hmp; m += 2) {
-            tab.push_back(dct_at(sl, m));
-            tab.push_back(dct_at(sl + kSlots, m));
-            tab.push_back(dct_at(sl, m + 1));
-            tab.push_back(dct_at(sl + kSlots, m + 1));
-        }
-    for (int sl = 0; sl < kSlots; ++sl)
-        for (int m = 0; m < hmp; m += 2) {
-            tab.push_back(dct_at(sl + 2 * kSlots, m));
-            tab.push_back(dct_at(sl + 2 * kSlots, m + 1));
-        }
+        for (int m = 0; m < hmp; ++m) tab.push_back(dct_at(sl, m));
+    for (int sl = 0; sl < n2; ++sl)
+        for (int m = 0; m < hmp; ++m) tab.push_back(dct_at(sl + kSlots, m));
     align4();
     lay.total = static_cast<int>(tab.size());
 
@@ -688,6 +720,7 @@ int wide_prepare(mfcc_plan *plan)
     st->args.ls = h.out_dim | 1;
     st->args.mel_magic = (1 << 20) / h.out_dim + 1;
     st->args.hmp = hmp;
+    st->args.n2 = n2;
     st->args.rf = (F * std::max(h.out_dim | 1, M) + 3) / 4 * 4;
     st->args.ef = st->args.rf + 2 * F * (M + 3);
     st->args.preemph = p.preemph;
