@@ -106,7 +106,7 @@ struct Geo {
 };
 
 struct WideLayout {
-    int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), s * w}
+    int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), unused}
     int dct;      // [32 slots][hmp] d[s][m], then [n2 slots][hmp] d[s + 32][m]; m < hmp = ceil(n_mel / 2) rounded up to
                   // even (the mirrored half follows from the symmetry); zero past n_cep
     int total;
@@ -121,6 +121,7 @@ struct WideArgs {
     int n_mel, n_cep, logmel;
     int energy, od;       // MFCC_ENERGY_*; floats per output row
     int nseg;             // segments walked: n_mel + 1, + the two pseudo-segments outside the filterbank when the energy term is on
+    float inv_n;          // 1 / NFFT
     int ls, mel_magic, hmp;
     int n2;               // slots that form a second cepstrum (k = slot + 32): n_cep - 32 rounded up to a multiple of 4, or 0
     int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 3][F] x 2
@@ -493,10 +494,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         }
 
         // ---- S3: filterbank sums (see mfcc_fused_sp.cu S3): per segment S = sum P, T = sum i P give the rise into
-        // filter j, s T, and the fall out of filter j - 1, s (w S - T).  Slot s takes segments s, s + 16, s + 32, ...:
+        // filter j, s T, and the fall out of filter j - 1, s (w S - T).  Slot s takes segments s, s + 32, s + 64:
         // the four slots of a warp then walk NEIGHBOURING segments of nearly equal width in every round, so their
         // loop counts agree (with a contiguous filter group per slot the warp ran the longest of four different
-        // walks).  rise[j][frame] and fall[j][frame] go through the scratch; S3b adds the two halves of each band. ----
+        // walks).  rise[j][frame] and fall[j][frame] go through the scratch; S3b adds the two halves of each band.
+        // Measured and dropped in round 2 (profiles/r2_wide_16warps.md): segments dealt out by width in a snake over the
+        // slots (equal bin totals per slot: -0.6 %, more index arithmetic than the balance gains) and a warp-cooperative walk
+        // (lane = sub * 8 + frame takes every fourth bin, two shuffles add the partial sums: -19 %, ten segments per warp
+        // one after the other, each paying the descriptor-load and shuffle latencies, instead of four in flight). ----
         {
             float *rise = scr + a.rf + f, *fall = rise + (a.n_mel + 3) * F;
 #pragma unroll 1
@@ -504,9 +509,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 const float4 sg = t_seg[j];
                 const float *p = pw + __float_as_int(sg.x) + f;
                 const int w = __float_as_int(sg.y);
-                float S = 0.0f, T = 0.0f, i0 = 0.0f;
+                float S = 0.0f, T = 0.0f, U = 0.0f, i0 = 0.0f;
+                int c = w >> 2;
 #pragma unroll 1
-                for (int c = w >> 2; c > 0; --c) {
+                for (; c >= 2; c -= 2) {                    // 8 bins per step: all loads first, two independent chains
+                    const float a0 = p[0], a1 = p[F], a2 = p[2 * F], a3 = p[3 * F];
+                    const float b0 = p[4 * F], b1 = p[5 * F], b2 = p[6 * F], b3 = p[7 * F];
+                    const float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
+                    T = fmaf(i0, sa, T) + fmaf(3.0f, a3, fmaf(2.0f, a2, a1));
+                    U = fmaf(i0 + 4.0f, sb, U) + fmaf(3.0f, b3, fmaf(2.0f, b2, b1));
+                    S += sa + sb;
+                    i0 += 8.0f;
+                    p += 8 * F;
+                }
+                if (c) {
                     const float a0 = p[0], a1 = p[F], a2 = p[2 * F], a3 = p[3 * F];
                     const float sa = (a0 + a1) + (a2 + a3);
                     T = fmaf(i0, sa, T) + fmaf(3.0f, a3, fmaf(2.0f, a2, a1));
@@ -514,6 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     i0 += 4.0f;
                     p += 4 * F;
                 }
+                T += U;
                 if (const int lo = w & 3) {                 // 1..3 leftover bins, no loop: the rows past the segment are
                     const float a0 = p[0];                  // finite (next segment or the zeroed slack rows) and deselected
                     const float a1 = lo > 1 ? p[F] : 0.0f;
@@ -522,9 +539,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     T = fmaf(i0, sa, T) + fmaf(2.0f, a2, a1);
                     S += sa;
                 }
-                const float r = sg.z * T;
-                rise[j * F] = r;
-                fall[j * F] = fmaf(sg.w, S, -r);
+                const float rs = sg.z * T;                  // s = 1 / (w NFFT); pseudo-segments (energy term): s = 0
+                rise[j * F] = rs;
+                fall[j * F] = fmaf(a.inv_n, S, -rs);
             }
         }
         lock_at(4);
@@ -534,23 +551,43 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             poison(pw, G::NB * F);
             half_sync(half);
         }
-        // ---- S3b: band m = rise of segment m + fall of segment m + 1; log -> lg[m][frame] or the frame's log-mel row ----
+        // ---- S3b: band m = rise of segment m + fall of segment m + 1, log.  Log-mel output: the frame's row, staged for a
+        // coalesced copy.  Cepstra: the DCT symmetry d[k][M-1-m] = (-1)^k d[k][m] is applied HERE, once per frame: thread
+        // (q, frame) forms both logs of the mirrored pair and stores vp[q] = lg[q] + lg[M-1-q] (even cepstra) and
+        // vm[q] = lg[q] - lg[M-1-q] (odd cepstra); S4 then needs one load per term instead of re-folding the pair in
+        // every one of its 32 slots. ----
         {
             const float *rise = scr + a.rf, *fall = rise + (a.n_mel + 3) * F;
-            const int total = a.n_mel * F;
-            for (int i = tid; i < total; i += kHalfThreads) {
-                const int m = i / F, fr = i % F;
-                const float lg = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + F], a.log_floor));
-                if (a.logmel) scr[fr * a.ls + m] = lg;
-                else scr[i] = lg;
+            if (a.logmel) {
+                const int total = a.n_mel * F;
+                for (int i = tid; i < total; i += kHalfThreads) {
+                    const int m = i / F, fr = i % F;
+                    scr[fr * a.ls + m] = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + F], a.log_floor));
+                }
+            } else {
+                const int hm = (a.n_mel + 1) >> 1, total = a.hmp * F;     // hmp = hm rounded up to even: the pad row is zeroed
+                float *vp = scr, *vm = scr + a.hmp * F;
+                for (int i = tid; i < total; i += kHalfThreads) {
+                    const int q = i / F;
+                    float sum = 0.0f, dif = 0.0f;
+                    if (q < hm) {
+                        const int im = (a.n_mel - 1 - q) * F + (i % F);
+                        const float la = kLn2 * lg2_fast(fmaxf(rise[i] + fall[i + F], a.log_floor));
+                        const float lb = kLn2 * lg2_fast(fmaxf(rise[im] + fall[im + F], a.log_floor));
+                        sum = la + lb;
+                        dif = la - lb;
+                    }
+                    vp[i] = sum;
+                    vm[i] = dif;
+                }
             }
             // frame energy = all segment sums of the frame (the filterbank's and the two pseudo-segments outside it)
             if (a.energy != MFCC_ENERGY_NONE && tid >= kHalfThreads - F) {
                 const int fr = tid - (kHalfThreads - F);
                 float e0 = 0.0f, e1 = 0.0f;
-                for (int j = 0; j < a.n_mel + 3; ++j) {
-                    e0 += rise[j * F + fr];
-                    e1 += fall[j * F + fr];
+                for (int jj = 0; jj < a.n_mel + 3; ++jj) {
+                    e0 += rise[jj * F + fr];
+                    e1 += fall[jj * F + fr];
                 }
                 const float le = kLn2 * lg2_fast(fmaxf(e0 + e1, a.log_floor));
                 if (a.logmel) scr[fr * a.ls + a.n_mel] = le;
@@ -558,12 +595,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             }
         }
         lock_at(5);
-        half_sync(half);   // B4: every band's log energy is in the scratch
+        half_sync(half);   // B4: the folded log energies (or the log-mel rows) are in the scratch
         unlock_at(5);
 
-        // ---- S4: log-mel rows are copied out coalesced.  Cepstra: thread (slot, frame) forms c[slot], c[slot + 16]
-        // and c[slot + 32] — all of one parity, so the DCT symmetry d[k][M-1-m] = (-1)^k d[k][m] folds the band
-        // pairs first: v[m] = lg[m] +- lg[M-1-m], then ceil(M/2) terms per cepstrum ----
+        // ---- S4: log-mel rows are copied out coalesced.  Cepstra: thread (slot, frame) forms c[slot] and, for
+        // slot < n2, c[slot + 32] — both of one parity — from the folded pairs: ceil(M/2) terms per cepstrum, one load
+        // of v and half a 64-bit load of the table per term ----
         if (a.logmel) {
             const int M = a.od, total = n_frames * M;
             float *o = a.out + tile.out_row * M;
@@ -572,17 +609,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 o[i] = scr[fr * a.ls + m];
             }
         } else if (slot < a.n_cep) {
-            const float sgn = (slot & 1) ? -1.0f : 1.0f;
-            const bool second = slot < a.n2;               // this thread also forms c[slot + 32] (uniform per warp when n2 is a multiple of 4)
+            const bool second = slot < a.n2;               // this thread also forms c[slot + 32] (uniform per warp: n2 is a multiple of 4)
             float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
-            auto dct_terms = [&](int hq, const float *lg, const float *lgm) {
-                const float2 *da = reinterpret_cast<const float2 *>(t_dct) + slot * hq;                    // {d[s][m], d[s][m+1]}
-                const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * hq * 2) + slot * hq;  // {d[s+32][m], d[s+32][m+1]}, s < n2
+            auto dct_terms = [&](int hq) {
+                const float *v = scr + ((slot & 1) ? a.hmp * F : 0) + f;
+                const float2 *da = reinterpret_cast<const float2 *>(t_dct) + slot * hq;                    // {d[s][q], d[s][q+1]}
+                const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * hq * 2) + slot * hq;  // {d[s+32][q], d[s+32][q+1]}, s < n2
 #pragma unroll 4
                 for (int q2 = 0; q2 < hq; ++q2) {
-                    const int m = 2 * q2;
-                    const float v0 = fmaf(sgn, lgm[-m * F], lg[m * F]);
-                    const float v1 = fmaf(sgn, lgm[-(m + 1) * F], lg[(m + 1) * F]);
+                    const float v0 = v[2 * q2 * F], v1 = v[(2 * q2 + 1) * F];
                     const float2 d = da[q2];
                     c0 = fmaf(d.x, v0, c0);
                     e0 = fmaf(d.y, v1, e0);
@@ -593,8 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     }
                 }
             };
-            if constexpr (MEL > 0) dct_terms(MEL / 4, scr + f, scr + (MEL - 1) * F + f);   // band pairs two at a time: hmp / 2
-            else dct_terms(a.hmp >> 1, scr + f, scr + (a.n_mel - 1) * F + f);
+            if constexpr (MEL > 0) dct_terms(MEL / 4);     // two folded pairs per step: hmp / 2 steps
+            else dct_terms(a.hmp >> 1);
             if (f < n_frames) {
                 float *o = a.out + (tile.out_row + f) * a.od + slot;
                 o[0] = c0 + e0;
@@ -717,11 +752,12 @@ int wide_prepare(mfcc_plan *plan)
     st->args.energy = p.energy;
     st->args.od = h.out_dim;
     st->args.nseg = M + 1 + (p.energy != MFCC_ENERGY_NONE ? 2 : 0);
+    st->args.inv_n = static_cast<float>(1.0 / N);
     st->args.ls = h.out_dim | 1;
     st->args.mel_magic = (1 << 20) / h.out_dim + 1;
     st->args.hmp = hmp;
     st->args.n2 = n2;
-    st->args.rf = (F * std::max(h.out_dim | 1, M) + 3) / 4 * 4;
+    st->args.rf = (F * std::max(std::max(h.out_dim | 1, M), 2 * hmp) + 3) / 4 * 4;
     st->args.ef = st->args.rf + 2 * F * (M + 3);
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
