@@ -16,8 +16,9 @@ e2e       same metric through mfcc_compute_host: pinned HOST buffers, H2D + kern
 roofline  FFT FLOPs (2.5 N log2 N per frame) against the FP32 FMA peak measured live by
           tools/microbench; `roofline_hbm` is the stream-bytes view (hop*2 + n_cep*4 B per frame)
 cpu_baseline / --impl reference
-          the in-repo scalar C oracle on the host cores (the nominal reference,
-          simotin13/mfcc, is a C compiler with no MFCC path to time — SURVEY.md §0)
+          the in-repo C baseline (oracle/mfcc_cpu_fast.c: the oracle's spec with a real-input FFT, -O3, AVX2
+          clones; checked against the plain oracle) on all host cores — the nominal reference,
+          simotin13/mfcc, is a C compiler with no MFCC path to time
 """
 from __future__ import annotations
 
@@ -133,12 +134,12 @@ def cpu_leg(p, pcm, offsets, n_utts_sample, threads, repeats=1):
     import oracle
     off = offsets[: n_utts_sample + 1]
     x = pcm[: int(off[-1])]
-    oracle.mfcc_batch(p, x[: int(off[1])], off[:2], nthreads=1)  # build + page in
+    oracle.mfcc_batch(p, x[: int(off[1])], off[:2], nthreads=1, fast=True)  # build + page in
     best = float("inf")
     frames = 0
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out, fo = oracle.mfcc_batch(p, x, off, nthreads=threads)
+        out, fo = oracle.mfcc_batch(p, x, off, nthreads=threads, fast=True)
         best = min(best, time.perf_counter() - t0)
         frames = int(fo[-1])
     return frames / best, frames, best
@@ -154,13 +155,13 @@ def run_reference(args, p, cfg_name, desc, ref_maker):
     pcm, off = ref_maker(1000)
     n_utts = len(off) - 1
     import oracle
-    oracle.mfcc_batch(p, pcm[: int(off[1])], off[:2], nthreads=1)
+    oracle.mfcc_batch(p, pcm[: int(off[1])], off[:2], nthreads=1, fast=True)
     for _ in range(args.warmup):
-        oracle.mfcc_batch(p, pcm, off, nthreads=cores)
+        oracle.mfcc_batch(p, pcm, off, nthreads=cores, fast=True)
     t0 = time.perf_counter()
     frames = 0
     for _ in range(args.steps):
-        _, fo = oracle.mfcc_batch(p, pcm, off, nthreads=cores)
+        _, fo = oracle.mfcc_batch(p, pcm, off, nthreads=cores, fast=True)
         frames += int(fo[-1])
     dt = time.perf_counter() - t0
     v = frames / dt
@@ -173,7 +174,9 @@ def run_reference(args, p, cfg_name, desc, ref_maker):
         "config": workload_config(args.workload, args.gpus),
         "audio_seconds_per_s": v * p.hop_len / p.sample_rate,
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "in-repo scalar C oracle; simotin13/mfcc has no MFCC path to time"},
+                         "note": "in-repo C baseline (oracle/mfcc_cpu_fast.c: real-input FFT through a half-size complex FFT, -O3, "
+                                 "AVX2 + FMA clones of the hot loops, pthreads over utterances; checked against the plain parity "
+                                 "oracle); simotin13/mfcc has no MFCC path to time"},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -364,7 +367,8 @@ def measure(ctx, name, steps, warmup, e2e_steps, with_cpu, peak=None):
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"{n_s} utterances of the workload ({fr_s} frames), {cores} pthreads over utterances, best of 3 passes, {dt:.2f} s; single thread: first {n_1} utterances, {dt1:.2f} s",
                "single_thread_value": v1,
-               "note": "in-repo scalar C oracle (gcc -O2); simotin13/mfcc has no MFCC path to time"}
+               "note": "in-repo C baseline (oracle/mfcc_cpu_fast.c: real-input FFT through a half-size complex FFT, -O3, AVX2 + FMA "
+                       "clones of the hot loops; 2.1 x the plain parity oracle per thread); simotin13/mfcc has no MFCC path to time"}
 
     return {
         "value": value, "unit": "frames/s", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,

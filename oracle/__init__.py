@@ -20,7 +20,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("mfcc_oracle.c", "mfcc_oracle_impl.h", "mfcc_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("mfcc_oracle.c", "mfcc_oracle_impl.h", "mfcc_oracle.h", "mfcc_cpu_fast.c")]
     srcs.append(os.path.join(_HERE, "..", "include", "mfcc_b200.h"))
     stale = force or not os.path.exists(_SO) or any(
         os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
@@ -47,8 +47,9 @@ def lib() -> C.CDLL:
             getattr(L, f).restype = i64
         for f in ("oracle_stages_f32", "oracle_stages_f64"):
             getattr(L, f).argtypes = [P, vp, i64, i64, vp, vp, vp, vp]
-        L.oracle_mfcc_batch_f32.argtypes = [P, vp, vp, i64, vp, vp, C.c_int]
-        L.oracle_mfcc_batch_f32.restype = i64
+        for f in ("oracle_mfcc_batch_f32", "oracle_fast_mfcc_batch_f32"):
+            getattr(L, f).argtypes = [P, vp, vp, i64, vp, vp, C.c_int]
+            getattr(L, f).restype = i64
         L.oracle_cmvn_f32.argtypes = [vp, vp, i64, C.c_int, C.c_int]
         L.oracle_delta_f32.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
         L.oracle_decode_g711.argtypes = [vp, i64, C.c_int, vp]
@@ -114,18 +115,19 @@ def stages(p: MfccParams, pcm: np.ndarray, frame: int, dtype=np.float64):
     return fr, pw, mel, out
 
 
-def mfcc_batch(p: MfccParams, pcm: np.ndarray, offsets: np.ndarray, nthreads: int = 1):
-    """Returns (features [total_frames, out_dim] f32, frame_offsets [B+1] i64)."""
+def mfcc_batch(p: MfccParams, pcm: np.ndarray, offsets: np.ndarray, nthreads: int = 1, fast: bool = False):
+    """Returns (features [total_frames, out_dim] f32, frame_offsets [B+1] i64).  ``fast``: the CPU BASELINE build of the
+    same spec (mfcc_cpu_fast.c: real-input FFT, -O3, AVX2 clones) instead of the plain parity oracle."""
     pcm = np.ascontiguousarray(pcm, np.int16)
     offsets = np.ascontiguousarray(offsets, np.int64)
     B = offsets.size - 1
     fo = np.empty(B + 1, np.int64)
-    total = lib().oracle_mfcc_batch_f32(C.byref(p), _ptr(pcm), _ptr(offsets), B, None, _ptr(fo), 1)
+    fn = lib().oracle_fast_mfcc_batch_f32 if fast else lib().oracle_mfcc_batch_f32
+    total = fn(C.byref(p), _ptr(pcm), _ptr(offsets), B, None, _ptr(fo), 1)
     if total < 0:
         raise ValueError(f"oracle_mfcc_batch: {total}")
     out = np.empty((total, p.out_dim), np.float32)
-    rc = lib().oracle_mfcc_batch_f32(C.byref(p), _ptr(pcm), _ptr(offsets), B, _ptr(out), _ptr(fo),
-                                     nthreads)
+    rc = fn(C.byref(p), _ptr(pcm), _ptr(offsets), B, _ptr(out), _ptr(fo), nthreads)
     if rc != total:
         raise RuntimeError(f"oracle_mfcc_batch: {rc}")
     return out, fo

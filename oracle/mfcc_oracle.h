@@ -23,6 +23,9 @@ int     oracle_stages_f64(const mfcc_params *p, const int16_t *pcm, int64_t n, i
                           double *framed, double *power, double *mel, double *out);
 int64_t oracle_mfcc_batch_f32(const mfcc_params *p, const int16_t *pcm, const int64_t *offsets,
                               int64_t n_utts, float *out, int64_t *frame_offsets, int nthreads);
+/* the CPU baseline of bench.py (mfcc_cpu_fast.c): same contract as oracle_mfcc_batch_f32, real-input FFT, -O3 / AVX2 */
+int64_t oracle_fast_mfcc_batch_f32(const mfcc_params *p, const int16_t *pcm, const int64_t *offsets,
+                                   int64_t n_utts, float *out, int64_t *frame_offsets, int nthreads);
 int     oracle_cmvn_f32(float *feat, const int64_t *frame_offsets, int64_t n_utts, int dim,
                         int norm_var);
 int     oracle_delta_f32(const float *feat, const int64_t *frame_offsets, int64_t n_utts, int dim,

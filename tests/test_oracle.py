@@ -241,3 +241,24 @@ def test_hostile_golden_vectors(name):
                 assert f64.shape == ref.shape == (41 + (pad == PAD_ZERO_TAIL), p.out_dim)
                 assert np.abs(f64 - ref).max() <= 4e-6 * max(1.0, np.abs(ref).max())
                 assert_parity(oracle.mfcc(p, x, np.float32), f64, what=f"{name}/{kind}/{oname}/{pname}")
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_cpu_baseline_build_matches_the_plain_oracle(name):
+    """oracle/mfcc_cpu_fast.c (bench.py's cpu_baseline / --impl reference: real-input FFT through a half-size complex FFT,
+    -O3, AVX2 clones) computes the same features as the plain oracle: frame offsets identical, values within the
+    stated tolerance, ragged batch with every framing edge, all output options."""
+    p0 = CFG[name]()
+    L, H = p0.frame_len, p0.hop_len
+    lens = [0, 1, L - 1, L, L + 1, L + H, L + 31 * H + 5, 3 * L, L + 64 * H]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pcm = noise_utterance(int(off[-1]), seed=33)
+    for kw in ({}, dict(output=OUT_LOGMEL), dict(pad_mode=PAD_ZERO_TAIL, lifter=22), dict(energy=1), dict(energy=2, output=OUT_LOGMEL),
+               dict(window=WINDOW_HANN, preemph=0.0)):
+        p = p0.copy(**kw)
+        ref, fo = oracle.mfcc_batch(p, pcm, off, nthreads=2)
+        got, fo2 = oracle.mfcc_batch(p, pcm, off, nthreads=3, fast=True)
+        assert np.array_equal(fo, fo2) and got.shape == ref.shape
+        truth = np.concatenate([oracle.mfcc(p, pcm[off[u]:off[u + 1]], dtype=np.float64) for u in range(len(lens))])
+        from util import lifter_gains
+        assert_parity(got, ref, what=f"{name} {kw}", truth=truth, col_scale=lifter_gains(p), max_escapes=2)
