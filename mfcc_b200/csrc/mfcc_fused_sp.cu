@@ -179,6 +179,8 @@ struct SpArgs {
     int rf;               // scratch offset (floats) of the per-segment rise / fall sums [n_mel + 3][32] x 2 (segments 0 .. n_mel, then the two
                           // pseudo-segments below / above the filterbank that only the energy term reads)
     int ef;               // scratch offset of the log frame energy [32] (generic tail)
+    int raw32_off;        // f32 PCM: float offset in the workspace of the raw buffer the NEXT tile's samples are bulk-copied into
+                          // (the end of the workspace, past the tail scratch); 0: no room, f32 tiles are staged straight from HBM
     float inv_n;          // 1 / NFFT
     int mp;               // n_mel rounded up to even (DCT row length in the table)
     int mel_magic;        // i / od == (i * mel_magic) >> 20 for i < 32 * od
@@ -352,6 +354,20 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     // f32 PCM: same eligibility, but the samples are read straight from HBM with 16-byte loads in S0 (a raw f32
     // buffer would need 21 KB per group, which the 512-point geometry does not have)
     auto tile_vec = [&](const Tile &tl) -> bool { return sizeof(PcmT) == 4 && base_aligned && (tl.flags & kTileInside) != 0; };
+    // ... unless the workspace has room for a raw f32 buffer past the tail scratch: then the next tile's samples are
+    // bulk-copied there as soon as pass 2 has released the workspace (after B3) and S0 reads them from shared memory
+    // (round 1 staged f32 PCM with exposed HBM latency: 1.22 G against 1.75 G frames/s for int16)
+    const float *raw32 = scr + a.raw32_off;
+    auto tile_pre32 = [&](const Tile &tl) -> bool { return a.raw32_off > 0 && tile_vec(tl); };
+    auto issue_copy32 = [&](const Tile &tl) {
+        const int s = static_cast<int>(tl.first_sample & 7);
+        const int64_t o = tl.first_sample - s;
+        const int lead = o >= 8 ? 8 : 0;
+        const uint32_t bytes = static_cast<uint32_t>(lead + G::tceil_s(tl.n_frames, s)) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the workspace was last touched through the generic proxy
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(raw32) + (8 - lead) * 4, pcm + o - lead, bytes, bar);
+    };
     // raw16[8 + i] = x[o + i]; the 8 samples before o ride along when they exist
     auto issue_copy = [&](const Tile &tl) {
         const int s = static_cast<int>(tl.first_sample & 7);
@@ -454,6 +470,7 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     if (first < a.n_tiles && tid == 0) {
         const Tile t0 = desc[0];
         if (tile_fast(t0)) issue_copy(t0);
+        if (tile_pre32(t0)) issue_copy32(t0);
     }
     // Start the two groups of the 512-point CTA half a tile (2.7 us) apart.  Inside a phase the 8 warps of a group do
     // the same thing at the same time (a burst of loads, FP32, a burst of stores), so how well the groups fill each other's
@@ -470,21 +487,21 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         if (!stager && prev_nf > 0) tail(prev_row, prev_nf);
         if (t >= a.n_tiles) break;
         const Tile tile = desc[cur];
-        const bool fast = tile_fast(tile), vec = tile_vec(tile);
+        const bool fast = tile_fast(tile), pre32 = tile_pre32(tile), vec = tile_vec(tile) && !pre32;
         const bool has_next = t + step < a.n_tiles;
         if (has_next) fetch_desc(cur ^ 1, t + step);   // lands while S0 runs
         const int n_frames = tile.n_frames;
         const int tc = G::tceil(n_frames);
         // alignment shift of a bulk-copied tile: s = e + d, e even (absorbed as a word offset of the frame
         // columns in the staged layout), d = 0/1 (absorbed by staging y one sample ahead of x)
-        const int sh = (fast || vec) ? static_cast<int>(tile.first_sample & 7) : 0;
+        const int sh = (fast || vec || pre32) ? static_cast<int>(tile.first_sample & 7) : 0;
         const int e = sh & 6, d = sh & 1;
 
         // ---- S0: stage y[n] = x[n] - a x[n-1] once per sample: staged index i holds sample o + d + i (o = the
         // 8-sample boundary below the tile), with kPad words inserted at i = e + k HOP, so that frame f starts
         // at word e + f STRIDE ----
         if (!stager) {
-            if (fast) phase ^= 1u;
+            if (fast || pre32) phase ^= 1u;
         } else if (fast && sizeof(PcmT) == 1) {
             // G.711 codes (mu-law / A-law bytes): expanded here, on the way from the raw buffer to the staged tile — the
             // PCM never exists as int16 anywhere (1 byte per sample over PCIe and from HBM)
@@ -648,6 +665,35 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                 if (tid == 0) staged[e] = static_cast<float>(raw16[8 + sh]);
             }
 #endif
+        } else if (pre32) {
+            if constexpr (sizeof(PcmT) == 4) {
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                const float *x = raw32 + 8;                     // x[i] = sample o + i, o = the 8-sample boundary below the tile
+                const bool has_before = tile.first_sample - sh > 0;
+                const int nchunks = G::tceil_s(n_frames, sh) >> 3;
+                const float na = -a.preemph;
+#pragma unroll 1
+                for (int c = tid; c < nchunks; c += kStage) {
+                    const float4 lo4 = lds_f4(x + 8 * c), hi4 = lds_f4(x + 8 * c + 4);
+                    // d = 0: the sample before the chunk; d = 1: the sample after it (inside the copied span + 1: finite, unused)
+                    const float nb = (d || c > 0 || has_before) ? x[8 * c + (d ? 8 : -1)] : 0.0f;
+                    const float v0 = d ? lo4.x : nb, v1 = d ? lo4.y : lo4.x, v2 = d ? lo4.z : lo4.y, v3 = d ? lo4.w : lo4.z;
+                    const float v4 = d ? hi4.x : lo4.w, v5 = d ? hi4.y : hi4.x, v6 = d ? hi4.z : hi4.y, v7 = d ? hi4.w : hi4.z;
+                    const float v8 = d ? nb : hi4.w;        // staged word j = v[j + 1] - a v[j]
+                    const int k = c / (HOP / 8);
+                    const int pad = kPad * k;
+                    const int pad_first = (c == k * (HOP / 8) && k > 0) ? pad - kPad : pad;
+                    float *dst = staged + 8 * c;
+                    *reinterpret_cast<float2 *>(dst + (0 < e ? pad_first : pad)) = make_float2(fmaf(na, v0, v1), fmaf(na, v1, v2));
+                    *reinterpret_cast<float2 *>(dst + 2 + (2 < e ? pad_first : pad)) = make_float2(fmaf(na, v2, v3), fmaf(na, v3, v4));
+                    *reinterpret_cast<float2 *>(dst + 4 + (4 < e ? pad_first : pad)) = make_float2(fmaf(na, v4, v5), fmaf(na, v5, v6));
+                    *reinterpret_cast<float2 *>(dst + 6 + pad) = make_float2(fmaf(na, v6, v7), fmaf(na, v7, v8));
+                }
+                if (tile.first_sample == tile.utt_begin) {
+                    if (tid == 0) staged[e] = x[sh];           // the utterance's first sample has no predecessor: y = x
+                }
+            }
         } else if (vec) {
             if constexpr (sizeof(PcmT) == 4) {
                 const float *x = reinterpret_cast<const float *>(pcm) + (tile.first_sample - sh);   // x[i] = sample o + i
@@ -827,6 +873,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         if constexpr (MFCC_POISON) {   // the workspace is dead: S3 writes every segment's two sums into it
             poison(scr, G::WS);
             half_sync(half);
+        }
+        if constexpr (sizeof(PcmT) == 4) {   // f32 PCM: the next tile's samples land in the idle end of the workspace
+            if (has_next && tid == 0) {
+                const Tile nt = desc[cur ^ 1];
+                if (tile_pre32(nt)) issue_copy32(nt);
+            }
         }
 
         // ---- S3: filterbank sums.  Segment j = bins [b_j, b_j + w) rises into filter j with weight i / w and
@@ -1228,6 +1280,12 @@ int sp_prepare(mfcc_plan *plan)
     st->args.mp = MP;
     st->args.rf = scratch_rf(p);
     st->args.ef = st->args.rf + 2 * 32 * (M + 3);
+    {   // raw f32 buffer (8 lead + TCEIL + 8 samples) at the end of the workspace, when the tail scratch leaves room for it
+        const int ws_floats = H * RA * 32 * 2;
+        const int tceil32 = ((31 * p.hop_len + p.frame_len + (RA * NZ - p.frame_len) + 7) / 8 * 8 + 8 + 16 + 3) / 4 * 4;
+        const int scratch = st->args.ef + 32;
+        st->args.raw32_off = scratch + tceil32 <= ws_floats ? ws_floats - tceil32 : 0;
+    }
     st->args.inv_n = static_cast<float>(1.0 / N);
     st->args.mel_magic = (1 << 20) / st->args.od + 1;
     st->args.preemph = p.preemph;
