@@ -81,6 +81,10 @@
 #ifndef MFCC_SP_LOCK_NS
 #define MFCC_SP_LOCK_NS 32
 #endif
+// how many groups may hold the lock at once (a counting semaphore when > 1; only meaningful for the three-group CTA)
+#ifndef MFCC_SP_LOCK_HOLDERS
+#define MFCC_SP_LOCK_HOLDERS 1
+#endif
 // S0 of bulk-copied int16 tiles, second form: the predecessor sample loaded with the chunk, the rare split-pad chunk on a
 // branch instead of four selects per chunk; MFCC_SP_I2F: int16 -> f32 on the conversion pipe (one I2F per sample).
 #ifndef MFCC_SP_S0V2
@@ -298,7 +302,14 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
 #pragma unroll
         for (int i = 0; i < 2; ++i)
             if (kLockOn[i] && point == kLockFrom[i] && threadIdx.x % kHalfThreads == 0) {
-                while (atomicCAS(&phase_lock[i], 0, 1) != 0) __nanosleep(MFCC_SP_LOCK_NS);
+                if constexpr (MFCC_SP_LOCK_HOLDERS <= 1) {
+                    while (atomicCAS(&phase_lock[i], 0, 1) != 0) __nanosleep(MFCC_SP_LOCK_NS);
+                } else {
+                    while (atomicAdd(&phase_lock[i], 1) >= MFCC_SP_LOCK_HOLDERS) {
+                        atomicSub(&phase_lock[i], 1);
+                        __nanosleep(MFCC_SP_LOCK_NS);
+                    }
+                }
                 held[i] = true;
             }
     };
@@ -306,7 +317,8 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
 #pragma unroll
         for (int i = 0; i < 2; ++i)
             if (kLockOn[i] && point == kLockTo[i] && held[i]) {
-                atomicExch(&phase_lock[i], 0);
+                if constexpr (MFCC_SP_LOCK_HOLDERS <= 1) atomicExch(&phase_lock[i], 0);
+                else atomicSub(&phase_lock[i], 1);
                 held[i] = false;
             }
     };
@@ -891,6 +903,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         } else if constexpr (kTail) {
             // Forward walk with running sums: run_i = P_0 + .. + P_i and acc = run_0 + .. + run_(w-1) = sum (w - i) P_i,
             // so fall = s acc and rise = S / NFFT - fall: one load and two additions per bin, no constants, no counter.
+            // (rise is formed by subtraction: a bin carries weight i / w in it, and the subtraction leaves an error of
+            // eps P_i, i.e. eps w / i relative to that bin's contribution — harmless except for a bin of weight 0 (i = 0)
+            // that towers over its neighbours by more than 1 / (eps w).  The frames of this kernel are shorter than the
+            // transform (L < NFFT), so even a bin-centred tone under a rectangular window leaks at the -13 dB level into the
+            // neighbouring bins: the bound is eps w P_peak / P_neighbour ~ 3e-5 relative, and
+            // tests/test_gpu_parity.py::test_bin_centred_tone_known_answer holds every band to the stated tolerance there.)
             // The descriptors come from the parameter bank under a warp-uniform index (uniform registers, uniform
             // branches); the width is taken apart in binary (8-bin loop, then 4, 2, 1).
             const int uw = __shfl_sync(0xffffffffu, warp, 0);
@@ -1072,7 +1090,10 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
     }
     // a lock whose span wraps around the loop is still held after the last tile
     for (int i = 0; i < 2; ++i)
-        if (held[i]) atomicExch(&phase_lock[i], 0);
+        if (held[i]) {
+            if constexpr (MFCC_SP_LOCK_HOLDERS <= 1) atomicExch(&phase_lock[i], 0);
+            else atomicSub(&phase_lock[i], 1);
+        }
 }
 
 // ---------------------------------------------------------------------------------------
