@@ -10,6 +10,6 @@ for w in ${1:-A B3 C8}; do
 done
 if [ "$2" != "nolist" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 fi
