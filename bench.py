@@ -448,6 +448,67 @@ def measure_stream(ctx, n_streams=1024, chunk_ms=20, calls=100, warm=10):
     return out
 
 
+def measure_post(ctx, steps=20, warmup=3, n_utts=4096, frames_per_utt=998):
+    """Post-processing: per-utterance CMVN (mean and variance) + delta + delta-delta, fused and stacked
+    (mfcc_post_batch), on a feature matrix of 4 x configs[1] (4,096 utterances x 998 frames x 13 cepstra = 212 MB, larger
+    than the 126 MB L2, so every timed step re-reads it from HBM).  HBM-bound: the roofline is bytes over time."""
+    import torch
+    from mfcc_b200 import api
+    p = CONFIGS["A"]()
+    plan = api.Plan(p, device=ctx.local, kernel=ctx.kernel)
+    L, H = p.frame_len, p.hop_len
+    off = np.arange(n_utts + 1, dtype=np.int64) * (L + (frames_per_utt - 1) * H)
+    batch = plan.batch(off)
+    frames, dim = batch.total_frames, plan.out_dim
+    assert frames == n_utts * frames_per_utt
+    g = torch.Generator(device="cuda").manual_seed(11)
+    feat = torch.randn((frames, dim), generator=g, device="cuda", dtype=torch.float32) * 4.0
+    feat[:, 0] += 60.0
+    out = torch.empty((frames, 3 * dim), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    res = {}
+    l0 = l1 = 0
+    for key, cmvn in (("cmvn_delta2", 2), ("delta2_only", 0)):
+        for _ in range(warmup):
+            plan.post(batch, feat, cmvn, 2, 2, out, stream)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = api.launch_count()
+        ev0.record(stream)
+        for _ in range(steps):
+            plan.post(batch, feat, cmvn, 2, 2, out, stream)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        l1 = api.launch_count()
+        res[key] = ev0.elapsed_time(ev1) / steps
+    ms = res["cmvn_delta2"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    b_full = (2 * dim + 3 * dim) * 4      # statistics pass read + apply pass read + stacked row written
+    b_apply = (dim + 3 * dim) * 4
+    line = {"value": frames / (ms * 1e-3), "unit": "frames/s", "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "gpu_launches": (l1 - l0), "kernel": "post_stats_kernel + post_apply_kernel<2>",
+            "api": "mfcc_post_batch (device feature matrix in, stacked static | delta | delta-delta matrix out)",
+            "config": {"workload": f"{n_utts} utterances x {frames_per_utt} frames x {dim} cepstra (4 x configs[1]) -> {3 * dim} columns; "
+                                   "CMVN mean + variance, regression window 2, order 2", "params": "A",
+                       "l2": "input 212 MB and output 638 MB per step both exceed the 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": b_full * frames / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": b_full * frames / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "algorithmic": f"{b_full} B/frame (2 reads of {dim * 4} B: statistics pass and apply pass; {3 * dim * 4} B written) x {frames} frames per step (two launches)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+            "delta2_only": {"ms_per_step": res["delta2_only"], "value": frames / (res["delta2_only"] * 1e-3),
+                            "roofline_frac": b_apply * frames / (res["delta2_only"] * 1e-3) / 1e9 / hbm_peak,
+                            "algorithmic": f"{b_apply} B/frame, one launch (no statistics pass)"}}
+    del feat, out, batch
+    plan.close()
+    torch.cuda.empty_cache()
+    return line
+
+
 def run_shard(ctx, args):
     """--shard: ONE ragged configs[2] batch (the same on every rank, as if read from shared storage), partitioned by
     cumulative frame count (sharding.partition); every rank runs mfcc_compute_host on ITS slice (host buffers in, host
@@ -605,6 +666,7 @@ def main():
             r.pop("_peak", None)
             nested[name] = r
         nested["stream"] = measure_stream(ctx)
+        nested["post"] = measure_post(ctx)
     if rank == 0:
         res.pop("_peak", None)
         line = {"metric": "mfcc_frames_per_sec", "value": res.pop("value"), "unit": res.pop("unit"), "n_gpus": world,

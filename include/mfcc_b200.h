@@ -176,6 +176,17 @@ int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_fea
 int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat,
                      int32_t window, float *d_delta, void *cuda_stream);
 
+/* The same post-processing FUSED (mfcc_b200/csrc/mfcc_post.cu): per-utterance CMVN, then delta and
+ * delta-delta regression, written once as the stacked matrix acoustic models consume,
+ *     d_out [total_frames][out_dim * (1 + delta_order)] = static | delta | delta-delta      (e.g. 13 -> 39 columns),
+ * equal to mfcc_cmvn_batch followed by mfcc_delta_batch (twice) and a concatenation.  cmvn: MFCC_CMVN_*; delta_order
+ * 0, 1 or 2; delta_window 1..8 (ignored when delta_order == 0).  Asynchronous on the stream, allocates nothing (the
+ * statistics scratch belongs to the batch, so calls on ONE batch must be stream-ordered); one launch, two with CMVN.
+ * d_out must not overlap d_feat.  HBM-bound: reads out_dim floats per frame (twice with CMVN), writes the stacked row. */
+enum { MFCC_CMVN_NONE = 0, MFCC_CMVN_MEAN = 1, MFCC_CMVN_MEAN_VAR = 2 };
+int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t cmvn,
+                    int32_t delta_window, int32_t delta_order, float *d_out, void *cuda_stream);
+
 /* Input format widening: G.711 mu-law / A-law bytes to
  * int16 PCM on the device, elementwise, async on the stream. */
 int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst,

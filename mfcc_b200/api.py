@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .params import (MfccParams, KERNEL_AUTO, MFCC_OK)
+from .params import (MfccParams, KERNEL_AUTO, MFCC_OK, MFCC_EINVAL)  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MFCC_B200_LIB selects another BUILD of the same library (the poison build libmfcc_b200_poison.so of the tests);
@@ -55,6 +55,7 @@ ABI = {
     "mfcc_compute": (C.c_int, [_vp, _vp, _i64, _vp, C.POINTER(_i64)]),
     "mfcc_cmvn_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mfcc_delta_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "mfcc_post_batch": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "mfcc_decode_g711": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "mfcc_wav_parse": (C.c_int, [_vp, _i64, _vp]),
     "mfcc_stream_create": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -300,6 +301,24 @@ class Plan:
             _check(load().mfcc_delta_batch(self._h, batch._h, feat.data_ptr(), window, d.data_ptr(),
                                            _stream_handle(stream)), "mfcc_delta_batch")
         return d
+
+    def post(self, batch: Batch, feat, cmvn: int = 1, window: int = 2, order: int = 2, out=None, stream=None):
+        """Fused CMVN + delta + delta-delta (``mfcc_post_batch``): the stacked ``[frames][out_dim * (1 + order)]`` matrix
+        static | delta | delta-delta.  ``cmvn``: 0 none, 1 mean, 2 mean and variance."""
+        import torch
+        self._check_feat(batch, feat, "post")
+        if cmvn not in (0, 1, 2) or order not in (0, 1, 2) or (order > 0 and not 1 <= window <= 8):
+            raise ValueError("post: cmvn in 0..2, order in 0..2, window in 1..8")
+        od = self.out_dim * (1 + order)
+        if out is None:
+            out = torch.empty((batch.total_frames, od), dtype=torch.float32, device=feat.device)
+        elif (not isinstance(out, torch.Tensor) or not out.is_cuda or out.device != feat.device
+              or out.dtype != torch.float32 or not out.is_contiguous() or out.numel() < batch.total_frames * od):
+            raise ValueError(f"post: out must be a contiguous float32 CUDA tensor with at least {batch.total_frames} x {od} elements")
+        with torch.cuda.device(self.device):
+            _check(load().mfcc_post_batch(self._h, batch._h, feat.data_ptr(), cmvn, window, order, out.data_ptr(),
+                                          _stream_handle(stream)), "mfcc_post_batch")
+        return out
 
 
 class Stream:

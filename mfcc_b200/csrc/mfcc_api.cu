@@ -284,6 +284,25 @@ int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n
     ok = ok && cudaMemcpy(b->d_frame_offsets, b->frame_offsets.data(), fb, cudaMemcpyHostToDevice) ==
                    cudaSuccess;
     if (!ok) { mfcc_batch_destroy(b); return MFCC_ECUDA; }
+    // post-processing tables (mfcc_post_batch): chunk table + statistics scratch, a few MB at most
+    mfcc::post_build_chunks(b->frame_offsets, b->out_dim, b->post_chunks, &b->post_rows);
+    if (!b->post_chunks.empty()) {
+        const size_t nc = b->post_chunks.size(), dim = static_cast<size_t>(b->out_dim);
+        const size_t nu = static_cast<size_t>(n_utts);
+        if (cudaMalloc(&b->d_post_chunks, nc * sizeof(mfcc::PostChunk)) != cudaSuccess ||
+            cudaMalloc(&b->d_post_partial, nc * dim * sizeof(double2)) != cudaSuccess ||
+            cudaMalloc(&b->d_post_stats, nu * dim * sizeof(double2)) != cudaSuccess ||
+            cudaMalloc(&b->d_post_count, nu * sizeof(unsigned)) != cudaSuccess) {
+            cudaGetLastError();
+            mfcc_batch_destroy(b);
+            return MFCC_ENOMEM;
+        }
+        if (cudaMemcpy(b->d_post_chunks, b->post_chunks.data(), nc * sizeof(mfcc::PostChunk), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemset(b->d_post_count, 0, nu * sizeof(unsigned)) != cudaSuccess) {
+            mfcc_batch_destroy(b);
+            return MFCC_ECUDA;
+        }
+    }
     *out = b;
     return MFCC_OK;
 }
@@ -294,6 +313,10 @@ void mfcc_batch_destroy(mfcc_batch *b)
     DeviceGuard guard(b->device);
     if (b->d_tiles && !b->tiles_borrowed) cudaFree(b->d_tiles);
     if (b->d_frame_offsets) cudaFree(b->d_frame_offsets);
+    if (b->d_post_chunks) cudaFree(b->d_post_chunks);
+    if (b->d_post_partial) cudaFree(b->d_post_partial);
+    if (b->d_post_stats) cudaFree(b->d_post_stats);
+    if (b->d_post_count) cudaFree(b->d_post_count);
     delete b;
 }
 
@@ -777,6 +800,25 @@ int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
     return mfcc::launch_delta(batch, d_feat, batch->out_dim, window, d_delta, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t cmvn,
+                    int32_t delta_window, int32_t delta_order, float *d_out, void *cuda_stream)
+{
+    if (!batch_fits(plan, batch)) return MFCC_EINVAL;
+    if (cmvn < MFCC_CMVN_NONE || cmvn > MFCC_CMVN_MEAN_VAR || delta_order < 0 || delta_order > 2) return MFCC_EINVAL;
+    if (delta_order > 0 && (delta_window < 1 || delta_window > 8)) return MFCC_EINVAL;
+    if (batch->total_frames == 0) return MFCC_OK;
+    if (d_feat == nullptr || d_out == nullptr) return MFCC_EINVAL;
+    {   // the input is read through the read-only path while the output is written: the two must not overlap
+        const char *a = reinterpret_cast<const char *>(d_feat), *o = reinterpret_cast<const char *>(d_out);
+        const size_t ab = sizeof(float) * static_cast<size_t>(batch->total_frames) * batch->out_dim;
+        if (a < o + ab * (1 + delta_order) && o < a + ab) return MFCC_EINVAL;
+    }
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return MFCC_ECUDA;
+    return mfcc::launch_post(batch, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, d_out,
+                             static_cast<cudaStream_t>(cuda_stream));
 }
 
 int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst, void *cuda_stream)

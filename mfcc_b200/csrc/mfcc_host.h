@@ -41,6 +41,18 @@ inline int32_t tile_flags(const mfcc_params &p, const Tile &t, int64_t total_sam
                ? kTileInside : 0;
 }
 
+// Post-processing (mfcc_post.cu): one chunk = up to mfcc_batch::post_rows consecutive feature rows of ONE utterance, i.e. one
+// contiguous block of the feature matrix and of the stacked output matrix.
+struct PostChunk {
+    int64_t row0;          // first row of the chunk
+    int64_t f0, f1;        // row range of its utterance (regression indices are clamped to it)
+    int32_t n;             // rows in the chunk
+    int32_t utt;
+    int32_t first_chunk;   // chunk range of the utterance: the statistics are combined in this order
+    int32_t n_chunks;
+};
+constexpr size_t kPostSmemMax = 96 * 1024;
+
 // Host-side tables, evaluated in double and rounded once to f32 (DESIGN.md "Tables").
 struct HostTables {
     int nbins = 0;                   // nfft/2 + 1
@@ -110,6 +122,14 @@ struct mfcc_batch {
     mfcc::Tile *d_tiles = nullptr;
     bool tiles_borrowed = false;         // d_tiles belongs to the plan (mfcc_compute_host)
     int64_t *d_frame_offsets = nullptr;
+    // post-processing (mfcc_post_batch): chunk table and the statistics scratch, allocated with the batch so that the
+    // call itself allocates nothing; calls on one batch must be stream-ordered (they share the scratch)
+    std::vector<mfcc::PostChunk> post_chunks;
+    int post_rows = 0;
+    mfcc::PostChunk *d_post_chunks = nullptr;
+    void *d_post_partial = nullptr;      // [chunks][out_dim] double2 {sum, sum of squares} about the utterance's first row
+    void *d_post_stats = nullptr;        // [n_utts][out_dim] double2 {mean, 1 / sigma}
+    unsigned *d_post_count = nullptr;    // [n_utts] chunks of the utterance done so far (zero between calls)
 };
 
 namespace mfcc {
@@ -156,6 +176,10 @@ int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, con
 int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s);
 int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
                  cudaStream_t s);
+void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks, int *rows_out);
+size_t post_smem_bytes(int dim, int rows, int window, int order);
+int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
+                cudaStream_t s);
 int launch_g711(const uint8_t *d_src, int64_t n, int alaw, int16_t *d_dst, cudaStream_t s);
 
 }  // namespace mfcc

@@ -1,0 +1,264 @@
+// mfcc_post.cu — fused post-processing of the feature matrix: per-utterance cepstral mean /
+// variance normalisation, delta and delta-delta regression, written ONCE as the stacked matrix
+// [frames][dim * (1 + order)] = static | delta | delta-delta that acoustic models consume.
+//
+// Unlike the transform kernels this path is HBM-bound: per frame it reads dim floats (twice when CMVN needs the
+// statistics first; the second read is served by the L2 when the matrix fits its 126 MB) and writes dim * (1 + order)
+// floats, against ~40 FP32 operations.  So the design rules are the memory ones:
+//   * every global access is a sweep over a CONTIGUOUS range (a chunk = up to `post_rows` consecutive rows of one
+//     utterance is one contiguous block of the input and one contiguous block of the output), consecutive threads on
+//     consecutive floats;
+//   * the three output parts of a row are produced by the same sweep (thread = output column, rows strided), so an output
+//     sector is written once, completely, by neighbouring threads — not by three passes with a 3 * dim stride;
+//   * the chunk (plus the +-2 * window halo rows the two regressions need, edge rows replicated as the spec says) is
+//     staged in shared memory once; the delta of the halo rows is recomputed instead of exchanged;
+//   * the grid is one CTA per chunk with 8 CTAs resident per SM (27 KB of shared memory each for 13 cepstra), enough
+//     loads in flight to cover the HBM latency; nothing is allocated per call.
+// Statistics: chunk sums of (x - pivot) and (x - pivot)^2 in double (pivot = the utterance's first row, which keeps the
+// uncentred variance formula free of cancellation), one partial per chunk, combined in chunk order by the LAST chunk of
+// the utterance to finish (counter + fence) — deterministic, no floating-point atomics, no extra launch.
+//
+// Spec (oracle/mfcc_oracle.c oracle_cmvn_f32 + oracle_delta_f32 applied twice): x' = (x - mu) [* 1 / sqrt(max(var,
+// 1e-20))], d[t] = sum_n n (x'[t + n] - x'[t - n]) / (2 sum n^2) with frame indices clamped to the utterance,
+// dd = the same regression of d.  No reference code corresponds to this (SURVEY.md §8a "Ref file:line = none").
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "mfcc_host.h"
+
+namespace mfcc {
+
+namespace {
+
+constexpr int kPostThreads = 256;
+constexpr int kPostMaxDim = 256;   // dim <= n_mel + 1 <= 129 for any valid plan
+
+// ---- per-utterance statistics: one CTA per chunk, the utterance's last CTA to finish combines the partials ----
+__global__ void __launch_bounds__(kPostThreads)
+post_stats_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat, int dim, int norm_var,
+                  double2 *__restrict__ partial, double2 *__restrict__ stats, unsigned *__restrict__ count)
+{
+    __shared__ double s_s[kPostThreads], s_q[kPostThreads];
+    __shared__ int s_last;
+    const PostChunk ck = chunks[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int per = (kPostThreads / dim) * dim;     // thread t < per always meets coefficient t % dim
+    const int total = ck.n * dim;
+    double s = 0.0, q = 0.0;
+    if (tid < per) {
+        const double pivot = static_cast<double>(__ldg(feat + ck.f0 * dim + tid % dim));
+        const float *src = feat + ck.row0 * dim;
+        for (int i = tid; i < total; i += per) {
+            const double v = static_cast<double>(__ldg(src + i)) - pivot;
+            s += v;
+            q = fma(v, v, q);
+        }
+    }
+    s_s[tid] = s;
+    s_q[tid] = q;
+    __syncthreads();
+    if (tid < dim) {
+        double ts = 0.0, tq = 0.0;
+        for (int j = tid; j < per; j += dim) { ts += s_s[j]; tq += s_q[j]; }
+        partial[static_cast<int64_t>(blockIdx.x) * dim + tid] = make_double2(ts, tq);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&count[ck.utt], 1u) + 1u == static_cast<unsigned>(ck.n_chunks);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < dim) {
+        double ts = 0.0, tq = 0.0;
+        const double2 *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
+        for (int c = 0; c < ck.n_chunks; ++c) {      // chunk order: the result does not depend on which CTA came last
+            const double2 v = __ldcg(p + static_cast<int64_t>(c) * dim);
+            ts += v.x;
+            tq += v.y;
+        }
+        const double T = static_cast<double>(ck.f1 - ck.f0);
+        const double m = ts / T;
+        double var = tq / T - m * m;
+        if (var < 0.0) var = 0.0;
+        const double pivot = static_cast<double>(__ldg(feat + ck.f0 * dim + tid));
+        const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
+        stats[static_cast<int64_t>(ck.utt) * dim + tid] = make_double2(pivot + m, inv);
+    }
+    if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
+}
+
+// ---- normalise + delta + delta-delta + stack: one CTA per chunk ----
+// W_ > 0: regression window known at compile time (2 = the HTK / Kaldi default), 0: run-time window 1..8.
+template <int W_>
+__global__ void __launch_bounds__(kPostThreads)
+post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
+                  const double2 *__restrict__ stats, int dim, int rows, int cmvn, int window, int order,
+                  float inv_den, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int W = W_ ? W_ : window;
+    const PostChunk ck = chunks[blockIdx.x];
+    const int tid = threadIdx.x, n = ck.n;
+    const int HX = order * W;                 // halo rows of X on each side (order 2: the delta of the +-W rows needs +-2W)
+    const int HD = order == 2 ? W : 0;        // halo rows of D1
+    float *X = sm;                            // [rows + 2 HX][dim]  normalised features, edge rows replicated
+    float *D1 = X + (rows + 2 * HX) * dim;    // [rows + 2 HD][dim]  first regression (order 2 only)
+    const int per = (kPostThreads / dim) * dim;
+
+    // phase A: the chunk and its halo, one contiguous sweep; rows outside the utterance are copies of its edge rows
+    const int64_t lo = max(ck.f0, ck.row0 - HX), hi = min(ck.f1, ck.row0 + n + HX);
+    const int nb = static_cast<int>(lo - (ck.row0 - HX));       // halo rows missing below
+    const int na = static_cast<int>(ck.row0 + n + HX - hi);     // and above
+    const int cnt = static_cast<int>(hi - lo) * dim;
+    {
+        const float *src = feat + lo * dim;
+        float *dst = X + nb * dim;
+        if (cmvn) {
+            if (tid < per) {
+                const double2 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + tid % dim);
+                for (int i = tid; i < cnt; i += per)
+                    dst[i] = static_cast<float>((static_cast<double>(__ldg(src + i)) - st.x) * st.y);
+            }
+        } else {
+            for (int i = tid; i < cnt; i += kPostThreads) dst[i] = __ldg(src + i);
+        }
+    }
+    __syncthreads();
+    if (nb > 0 || na > 0) {
+        const float *first = X + nb * dim, *last = X + nb * dim + cnt - dim;
+        for (int i = tid; i < nb * dim; i += kPostThreads) X[i] = first[i % dim];
+        for (int i = tid; i < na * dim; i += kPostThreads) X[nb * dim + cnt + i] = last[i % dim];
+        __syncthreads();
+    }
+
+    // phase B (order 2): the first regression on rows [row0 - W, row0 + n + W), row index clamped to the utterance
+    if (order == 2) {
+        if (tid < per) {
+            const int d = tid % dim, rstep = per / dim;
+            for (int q = tid / dim; q < n + 2 * HD; q += rstep) {
+                int64_t p = ck.row0 - HD + q;
+                p = p < ck.f0 ? ck.f0 : (p >= ck.f1 ? ck.f1 - 1 : p);
+                const float *x = X + (static_cast<int>(p - ck.row0) + HX) * dim + d;
+                float acc;
+                if constexpr (W_ == 2) {
+                    acc = fmaf(2.0f, x[2 * dim] - x[-2 * dim], x[dim] - x[-dim]);
+                } else {
+                    acc = 0.0f;
+                    for (int k = 1; k <= W; ++k) acc = fmaf(static_cast<float>(k), x[k * dim] - x[-k * dim], acc);
+                }
+                D1[q * dim + d] = acc * inv_den;
+            }
+        }
+        __syncthreads();
+    }
+
+    // phase C: thread = output column (static | delta | delta-delta), rows strided, so a warp writes consecutive floats.
+    // One loop body for all three parts (a warp spans two or three of them): the regression is evaluated on every lane —
+    // the halo makes its loads legal for the static columns too — and the static columns select the centre value.
+    float *orow = out + ck.row0 * (dim * (1 + order));
+    if (order == 0) {
+        for (int i = tid; i < n * dim; i += kPostThreads) orow[i] = X[i];
+        return;
+    }
+    const int OD = dim * (1 + order);
+    const int CW = OD < kPostThreads ? OD : kPostThreads;    // columns per pass
+    const int R = kPostThreads / CW;                         // rows in flight
+    const int cl = tid % CW, ry = tid / CW;
+    if (ry >= R) return;
+    for (int c = cl; c < OD; c += CW) {
+        const int part = c / dim, d = c - part * dim;
+        const float *A = (part == 2 ? D1 + HD * dim : X + HX * dim) + d;
+        const bool stat = part == 0;
+        if constexpr (W_ == 2) {
+#pragma unroll 2
+            for (int r = ry; r < n; r += R) {
+                const float *x = A + r * dim;
+                const float v = fmaf(2.0f, x[2 * dim] - x[-2 * dim], x[dim] - x[-dim]) * inv_den;
+                orow[r * OD + c] = stat ? x[0] : v;
+            }
+        } else {
+            for (int r = ry; r < n; r += R) {
+                const float *x = A + r * dim;
+                float acc = 0.0f;
+                for (int k = 1; k <= W; ++k) acc = fmaf(static_cast<float>(k), x[k * dim] - x[-k * dim], acc);
+                orow[r * OD + c] = stat ? x[0] : acc * inv_den;
+            }
+        }
+    }
+}
+
+std::atomic<uint64_t> g_optin2{0}, g_optin0{0};
+
+}  // namespace
+
+// Chunk table of a batch: utterance u's rows [f0, f1) cut into pieces of at most `rows` rows.
+void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks, int *rows_out)
+{
+    // ~4,096 staged elements per chunk (27 KB of shared memory with both halos at window 2): 256 rows of 13 cepstra, 48 rows
+    // of an 80-band log-mel matrix
+    int rows = (4096 / std::max(dim, 1)) & ~7;
+    rows = std::min(256, std::max(32, rows));
+    *rows_out = rows;
+    chunks.clear();
+    const int64_t n_utts = static_cast<int64_t>(frame_offsets.size()) - 1;
+    for (int64_t u = 0; u < n_utts; ++u) {
+        const int64_t f0 = frame_offsets[u], f1 = frame_offsets[u + 1];
+        if (f1 <= f0) continue;
+        const int64_t nc = (f1 - f0 + rows - 1) / rows;
+        const int32_t first = static_cast<int32_t>(chunks.size());
+        for (int64_t c = 0; c < nc; ++c) {
+            PostChunk ck{};
+            ck.row0 = f0 + c * rows;
+            ck.f0 = f0;
+            ck.f1 = f1;
+            ck.n = static_cast<int32_t>(std::min<int64_t>(rows, f1 - ck.row0));
+            ck.utt = static_cast<int32_t>(u);
+            ck.first_chunk = first;
+            ck.n_chunks = static_cast<int32_t>(nc);
+            chunks.push_back(ck);
+        }
+    }
+}
+
+size_t post_smem_bytes(int dim, int rows, int window, int order)
+{
+    const int hx = order * window, hd = order == 2 ? window : 0;
+    return sizeof(float) * static_cast<size_t>(dim) * ((rows + 2 * hx) + (order == 2 ? rows + 2 * hd : 0));
+}
+
+int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
+                cudaStream_t s)
+{
+    const int64_t n_chunks = static_cast<int64_t>(batch->post_chunks.size());
+    if (n_chunks == 0) return MFCC_OK;
+    if (dim > kPostMaxDim || batch->d_post_chunks == nullptr) return MFCC_EINVAL;
+    if (cmvn != MFCC_CMVN_NONE) {
+        post_stats_kernel<<<static_cast<unsigned>(n_chunks), kPostThreads, 0, s>>>(
+            batch->d_post_chunks, d_feat, dim, cmvn == MFCC_CMVN_MEAN_VAR, static_cast<double2 *>(batch->d_post_partial),
+            static_cast<double2 *>(batch->d_post_stats), batch->d_post_count);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    double den = 0.0;
+    for (int k = 1; k <= window; ++k) den += 2.0 * k * k;
+    const float inv_den = static_cast<float>(1.0 / den);
+    const size_t smem = post_smem_bytes(dim, batch->post_rows, window, order);
+    if (smem > kPostSmemMax) return MFCC_EINVAL;
+    if (window == 2) {
+        if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<2>, batch->device, kPostSmemMax, g_optin2) != MFCC_OK)
+            return MFCC_ECUDA;
+        post_apply_kernel<2><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
+            batch->d_post_chunks, d_feat, static_cast<const double2 *>(batch->d_post_stats), dim, batch->post_rows,
+            cmvn != MFCC_CMVN_NONE, window, order, inv_den, d_out);
+    } else {
+        if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<0>, batch->device, kPostSmemMax, g_optin0) != MFCC_OK)
+            return MFCC_ECUDA;
+        post_apply_kernel<0><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
+            batch->d_post_chunks, d_feat, static_cast<const double2 *>(batch->d_post_stats), dim, batch->post_rows,
+            cmvn != MFCC_CMVN_NONE, window, order, inv_den, d_out);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
+}
+
+}  // namespace mfcc

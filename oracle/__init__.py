@@ -140,6 +140,16 @@ def cmvn(feat: np.ndarray, frame_offsets: np.ndarray, norm_var: bool) -> np.ndar
     return f
 
 
+def post(feat: np.ndarray, frame_offsets: np.ndarray, cmvn_mode: int = 1, window: int = 2, order: int = 2) -> np.ndarray:
+    """The stacked matrix static | delta | delta-delta the fused post-processing kernel writes, by composition of the
+    oracle's own functions: cmvn (mode 0 none, 1 mean, 2 mean and variance), delta, delta of delta."""
+    x = np.ascontiguousarray(feat, np.float32) if cmvn_mode == 0 else cmvn(feat, frame_offsets, cmvn_mode == 2)
+    parts = [x]
+    for _ in range(order):
+        parts.append(delta(parts[-1], frame_offsets, window))
+    return np.concatenate(parts, axis=1)
+
+
 def delta(feat: np.ndarray, frame_offsets: np.ndarray, window: int = 2) -> np.ndarray:
     f = np.ascontiguousarray(feat, np.float32)
     fo = np.ascontiguousarray(frame_offsets, np.int64)

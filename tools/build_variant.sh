@@ -11,7 +11,7 @@ out=$root/build_variants/$name
 mkdir -p $out
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -I$csrc"
 objs=""
-for o in mfcc_api mfcc_generic mfcc_fused_sp mfcc_fused_sp_f32 mfcc_fused_sp_g711 mfcc_fused_wide mfcc_tables mfcc_wav; do
+for o in mfcc_api mfcc_generic mfcc_fused_sp mfcc_fused_sp_f32 mfcc_fused_sp_g711 mfcc_fused_wide mfcc_post mfcc_tables mfcc_wav; do
   src=$csrc/$o.o
   if [ "$o" = mfcc_fused_sp ] && [ "$which" != wide ]; then
     $NV -Xptxas -v $flags -DMFCC_SP_PCM_TYPES=1 -c -o $out/$o.o $csrc/mfcc_fused_sp.cu 2> $out/$o.ptxas; src=$out/$o.o
