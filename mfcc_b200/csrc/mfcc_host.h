@@ -128,7 +128,7 @@ struct mfcc_batch {
     int post_rows = 0;
     mfcc::PostChunk *d_post_chunks = nullptr;
     void *d_post_partial = nullptr;      // [chunks][out_dim] double2 {sum, sum of squares} about the utterance's first row
-    void *d_post_stats = nullptr;        // [n_utts][out_dim] double2 {mean, 1 / sigma}
+    void *d_post_stats = nullptr;        // [n_utts][out_dim] float4 {mean hi, lo, 1 / sigma hi, lo}
     unsigned *d_post_count = nullptr;    // [n_utts] chunks of the utterance done so far (zero between calls)
 };
 

@@ -35,32 +35,55 @@ constexpr int kPostThreads = 256;
 constexpr int kPostMaxDim = 256;   // dim <= n_mel + 1 <= 129 for any valid plan
 
 // ---- per-utterance statistics: one CTA per chunk, the utterance's last CTA to finish combines the partials ----
+// Inside a thread the ~14 values it meets are summed in f32 about the pivot (|x - pivot| is a few sigma, so the sums keep
+// 7 digits of a quantity whose mean needs 5); across threads and chunks everything is double, in a fixed order.
+// The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with four FP32
+// instructions and no conversions, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the
+// magnitude of the RESULT, which is what the tolerance is stated on).
 __global__ void __launch_bounds__(kPostThreads)
 post_stats_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat, int dim, int norm_var,
-                  double2 *__restrict__ partial, double2 *__restrict__ stats, unsigned *__restrict__ count)
+                  double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
 {
-    __shared__ double s_s[kPostThreads], s_q[kPostThreads];
+    __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
     __shared__ int s_last;
     const PostChunk ck = chunks[blockIdx.x];
     const int tid = threadIdx.x;
     const int per = (kPostThreads / dim) * dim;     // thread t < per always meets coefficient t % dim
     const int total = ck.n * dim;
-    double s = 0.0, q = 0.0;
+    float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
     if (tid < per) {
-        const double pivot = static_cast<double>(__ldg(feat + ck.f0 * dim + tid % dim));
+        const float pivot = __ldg(feat + ck.f0 * dim + tid % dim);
         const float *src = feat + ck.row0 * dim;
-        for (int i = tid; i < total; i += per) {
-            const double v = static_cast<double>(__ldg(src + i)) - pivot;
-            s += v;
-            q = fma(v, v, q);
+        int i = tid;
+        for (; i + 3 * per < total; i += 4 * per) {     // four independent loads in flight per thread
+            const float a = __ldg(src + i) - pivot, b = __ldg(src + i + per) - pivot;
+            const float c = __ldg(src + i + 2 * per) - pivot, d = __ldg(src + i + 3 * per) - pivot;
+            s0 += a; q0 = fmaf(a, a, q0);
+            s1 += b; q1 = fmaf(b, b, q1);
+            s0 += c; q0 = fmaf(c, c, q0);
+            s1 += d; q1 = fmaf(d, d, q1);
+        }
+        for (; i < total; i += per) {
+            const float a = __ldg(src + i) - pivot;
+            s0 += a; q0 = fmaf(a, a, q0);
         }
     }
-    s_s[tid] = s;
-    s_q[tid] = q;
+    s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
+    s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
+    __syncthreads();
+    // coefficient d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
+    const int nsub = per / dim, G = nsub < 4 ? nsub : 4;
+    if (tid < G * dim) {
+        const int d = tid % dim, g = tid / dim;
+        double ts = 0.0, tq = 0.0;
+        for (int j = g; j < nsub; j += G) { ts += s_s[d + j * dim]; tq += s_q[d + j * dim]; }
+        s2_s[tid] = ts;
+        s2_q[tid] = tq;
+    }
     __syncthreads();
     if (tid < dim) {
         double ts = 0.0, tq = 0.0;
-        for (int j = tid; j < per; j += dim) { ts += s_s[j]; tq += s_q[j]; }
+        for (int g = 0; g < G; ++g) { ts += s2_s[tid + g * dim]; tq += s2_q[tid + g * dim]; }
         partial[static_cast<int64_t>(blockIdx.x) * dim + tid] = make_double2(ts, tq);
     }
     __threadfence();
@@ -81,19 +104,32 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
         const double m = ts / T;
         double var = tq / T - m * m;
         if (var < 0.0) var = 0.0;
-        const double pivot = static_cast<double>(__ldg(feat + ck.f0 * dim + tid));
+        const double mu = static_cast<double>(__ldg(feat + ck.f0 * dim + tid)) + m;
         const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
-        stats[static_cast<int64_t>(ck.utt) * dim + tid] = make_double2(pivot + m, inv);
+        const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
+        stats[static_cast<int64_t>(ck.utt) * dim + tid] =
+            make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
+                        static_cast<float>(inv - static_cast<double>(inv_hi)));
     }
     if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
 }
 
+// regression of one column at row pointer x (row stride `dim` floats), run-time window
+__device__ __forceinline__ float regress(const float *x, int dim, int W, float inv_den)
+{
+    float acc = 0.0f;
+    for (int k = 1; k <= W; ++k) acc = fmaf(static_cast<float>(k), x[k * dim] - x[-k * dim], acc);
+    return acc * inv_den;
+}
+
 // ---- normalise + delta + delta-delta + stack: one CTA per chunk ----
 // W_ > 0: regression window known at compile time (2 = the HTK / Kaldi default), 0: run-time window 1..8.
+// The regressions walk DOWN a column: a thread keeps the 2 W + 1 values of its window in registers and loads one new
+// value per row (W_ = 2: one LDS, two FADD, one FFMA, one FMUL, one select, one store per output element).
 template <int W_>
 __global__ void __launch_bounds__(kPostThreads)
 post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
-                  const double2 *__restrict__ stats, int dim, int rows, int cmvn, int window, int order,
+                  const float4 *__restrict__ stats, int dim, int rows, int cmvn, int window, int order,
                   float inv_den, float *__restrict__ out)
 {
     extern __shared__ __align__(16) float sm[];
@@ -116,12 +152,32 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
         float *dst = X + nb * dim;
         if (cmvn) {
             if (tid < per) {
-                const double2 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + tid % dim);
-                for (int i = tid; i < cnt; i += per)
-                    dst[i] = static_cast<float>((static_cast<double>(__ldg(src + i)) - st.x) * st.y);
+                const float4 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + tid % dim);
+                int i = tid;
+                for (; i + 3 * per < cnt; i += 4 * per) {
+                    const float a = __ldg(src + i), b = __ldg(src + i + per), c = __ldg(src + i + 2 * per), d = __ldg(src + i + 3 * per);
+                    const float ta = (a - st.x) - st.y, tb = (b - st.x) - st.y, tc = (c - st.x) - st.y, td = (d - st.x) - st.y;
+                    dst[i] = fmaf(ta, st.w, ta * st.z);
+                    dst[i + per] = fmaf(tb, st.w, tb * st.z);
+                    dst[i + 2 * per] = fmaf(tc, st.w, tc * st.z);
+                    dst[i + 3 * per] = fmaf(td, st.w, td * st.z);
+                }
+                for (; i < cnt; i += per) {
+                    const float t = (__ldg(src + i) - st.x) - st.y;
+                    dst[i] = fmaf(t, st.w, t * st.z);
+                }
             }
         } else {
-            for (int i = tid; i < cnt; i += kPostThreads) dst[i] = __ldg(src + i);
+            int i = tid;
+            for (; i + 3 * kPostThreads < cnt; i += 4 * kPostThreads) {
+                const float a = __ldg(src + i), b = __ldg(src + i + kPostThreads);
+                const float c = __ldg(src + i + 2 * kPostThreads), d = __ldg(src + i + 3 * kPostThreads);
+                dst[i] = a;
+                dst[i + kPostThreads] = b;
+                dst[i + 2 * kPostThreads] = c;
+                dst[i + 3 * kPostThreads] = d;
+            }
+            for (; i < cnt; i += kPostThreads) dst[i] = __ldg(src + i);
         }
     }
     __syncthreads();
@@ -132,58 +188,79 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
         __syncthreads();
     }
 
-    // phase B (order 2): the first regression on rows [row0 - W, row0 + n + W), row index clamped to the utterance
+    // phase B (order 2): the first regression at the positions [row0 - W, row0 + n + W) that lie inside the utterance
+    // (D1 row q = position row0 - W + q = X row q + W); positions outside take the value of the utterance's edge row
     if (order == 2) {
+        const int qlo = static_cast<int>(max(ck.f0 - (ck.row0 - HD), static_cast<int64_t>(0)));
+        const int qhi = static_cast<int>(min(ck.f1 - (ck.row0 - HD), static_cast<int64_t>(n + 2 * HD)));
         if (tid < per) {
-            const int d = tid % dim, rstep = per / dim;
-            for (int q = tid / dim; q < n + 2 * HD; q += rstep) {
-                int64_t p = ck.row0 - HD + q;
-                p = p < ck.f0 ? ck.f0 : (p >= ck.f1 ? ck.f1 - 1 : p);
-                const float *x = X + (static_cast<int>(p - ck.row0) + HX) * dim + d;
-                float acc;
+            const int d = tid % dim, nblk = per / dim, blk = tid / dim;
+            const int rpt = (qhi - qlo + nblk - 1) / nblk;
+            const int q0 = qlo + blk * rpt, q1 = min(qhi, q0 + rpt);
+            if (q0 < q1) {
+                const float *x = X + (q0 + W) * dim + d;
+                float *o = D1 + q0 * dim + d;
                 if constexpr (W_ == 2) {
-                    acc = fmaf(2.0f, x[2 * dim] - x[-2 * dim], x[dim] - x[-dim]);
+                    float m2 = x[-2 * dim], m1 = x[-dim], c0 = x[0], p1 = x[dim];
+                    x += 2 * dim;
+#pragma unroll 5
+                    for (int q = q0; q < q1; ++q) {
+                        const float p2 = *x;
+                        *o = fmaf(2.0f, p2 - m2, p1 - m1) * inv_den;
+                        x += dim;
+                        o += dim;
+                        m2 = m1; m1 = c0; c0 = p1; p1 = p2;
+                    }
                 } else {
-                    acc = 0.0f;
-                    for (int k = 1; k <= W; ++k) acc = fmaf(static_cast<float>(k), x[k * dim] - x[-k * dim], acc);
+                    for (int q = q0; q < q1; ++q, x += dim, o += dim) *o = regress(x, dim, W, inv_den);
                 }
-                D1[q * dim + d] = acc * inv_den;
             }
         }
         __syncthreads();
+        if (qlo > 0 || qhi < n + 2 * HD) {
+            const float *first = D1 + qlo * dim, *last = D1 + (qhi - 1) * dim;
+            for (int i = tid; i < qlo * dim; i += kPostThreads) D1[i] = first[i % dim];
+            for (int i = tid; i < (n + 2 * HD - qhi) * dim; i += kPostThreads) D1[qhi * dim + i] = last[i % dim];
+            __syncthreads();
+        }
     }
 
-    // phase C: thread = output column (static | delta | delta-delta), rows strided, so a warp writes consecutive floats.
-    // One loop body for all three parts (a warp spans two or three of them): the regression is evaluated on every lane —
-    // the halo makes its loads legal for the static columns too — and the static columns select the centre value.
-    float *orow = out + ck.row0 * (dim * (1 + order));
+    // phase C: thread = output column (static | delta | delta-delta) x a block of consecutive rows, so that at every step
+    // the lanes of a warp write consecutive floats of one (or two) output rows, and the next step continues right behind
+    // them.  One loop body for all three parts (a warp spans two or three of them): the regression is evaluated on every
+    // lane — the halo makes its loads legal for the static columns too — and the static columns select the centre value.
+    const int OD = dim * (1 + order);
+    float *orow = out + ck.row0 * OD;
     if (order == 0) {
         for (int i = tid; i < n * dim; i += kPostThreads) orow[i] = X[i];
         return;
     }
-    const int OD = dim * (1 + order);
     const int CW = OD < kPostThreads ? OD : kPostThreads;    // columns per pass
-    const int R = kPostThreads / CW;                         // rows in flight
-    const int cl = tid % CW, ry = tid / CW;
-    if (ry >= R) return;
+    const int nblk = kPostThreads / CW;                      // row blocks
+    const int cl = tid % CW, blk = tid / CW;
+    if (blk >= nblk) return;
+    const int rpt = (n + nblk - 1) / nblk;
+    const int r0 = blk * rpt, r1 = min(n, r0 + rpt);
+    if (r0 >= r1) return;
     for (int c = cl; c < OD; c += CW) {
         const int part = c / dim, d = c - part * dim;
-        const float *A = (part == 2 ? D1 + HD * dim : X + HX * dim) + d;
+        const float *x = (part == 2 ? D1 + HD * dim : X + HX * dim) + r0 * dim + d;
+        float *o = orow + r0 * OD + c;
         const bool stat = part == 0;
         if constexpr (W_ == 2) {
-#pragma unroll 2
-            for (int r = ry; r < n; r += R) {
-                const float *x = A + r * dim;
-                const float v = fmaf(2.0f, x[2 * dim] - x[-2 * dim], x[dim] - x[-dim]) * inv_den;
-                orow[r * OD + c] = stat ? x[0] : v;
+            float m2 = x[-2 * dim], m1 = x[-dim], c0 = x[0], p1 = x[dim];
+            x += 2 * dim;
+#pragma unroll 5
+            for (int r = r0; r < r1; ++r) {
+                const float p2 = *x;
+                const float v = fmaf(2.0f, p2 - m2, p1 - m1) * inv_den;
+                *o = stat ? c0 : v;
+                x += dim;
+                o += OD;
+                m2 = m1; m1 = c0; c0 = p1; p1 = p2;
             }
         } else {
-            for (int r = ry; r < n; r += R) {
-                const float *x = A + r * dim;
-                float acc = 0.0f;
-                for (int k = 1; k <= W; ++k) acc = fmaf(static_cast<float>(k), x[k * dim] - x[-k * dim], acc);
-                orow[r * OD + c] = stat ? x[0] : acc * inv_den;
-            }
+            for (int r = r0; r < r1; ++r, x += dim, o += OD) *o = stat ? x[0] : regress(x, dim, W, inv_den);
         }
     }
 }
@@ -236,7 +313,7 @@ int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn,
     if (cmvn != MFCC_CMVN_NONE) {
         post_stats_kernel<<<static_cast<unsigned>(n_chunks), kPostThreads, 0, s>>>(
             batch->d_post_chunks, d_feat, dim, cmvn == MFCC_CMVN_MEAN_VAR, static_cast<double2 *>(batch->d_post_partial),
-            static_cast<double2 *>(batch->d_post_stats), batch->d_post_count);
+            static_cast<float4 *>(batch->d_post_stats), batch->d_post_count);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     double den = 0.0;
@@ -248,13 +325,13 @@ int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn,
         if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<2>, batch->device, kPostSmemMax, g_optin2) != MFCC_OK)
             return MFCC_ECUDA;
         post_apply_kernel<2><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
-            batch->d_post_chunks, d_feat, static_cast<const double2 *>(batch->d_post_stats), dim, batch->post_rows,
+            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), dim, batch->post_rows,
             cmvn != MFCC_CMVN_NONE, window, order, inv_den, d_out);
     } else {
         if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<0>, batch->device, kPostSmemMax, g_optin0) != MFCC_OK)
             return MFCC_ECUDA;
         post_apply_kernel<0><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
-            batch->d_post_chunks, d_feat, static_cast<const double2 *>(batch->d_post_stats), dim, batch->post_rows,
+            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), dim, batch->post_rows,
             cmvn != MFCC_CMVN_NONE, window, order, inv_den, d_out);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
