@@ -33,85 +33,108 @@ namespace {
 
 constexpr int kPostThreads = 256;
 constexpr int kPostMaxDim = 256;   // dim <= n_mel + 1 <= 129 for any valid plan
+constexpr int kStatGroup = 4;      // chunks one CTA of the statistics kernel walks (consecutive chunks of one utterance are summed as one block)
 
-// ---- per-utterance statistics: one CTA per chunk, the utterance's last CTA to finish combines the partials ----
-// Inside a thread the ~14 values it meets are summed in f32 about the pivot (|x - pivot| is a few sigma, so the sums keep
-// 7 digits of a quantity whose mean needs 5); across threads and chunks everything is double, in a fixed order.
+// Everything the kernels would otherwise derive with integer divisions by run-time values, prepared on the host: a chunk
+// gives a thread only ~40 output elements, so a handful of 20-instruction divisions per thread is a third of the work.
+struct PostGeom {
+    int dim, rows, order, window, cmvn;
+    int per;              // (256 / dim) * dim: thread t < per always meets column t % dim
+    int nsub;             // per / dim
+    int od, cw, nblk;     // output columns, columns per pass of the stacking sweep, row blocks in it
+    unsigned m_dim, m_cw, m_nblk, m_nsub;   // t / d == (t * m) >> 20 for t < 4096, d <= 256
+    float inv_den;
+};
+__device__ __forceinline__ int div20(int t, unsigned m) { return static_cast<int>((static_cast<unsigned>(t) * m) >> 20); }
+unsigned magic20(int d) { return ((1u << 20) + static_cast<unsigned>(d) - 1u) / static_cast<unsigned>(d); }
+
+// ---- per-utterance statistics: one CTA per kStatGroup chunks, the utterance's last CTA to finish combines the partials ----
+// Inside a thread the values it meets are summed in f32 about the pivot (|x - pivot| is a few sigma, so the sums keep 7
+// digits of a quantity whose mean needs 5); across threads and chunks everything is double, in a fixed order.
 // The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with four FP32
 // instructions and no conversions, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the
 // magnitude of the RESULT, which is what the tolerance is stated on).
 __global__ void __launch_bounds__(kPostThreads)
-post_stats_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat, int dim, int norm_var,
-                  double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
+post_stats_kernel(const PostChunk *__restrict__ chunks, int n_chunks, const float *__restrict__ feat, const PostGeom g,
+                  int norm_var, double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
 {
     __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
     __shared__ int s_last;
-    const PostChunk ck = chunks[blockIdx.x];
-    const int tid = threadIdx.x;
-    const int per = (kPostThreads / dim) * dim;     // thread t < per always meets coefficient t % dim
-    const int total = ck.n * dim;
-    float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
-    if (tid < per) {
-        const float pivot = __ldg(feat + ck.f0 * dim + tid % dim);
-        const float *src = feat + ck.row0 * dim;
-        int i = tid;
-        for (; i + 3 * per < total; i += 4 * per) {     // four independent loads in flight per thread
-            const float a = __ldg(src + i) - pivot, b = __ldg(src + i + per) - pivot;
-            const float c = __ldg(src + i + 2 * per) - pivot, d = __ldg(src + i + 3 * per) - pivot;
-            s0 += a; q0 = fmaf(a, a, q0);
-            s1 += b; q1 = fmaf(b, b, q1);
-            s0 += c; q0 = fmaf(c, c, q0);
-            s1 += d; q1 = fmaf(d, d, q1);
+    const int tid = threadIdx.x, dim = g.dim, per = g.per;
+    const int col = tid - div20(tid, g.m_dim) * dim, sub = div20(tid, g.m_dim);
+    const int c_end = min(n_chunks, (static_cast<int>(blockIdx.x) + 1) * kStatGroup);
+    for (int c = blockIdx.x * kStatGroup; c < c_end;) {
+        const PostChunk ck = chunks[c];
+        int e = c + 1, run_rows = ck.n;             // run = the chunks c .. e - 1 of this utterance: one contiguous block
+        while (e < c_end && chunks[e].utt == ck.utt) run_rows += chunks[e++].n;
+        const int total = run_rows * dim;
+        float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
+        if (tid < per) {
+            const float pivot = __ldg(feat + ck.f0 * dim + col);
+            const float *src = feat + ck.row0 * dim;
+            int i = tid;
+            for (; i + 3 * per < total; i += 4 * per) {     // four independent loads in flight per thread
+                const float a = __ldg(src + i) - pivot, b = __ldg(src + i + per) - pivot;
+                const float cc = __ldg(src + i + 2 * per) - pivot, d = __ldg(src + i + 3 * per) - pivot;
+                s0 += a; q0 = fmaf(a, a, q0);
+                s1 += b; q1 = fmaf(b, b, q1);
+                s0 += cc; q0 = fmaf(cc, cc, q0);
+                s1 += d; q1 = fmaf(d, d, q1);
+            }
+            for (; i < total; i += per) {
+                const float a = __ldg(src + i) - pivot;
+                s0 += a; q0 = fmaf(a, a, q0);
+            }
         }
-        for (; i < total; i += per) {
-            const float a = __ldg(src + i) - pivot;
-            s0 += a; q0 = fmaf(a, a, q0);
+        s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
+        s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
+        __syncthreads();
+        // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
+        const int G = g.nsub < 4 ? g.nsub : 4;
+        if (sub < G) {
+            double ts = 0.0, tq = 0.0;
+            for (int j = sub; j < g.nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
+            s2_s[tid] = ts;
+            s2_q[tid] = tq;
         }
-    }
-    s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
-    s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
-    __syncthreads();
-    // coefficient d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
-    const int nsub = per / dim, G = nsub < 4 ? nsub : 4;
-    if (tid < G * dim) {
-        const int d = tid % dim, g = tid / dim;
-        double ts = 0.0, tq = 0.0;
-        for (int j = g; j < nsub; j += G) { ts += s_s[d + j * dim]; tq += s_q[d + j * dim]; }
-        s2_s[tid] = ts;
-        s2_q[tid] = tq;
-    }
-    __syncthreads();
-    if (tid < dim) {
-        double ts = 0.0, tq = 0.0;
-        for (int g = 0; g < G; ++g) { ts += s2_s[tid + g * dim]; tq += s2_q[tid + g * dim]; }
-        partial[static_cast<int64_t>(blockIdx.x) * dim + tid] = make_double2(ts, tq);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&count[ck.utt], 1u) + 1u == static_cast<unsigned>(ck.n_chunks);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid < dim) {
-        double ts = 0.0, tq = 0.0;
-        const double2 *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
-        for (int c = 0; c < ck.n_chunks; ++c) {      // chunk order: the result does not depend on which CTA came last
-            const double2 v = __ldcg(p + static_cast<int64_t>(c) * dim);
-            ts += v.x;
-            tq += v.y;
+        __syncthreads();
+        if (tid < dim) {
+            double ts = 0.0, tq = 0.0;
+            for (int k = 0; k < G; ++k) { ts += s2_s[tid + k * dim]; tq += s2_q[tid + k * dim]; }
+            partial[static_cast<int64_t>(c) * dim + tid] = make_double2(ts, tq);
+            for (int k = c + 1; k < e; ++k) partial[static_cast<int64_t>(k) * dim + tid] = make_double2(0.0, 0.0);
         }
-        const double T = static_cast<double>(ck.f1 - ck.f0);
-        const double m = ts / T;
-        double var = tq / T - m * m;
-        if (var < 0.0) var = 0.0;
-        const double mu = static_cast<double>(__ldg(feat + ck.f0 * dim + tid)) + m;
-        const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
-        const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
-        stats[static_cast<int64_t>(ck.utt) * dim + tid] =
-            make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
-                        static_cast<float>(inv - static_cast<double>(inv_hi)));
+        __syncthreads();
+        if (tid == 0) {      // the fence is cumulative: the partials the other threads wrote before the barrier are ordered with it
+            __threadfence();
+            s_last = atomicAdd(&count[ck.utt], static_cast<unsigned>(e - c)) + static_cast<unsigned>(e - c) == static_cast<unsigned>(ck.n_chunks);
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_last) {
+            if (tid < dim) {
+                double ts = 0.0, tq = 0.0;
+                const double2 *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
+                for (int k = 0; k < ck.n_chunks; ++k) {      // chunk order: the result does not depend on which CTA came last
+                    const double2 v = __ldcg(p + static_cast<int64_t>(k) * dim);
+                    ts += v.x;
+                    tq += v.y;
+                }
+                const double T = static_cast<double>(ck.f1 - ck.f0);
+                const double m = ts / T;
+                double var = tq / T - m * m;
+                if (var < 0.0) var = 0.0;
+                const double mu = static_cast<double>(__ldg(feat + ck.f0 * dim + tid)) + m;
+                const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
+                const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
+                stats[static_cast<int64_t>(ck.utt) * dim + tid] =
+                    make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
+                                static_cast<float>(inv - static_cast<double>(inv_hi)));
+            }
+            if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
+        }
+        c = e;
     }
-    if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
 }
 
 // regression of one column at row pointer x (row stride `dim` floats), run-time window
@@ -129,18 +152,19 @@ __device__ __forceinline__ float regress(const float *x, int dim, int W, float i
 template <int W_>
 __global__ void __launch_bounds__(kPostThreads)
 post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
-                  const float4 *__restrict__ stats, int dim, int rows, int cmvn, int window, int order,
-                  float inv_den, float *__restrict__ out)
+                  const float4 *__restrict__ stats, const PostGeom g, float *__restrict__ out)
 {
     extern __shared__ __align__(16) float sm[];
-    const int W = W_ ? W_ : window;
+    const int W = W_ ? W_ : g.window;
+    const int dim = g.dim, order = g.order, per = g.per;
+    const float inv_den = g.inv_den;
     const PostChunk ck = chunks[blockIdx.x];
     const int tid = threadIdx.x, n = ck.n;
     const int HX = order * W;                 // halo rows of X on each side (order 2: the delta of the +-W rows needs +-2W)
     const int HD = order == 2 ? W : 0;        // halo rows of D1
     float *X = sm;                            // [rows + 2 HX][dim]  normalised features, edge rows replicated
-    float *D1 = X + (rows + 2 * HX) * dim;    // [rows + 2 HD][dim]  first regression (order 2 only)
-    const int per = (kPostThreads / dim) * dim;
+    float *D1 = X + (g.rows + 2 * HX) * dim;  // [rows + 2 HD][dim]  first regression (order 2 only)
+    const int sub = div20(tid, g.m_dim), col = tid - sub * dim;
 
     // phase A: the chunk and its halo, one contiguous sweep; rows outside the utterance are copies of its edge rows
     const int64_t lo = max(ck.f0, ck.row0 - HX), hi = min(ck.f1, ck.row0 + n + HX);
@@ -150,9 +174,9 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
     {
         const float *src = feat + lo * dim;
         float *dst = X + nb * dim;
-        if (cmvn) {
+        if (g.cmvn) {
             if (tid < per) {
-                const float4 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + tid % dim);
+                const float4 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + col);
                 int i = tid;
                 for (; i + 3 * per < cnt; i += 4 * per) {
                     const float a = __ldg(src + i), b = __ldg(src + i + per), c = __ldg(src + i + 2 * per), d = __ldg(src + i + 3 * per);
@@ -183,8 +207,10 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
     __syncthreads();
     if (nb > 0 || na > 0) {
         const float *first = X + nb * dim, *last = X + nb * dim + cnt - dim;
-        for (int i = tid; i < nb * dim; i += kPostThreads) X[i] = first[i % dim];
-        for (int i = tid; i < na * dim; i += kPostThreads) X[nb * dim + cnt + i] = last[i % dim];
+        if (tid < per) {
+            for (int i = tid; i < nb * dim; i += per) X[i] = first[col];
+            for (int i = tid; i < na * dim; i += per) X[nb * dim + cnt + i] = last[col];
+        }
         __syncthreads();
     }
 
@@ -194,12 +220,11 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
         const int qlo = static_cast<int>(max(ck.f0 - (ck.row0 - HD), static_cast<int64_t>(0)));
         const int qhi = static_cast<int>(min(ck.f1 - (ck.row0 - HD), static_cast<int64_t>(n + 2 * HD)));
         if (tid < per) {
-            const int d = tid % dim, nblk = per / dim, blk = tid / dim;
-            const int rpt = (qhi - qlo + nblk - 1) / nblk;
-            const int q0 = qlo + blk * rpt, q1 = min(qhi, q0 + rpt);
+            const int rpt = div20(qhi - qlo + g.nsub - 1, g.m_nsub);
+            const int q0 = qlo + sub * rpt, q1 = min(qhi, q0 + rpt);
             if (q0 < q1) {
-                const float *x = X + (q0 + W) * dim + d;
-                float *o = D1 + q0 * dim + d;
+                const float *x = X + (q0 + W) * dim + col;
+                float *o = D1 + q0 * dim + col;
                 if constexpr (W_ == 2) {
                     float m2 = x[-2 * dim], m1 = x[-dim], c0 = x[0], p1 = x[dim];
                     x += 2 * dim;
@@ -219,8 +244,10 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
         __syncthreads();
         if (qlo > 0 || qhi < n + 2 * HD) {
             const float *first = D1 + qlo * dim, *last = D1 + (qhi - 1) * dim;
-            for (int i = tid; i < qlo * dim; i += kPostThreads) D1[i] = first[i % dim];
-            for (int i = tid; i < (n + 2 * HD - qhi) * dim; i += kPostThreads) D1[qhi * dim + i] = last[i % dim];
+            if (tid < per) {
+                for (int i = tid; i < qlo * dim; i += per) D1[i] = first[col];
+                for (int i = tid; i < (n + 2 * HD - qhi) * dim; i += per) D1[qhi * dim + i] = last[col];
+            }
             __syncthreads();
         }
     }
@@ -229,21 +256,19 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
     // the lanes of a warp write consecutive floats of one (or two) output rows, and the next step continues right behind
     // them.  One loop body for all three parts (a warp spans two or three of them): the regression is evaluated on every
     // lane — the halo makes its loads legal for the static columns too — and the static columns select the centre value.
-    const int OD = dim * (1 + order);
+    const int OD = g.od;
     float *orow = out + ck.row0 * OD;
     if (order == 0) {
         for (int i = tid; i < n * dim; i += kPostThreads) orow[i] = X[i];
         return;
     }
-    const int CW = OD < kPostThreads ? OD : kPostThreads;    // columns per pass
-    const int nblk = kPostThreads / CW;                      // row blocks
-    const int cl = tid % CW, blk = tid / CW;
-    if (blk >= nblk) return;
-    const int rpt = (n + nblk - 1) / nblk;
+    const int blk = div20(tid, g.m_cw), cl = tid - blk * g.cw;
+    if (blk >= g.nblk) return;
+    const int rpt = div20(n + g.nblk - 1, g.m_nblk);
     const int r0 = blk * rpt, r1 = min(n, r0 + rpt);
     if (r0 >= r1) return;
-    for (int c = cl; c < OD; c += CW) {
-        const int part = c / dim, d = c - part * dim;
+    for (int c = cl; c < OD; c += g.cw) {
+        const int part = div20(c, g.m_dim), d = c - part * dim;
         const float *x = (part == 2 ? D1 + HD * dim : X + HX * dim) + r0 * dim + d;
         float *o = orow + r0 * OD + c;
         const bool stat = part == 0;
@@ -309,30 +334,44 @@ int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn,
 {
     const int64_t n_chunks = static_cast<int64_t>(batch->post_chunks.size());
     if (n_chunks == 0) return MFCC_OK;
-    if (dim > kPostMaxDim || batch->d_post_chunks == nullptr) return MFCC_EINVAL;
-    if (cmvn != MFCC_CMVN_NONE) {
-        post_stats_kernel<<<static_cast<unsigned>(n_chunks), kPostThreads, 0, s>>>(
-            batch->d_post_chunks, d_feat, dim, cmvn == MFCC_CMVN_MEAN_VAR, static_cast<double2 *>(batch->d_post_partial),
-            static_cast<float4 *>(batch->d_post_stats), batch->d_post_count);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
+    if (dim > kPostMaxDim || batch->d_post_chunks == nullptr || n_chunks > (1 << 30)) return MFCC_EINVAL;
+    PostGeom g{};
+    g.dim = dim;
+    g.rows = batch->post_rows;
+    g.order = order;
+    g.window = window;
+    g.cmvn = cmvn != MFCC_CMVN_NONE;
+    g.per = (kPostThreads / dim) * dim;
+    g.nsub = g.per / dim;
+    g.od = dim * (1 + order);
+    g.cw = std::min(g.od, kPostThreads);
+    g.nblk = kPostThreads / g.cw;
+    g.m_dim = magic20(dim);
+    g.m_cw = magic20(g.cw);
+    g.m_nblk = magic20(g.nblk);
+    g.m_nsub = magic20(g.nsub);
     double den = 0.0;
     for (int k = 1; k <= window; ++k) den += 2.0 * k * k;
-    const float inv_den = static_cast<float>(1.0 / den);
+    g.inv_den = static_cast<float>(1.0 / den);
+    if (cmvn != MFCC_CMVN_NONE) {
+        const unsigned grid = static_cast<unsigned>((n_chunks + kStatGroup - 1) / kStatGroup);
+        post_stats_kernel<<<grid, kPostThreads, 0, s>>>(
+            batch->d_post_chunks, static_cast<int>(n_chunks), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
+            static_cast<double2 *>(batch->d_post_partial), static_cast<float4 *>(batch->d_post_stats), batch->d_post_count);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     const size_t smem = post_smem_bytes(dim, batch->post_rows, window, order);
     if (smem > kPostSmemMax) return MFCC_EINVAL;
     if (window == 2) {
         if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<2>, batch->device, kPostSmemMax, g_optin2) != MFCC_OK)
             return MFCC_ECUDA;
         post_apply_kernel<2><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
-            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), dim, batch->post_rows,
-            cmvn != MFCC_CMVN_NONE, window, order, inv_den, d_out);
+            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), g, d_out);
     } else {
         if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<0>, batch->device, kPostSmemMax, g_optin0) != MFCC_OK)
             return MFCC_ECUDA;
         post_apply_kernel<0><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
-            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), dim, batch->post_rows,
-            cmvn != MFCC_CMVN_NONE, window, order, inv_den, d_out);
+            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), g, d_out);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
