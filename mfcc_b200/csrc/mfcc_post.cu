@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "mfcc_host.h"
 
@@ -54,7 +55,7 @@ unsigned magic20(int d) { return ((1u << 20) + static_cast<unsigned>(d) - 1u) / 
 // The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with four FP32
 // instructions and no conversions, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the
 // magnitude of the RESULT, which is what the tolerance is stated on).
-__global__ void __launch_bounds__(kPostThreads)
+__global__ void __launch_bounds__(kPostThreads, 6)
 post_stats_kernel(const PostChunk *__restrict__ chunks, int n_chunks, const float *__restrict__ feat, const PostGeom g,
                   int norm_var, double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
 {
@@ -73,17 +74,16 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int n_chunks, const floa
             const float pivot = __ldg(feat + ck.f0 * dim + col);
             const float *src = feat + ck.row0 * dim;
             int i = tid;
-            for (; i + 3 * per < total; i += 4 * per) {     // four independent loads in flight per thread
-                const float a = __ldg(src + i) - pivot, b = __ldg(src + i + per) - pivot;
-                const float cc = __ldg(src + i + 2 * per) - pivot, d = __ldg(src + i + 3 * per) - pivot;
-                s0 += a; q0 = fmaf(a, a, q0);
-                s1 += b; q1 = fmaf(b, b, q1);
-                s0 += cc; q0 = fmaf(cc, cc, q0);
-                s1 += d; q1 = fmaf(d, d, q1);
-            }
-            for (; i < total; i += per) {
-                const float a = __ldg(src + i) - pivot;
-                s0 += a; q0 = fmaf(a, a, q0);
+            for (; i < total; i += 8 * per) {     // eight independent loads in flight per thread (past the end: the pivot, which adds 0)
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = i + k * per < total ? __ldg(src + i + k * per) : pivot;
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    const float a = v[k] - pivot, b = v[k + 1] - pivot;
+                    s0 += a; q0 = fmaf(a, a, q0);
+                    s1 += b; q1 = fmaf(b, b, q1);
+                }
             }
         }
         s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
@@ -150,7 +150,7 @@ __device__ __forceinline__ float regress(const float *x, int dim, int W, float i
 // The regressions walk DOWN a column: a thread keeps the 2 W + 1 values of its window in registers and loads one new
 // value per row (W_ = 2: one LDS, two FADD, one FFMA, one FMUL, one select, one store per output element).
 template <int W_>
-__global__ void __launch_bounds__(kPostThreads)
+__global__ void __launch_bounds__(kPostThreads, 8)
 post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
                   const float4 *__restrict__ stats, const PostGeom g, float *__restrict__ out)
 {
@@ -178,7 +178,7 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
             if (tid < per) {
                 const float4 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + col);
                 int i = tid;
-                for (; i + 3 * per < cnt; i += 4 * per) {
+                for (; i + 3 * per < cnt; i += 4 * per) {       // four independent loads in flight per thread
                     const float a = __ldg(src + i), b = __ldg(src + i + per), c = __ldg(src + i + 2 * per), d = __ldg(src + i + 3 * per);
                     const float ta = (a - st.x) - st.y, tb = (b - st.x) - st.y, tc = (c - st.x) - st.y, td = (d - st.x) - st.y;
                     dst[i] = fmaf(ta, st.w, ta * st.z);
@@ -186,9 +186,13 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
                     dst[i + 2 * per] = fmaf(tc, st.w, tc * st.z);
                     dst[i + 3 * per] = fmaf(td, st.w, td * st.z);
                 }
-                for (; i < cnt; i += per) {
-                    const float t = (__ldg(src + i) - st.x) - st.y;
-                    dst[i] = fmaf(t, st.w, t * st.z);
+                if (i < cnt) {                                   // up to three left: loaded together as well
+                    const bool h1 = i + per < cnt, h2 = i + 2 * per < cnt;
+                    const float a = __ldg(src + i), b = h1 ? __ldg(src + i + per) : 0.0f, c = h2 ? __ldg(src + i + 2 * per) : 0.0f;
+                    const float ta = (a - st.x) - st.y, tb = (b - st.x) - st.y, tc = (c - st.x) - st.y;
+                    dst[i] = fmaf(ta, st.w, ta * st.z);
+                    if (h1) dst[i + per] = fmaf(tb, st.w, tb * st.z);
+                    if (h2) dst[i + 2 * per] = fmaf(tc, st.w, tc * st.z);
                 }
             }
         } else {
@@ -201,7 +205,14 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
                 dst[i + 2 * kPostThreads] = c;
                 dst[i + 3 * kPostThreads] = d;
             }
-            for (; i < cnt; i += kPostThreads) dst[i] = __ldg(src + i);
+            if (i < cnt) {
+                const bool h1 = i + kPostThreads < cnt, h2 = i + 2 * kPostThreads < cnt;
+                const float a = __ldg(src + i), b = h1 ? __ldg(src + i + kPostThreads) : 0.0f;
+                const float c = h2 ? __ldg(src + i + 2 * kPostThreads) : 0.0f;
+                dst[i] = a;
+                if (h1) dst[i + kPostThreads] = b;
+                if (h2) dst[i + 2 * kPostThreads] = c;
+            }
         }
     }
     __syncthreads();
@@ -301,6 +312,10 @@ void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::
     // of an 80-band log-mel matrix
     int rows = (4096 / std::max(dim, 1)) & ~7;
     rows = std::min(256, std::max(32, rows));
+    if (const char *e = std::getenv("MFCC_POST_ROWS")) {   // tuning experiments only (tools/gpu_post.sh)
+        const int v = std::atoi(e);
+        if (v >= 8 && v <= 1024 && post_smem_bytes(dim, v, 8, 2) <= kPostSmemMax) rows = v;
+    }
     *rows_out = rows;
     chunks.clear();
     const int64_t n_utts = static_cast<int64_t>(frame_offsets.size()) - 1;
