@@ -328,6 +328,29 @@ def measure(ctx, name, steps, warmup, e2e_steps, with_cpu, peak=None):
         e2e_g711 = {"value": total_frames * e2e_steps / dt_g, "unit": "frames/s", "h2d_bytes_per_step": int(pcm.size),
                     "d2h_bytes_per_step": out_bytes, "api": "mfcc_compute_host_g711 (mu-law codes in pinned host memory)"}
         h_codes.close()
+    # the same pipeline with the fused post-processing between kernel and read-back (mfcc_compute_host_post): PCM in,
+    # per-utterance CMVN + delta + delta-delta rows (3 x out_dim columns) out — three times the bytes on the way back
+    e2e_post = None
+    if name == "A":
+        h_out3 = api.PinnedBuffer((frames, 3 * plan.out_dim), np.float32)
+        plan.compute_host(h_in.array, off, h_out3.array, post=(2, 2, 2))
+        plan.compute_host(h_in.array, off, h_out3.array, post=(2, 2, 2))
+        barrier()
+        l_p0 = api.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.compute_host(h_in.array, off, h_out3.array, post=(2, 2, 2))
+        torch.cuda.synchronize()
+        dt_p = time.perf_counter() - t0
+        l_p1 = api.launch_count()
+        if world > 1:
+            t = torch.tensor([dt_p], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_p = float(t.item())
+        e2e_post = {"value": total_frames * e2e_steps / dt_p, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": 3 * out_bytes, "gpu_launches_per_step": (l_p1 - l_p0) // max(e2e_steps, 1),
+                    "api": "mfcc_compute_host_post (CMVN mean + variance, regression window 2, order 2: 39 columns back)"}
+        h_out3.close()
     kernel_name = plan.kernel_name
     out_dim = plan.out_dim
     h_in.close()
@@ -403,6 +426,7 @@ def measure(ctx, name, steps, warmup, e2e_steps, with_cpu, peak=None):
                 "host_cores_bound": len(ctx.numa_cores) if ctx.numa_cores else None,
                 "matches_device_path": e2e_ok},
         "e2e_g711": e2e_g711,
+        "e2e_post": e2e_post,
         "gpu_launches": launches,
         "roofline": roofline, "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,

@@ -187,6 +187,12 @@ enum { MFCC_CMVN_NONE = 0, MFCC_CMVN_MEAN = 1, MFCC_CMVN_MEAN_VAR = 2 };
 int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t cmvn,
                     int32_t delta_window, int32_t delta_order, float *d_out, void *cuda_stream);
 
+/* mfcc_compute_host with the fused post-processing between the transform kernel and the read-back: int16 PCM in host
+ * memory in, h_out [total_frames][out_dim * (1 + delta_order)] (static | delta | delta-delta, per-utterance CMVN) out.
+ * Same pipeline, same serialisation per plan; the link carries out_dim * (1 + delta_order) floats per frame back. */
+int mfcc_compute_host_post(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets, int64_t n_utts, int32_t cmvn,
+                           int32_t delta_window, int32_t delta_order, float *h_out, int64_t *h_frame_offsets);
+
 /* Input format widening: G.711 mu-law / A-law bytes to
  * int16 PCM on the device, elementwise, async on the stream. */
 int mfcc_decode_g711(const uint8_t *d_src, int64_t n, int32_t alaw, int16_t *d_dst,

@@ -52,6 +52,7 @@ ABI = {
     "mfcc_compute_batch_g711": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "mfcc_compute_host": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "mfcc_compute_host_g711": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "mfcc_compute_host_post": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "mfcc_compute": (C.c_int, [_vp, _vp, _i64, _vp, C.POINTER(_i64)]),
     "mfcc_cmvn_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "mfcc_delta_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
@@ -236,10 +237,19 @@ class Plan:
 
     # ---- end to end with host buffers (H2D + kernels + D2H inside) ----
     def compute_host(self, pcm: np.ndarray, offsets: Sequence[int], out: Optional[np.ndarray] = None,
-                     alaw: Optional[bool] = None):
+                     alaw: Optional[bool] = None, post: Optional[Sequence[int]] = None):
         """Host buffers in, host buffers out.  ``alaw`` given (False: mu-law, True: A-law): ``pcm`` holds G.711 codes
-        (uint8) and goes through ``mfcc_compute_host_g711`` — 1 byte per sample over PCIe."""
+        (uint8) and goes through ``mfcc_compute_host_g711`` — 1 byte per sample over PCIe.  ``post`` = (cmvn, window,
+        order): int16 PCM through ``mfcc_compute_host_post`` — the rows that come back are the stacked static | delta |
+        delta-delta matrix (``out_dim * (1 + order)`` columns) after per-utterance CMVN."""
         g711 = alaw is not None
+        if post is not None:
+            if g711:
+                raise ValueError("compute_host: post-processing is offered for int16 PCM")
+            cmvn, window, order = (int(v) for v in post)
+            if cmvn not in (0, 1, 2) or order not in (0, 1, 2) or (order > 0 and not 1 <= window <= 8):
+                raise ValueError("compute_host: post = (cmvn in 0..2, window in 1..8, order in 0..2)")
+        width = self.out_dim * (1 + (post[2] if post is not None else 0))
         pcm = np.ascontiguousarray(pcm, np.uint8 if g711 else np.int16)
         offsets = np.ascontiguousarray(offsets, np.int64)
         if offsets.ndim != 1 or offsets.size < 1:
@@ -253,11 +263,14 @@ class Plan:
         from .sharding import frame_counts
         total = int(frame_counts(self.params, offsets).sum())
         if out is None:
-            out = np.empty((total, self.out_dim), np.float32)
+            out = np.empty((total, width), np.float32)
         elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags.c_contiguous
-              or out.size < total * self.out_dim):
-            raise ValueError(f"out must be a C-contiguous float32 array of at least {total} x {self.out_dim} elements")
-        if g711:
+              or out.size < total * width):
+            raise ValueError(f"out must be a C-contiguous float32 array of at least {total} x {width} elements")
+        if post is not None:
+            _check(load().mfcc_compute_host_post(self._h, pcm.ctypes.data, offsets.ctypes.data, n_utts, cmvn, window, order,
+                                                 out.ctypes.data, fo.ctypes.data), "mfcc_compute_host_post")
+        elif g711:
             _check(load().mfcc_compute_host_g711(self._h, pcm.ctypes.data, int(bool(alaw)), offsets.ctypes.data, n_utts,
                                                  out.ctypes.data, fo.ctypes.data), "mfcc_compute_host_g711")
         else:

@@ -162,6 +162,12 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     if (plan->d2h_out) cudaFree(plan->d2h_out);
     if (plan->d_tiles) cudaFree(plan->d_tiles);
     if (plan->h_tiles) cudaFreeHost(plan->h_tiles);
+    if (plan->d_post_out) cudaFree(plan->d_post_out);
+    if (plan->d_post_chunks) cudaFree(plan->d_post_chunks);
+    if (plan->h_post_chunks) cudaFreeHost(plan->h_post_chunks);
+    if (plan->d_post_partial) cudaFree(plan->d_post_partial);
+    if (plan->d_post_stats) cudaFree(plan->d_post_stats);
+    if (plan->d_post_count) cudaFree(plan->d_post_count);
     if (plan->h_stage_pcm) cudaFreeHost(plan->h_stage_pcm);
     if (plan->h_stage_out) cudaFreeHost(plan->h_stage_out);
     if (plan->tiles_ready) cudaEventDestroy(plan->tiles_ready);
@@ -285,7 +291,7 @@ int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n
                    cudaSuccess;
     if (!ok) { mfcc_batch_destroy(b); return MFCC_ECUDA; }
     // post-processing tables (mfcc_post_batch): chunk table + statistics scratch, a few MB at most
-    mfcc::post_build_chunks(b->frame_offsets, b->out_dim, b->post_chunks, &b->post_rows);
+    mfcc::post_build_chunks(b->frame_offsets, b->out_dim, b->post_chunks, b->utt_first_post_chunk, &b->post_rows);
     if (!b->post_chunks.empty()) {
         const size_t nc = b->post_chunks.size(), dim = static_cast<size_t>(b->out_dim);
         const size_t nu = static_cast<size_t>(n_utts);
@@ -373,20 +379,28 @@ int mfcc_compute_batch_f32(const mfcc_plan *plan, const mfcc_batch *batch, const
 
 namespace {
 
+// post != nullptr: every chunk of utterances also goes through the fused post-processing kernels (CMVN + regressions,
+// mfcc_post.cu) on its compute stream and the STACKED rows are what travels back — the normalisation is per utterance and
+// a chunk holds whole utterances, so nothing crosses chunks.
+struct PostOpts { int cmvn, window, order; };
+
 template <typename PcmT>
 int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_t *h_offsets, int64_t n_utts,
-                      float *h_out, int64_t *h_frame_offsets)
+                      float *h_out, int64_t *h_frame_offsets, const PostOpts *post = nullptr)
 {
     if (plan == nullptr || n_utts < 0 || (n_utts > 0 && h_offsets == nullptr)) return MFCC_EINVAL;
     const mfcc_params &p = plan->p;
     const int od = plan->host.out_dim;
     // 1. sizes
-    int64_t total_frames = 0, n_tiles = 0;
+    int64_t total_frames = 0, n_tiles = 0, n_post_chunks = 0;
+    const int post_rows = post ? mfcc::post_rows_for(od) : 1;
+    const int od_out = post ? od * (1 + post->order) : od;     // floats per row that travels back
     for (int64_t u = 0; u < n_utts; ++u) {
         if (h_offsets[u] < 0 || h_offsets[u + 1] < h_offsets[u]) return MFCC_EINVAL;
         const int64_t nf = mfcc_num_frames(&p, h_offsets[u + 1] - h_offsets[u]);
         total_frames += nf;
         n_tiles += (nf + mfcc::kTileFrames - 1) / mfcc::kTileFrames;
+        n_post_chunks += (nf + post_rows - 1) / post_rows;
     }
     const int64_t total_samples = n_utts > 0 ? h_offsets[n_utts] : 0;
     if (total_frames == 0) {
@@ -404,6 +418,23 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     if (rc == MFCC_OK)
         rc = grow(&plan->d2h_out, &plan->d2h_out_bytes, sizeof(float) * static_cast<size_t>(total_frames) * od);
     if (rc == MFCC_OK) rc = grow(&plan->d_tiles, &plan->d_tiles_bytes, tile_bytes);
+    const size_t pc_bytes = sizeof(mfcc::PostChunk) * static_cast<size_t>(n_post_chunks);
+    if (post != nullptr) {
+        const size_t nu = static_cast<size_t>(n_utts), d = static_cast<size_t>(od);
+        if (rc == MFCC_OK) rc = grow(&plan->d_post_out, &plan->d_post_out_bytes, sizeof(float) * static_cast<size_t>(total_frames) * od_out);
+        if (rc == MFCC_OK) rc = grow(&plan->d_post_chunks, &plan->d_post_chunks_bytes, pc_bytes);
+        if (rc == MFCC_OK) rc = grow(&plan->d_post_partial, &plan->d_post_partial_bytes, static_cast<size_t>(n_post_chunks) * d * sizeof(double2));
+        if (rc == MFCC_OK) rc = grow(&plan->d_post_stats, &plan->d_post_stats_bytes, nu * d * sizeof(float4));
+        if (rc == MFCC_OK) rc = grow(&plan->d_post_count, &plan->d_post_count_bytes, nu * sizeof(unsigned));
+        if (rc == MFCC_OK && plan->h_post_chunks_bytes < pc_bytes) {
+            if (plan->h_post_chunks) cudaFreeHost(plan->h_post_chunks);
+            plan->h_post_chunks = nullptr;
+            plan->h_post_chunks_bytes = 0;
+            const size_t want = align_up(pc_bytes + pc_bytes / 8, 1 << 16);
+            if (cudaHostAlloc(&plan->h_post_chunks, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = MFCC_ENOMEM; }
+            else plan->h_post_chunks_bytes = want;
+        }
+    }
     if (rc == MFCC_OK && plan->h_tiles_bytes < tile_bytes) {   // pinned staging of the tile table
         if (plan->h_tiles) cudaFreeHost(plan->h_tiles);
         plan->h_tiles = nullptr;
@@ -471,6 +502,13 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     batch->d_tiles = static_cast<Tile *>(plan->d_tiles);
     batch->tiles_borrowed = true;
     ok = cudaMemcpyAsync(plan->d_tiles, plan->h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
+    if (post != nullptr) {   // chunk table of the post-processing kernels: same route; the counters start from zero
+        mfcc::post_build_chunks(batch->frame_offsets, od, batch->post_chunks, batch->utt_first_post_chunk, &batch->post_rows);
+        ok = ok && static_cast<int64_t>(batch->post_chunks.size()) == n_post_chunks;
+        if (ok) std::memcpy(plan->h_post_chunks, batch->post_chunks.data(), pc_bytes);
+        ok = ok && cudaMemcpyAsync(plan->d_post_chunks, plan->h_post_chunks, pc_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
+        ok = ok && cudaMemsetAsync(plan->d_post_count, 0, sizeof(unsigned) * static_cast<size_t>(n_utts), plan->streams[2]) == cudaSuccess;
+    }
     ok = ok && cudaEventRecord(plan->tiles_ready, plan->streams[2]) == cudaSuccess;
     ok = ok && cudaStreamWaitEvent(plan->streams[3], plan->tiles_ready, 0) == cudaSuccess;
     for (size_t c = 1; c < n_chunks; ++c) queue_h2d(c);
@@ -484,8 +522,17 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         ok = cudaStreamWaitEvent(s, plan->chunk_ready[c], 0) == cudaSuccess;
         if (ok && t1 > t0)
             ok = compute_batch_impl<PcmT>(plan, batch, d_pcm, d_out, t0, t1 - t0, s, alaw) == MFCC_OK;
+        const float *d_rows = d_out;
+        if (ok && post != nullptr && f1 > f0) {
+            const int64_t c0 = batch->utt_first_post_chunk[u0], c1 = batch->utt_first_post_chunk[u1];
+            const mfcc::PostView view{static_cast<const mfcc::PostChunk *>(plan->d_post_chunks), c0, c1 - c0, batch->post_rows,
+                                      plan->d_post_partial, plan->d_post_stats, static_cast<unsigned *>(plan->d_post_count), plan->device};
+            ok = mfcc::launch_post(view, d_out, od, post->cmvn, post->order > 0 ? post->window : 1, post->order,
+                                   static_cast<float *>(plan->d_post_out), s) == MFCC_OK;
+            d_rows = static_cast<const float *>(plan->d_post_out);
+        }
         if (ok && f1 > f0)
-            ok = cudaMemcpyAsync(h_out + f0 * od, d_out + f0 * od, sizeof(float) * (f1 - f0) * od,
+            ok = cudaMemcpyAsync(h_out + f0 * od_out, d_rows + f0 * od_out, sizeof(float) * (f1 - f0) * od_out,
                                  cudaMemcpyDeviceToHost, s) == cudaSuccess;
     }
     for (auto &s : plan->streams)
@@ -503,6 +550,17 @@ int mfcc_compute_host(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_of
                       float *h_out, int64_t *h_frame_offsets)
 {
     return compute_host_impl<int16_t>(plan, h_pcm, 0, h_offsets, n_utts, h_out, h_frame_offsets);
+}
+
+// PCM in, the stacked static | delta | delta-delta rows out: the post-processing kernels run per chunk of utterances between
+// the transform kernel and the read-back.
+int mfcc_compute_host_post(mfcc_plan *plan, const int16_t *h_pcm, const int64_t *h_offsets, int64_t n_utts, int32_t cmvn,
+                           int32_t delta_window, int32_t delta_order, float *h_out, int64_t *h_frame_offsets)
+{
+    if (cmvn < MFCC_CMVN_NONE || cmvn > MFCC_CMVN_MEAN_VAR || delta_order < 0 || delta_order > 2) return MFCC_EINVAL;
+    if (delta_order > 0 && (delta_window < 1 || delta_window > 8)) return MFCC_EINVAL;
+    const PostOpts post{cmvn, delta_window, delta_order};
+    return compute_host_impl<int16_t>(plan, h_pcm, 0, h_offsets, n_utts, h_out, h_frame_offsets, &post);
 }
 
 // G.711 bytes end to end: 1 byte per sample over PCIe and from HBM, expanded inside the fused kernel's staging.
@@ -817,7 +875,9 @@ int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float 
     }
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
-    return mfcc::launch_post(batch, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, d_out,
+    const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
+                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device};
+    return mfcc::launch_post(view, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, d_out,
                              static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -103,6 +103,13 @@ struct mfcc_plan {
     void *h_tiles = nullptr;   size_t h_tiles_bytes = 0;   // its pinned staging copy
     void *h_stage_pcm = nullptr; size_t h_stage_pcm_bytes = 0;   // streaming: pinned staging of the packed stream buffers
     void *h_stage_out = nullptr; size_t h_stage_out_bytes = 0;   // streaming: pinned landing area of the feature rows
+    // mfcc_compute_host_post: stacked output rows, chunk table (device + pinned staging) and statistics scratch
+    void *d_post_out = nullptr;      size_t d_post_out_bytes = 0;
+    void *d_post_chunks = nullptr;   size_t d_post_chunks_bytes = 0;
+    void *h_post_chunks = nullptr;   size_t h_post_chunks_bytes = 0;
+    void *d_post_partial = nullptr;  size_t d_post_partial_bytes = 0;
+    void *d_post_stats = nullptr;    size_t d_post_stats_bytes = 0;
+    void *d_post_count = nullptr;    size_t d_post_count_bytes = 0;
     cudaEvent_t tiles_ready = nullptr;
     std::vector<cudaEvent_t> chunk_ready;   // one per H2D chunk of the call in flight (reused across calls)
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};   // compute_host: two H2D queues, two compute + D2H queues
@@ -125,6 +132,7 @@ struct mfcc_batch {
     // post-processing (mfcc_post_batch): chunk table and the statistics scratch, allocated with the batch so that the
     // call itself allocates nothing; calls on one batch must be stream-ordered (they share the scratch)
     std::vector<mfcc::PostChunk> post_chunks;
+    std::vector<int64_t> utt_first_post_chunk;   // [n_utts + 1]
     int post_rows = 0;
     mfcc::PostChunk *d_post_chunks = nullptr;
     void *d_post_partial = nullptr;      // [chunks][out_dim] double2 {sum, sum of squares} about the utterance's first row
@@ -176,9 +184,22 @@ int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, con
 int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s);
 int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
                  cudaStream_t s);
-void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks, int *rows_out);
+// what a launch of the post-processing kernels works on: the chunks [chunk0, chunk0 + n_chunks) of a device chunk table and
+// the statistics scratch that goes with the table (indexed by global chunk / utterance number)
+struct PostView {
+    const PostChunk *chunks;
+    int64_t chunk0, n_chunks;
+    int rows;            // rows per chunk the table was cut with
+    void *partial;       // [chunks][dim] double2
+    void *stats;         // [utterances][dim] float4
+    unsigned *count;     // [utterances], zero between calls
+    int device;
+};
+int post_rows_for(int dim);
+void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks,
+                       std::vector<int64_t> &utt_first, int *rows_out);
 size_t post_smem_bytes(int dim, int rows, int window, int order);
-int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
+int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
                 cudaStream_t s);
 int launch_g711(const uint8_t *d_src, int64_t n, int alaw, int16_t *d_dst, cudaStream_t s);
 

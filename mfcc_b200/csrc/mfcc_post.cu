@@ -49,25 +49,29 @@ struct PostGeom {
 __device__ __forceinline__ int div20(int t, unsigned m) { return static_cast<int>((static_cast<unsigned>(t) * m) >> 20); }
 unsigned magic20(int d) { return ((1u << 20) + static_cast<unsigned>(d) - 1u) / static_cast<unsigned>(d); }
 
-// ---- per-utterance statistics: one CTA per kStatGroup chunks, the utterance's last CTA to finish combines the partials ----
+// ---- per-utterance statistics: one CTA per group of kStatGroup chunks, the utterance's last CTA to finish combines the partials ----
+// Groups are aligned to the utterance (chunks first + 4 k .. first + 4 k + 3), so the summation order — and with it every
+// bit of the result — does not depend on which range of the batch a launch covers; the CTAs of the other chunks exit at once.
 // Inside a thread the values it meets are summed in f32 about the pivot (|x - pivot| is a few sigma, so the sums keep 7
 // digits of a quantity whose mean needs 5); across threads and chunks everything is double, in a fixed order.
 // The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with four FP32
 // instructions and no conversions, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the
 // magnitude of the RESULT, which is what the tolerance is stated on).
 __global__ void __launch_bounds__(kPostThreads, 6)
-post_stats_kernel(const PostChunk *__restrict__ chunks, int n_chunks, const float *__restrict__ feat, const PostGeom g,
+post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, const float *__restrict__ feat, const PostGeom g,
                   int norm_var, double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
 {
     __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
     __shared__ int s_last;
     const int tid = threadIdx.x, dim = g.dim, per = g.per;
     const int col = tid - div20(tid, g.m_dim) * dim, sub = div20(tid, g.m_dim);
-    const int c_end = min(n_chunks, (static_cast<int>(blockIdx.x) + 1) * kStatGroup);
-    for (int c = blockIdx.x * kStatGroup; c < c_end;) {
+    {
+        const int c = chunk0 + static_cast<int>(blockIdx.x);
         const PostChunk ck = chunks[c];
-        int e = c + 1, run_rows = ck.n;             // run = the chunks c .. e - 1 of this utterance: one contiguous block
-        while (e < c_end && chunks[e].utt == ck.utt) run_rows += chunks[e++].n;
+        if ((c - ck.first_chunk) % kStatGroup != 0) return;
+        const int e = min(c + kStatGroup, ck.first_chunk + ck.n_chunks);   // run = the chunks c .. e - 1: one contiguous block
+        int run_rows = ck.n;
+        for (int k = c + 1; k < e; ++k) run_rows += chunks[k].n;
         const int total = run_rows * dim;
         float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
         if (tid < per) {
@@ -133,7 +137,6 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int n_chunks, const floa
             }
             if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
         }
-        c = e;
     }
 }
 
@@ -152,7 +155,7 @@ __device__ __forceinline__ float regress(const float *x, int dim, int W, float i
 template <int W_>
 __global__ void __launch_bounds__(kPostThreads, 8)
 post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
-                  const float4 *__restrict__ stats, const PostGeom g, float *__restrict__ out)
+                  const float4 *__restrict__ stats, const PostGeom g, float *__restrict__ out)   // chunks: first chunk of the launch
 {
     extern __shared__ __align__(16) float sm[];
     const int W = W_ ? W_ : g.window;
@@ -305,21 +308,31 @@ std::atomic<uint64_t> g_optin2{0}, g_optin0{0};
 
 }  // namespace
 
-// Chunk table of a batch: utterance u's rows [f0, f1) cut into pieces of at most `rows` rows.
-void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks, int *rows_out)
+int post_rows_for(int dim)
 {
     // ~4,096 staged elements per chunk (27 KB of shared memory with both halos at window 2): 256 rows of 13 cepstra, 48 rows
     // of an 80-band log-mel matrix
     int rows = (4096 / std::max(dim, 1)) & ~7;
     rows = std::min(256, std::max(32, rows));
-    if (const char *e = std::getenv("MFCC_POST_ROWS")) {   // tuning experiments only (tools/gpu_post.sh)
+    if (const char *e = std::getenv("MFCC_POST_ROWS")) {   // tuning experiments only (tools/gpu_post_rows.sh)
         const int v = std::atoi(e);
         if (v >= 8 && v <= 1024 && post_smem_bytes(dim, v, 8, 2) <= kPostSmemMax) rows = v;
     }
+    return rows;
+}
+
+// Chunk table of a batch: utterance u's rows [f0, f1) cut into pieces of at most `rows` rows; utt_first[u] = index of its
+// first chunk (utt_first[n_utts] = number of chunks), so a range of utterances is a range of chunks.
+void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks,
+                       std::vector<int64_t> &utt_first, int *rows_out)
+{
+    const int rows = post_rows_for(dim);
     *rows_out = rows;
     chunks.clear();
     const int64_t n_utts = static_cast<int64_t>(frame_offsets.size()) - 1;
+    utt_first.assign(static_cast<size_t>(std::max<int64_t>(n_utts, 0)) + 1, 0);
     for (int64_t u = 0; u < n_utts; ++u) {
+        utt_first[u] = static_cast<int64_t>(chunks.size());
         const int64_t f0 = frame_offsets[u], f1 = frame_offsets[u + 1];
         if (f1 <= f0) continue;
         const int64_t nc = (f1 - f0 + rows - 1) / rows;
@@ -336,6 +349,7 @@ void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::
             chunks.push_back(ck);
         }
     }
+    if (n_utts >= 0) utt_first[n_utts] = static_cast<int64_t>(chunks.size());
 }
 
 size_t post_smem_bytes(int dim, int rows, int window, int order)
@@ -344,15 +358,14 @@ size_t post_smem_bytes(int dim, int rows, int window, int order)
     return sizeof(float) * static_cast<size_t>(dim) * ((rows + 2 * hx) + (order == 2 ? rows + 2 * hd : 0));
 }
 
-int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
+int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
                 cudaStream_t s)
 {
-    const int64_t n_chunks = static_cast<int64_t>(batch->post_chunks.size());
-    if (n_chunks == 0) return MFCC_OK;
-    if (dim > kPostMaxDim || batch->d_post_chunks == nullptr || n_chunks > (1 << 30)) return MFCC_EINVAL;
+    if (v.n_chunks <= 0) return MFCC_OK;
+    if (dim > kPostMaxDim || v.chunks == nullptr || v.chunk0 + v.n_chunks > (1 << 30)) return MFCC_EINVAL;
     PostGeom g{};
     g.dim = dim;
-    g.rows = batch->post_rows;
+    g.rows = v.rows;
     g.order = order;
     g.window = window;
     g.cmvn = cmvn != MFCC_CMVN_NONE;
@@ -368,25 +381,23 @@ int launch_post(const mfcc_batch *batch, const float *d_feat, int dim, int cmvn,
     double den = 0.0;
     for (int k = 1; k <= window; ++k) den += 2.0 * k * k;
     g.inv_den = static_cast<float>(1.0 / den);
+    const unsigned grid = static_cast<unsigned>(v.n_chunks);
     if (cmvn != MFCC_CMVN_NONE) {
-        const unsigned grid = static_cast<unsigned>((n_chunks + kStatGroup - 1) / kStatGroup);
         post_stats_kernel<<<grid, kPostThreads, 0, s>>>(
-            batch->d_post_chunks, static_cast<int>(n_chunks), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
-            static_cast<double2 *>(batch->d_post_partial), static_cast<float4 *>(batch->d_post_stats), batch->d_post_count);
+            v.chunks, static_cast<int>(v.chunk0), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
+            static_cast<double2 *>(v.partial), static_cast<float4 *>(v.stats), v.count);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    const size_t smem = post_smem_bytes(dim, batch->post_rows, window, order);
+    const size_t smem = post_smem_bytes(dim, v.rows, window, order);
     if (smem > kPostSmemMax) return MFCC_EINVAL;
     if (window == 2) {
-        if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<2>, batch->device, kPostSmemMax, g_optin2) != MFCC_OK)
+        if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<2>, v.device, kPostSmemMax, g_optin2) != MFCC_OK)
             return MFCC_ECUDA;
-        post_apply_kernel<2><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
-            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), g, d_out);
+        post_apply_kernel<2><<<grid, kPostThreads, smem, s>>>(v.chunks + v.chunk0, d_feat, static_cast<const float4 *>(v.stats), g, d_out);
     } else {
-        if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<0>, batch->device, kPostSmemMax, g_optin0) != MFCC_OK)
+        if (smem > 48 * 1024 && ensure_smem_optin(post_apply_kernel<0>, v.device, kPostSmemMax, g_optin0) != MFCC_OK)
             return MFCC_ECUDA;
-        post_apply_kernel<0><<<static_cast<unsigned>(n_chunks), kPostThreads, smem, s>>>(
-            batch->d_post_chunks, d_feat, static_cast<const float4 *>(batch->d_post_stats), g, d_out);
+        post_apply_kernel<0><<<grid, kPostThreads, smem, s>>>(v.chunks + v.chunk0, d_feat, static_cast<const float4 *>(v.stats), g, d_out);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;

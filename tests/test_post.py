@@ -149,6 +149,31 @@ def test_post_equals_the_separate_entries_and_hostile_statistics():
 
 
 @pytest.mark.gpu
+def test_host_pipeline_with_post_equals_the_device_path():
+    """mfcc_compute_host_post: PCM in host memory in, stacked rows out, the post-processing kernels run per CHUNK of
+    utterances inside the copy / compute pipeline.  Same bits as compute_batch + post on the whole batch (the statistics are
+    summed in an order that depends on the utterance alone), and within tolerance of the oracle."""
+    p = config_a()
+    plan = api.Plan(p)
+    # 70 MB of PCM: several pipeline chunks (32 MiB each), ragged lengths incl. empty and sub-frame utterances
+    pcm, off = ragged_batch(300, 0, 240000, seed=12)
+    b = plan.batch(off)
+    feat = plan.compute_batch(b, torch.from_numpy(pcm).cuda())
+    for cmvn_mode, window, order in ((2, 2, 2), (1, 3, 1), (0, 2, 2), (2, 2, 0)):
+        want = plan.post(b, feat, cmvn_mode, window, order).cpu().numpy()
+        got, fo = plan.compute_host(pcm, off, post=(cmvn_mode, window, order))
+        assert np.array_equal(fo, b.frame_offsets)
+        assert got.shape == want.shape and np.array_equal(got, want), (cmvn_mode, window, order)
+    ref = oracle.post(feat.cpu().numpy(), b.frame_offsets, 2, 2, 2)
+    got, _ = plan.compute_host(pcm, off, post=(2, 2, 2))
+    assert np.abs(got.astype(np.float64) - ref).max() <= POST_TOL
+    plain, _ = plan.compute_host(pcm, off)                       # the plain entry still returns the plain rows
+    assert np.array_equal(plain, feat.cpu().numpy())
+    with pytest.raises(ValueError):
+        plan.compute_host(pcm, off, post=(1, 2, 3))
+
+
+@pytest.mark.gpu
 def test_post_argument_errors():
     plan, b, feat = device_batch(config_a(), [10, 20])
     lib = api.load()
