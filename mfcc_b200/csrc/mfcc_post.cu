@@ -32,9 +32,17 @@ namespace mfcc {
 
 namespace {
 
+// resident CTAs per SM the apply / statistics kernels are compiled for (register budget 65,536 / (256 x this)): with 8
+// the apply kernel spills (32 registers) and runs at 78 % of the HBM roofline, with 6 (40 registers, no spills) at 88 %
+#ifndef MFCC_POST_MINB
+#define MFCC_POST_MINB 6
+#endif
+#ifndef MFCC_POST_MINB_STATS
+#define MFCC_POST_MINB_STATS 8
+#endif
 constexpr int kPostThreads = 256;
 constexpr int kPostMaxDim = 256;   // dim <= n_mel + 1 <= 129 for any valid plan
-constexpr int kStatGroup = 4;      // chunks one CTA of the statistics kernel walks (consecutive chunks of one utterance are summed as one block)
+constexpr int kPostFront = 8;      // floats kept free in front of a staged block: alignment shift of the bulk copy (<= 7)
 
 // Everything the kernels would otherwise derive with integer divisions by run-time values, prepared on the host: a chunk
 // gives a thread only ~40 output elements, so a handful of 20-instruction divisions per thread is a third of the work.
@@ -49,187 +57,206 @@ struct PostGeom {
 __device__ __forceinline__ int div20(int t, unsigned m) { return static_cast<int>((static_cast<unsigned>(t) * m) >> 20); }
 unsigned magic20(int d) { return ((1u << 20) + static_cast<unsigned>(d) - 1u) / static_cast<unsigned>(d); }
 
-// ---- per-utterance statistics: one CTA per group of kStatGroup chunks, the utterance's last CTA to finish combines the partials ----
-// Groups are aligned to the utterance (chunks first + 4 k .. first + 4 k + 3), so the summation order — and with it every
-// bit of the result — does not depend on which range of the batch a launch covers; the CTAs of the other chunks exit at once.
-// Inside a thread the values it meets are summed in f32 about the pivot (|x - pivot| is a few sigma, so the sums keep 7
-// digits of a quantity whose mean needs 5); across threads and chunks everything is double, in a fixed order.
-// The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with four FP32
-// instructions and no conversions, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the
-// magnitude of the RESULT, which is what the tolerance is stated on).
-__global__ void __launch_bounds__(kPostThreads, 6)
+// ---- mbarrier + 1-D bulk async copy (TMA engine) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Stage `cnt` floats starting at `src` into shared memory so that element i lands at block[i].  `floor` is a 16-byte aligned
+// region; the block starts at least `min_off` floats into it (the apply kernel keeps its halo rows in front) and at most 3
+// floats later: where exactly follows from the alignment of src.
+// Fast path (matrix base 16-byte aligned): ONE bulk copy from the 16-byte boundary below src up to the last 16-byte boundary
+// inside the range — no load instructions, no registers, the whole chunk in flight at once — and the <= 3 floats behind it by
+// plain loads; the bytes in front of src belong to the previous row of the same matrix.  Nothing past the range is read.
+// Returns the block pointer; every thread must call this (it contains the barrier that publishes the mbarrier) and must
+// call stage_wait before reading the block.  min_off >= 4.
+struct Staged { float *block; bool bulk; };
+__device__ __forceinline__ Staged stage_issue(float *floor, int min_off, uint32_t bar, const float *src, int cnt, bool base_aligned, int tid)
+{
+    const int a = base_aligned ? static_cast<int>((reinterpret_cast<uintptr_t>(src) >> 2) & 3) : 0;   // floats between the boundary and src
+    float *block = floor + min_off + ((a - min_off) & 3);      // block - a is 16-byte aligned
+    const int body = base_aligned ? ((a + cnt) & ~3) : 0;      // floats the bulk copy brings (from src - a)
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        if (body > 0) {
+            mbar_expect_tx(bar, static_cast<uint32_t>(body) * 4u);
+            bulk_g2s(smem_u32(block - a), src - a, static_cast<uint32_t>(body) * 4u, bar);
+        }
+    }
+    // what the bulk copy leaves out: everything without it, else the <= 3 floats behind the last 16-byte boundary
+    for (int i = (body > 0 ? body - a : 0) + tid; i < cnt; i += kPostThreads) block[i] = __ldg(src + i);
+    __syncthreads();                                // mbarrier initialised and visible to the waiters
+    return Staged{block, body > 0};
+}
+__device__ __forceinline__ void stage_wait(const Staged &st, uint32_t bar)
+{
+    if (st.bulk) mbar_wait(bar, 0);
+}
+
+// ---- per-utterance statistics: one CTA per chunk, the utterance's last CTA to finish combines the partials ----
+// Inside a thread the ~14 values it meets are summed in f32 about the pivot (the utterance's first row: |x - pivot| is a few
+// sigma, so the sums keep 7 digits of a quantity whose mean needs 5, and the uncentred variance formula is free of
+// cancellation); across threads and chunks everything is double, in a fixed order — no floating-point atomics, so the
+// result is bit-reproducible and does not depend on which range of the batch a launch covers.
+// The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with FP32
+// instructions only, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the magnitude of the
+// RESULT, which is what the tolerance is stated on).
+__global__ void __launch_bounds__(kPostThreads, MFCC_POST_MINB_STATS)
 post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, const float *__restrict__ feat, const PostGeom g,
                   int norm_var, double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
 {
+    extern __shared__ __align__(16) float sm[];     // [4: mbarrier][kPostFront + rows * dim + 4]
     __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
     __shared__ int s_last;
     const int tid = threadIdx.x, dim = g.dim, per = g.per;
-    const int col = tid - div20(tid, g.m_dim) * dim, sub = div20(tid, g.m_dim);
-    {
-        const int c = chunk0 + static_cast<int>(blockIdx.x);
-        const PostChunk ck = chunks[c];
-        if ((c - ck.first_chunk) % kStatGroup != 0) return;
-        const int e = min(c + kStatGroup, ck.first_chunk + ck.n_chunks);   // run = the chunks c .. e - 1: one contiguous block
-        int run_rows = ck.n;
-        for (int k = c + 1; k < e; ++k) run_rows += chunks[k].n;
-        const int total = run_rows * dim;
-        float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
-        if (tid < per) {
-            const float pivot = __ldg(feat + ck.f0 * dim + col);
-            const float *src = feat + ck.row0 * dim;
-            int i = tid;
-            for (; i < total; i += 8 * per) {     // eight independent loads in flight per thread (past the end: the pivot, which adds 0)
-                float v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = i + k * per < total ? __ldg(src + i + k * per) : pivot;
-#pragma unroll
-                for (int k = 0; k < 8; k += 2) {
-                    const float a = v[k] - pivot, b = v[k + 1] - pivot;
-                    s0 += a; q0 = fmaf(a, a, q0);
-                    s1 += b; q1 = fmaf(b, b, q1);
-                }
-            }
+    const int sub = div20(tid, g.m_dim), col = tid - sub * dim;
+    const int c = chunk0 + static_cast<int>(blockIdx.x);
+    const PostChunk ck = chunks[c];
+    const int total = ck.n * dim;
+    const uint32_t bar = smem_u32(sm);
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+    const Staged st = stage_issue(sm + 4, 4, bar, feat + ck.row0 * dim, total, base_aligned, tid);
+    float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
+    const float pivot = tid < per ? __ldg(feat + ck.f0 * dim + col) : 0.0f;
+    stage_wait(st, bar);
+    if (tid < per) {
+        const float *x = st.block;
+        int i = tid;
+        for (; i + per < total; i += 2 * per) {
+            const float a = x[i] - pivot, b = x[i + per] - pivot;
+            s0 += a; q0 = fmaf(a, a, q0);
+            s1 += b; q1 = fmaf(b, b, q1);
         }
-        s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
-        s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
-        __syncthreads();
-        // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
-        const int G = g.nsub < 4 ? g.nsub : 4;
-        if (sub < G) {
-            double ts = 0.0, tq = 0.0;
-            for (int j = sub; j < g.nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
-            s2_s[tid] = ts;
-            s2_q[tid] = tq;
-        }
-        __syncthreads();
-        if (tid < dim) {
-            double ts = 0.0, tq = 0.0;
-            for (int k = 0; k < G; ++k) { ts += s2_s[tid + k * dim]; tq += s2_q[tid + k * dim]; }
-            partial[static_cast<int64_t>(c) * dim + tid] = make_double2(ts, tq);
-            for (int k = c + 1; k < e; ++k) partial[static_cast<int64_t>(k) * dim + tid] = make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        if (tid == 0) {      // the fence is cumulative: the partials the other threads wrote before the barrier are ordered with it
-            __threadfence();
-            s_last = atomicAdd(&count[ck.utt], static_cast<unsigned>(e - c)) + static_cast<unsigned>(e - c) == static_cast<unsigned>(ck.n_chunks);
-            __threadfence();
-        }
-        __syncthreads();
-        if (s_last) {
-            if (tid < dim) {
-                double ts = 0.0, tq = 0.0;
-                const double2 *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
-                for (int k = 0; k < ck.n_chunks; ++k) {      // chunk order: the result does not depend on which CTA came last
-                    const double2 v = __ldcg(p + static_cast<int64_t>(k) * dim);
-                    ts += v.x;
-                    tq += v.y;
-                }
-                const double T = static_cast<double>(ck.f1 - ck.f0);
-                const double m = ts / T;
-                double var = tq / T - m * m;
-                if (var < 0.0) var = 0.0;
-                const double mu = static_cast<double>(__ldg(feat + ck.f0 * dim + tid)) + m;
-                const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
-                const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
-                stats[static_cast<int64_t>(ck.utt) * dim + tid] =
-                    make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
-                                static_cast<float>(inv - static_cast<double>(inv_hi)));
-            }
-            if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
+        if (i < total) {
+            const float a = x[i] - pivot;
+            s0 += a; q0 = fmaf(a, a, q0);
         }
     }
+    s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
+    s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
+    __syncthreads();
+    // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
+    const int G = g.nsub < 4 ? g.nsub : 4;
+    if (sub < G) {
+        double ts = 0.0, tq = 0.0;
+        for (int j = sub; j < g.nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
+        s2_s[tid] = ts;
+        s2_q[tid] = tq;
+    }
+    __syncthreads();
+    if (tid < dim) {
+        double ts = 0.0, tq = 0.0;
+        for (int k = 0; k < G; ++k) { ts += s2_s[tid + k * dim]; tq += s2_q[tid + k * dim]; }
+        partial[static_cast<int64_t>(c) * dim + tid] = make_double2(ts, tq);
+    }
+    __syncthreads();
+    if (tid == 0) {      // the fence is cumulative: the partials the other threads wrote before the barrier are ordered with it
+        __threadfence();
+        s_last = atomicAdd(&count[ck.utt], 1u) + 1u == static_cast<unsigned>(ck.n_chunks);
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (tid < dim) {
+        double ts = 0.0, tq = 0.0;
+        const double2 *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
+        for (int k = 0; k < ck.n_chunks; ++k) {      // chunk order: the result does not depend on which CTA came last
+            const double2 v = __ldcg(p + static_cast<int64_t>(k) * dim);
+            ts += v.x;
+            tq += v.y;
+        }
+        const double T = static_cast<double>(ck.f1 - ck.f0);
+        const double m = ts / T;
+        double var = tq / T - m * m;
+        if (var < 0.0) var = 0.0;
+        const double mu = static_cast<double>(pivot) + m;
+        const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
+        const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
+        stats[static_cast<int64_t>(ck.utt) * dim + tid] =
+            make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
+                        static_cast<float>(inv - static_cast<double>(inv_hi)));
+    }
+    if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
 }
 
-// regression of one column at row pointer x (row stride `dim` floats), run-time window
-__device__ __forceinline__ float regress(const float *x, int dim, int W, float inv_den)
+// regression sum of one column at row pointer x (row stride `dim` floats), run-time window: sum_k k (x[+k] - x[-k])
+__device__ __forceinline__ float regress(const float *x, int dim, int W)
 {
     float acc = 0.0f;
     for (int k = 1; k <= W; ++k) acc = fmaf(static_cast<float>(k), x[k * dim] - x[-k * dim], acc);
-    return acc * inv_den;
+    return acc;
 }
 
 // ---- normalise + delta + delta-delta + stack: one CTA per chunk ----
 // W_ > 0: regression window known at compile time (2 = the HTK / Kaldi default), 0: run-time window 1..8.
-// The regressions walk DOWN a column: a thread keeps the 2 W + 1 values of its window in registers and loads one new
-// value per row (W_ = 2: one LDS, two FADD, one FFMA, one FMUL, one select, one store per output element).
+// The chunk and its halo rows arrive RAW by one bulk copy; the regressions are linear and their weights sum to zero, so they
+// are taken on the raw values (delta of normalised = delta of raw times 1 / sigma) and the normalisation moves into the last
+// phase, where a thread owns ONE output column and keeps its mean and scale in registers.  The regressions walk DOWN a
+// column: a thread keeps the 2 W + 1 values of its window in registers and loads one new value per row.
 template <int W_>
-__global__ void __launch_bounds__(kPostThreads, 8)
+__global__ void __launch_bounds__(kPostThreads, MFCC_POST_MINB)
 post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
                   const float4 *__restrict__ stats, const PostGeom g, float *__restrict__ out)   // chunks: first chunk of the launch
 {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(16) float sm[];   // [4: mbarrier][kPostFront + (rows + 2 HX) dim + 4][(rows + 2 HD) dim]
     const int W = W_ ? W_ : g.window;
     const int dim = g.dim, order = g.order, per = g.per;
-    const float inv_den = g.inv_den;
     const PostChunk ck = chunks[blockIdx.x];
     const int tid = threadIdx.x, n = ck.n;
     const int HX = order * W;                 // halo rows of X on each side (order 2: the delta of the +-W rows needs +-2W)
     const int HD = order == 2 ? W : 0;        // halo rows of D1
-    float *X = sm;                            // [rows + 2 HX][dim]  normalised features, edge rows replicated
-    float *D1 = X + (g.rows + 2 * HX) * dim;  // [rows + 2 HD][dim]  first regression (order 2 only)
     const int sub = div20(tid, g.m_dim), col = tid - sub * dim;
+    const uint32_t bar = smem_u32(sm);
 
-    // phase A: the chunk and its halo, one contiguous sweep; rows outside the utterance are copies of its edge rows
+    // phase A: the chunk and its halo, raw, by one bulk copy; rows outside the utterance are copies of its edge rows
     const int64_t lo = max(ck.f0, ck.row0 - HX), hi = min(ck.f1, ck.row0 + n + HX);
     const int nb = static_cast<int>(lo - (ck.row0 - HX));       // halo rows missing below
     const int na = static_cast<int>(ck.row0 + n + HX - hi);     // and above
     const int cnt = static_cast<int>(hi - lo) * dim;
-    {
-        const float *src = feat + lo * dim;
-        float *dst = X + nb * dim;
-        if (g.cmvn) {
-            if (tid < per) {
-                const float4 st = __ldg(stats + static_cast<int64_t>(ck.utt) * dim + col);
-                int i = tid;
-                for (; i + 3 * per < cnt; i += 4 * per) {       // four independent loads in flight per thread
-                    const float a = __ldg(src + i), b = __ldg(src + i + per), c = __ldg(src + i + 2 * per), d = __ldg(src + i + 3 * per);
-                    const float ta = (a - st.x) - st.y, tb = (b - st.x) - st.y, tc = (c - st.x) - st.y, td = (d - st.x) - st.y;
-                    dst[i] = fmaf(ta, st.w, ta * st.z);
-                    dst[i + per] = fmaf(tb, st.w, tb * st.z);
-                    dst[i + 2 * per] = fmaf(tc, st.w, tc * st.z);
-                    dst[i + 3 * per] = fmaf(td, st.w, td * st.z);
-                }
-                if (i < cnt) {                                   // up to three left: loaded together as well
-                    const bool h1 = i + per < cnt, h2 = i + 2 * per < cnt;
-                    const float a = __ldg(src + i), b = h1 ? __ldg(src + i + per) : 0.0f, c = h2 ? __ldg(src + i + 2 * per) : 0.0f;
-                    const float ta = (a - st.x) - st.y, tb = (b - st.x) - st.y, tc = (c - st.x) - st.y;
-                    dst[i] = fmaf(ta, st.w, ta * st.z);
-                    if (h1) dst[i + per] = fmaf(tb, st.w, tb * st.z);
-                    if (h2) dst[i + 2 * per] = fmaf(tc, st.w, tc * st.z);
-                }
-            }
-        } else {
-            int i = tid;
-            for (; i + 3 * kPostThreads < cnt; i += 4 * kPostThreads) {
-                const float a = __ldg(src + i), b = __ldg(src + i + kPostThreads);
-                const float c = __ldg(src + i + 2 * kPostThreads), d = __ldg(src + i + 3 * kPostThreads);
-                dst[i] = a;
-                dst[i + kPostThreads] = b;
-                dst[i + 2 * kPostThreads] = c;
-                dst[i + 3 * kPostThreads] = d;
-            }
-            if (i < cnt) {
-                const bool h1 = i + kPostThreads < cnt, h2 = i + 2 * kPostThreads < cnt;
-                const float a = __ldg(src + i), b = h1 ? __ldg(src + i + kPostThreads) : 0.0f;
-                const float c = h2 ? __ldg(src + i + 2 * kPostThreads) : 0.0f;
-                dst[i] = a;
-                if (h1) dst[i + kPostThreads] = b;
-                if (h2) dst[i + 2 * kPostThreads] = c;
-            }
-        }
-    }
-    __syncthreads();
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+    // the staged block starts nb rows into X: leave room for them in front
+    const Staged st = stage_issue(sm + 4, HX * dim + 4, bar, feat + lo * dim, cnt, base_aligned, tid);
+    float *X = st.block - nb * dim;            // [n + 2 HX][dim], row r of the chunk at X + (r + HX) dim
+    float *D1 = sm + 4 + kPostFront + 4 + (g.rows + 3 * HX) * dim;   // [n + 2 HD][dim]: unscaled first regression (order 2 only)
+    // this thread's output column in the last phase: its mean / scale pair, fetched while the copy flies
+    const int OD = g.od;
+    const int blk = div20(tid, g.m_cw), cl = tid - blk * g.cw;
+    stage_wait(st, bar);
     if (nb > 0 || na > 0) {
-        const float *first = X + nb * dim, *last = X + nb * dim + cnt - dim;
+        const float *first = st.block, *last = st.block + cnt - dim;
         if (tid < per) {
             for (int i = tid; i < nb * dim; i += per) X[i] = first[col];
-            for (int i = tid; i < na * dim; i += per) X[nb * dim + cnt + i] = last[col];
+            for (int i = tid; i < na * dim; i += per) st.block[cnt + i] = last[col];
         }
         __syncthreads();
     }
 
-    // phase B (order 2): the first regression at the positions [row0 - W, row0 + n + W) that lie inside the utterance
-    // (D1 row q = position row0 - W + q = X row q + W); positions outside take the value of the utterance's edge row
+    // phase B (order 2): the first regression (unscaled sums) at the positions [row0 - W, row0 + n + W) that lie inside the
+    // utterance (D1 row q = position row0 - W + q = X row q + W); positions outside take the value of the utterance's edge row
     if (order == 2) {
         const int qlo = static_cast<int>(max(ck.f0 - (ck.row0 - HD), static_cast<int64_t>(0)));
         const int qhi = static_cast<int>(min(ck.f1 - (ck.row0 - HD), static_cast<int64_t>(n + 2 * HD)));
@@ -245,13 +272,13 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
 #pragma unroll 5
                     for (int q = q0; q < q1; ++q) {
                         const float p2 = *x;
-                        *o = fmaf(2.0f, p2 - m2, p1 - m1) * inv_den;
+                        *o = fmaf(2.0f, p2 - m2, p1 - m1);
                         x += dim;
                         o += dim;
                         m2 = m1; m1 = c0; c0 = p1; p1 = p2;
                     }
                 } else {
-                    for (int q = q0; q < q1; ++q, x += dim, o += dim) *o = regress(x, dim, W, inv_den);
+                    for (int q = q0; q < q1; ++q, x += dim, o += dim) *o = regress(x, dim, W);
                 }
             }
         }
@@ -269,37 +296,46 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
     // phase C: thread = output column (static | delta | delta-delta) x a block of consecutive rows, so that at every step
     // the lanes of a warp write consecutive floats of one (or two) output rows, and the next step continues right behind
     // them.  One loop body for all three parts (a warp spans two or three of them): the regression is evaluated on every
-    // lane — the halo makes its loads legal for the static columns too — and the static columns select the centre value.
-    const int OD = g.od;
+    // lane — the halo makes its loads legal for the static columns too — the static columns select the centred value, and
+    // one two-float scale per column finishes both: 1 / sigma for the static part, 1 / (sigma den) and 1 / (sigma den^2) for
+    // the regressions (den = 2 sum k^2).
     float *orow = out + ck.row0 * OD;
-    if (order == 0) {
-        for (int i = tid; i < n * dim; i += kPostThreads) orow[i] = X[i];
-        return;
-    }
-    const int blk = div20(tid, g.m_cw), cl = tid - blk * g.cw;
     if (blk >= g.nblk) return;
     const int rpt = div20(n + g.nblk - 1, g.m_nblk);
     const int r0 = blk * rpt, r1 = min(n, r0 + rpt);
     if (r0 >= r1) return;
     for (int c = cl; c < OD; c += g.cw) {
         const int part = div20(c, g.m_dim), d = c - part * dim;
+        const float4 ms = g.cmvn ? __ldg(stats + static_cast<int64_t>(ck.utt) * dim + d) : make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+        const float sc = part == 0 ? 1.0f : (part == 1 ? g.inv_den : g.inv_den * g.inv_den);
+        const float k_hi = ms.z * sc;
+        const float k_lo = fmaf(ms.z, sc, -k_hi) + ms.w * sc;     // (inv_hi + inv_lo) sc = k_hi + k_lo to two-float accuracy
         const float *x = (part == 2 ? D1 + HD * dim : X + HX * dim) + r0 * dim + d;
         float *o = orow + r0 * OD + c;
         const bool stat = part == 0;
-        if constexpr (W_ == 2) {
+        if (order == 0) {
+            for (int r = r0; r < r1; ++r, x += dim, o += OD) {
+                const float t = (*x - ms.x) - ms.y;
+                *o = fmaf(t, k_lo, t * k_hi);
+            }
+        } else if constexpr (W_ == 2) {
             float m2 = x[-2 * dim], m1 = x[-dim], c0 = x[0], p1 = x[dim];
             x += 2 * dim;
 #pragma unroll 5
             for (int r = r0; r < r1; ++r) {
                 const float p2 = *x;
-                const float v = fmaf(2.0f, p2 - m2, p1 - m1) * inv_den;
-                *o = stat ? c0 : v;
+                const float v = fmaf(2.0f, p2 - m2, p1 - m1);
+                const float t = stat ? (c0 - ms.x) - ms.y : v;
+                *o = fmaf(t, k_lo, t * k_hi);
                 x += dim;
                 o += OD;
                 m2 = m1; m1 = c0; c0 = p1; p1 = p2;
             }
         } else {
-            for (int r = r0; r < r1; ++r, x += dim, o += OD) *o = stat ? x[0] : regress(x, dim, W, inv_den);
+            for (int r = r0; r < r1; ++r, x += dim, o += OD) {
+                const float t = stat ? (x[0] - ms.x) - ms.y : regress(x, dim, W);
+                *o = fmaf(t, k_lo, t * k_hi);
+            }
         }
     }
 }
@@ -354,8 +390,10 @@ void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::
 
 size_t post_smem_bytes(int dim, int rows, int window, int order)
 {
+    // mbarrier slot, alignment room of the bulk copy, X with its halo (the staged block may start up to one halo further in),
+    // 4 floats behind it, D1 with its halo
     const int hx = order * window, hd = order == 2 ? window : 0;
-    return sizeof(float) * static_cast<size_t>(dim) * ((rows + 2 * hx) + (order == 2 ? rows + 2 * hd : 0));
+    return sizeof(float) * (4 + kPostFront + 4 + static_cast<size_t>(dim) * ((rows + 3 * hx) + (order == 2 ? rows + 2 * hd : 0)));
 }
 
 int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
@@ -383,7 +421,8 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
     g.inv_den = static_cast<float>(1.0 / den);
     const unsigned grid = static_cast<unsigned>(v.n_chunks);
     if (cmvn != MFCC_CMVN_NONE) {
-        post_stats_kernel<<<grid, kPostThreads, 0, s>>>(
+        const size_t smem_stats = sizeof(float) * (4 + kPostFront + 4 + static_cast<size_t>(v.rows) * dim);
+        post_stats_kernel<<<grid, kPostThreads, smem_stats, s>>>(
             v.chunks, static_cast<int>(v.chunk0), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
             static_cast<double2 *>(v.partial), static_cast<float4 *>(v.stats), v.count);
         g_launches.fetch_add(1, std::memory_order_relaxed);
