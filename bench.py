@@ -529,6 +529,13 @@ def measure_post(ctx, steps=20, warmup=3, n_utts=4096, frames_per_utt=998):
             "delta2_only": {"ms_per_step": res["delta2_only"], "value": frames / (res["delta2_only"] * 1e-3),
                             "roofline_frac": b_apply * frames / (res["delta2_only"] * 1e-3) / 1e9 / hbm_peak,
                             "algorithmic": f"{b_apply} B/frame, one launch (no statistics pass)"}}
+    try:   # measured DRAM bytes per frame of the two kernels together (one ncu --set full capture, profiles/r2_post.md)
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("post_cmvn_delta2")
+        if t:
+            line["roofline"]["traffic"] = int(round(t["bytes_per_frame"] * frames))
+            line["roofline"]["traffic_source"] = t["capture"]
+    except Exception:
+        pass
     del feat, out, batch
     plan.close()
     torch.cuda.empty_cache()

@@ -296,7 +296,7 @@ int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n
         const size_t nc = b->post_chunks.size(), dim = static_cast<size_t>(b->out_dim);
         const size_t nu = static_cast<size_t>(n_utts);
         if (cudaMalloc(&b->d_post_chunks, nc * sizeof(mfcc::PostChunk)) != cudaSuccess ||
-            cudaMalloc(&b->d_post_partial, nc * dim * sizeof(double2)) != cudaSuccess ||
+            cudaMalloc(&b->d_post_partial, nc * dim * mfcc::kPostPartialBytes) != cudaSuccess ||
             cudaMalloc(&b->d_post_stats, nu * dim * sizeof(double2)) != cudaSuccess ||
             cudaMalloc(&b->d_post_count, nu * sizeof(unsigned)) != cudaSuccess) {
             cudaGetLastError();
@@ -423,7 +423,7 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         const size_t nu = static_cast<size_t>(n_utts), d = static_cast<size_t>(od);
         if (rc == MFCC_OK) rc = grow(&plan->d_post_out, &plan->d_post_out_bytes, sizeof(float) * static_cast<size_t>(total_frames) * od_out);
         if (rc == MFCC_OK) rc = grow(&plan->d_post_chunks, &plan->d_post_chunks_bytes, pc_bytes);
-        if (rc == MFCC_OK) rc = grow(&plan->d_post_partial, &plan->d_post_partial_bytes, static_cast<size_t>(n_post_chunks) * d * sizeof(double2));
+        if (rc == MFCC_OK) rc = grow(&plan->d_post_partial, &plan->d_post_partial_bytes, static_cast<size_t>(n_post_chunks) * d * mfcc::kPostPartialBytes);
         if (rc == MFCC_OK) rc = grow(&plan->d_post_stats, &plan->d_post_stats_bytes, nu * d * sizeof(float4));
         if (rc == MFCC_OK) rc = grow(&plan->d_post_count, &plan->d_post_count_bytes, nu * sizeof(unsigned));
         if (rc == MFCC_OK && plan->h_post_chunks_bytes < pc_bytes) {
@@ -526,7 +526,7 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         if (ok && post != nullptr && f1 > f0) {
             const int64_t c0 = batch->utt_first_post_chunk[u0], c1 = batch->utt_first_post_chunk[u1];
             const mfcc::PostView view{static_cast<const mfcc::PostChunk *>(plan->d_post_chunks), c0, c1 - c0, batch->post_rows,
-                                      plan->d_post_partial, plan->d_post_stats, static_cast<unsigned *>(plan->d_post_count), plan->device};
+                                      plan->d_post_partial, plan->d_post_stats, static_cast<unsigned *>(plan->d_post_count), plan->device, plan->sm_count};
             ok = mfcc::launch_post(view, d_out, od, post->cmvn, post->order > 0 ? post->window : 1, post->order,
                                    static_cast<float *>(plan->d_post_out), s) == MFCC_OK;
             d_rows = static_cast<const float *>(plan->d_post_out);
@@ -876,7 +876,7 @@ int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float 
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
     const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
-                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device};
+                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
     return mfcc::launch_post(view, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, d_out,
                              static_cast<cudaStream_t>(cuda_stream));
 }

@@ -135,7 +135,7 @@ struct mfcc_batch {
     std::vector<int64_t> utt_first_post_chunk;   // [n_utts + 1]
     int post_rows = 0;
     mfcc::PostChunk *d_post_chunks = nullptr;
-    void *d_post_partial = nullptr;      // [chunks][out_dim] double2 {sum, sum of squares} about the utterance's first row
+    void *d_post_partial = nullptr;      // [chunks][out_dim] x kPostPartialBytes: per-group sums about the group's first row
     void *d_post_stats = nullptr;        // [n_utts][out_dim] float4 {mean hi, lo, 1 / sigma hi, lo}
     unsigned *d_post_count = nullptr;    // [n_utts] chunks of the utterance done so far (zero between calls)
 };
@@ -190,11 +190,13 @@ struct PostView {
     const PostChunk *chunks;
     int64_t chunk0, n_chunks;
     int rows;            // rows per chunk the table was cut with
-    void *partial;       // [chunks][dim] double2
+    void *partial;       // [chunks][dim] x 32 bytes (kPostPartialBytes)
     void *stats;         // [utterances][dim] float4
     unsigned *count;     // [utterances], zero between calls
     int device;
+    int sms;             // SMs of the device (grid of the persistent statistics kernel)
 };
+constexpr size_t kPostPartialBytes = 32;
 int post_rows_for(int dim);
 void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks,
                        std::vector<int64_t> &utt_first, int *rows_out);

@@ -117,90 +117,159 @@ __device__ __forceinline__ void stage_wait(const Staged &st, uint32_t bar)
     if (st.bulk) mbar_wait(bar, 0);
 }
 
-// ---- per-utterance statistics: one CTA per chunk, the utterance's last CTA to finish combines the partials ----
-// Inside a thread the ~14 values it meets are summed in f32 about the pivot (the utterance's first row: |x - pivot| is a few
-// sigma, so the sums keep 7 digits of a quantity whose mean needs 5, and the uncentred variance formula is free of
-// cancellation); across threads and chunks everything is double, in a fixed order — no floating-point atomics, so the
-// result is bit-reproducible and does not depend on which range of the batch a launch covers.
-// The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then normalises with FP32
-// instructions only, within 2 ulp of the double evaluation (x - mu_hi is exact or correctly rounded at the magnitude of the
-// RESULT, which is what the tolerance is stated on).
-__global__ void __launch_bounds__(kPostThreads, MFCC_POST_MINB_STATS)
-post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, const float *__restrict__ feat, const PostGeom g,
-                  int norm_var, double2 *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
+// ---- per-utterance statistics: persistent CTAs, each walks a contiguous range of chunks through a ring of bulk copies ----
+// Work is cut into GROUPS of up to kStatGroup consecutive chunks of one utterance, aligned to the utterance (chunks first +
+// 4 k .. first + 4 k + 3): a thread keeps its running sums in registers across the chunks of a group and the expensive part
+// — the cross-thread reduction, the partial to global memory, the fence and the counter — happens once per group, while the
+// bulk copies of the next chunks are already in flight (ring of kStatRing slots, one mbarrier each).  Which CTA walks which
+// group depends on the launch; what is summed in which order depends on the group alone, so every bit of the result is
+// independent of the grid and of the range of the batch a launch covers.
+// Inside a thread the values it meets are summed in f32 about a pivot (the first row of the group: |x - pivot| is a few sigma,
+// so the sums keep 7 digits of a quantity whose mean needs 5, and the uncentred variance formula is free of cancellation);
+// across threads and groups everything is double, in a fixed order, re-referenced to the utterance's first row — no
+// floating-point atomics.  The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then
+// normalises with FP32 instructions only, within 2 ulp of the double evaluation.
+constexpr int kStatGroup = 4, kStatRing = 3;
+struct StatPartial { double s, q, pivot, n; };    // sums of (x - pivot), (x - pivot)^2 over n rows
+
+__global__ void __launch_bounds__(kPostThreads, 4)
+post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks, const float *__restrict__ feat, const PostGeom g,
+                  int norm_var, StatPartial *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
 {
-    extern __shared__ __align__(16) float sm[];     // [4: mbarrier][kPostFront + rows * dim + 4]
+    extern __shared__ __align__(16) float sm[];     // [16: mbarriers][kStatRing slots of 4 + 4 + rows * dim (rounded up to 4) floats]
     __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
     __shared__ int s_last;
     const int tid = threadIdx.x, dim = g.dim, per = g.per;
     const int sub = div20(tid, g.m_dim), col = tid - sub * dim;
-    const int c = chunk0 + static_cast<int>(blockIdx.x);
-    const PostChunk ck = chunks[c];
-    const int total = ck.n * dim;
-    const uint32_t bar = smem_u32(sm);
+    const int slot_floats = 8 + ((g.rows * dim + 3) & ~3);
     const bool base_aligned = (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
-    const Staged st = stage_issue(sm + 4, 4, bar, feat + ck.row0 * dim, total, base_aligned, tid);
-    float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
-    const float pivot = tid < per ? __ldg(feat + ck.f0 * dim + col) : 0.0f;
-    stage_wait(st, bar);
-    if (tid < per) {
-        const float *x = st.block;
-        int i = tid;
-        for (; i + per < total; i += 2 * per) {
-            const float a = x[i] - pivot, b = x[i + per] - pivot;
-            s0 += a; q0 = fmaf(a, a, q0);
-            s1 += b; q1 = fmaf(b, b, q1);
+    const int end = chunk0 + n_chunks;
+    // this CTA's range of chunks, both ends moved up to the next start of a group
+    auto group_start = [&](int c) {
+        while (c < end) {
+            const int first = chunks[c].first_chunk;
+            if ((c - first) % kStatGroup == 0) break;
+            ++c;
         }
-        if (i < total) {
-            const float a = x[i] - pivot;
-            s0 += a; q0 = fmaf(a, a, q0);
+        return c;
+    };
+    const int lo = group_start(chunk0 + static_cast<int>(static_cast<int64_t>(n_chunks) * blockIdx.x / gridDim.x));
+    const int hi = group_start(chunk0 + static_cast<int>(static_cast<int64_t>(n_chunks) * (blockIdx.x + 1) / gridDim.x));
+    if (lo >= hi) return;
+
+    // where chunk k lands in its slot, and whether a bulk copy brings (most of) it: the same arithmetic for issuer and readers
+    struct Where { const float *block; const float *src; int cnt, a, body; };
+    auto where = [&](int k, const PostChunk &ck) {
+        Where w;
+        w.src = feat + ck.row0 * dim;
+        w.cnt = ck.n * dim;
+        w.a = base_aligned ? static_cast<int>((reinterpret_cast<uintptr_t>(w.src) >> 2) & 3) : 0;
+        w.body = base_aligned ? ((w.a + w.cnt) & ~3) : 0;
+        w.block = sm + 16 + ((k - lo) % kStatRing) * slot_floats + 4 + w.a;      // block - a is 16-byte aligned
+        return w;
+    };
+    auto issue = [&](int k) {
+        const PostChunk ck = chunks[k];
+        const Where w = where(k, ck);
+        float *block = const_cast<float *>(w.block);
+        if (tid == 0 && base_aligned) {     // every use of a slot completes one phase of its mbarrier, with or without a copy
+            const uint32_t bar = smem_u32(sm) + 8 * ((k - lo) % kStatRing);
+            if (w.body > 0) {
+                mbar_expect_tx(bar, static_cast<uint32_t>(w.body) * 4u);
+                bulk_g2s(smem_u32(block - w.a), w.src - w.a, static_cast<uint32_t>(w.body) * 4u, bar);
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            }
         }
-    }
-    s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
-    s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
+        for (int i = (w.body > 0 ? w.body - w.a : 0) + tid; i < w.cnt; i += kPostThreads) block[i] = __ldg(w.src + i);
+    };
+    if (tid == 0)
+        for (int r = 0; r < kStatRing; ++r) mbar_init(smem_u32(sm) + 8 * r, 1);
     __syncthreads();
-    // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
-    const int G = g.nsub < 4 ? g.nsub : 4;
-    if (sub < G) {
-        double ts = 0.0, tq = 0.0;
-        for (int j = sub; j < g.nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
-        s2_s[tid] = ts;
-        s2_q[tid] = tq;
-    }
+    for (int k = lo; k < hi && k < lo + kStatRing; ++k) issue(k);
     __syncthreads();
-    if (tid < dim) {
-        double ts = 0.0, tq = 0.0;
-        for (int k = 0; k < G; ++k) { ts += s2_s[tid + k * dim]; tq += s2_q[tid + k * dim]; }
-        partial[static_cast<int64_t>(c) * dim + tid] = make_double2(ts, tq);
-    }
-    __syncthreads();
-    if (tid == 0) {      // the fence is cumulative: the partials the other threads wrote before the barrier are ordered with it
-        __threadfence();
-        s_last = atomicAdd(&count[ck.utt], 1u) + 1u == static_cast<unsigned>(ck.n_chunks);
-        __threadfence();
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (tid < dim) {
-        double ts = 0.0, tq = 0.0;
-        const double2 *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
-        for (int k = 0; k < ck.n_chunks; ++k) {      // chunk order: the result does not depend on which CTA came last
-            const double2 v = __ldcg(p + static_cast<int64_t>(k) * dim);
-            ts += v.x;
-            tq += v.y;
+
+    float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f, pivot = 0.0f;
+    int gstart = lo, grows = 0;
+    for (int k = lo; k < hi; ++k) {
+        const PostChunk ck = chunks[k];
+        const Where w = where(k, ck);
+        if (base_aligned) mbar_wait(smem_u32(sm) + 8 * ((k - lo) % kStatRing), static_cast<uint32_t>(((k - lo) / kStatRing) & 1));
+        if (tid < per) {
+            const float *x = w.block;
+            if (k == gstart) pivot = x[col];
+            int i = tid;
+            for (; i + per < w.cnt; i += 2 * per) {
+                const float a = x[i] - pivot, b = x[i + per] - pivot;
+                s0 += a; q0 = fmaf(a, a, q0);
+                s1 += b; q1 = fmaf(b, b, q1);
+            }
+            if (i < w.cnt) {
+                const float a = x[i] - pivot;
+                s0 += a; q0 = fmaf(a, a, q0);
+            }
         }
-        const double T = static_cast<double>(ck.f1 - ck.f0);
-        const double m = ts / T;
-        double var = tq / T - m * m;
-        if (var < 0.0) var = 0.0;
-        const double mu = static_cast<double>(pivot) + m;
-        const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
-        const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
-        stats[static_cast<int64_t>(ck.utt) * dim + tid] =
-            make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
-                        static_cast<float>(inv - static_cast<double>(inv_hi)));
+        grows += ck.n;
+        const bool group_end = k + 1 == hi || k + 1 == ck.first_chunk + ck.n_chunks || (k + 1 - ck.first_chunk) % kStatGroup == 0;
+        if (group_end) {
+            s_s[tid] = static_cast<double>(s0) + static_cast<double>(s1);
+            s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
+        }
+        __syncthreads();                       // the slot is free (and the group's sums are in shared memory)
+        if (k + kStatRing < hi) issue(k + kStatRing);
+        if (!group_end) continue;
+        // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
+        const int G = g.nsub < 4 ? g.nsub : 4;
+        if (sub < G) {
+            double ts = 0.0, tq = 0.0;
+            for (int j = sub; j < g.nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
+            s2_s[tid] = ts;
+            s2_q[tid] = tq;
+        }
+        __syncthreads();
+        if (tid < dim) {
+            double ts = 0.0, tq = 0.0;
+            for (int j = 0; j < G; ++j) { ts += s2_s[tid + j * dim]; tq += s2_q[tid + j * dim]; }
+            partial[static_cast<int64_t>(gstart) * dim + tid] = StatPartial{ts, tq, static_cast<double>(pivot), static_cast<double>(grows)};
+        }
+        __syncthreads();
+        if (tid == 0) {      // the fence is cumulative: the partials the other threads wrote before the barrier are ordered with it
+            __threadfence();
+            const unsigned done = static_cast<unsigned>(k + 1 - gstart);
+            s_last = atomicAdd(&count[ck.utt], done) + done == static_cast<unsigned>(ck.n_chunks);
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_last) {
+            if (tid < dim) {
+                // group order, everything re-referenced to the utterance's first row P: sum (x - P) = s + n (p - P),
+                // sum (x - P)^2 = q + 2 (p - P) s + n (p - P)^2
+                const StatPartial *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
+                const double P = __ldcg(&p->pivot);
+                double ts = 0.0, tq = 0.0;
+                for (int j = 0; j < ck.n_chunks; j += kStatGroup) {
+                    const StatPartial *e = p + static_cast<int64_t>(j) * dim;
+                    const double s = __ldcg(&e->s), q = __ldcg(&e->q), dp = __ldcg(&e->pivot) - P, n = __ldcg(&e->n);
+                    ts += s + n * dp;
+                    tq += q + 2.0 * dp * s + n * dp * dp;
+                }
+                const double T = static_cast<double>(ck.f1 - ck.f0);
+                const double m = ts / T;
+                double var = tq / T - m * m;
+                if (var < 0.0) var = 0.0;
+                const double mu = P + m;
+                const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
+                const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
+                stats[static_cast<int64_t>(ck.utt) * dim + tid] =
+                    make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
+                                static_cast<float>(inv - static_cast<double>(inv_hi)));
+            }
+            if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
+        }
+        s0 = q0 = s1 = q1 = 0.0f;
+        gstart = k + 1;
+        grows = 0;
     }
-    if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
 }
 
 // regression sum of one column at row pointer x (row stride `dim` floats), run-time window: sum_k k (x[+k] - x[-k])
@@ -340,7 +409,7 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
     }
 }
 
-std::atomic<uint64_t> g_optin2{0}, g_optin0{0};
+std::atomic<uint64_t> g_optin2{0}, g_optin0{0}, g_optin_stats{0};
 
 }  // namespace
 
@@ -421,10 +490,15 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
     g.inv_den = static_cast<float>(1.0 / den);
     const unsigned grid = static_cast<unsigned>(v.n_chunks);
     if (cmvn != MFCC_CMVN_NONE) {
-        const size_t smem_stats = sizeof(float) * (4 + kPostFront + 4 + static_cast<size_t>(v.rows) * dim);
-        post_stats_kernel<<<grid, kPostThreads, smem_stats, s>>>(
-            v.chunks, static_cast<int>(v.chunk0), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
-            static_cast<double2 *>(v.partial), static_cast<float4 *>(v.stats), v.count);
+        const size_t smem_stats = sizeof(float) * (16 + static_cast<size_t>(kStatRing) * (8 + ((static_cast<size_t>(v.rows) * dim + 3) & ~static_cast<size_t>(3))));
+        if (smem_stats > kPostSmemMax) return MFCC_EINVAL;
+        // (the kernel also holds 8 KB of static shared memory: opt in whenever the sum could pass 48 KB — once per device)
+        if (smem_stats > 36 * 1024 && ensure_smem_optin(post_stats_kernel, v.device, kPostSmemMax, g_optin_stats) != MFCC_OK) return MFCC_ECUDA;
+        // persistent: 4 CTAs per SM, at least two chunks each
+        const int64_t want = std::min<int64_t>(4 * static_cast<int64_t>(std::max(v.sms, 1)), (v.n_chunks + 1) / 2);
+        post_stats_kernel<<<static_cast<unsigned>(std::max<int64_t>(want, 1)), kPostThreads, smem_stats, s>>>(
+            v.chunks, static_cast<int>(v.chunk0), static_cast<int>(v.n_chunks), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
+            static_cast<StatPartial *>(v.partial), static_cast<float4 *>(v.stats), v.count);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     const size_t smem = post_smem_bytes(dim, v.rows, window, order);

@@ -123,6 +123,23 @@ def test_post_other_row_widths(what):
 
 
 @pytest.mark.gpu
+def test_post_tiny_rows_and_unaligned_matrix():
+    """One and two columns per row (chunks of a few bytes: no bulk copy fits, the ring still has to turn), and a feature
+    matrix that starts 4 bytes off a 16-byte boundary (no bulk copies at all): same values."""
+    for n_cep in (1, 2, 3):
+        plan, b, feat = device_batch(make_params(n_cep=n_cep), [1, 2, 3, 0, 5, 300, 1, 1, 1, 1, 1, 2, 700])
+        g = plan.post(b, feat, 2, 2, 2).cpu().numpy()
+        ref = oracle.post(feat.cpu().numpy(), b.frame_offsets, 2, 2, 2)
+        assert np.abs(g.astype(np.float64) - ref).max() <= POST_TOL, n_cep
+    plan, b, feat = device_batch(config_a(), EDGE_FRAMES)
+    want = plan.post(b, feat, 2, 2, 2)
+    shifted = torch.empty(feat.numel() + 1, dtype=torch.float32, device="cuda")[1:].view_as(feat)
+    shifted.copy_(feat)
+    assert shifted.data_ptr() % 16 == 4
+    assert torch.equal(plan.post(b, shifted, 2, 2, 2), want)
+
+
+@pytest.mark.gpu
 def test_post_equals_the_separate_entries_and_hostile_statistics():
     plan, b, feat = device_batch(config_a(), [300, 1, 40, 700])
     stacked = plan.post(b, feat, 2, 2, 2).cpu().numpy()
