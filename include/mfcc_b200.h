@@ -79,9 +79,10 @@ typedef struct mfcc_params {
     int32_t energy;       /* MFCC_ENERGY_* */
 } mfcc_params;
 
-/* Threading.  A plan's parameters and device tables never change after creation, and mfcc_compute_batch(_f32),
- * mfcc_cmvn_batch and mfcc_delta_batch touch nothing else: they are reentrant (any number of host threads, distinct
- * streams).  The calls that take HOST buffers (mfcc_compute_host, mfcc_compute, mfcc_compute_host_g711 and every
+/* Threading.  A plan's parameters and device tables never change after creation, and mfcc_compute_batch(_f32, _g711)
+ * touch nothing else: they are reentrant (any number of host threads, distinct streams).  mfcc_post_batch,
+ * mfcc_cmvn_batch and mfcc_delta_batch additionally use the statistics scratch that belongs to the BATCH: reentrant across
+ * batches, stream-ordered on one batch.  The calls that take HOST buffers (mfcc_compute_host, mfcc_compute, mfcc_compute_host_g711 and every
  * mfcc_stream_* / mfcc_stream_feed_many call on the plan) share plan-owned staging buffers, streams and events that
  * grow on demand; they serialise on a mutex inside the plan, so they are safe to call from several threads but run
  * one at a time per plan.  Use one plan per thread for concurrent host-buffer traffic. */
@@ -166,7 +167,8 @@ int mfcc_compute_host_g711(mfcc_plan *plan, const uint8_t *h_codes, int32_t alaw
 int mfcc_compute(mfcc_plan *plan, const int16_t *pcm, int64_t n_samples,
                  float *out, int64_t *n_frames);
 
-/* Post-processing on the feature matrix on the device:
+/* Post-processing on the feature matrix on the device, one step at a time (the same kernels as
+ * mfcc_post_batch below, which does all of it in one pass and is the one to use when the stacked matrix is wanted):
  * mfcc_cmvn_batch : per-utterance cepstral mean (norm_var != 0: and variance) normalisation of d_feat IN PLACE;
  * mfcc_delta_batch: delta regression over +-window frames (HTK formula, edge frames replicated) of d_feat written to
  *                   d_delta (same shape, must not alias d_feat; both required).  Delta-delta = a second call on the

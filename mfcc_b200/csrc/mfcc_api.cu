@@ -527,7 +527,7 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
             const int64_t c0 = batch->utt_first_post_chunk[u0], c1 = batch->utt_first_post_chunk[u1];
             const mfcc::PostView view{static_cast<const mfcc::PostChunk *>(plan->d_post_chunks), c0, c1 - c0, batch->post_rows,
                                       plan->d_post_partial, plan->d_post_stats, static_cast<unsigned *>(plan->d_post_count), plan->device, plan->sm_count};
-            ok = mfcc::launch_post(view, d_out, od, post->cmvn, post->order > 0 ? post->window : 1, post->order,
+            ok = mfcc::launch_post(view, d_out, od, post->cmvn, post->order > 0 ? post->window : 1, post->order, 0,
                                    static_cast<float *>(plan->d_post_out), s) == MFCC_OK;
             d_rows = static_cast<const float *>(plan->d_post_out);
         }
@@ -845,7 +845,11 @@ int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_fea
     if (d_feat == nullptr) return MFCC_EINVAL;
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
-    return mfcc::launch_cmvn(batch, d_feat, batch->out_dim, norm_var != 0, static_cast<cudaStream_t>(cuda_stream));
+    // the fused kernels with no regression: a CTA reads its rows into shared memory, then writes them back normalised
+    const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
+                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
+    return mfcc::launch_post(view, d_feat, batch->out_dim, norm_var != 0 ? MFCC_CMVN_MEAN_VAR : MFCC_CMVN_MEAN, 1, 0, 0, d_feat,
+                             static_cast<cudaStream_t>(cuda_stream));
 }
 
 int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t window,
@@ -857,7 +861,11 @@ int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float
     if (d_feat == nullptr || d_delta == nullptr) return MFCC_EINVAL;
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
-    return mfcc::launch_delta(batch, d_feat, batch->out_dim, window, d_delta, static_cast<cudaStream_t>(cuda_stream));
+    // the fused kernels without normalisation, writing the regression part only
+    const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
+                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
+    return mfcc::launch_post(view, d_feat, batch->out_dim, MFCC_CMVN_NONE, window, 1, 1, d_delta,
+                             static_cast<cudaStream_t>(cuda_stream));
 }
 
 int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float *d_feat, int32_t cmvn,
@@ -877,7 +885,7 @@ int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float 
     if (!guard.ok) return MFCC_ECUDA;
     const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
                               batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
-    return mfcc::launch_post(view, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, d_out,
+    return mfcc::launch_post(view, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, 0, d_out,
                              static_cast<cudaStream_t>(cuda_stream));
 }
 

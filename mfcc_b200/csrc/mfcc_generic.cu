@@ -113,81 +113,6 @@ generic_radix2_kernel(const Tile *__restrict__ tiles, const PcmT *__restrict__ p
     }
 }
 
-// ---- §8(f) rank 2: per-utterance CMVN, one CTA per (utterance, coefficient group) ----
-__global__ void __launch_bounds__(256)
-cmvn_kernel(const int64_t *__restrict__ frame_offsets, float *__restrict__ feat, int dim, int norm_var)
-{
-    const int64_t f0 = frame_offsets[blockIdx.x], f1 = frame_offsets[blockIdx.x + 1];
-    const int64_t T = f1 - f0;
-    if (T <= 0) return;
-    __shared__ double s_sum[8][32];
-    __shared__ double s_stat[2][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Each lane owns coefficient d = lane (+32 per outer pass); warps stride over frames.
-    for (int d0 = 0; d0 < dim; d0 += 32) {
-        const int d = d0 + lane;
-        double acc = 0.0;
-        if (d < dim)
-            for (int64_t f = f0 + warp; f < f1; f += 8) acc += static_cast<double>(feat[f * dim + d]);
-        s_sum[warp][lane] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            double t = 0.0;
-            for (int w = 0; w < 8; ++w) t += s_sum[w][lane];
-            s_stat[0][lane] = t / static_cast<double>(T);
-        }
-        __syncthreads();
-        const double mu = s_stat[0][lane];
-        acc = 0.0;
-        if (d < dim)
-            for (int64_t f = f0 + warp; f < f1; f += 8) {
-                const double c = static_cast<double>(feat[f * dim + d]) - mu;
-                acc += c * c;
-            }
-        s_sum[warp][lane] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            double t = 0.0;
-            for (int w = 0; w < 8; ++w) t += s_sum[w][lane];
-            t /= static_cast<double>(T);
-            s_stat[1][lane] = norm_var ? 1.0 / sqrt(t > 1e-20 ? t : 1e-20) : 1.0;
-        }
-        __syncthreads();
-        const double inv = s_stat[1][lane];
-        if (d < dim)
-            for (int64_t f = f0 + warp; f < f1; f += 8)
-                feat[f * dim + d] = static_cast<float>((static_cast<double>(feat[f * dim + d]) - mu) * inv);
-        __syncthreads();
-    }
-}
-
-// ---- §8(f) rank 2: HTK regression deltas, one thread per output element ----
-__global__ void __launch_bounds__(256)
-delta_kernel(const int64_t *__restrict__ frame_offsets, int64_t n_utts, const float *__restrict__ feat,
-             int dim, int window, float *__restrict__ delta, int64_t total)
-{
-    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int64_t f = idx / dim;
-    const int d = static_cast<int>(idx - f * dim);
-    // binary search: utterance u with frame_offsets[u] <= f < frame_offsets[u+1]
-    int64_t lo = 0, hi = n_utts;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (frame_offsets[mid] <= f) lo = mid; else hi = mid;
-    }
-    const int64_t f0 = frame_offsets[lo], f1 = frame_offsets[lo + 1];
-    double acc = 0.0, den = 0.0;
-    for (int n = 1; n <= window; ++n) {
-        const int64_t fp = f + n < f1 ? f + n : f1 - 1;
-        const int64_t fm = f - n >= f0 ? f - n : f0;
-        acc += static_cast<double>(n) *
-               (static_cast<double>(feat[fp * dim + d]) - static_cast<double>(feat[fm * dim + d]));
-        den += 2.0 * n * n;
-    }
-    delta[idx] = static_cast<float>(acc / den);
-}
-
 // ---- §8(f) rank 3: G.711 expansion, 16 codes per thread (uint4 in, 2 x uint4 out) ----
 __device__ __forceinline__ int ulaw_expand(unsigned b)
 {
@@ -263,27 +188,6 @@ template int launch_generic<float>(const mfcc_plan *, const Tile *, int64_t, con
                                    cudaStream_t);
 template int launch_generic<uint8_t>(const mfcc_plan *, const Tile *, int64_t, const uint8_t *, float *, int,
                                      cudaStream_t);
-
-int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s)
-{
-    if (batch->n_utts <= 0) return MFCC_OK;
-    cmvn_kernel<<<static_cast<unsigned>(batch->n_utts), 256, 0, s>>>(batch->d_frame_offsets, d_feat, dim,
-                                                                     norm_var);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
-}
-
-int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
-                 cudaStream_t s)
-{
-    const int64_t total = batch->total_frames * dim;
-    if (total <= 0) return MFCC_OK;
-    const int64_t blocks = (total + 255) / 256;
-    delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(batch->d_frame_offsets, batch->n_utts,
-                                                               d_feat, dim, window, d_delta, total);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError() == cudaSuccess ? MFCC_OK : MFCC_ECUDA;
-}
 
 int launch_g711(const uint8_t *d_src, int64_t n, int alaw, int16_t *d_dst, cudaStream_t s)
 {

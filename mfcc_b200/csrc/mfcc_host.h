@@ -181,9 +181,6 @@ void wide_release(mfcc_plan *plan);
 template <typename PcmT>
 int wide_launch(const mfcc_plan *plan, const Tile *d_tiles, int64_t n_tiles, const PcmT *d_pcm, int64_t pcm_len,
                 float *d_out, cudaStream_t stream);
-int launch_cmvn(const mfcc_batch *batch, float *d_feat, int dim, int norm_var, cudaStream_t s);
-int launch_delta(const mfcc_batch *batch, const float *d_feat, int dim, int window, float *d_delta,
-                 cudaStream_t s);
 // what a launch of the post-processing kernels works on: the chunks [chunk0, chunk0 + n_chunks) of a device chunk table and
 // the statistics scratch that goes with the table (indexed by global chunk / utterance number)
 struct PostView {
@@ -201,7 +198,8 @@ int post_rows_for(int dim);
 void post_build_chunks(const std::vector<int64_t> &frame_offsets, int dim, std::vector<PostChunk> &chunks,
                        std::vector<int64_t> &utt_first, int *rows_out);
 size_t post_smem_bytes(int dim, int rows, int window, int order);
-int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
+// part0 = 0: out rows are static | delta | delta-delta (1 + order parts); part0 = 1: the regressions only (order parts)
+int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, int part0, float *d_out,
                 cudaStream_t s);
 int launch_g711(const uint8_t *d_src, int64_t n, int alaw, int16_t *d_dst, cudaStream_t s);
 

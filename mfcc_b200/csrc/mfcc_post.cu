@@ -48,6 +48,7 @@ constexpr int kPostFront = 8;      // floats kept free in front of a staged bloc
 // gives a thread only ~40 output elements, so a handful of 20-instruction divisions per thread is a third of the work.
 struct PostGeom {
     int dim, rows, order, window, cmvn;
+    int part0;            // first output part: 0 = static | delta | ..., 1 = the regressions only (mfcc_delta_batch)
     int per;              // (256 / dim) * dim: thread t < per always meets column t % dim
     int nsub;             // per / dim
     int od, cw, nblk;     // output columns, columns per pass of the stacking sweep, row blocks in it
@@ -288,8 +289,9 @@ __device__ __forceinline__ float regress(const float *x, int dim, int W)
 // column: a thread keeps the 2 W + 1 values of its window in registers and loads one new value per row.
 template <int W_>
 __global__ void __launch_bounds__(kPostThreads, MFCC_POST_MINB)
-post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict__ feat,
-                  const float4 *__restrict__ stats, const PostGeom g, float *__restrict__ out)   // chunks: first chunk of the launch
+post_apply_kernel(const PostChunk *__restrict__ chunks, const float *feat,
+                  const float4 *__restrict__ stats, const PostGeom g, float *out)   // chunks: first chunk of the launch; out may
+                                                                                     // be feat when order == 0 (a CTA reads its rows, then writes them)
 {
     extern __shared__ __align__(16) float sm[];   // [4: mbarrier][kPostFront + (rows + 2 HX) dim + 4][(rows + 2 HD) dim]
     const int W = W_ ? W_ : g.window;
@@ -374,7 +376,7 @@ post_apply_kernel(const PostChunk *__restrict__ chunks, const float *__restrict_
     const int r0 = blk * rpt, r1 = min(n, r0 + rpt);
     if (r0 >= r1) return;
     for (int c = cl; c < OD; c += g.cw) {
-        const int part = div20(c, g.m_dim), d = c - part * dim;
+        const int pc = div20(c, g.m_dim), d = c - pc * dim, part = pc + g.part0;
         const float4 ms = g.cmvn ? __ldg(stats + static_cast<int64_t>(ck.utt) * dim + d) : make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         const float sc = part == 0 ? 1.0f : (part == 1 ? g.inv_den : g.inv_den * g.inv_den);
         const float k_hi = ms.z * sc;
@@ -465,7 +467,7 @@ size_t post_smem_bytes(int dim, int rows, int window, int order)
     return sizeof(float) * (4 + kPostFront + 4 + static_cast<size_t>(dim) * ((rows + 3 * hx) + (order == 2 ? rows + 2 * hd : 0)));
 }
 
-int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, float *d_out,
+int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int window, int order, int part0, float *d_out,
                 cudaStream_t s)
 {
     if (v.n_chunks <= 0) return MFCC_OK;
@@ -476,9 +478,10 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
     g.order = order;
     g.window = window;
     g.cmvn = cmvn != MFCC_CMVN_NONE;
+    g.part0 = part0;
     g.per = (kPostThreads / dim) * dim;
     g.nsub = g.per / dim;
-    g.od = dim * (1 + order);
+    g.od = dim * (1 + order - part0);
     g.cw = std::min(g.od, kPostThreads);
     g.nblk = kPostThreads / g.cw;
     g.m_dim = magic20(dim);
