@@ -19,6 +19,9 @@ HOT = {
     "sp_A": ("fused_sp_kernel", ["Is", "Li400", "Li160", "Li32", "Li16", "Li26", "Li13"]),
     "sp_B": ("fused_sp_kernel", ["Is", "Li200", "Li80", "Li16", "Li16", "Li20", "Li13"]),
     "wide_C": ("fused_wide_kernel", ["Is", "Li1200", "Li480", "Li80"]),
+    # post-processing (mfcc_post.cu): matched by an exact substring of the mangled name
+    "post_apply": ("post_apply_kernel", "post_apply_kernelILi2EE"),
+    "post_stats": ("post_stats_kernel", "post_stats_kernel"),
 }
 
 
@@ -51,10 +54,13 @@ def main():
         if m and i + 1 < len(lines):
             usage[m.group(1)] = lines[i + 1].strip()
     for name, (stem, keys) in HOT.items():
-        cands = [f for f in funcs if stem in f and all(k in f for k in keys)]
-        # template args appear in order: require the exact sequence
-        seq = "I" + keys[0][1:] + "".join(k + "E" for k in keys[1:]) + "E"     # e.g. IsLi400ELi160E...Li13EE
-        cands = [f for f in cands if seq in f]
+        if isinstance(keys, str):
+            cands = [f for f in funcs if keys in f]
+        else:
+            cands = [f for f in funcs if stem in f and all(k in f for k in keys)]
+            # template args appear in order: require the exact sequence
+            seq = "I" + keys[0][1:] + "".join(k + "E" for k in keys[1:]) + "E"     # e.g. IsLi400ELi160E...Li13EE
+            cands = [f for f in cands if seq in f]
         if not cands:
             print("not found:", name)
             continue
