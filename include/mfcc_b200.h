@@ -128,6 +128,17 @@ int64_t mfcc_plan_dct(const mfcc_plan *plan, float *dst);
  * non-decreasing).  Computes frame rows and the tile table and uploads it. */
 int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts,
                       mfcc_batch **out);
+/* The same for PIECES of longer recordings (a 10-minute stream cut across GPUs, a file processed in slices): h_lead[u] != 0
+ * says the first sample of utterance u is HISTORY — the sample right before the piece in its recording.  It only serves as
+ * the pre-emphasis predecessor of the piece's first frame; the piece's frames start at h_offsets[u] + 1.  With pieces cut at
+ * frame boundaries (mfcc_piece_span) the rows of the pieces, one after the other, are the rows of the whole recording bit
+ * for bit.  h_lead == NULL: mfcc_batch_create. */
+int mfcc_batch_create_lead(const mfcc_plan *plan, const int64_t *h_offsets, const uint8_t *h_lead, int64_t n_utts,
+                           mfcc_batch **out);
+/* Sample span [*begin, *end) of the piece that holds frames [f0, f1) of a recording of n_samples samples, and whether it
+ * starts with one history sample (*lead = 1 whenever f0 > 0).  Pure host code. */
+int mfcc_piece_span(const mfcc_params *p, int64_t n_samples, int64_t f0, int64_t f1, int64_t *begin, int64_t *end,
+                    int32_t *lead);
 void mfcc_batch_destroy(mfcc_batch *batch);
 int64_t mfcc_batch_total_frames(const mfcc_batch *batch);
 int64_t mfcc_batch_total_samples(const mfcc_batch *batch);

@@ -43,6 +43,8 @@ ABI = {
     "mfcc_plan_mel_weights": (_i64, [_vp, _vp]),
     "mfcc_plan_dct": (_i64, [_vp, _vp]),
     "mfcc_batch_create": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp)]),
+    "mfcc_batch_create_lead": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(_vp)]),
+    "mfcc_piece_span": (C.c_int, [_vp, _i64, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "mfcc_batch_destroy": (None, [_vp]),
     "mfcc_batch_total_frames": (_i64, [_vp]),
     "mfcc_batch_total_samples": (_i64, [_vp]),
@@ -126,18 +128,32 @@ def _stream_handle(stream) -> Optional[int]:
     return getattr(stream, "cuda_stream", stream)
 
 
+def piece_span(params: MfccParams, n_samples: int, f0: int, f1: int):
+    """``mfcc_piece_span``: (begin, end, lead) of the piece holding frames [f0, f1) of a recording of n_samples samples."""
+    b, e, l = _i64(0), _i64(0), _i32(0)
+    _check(load().mfcc_piece_span(C.byref(params), n_samples, f0, f1, C.byref(b), C.byref(e), C.byref(l)), "mfcc_piece_span")
+    return int(b.value), int(e.value), int(l.value)
+
+
 class Batch:
     """The shape of one batch: utterance offsets -> frame rows -> tile table (device-resident)."""
 
-    def __init__(self, plan: "Plan", offsets: Sequence[int]):
+    def __init__(self, plan: "Plan", offsets: Sequence[int], lead: Optional[Sequence[int]] = None):
         self.plan = plan
         self.offsets = np.ascontiguousarray(offsets, np.int64)
         if self.offsets.ndim != 1 or self.offsets.size < 1:
             raise ValueError("offsets must be a 1-D array of n_utts + 1 entries")
         self.n_utts = self.offsets.size - 1
         h = _vp()
-        _check(load().mfcc_batch_create(plan._h, self.offsets.ctypes.data, self.n_utts, C.byref(h)),
-               "mfcc_batch_create")
+        if lead is None:
+            _check(load().mfcc_batch_create(plan._h, self.offsets.ctypes.data, self.n_utts, C.byref(h)),
+                   "mfcc_batch_create")
+        else:   # pieces of longer recordings: lead[u] = 1 marks a first sample that is history only
+            self.lead = np.ascontiguousarray(lead, np.uint8)
+            if self.lead.shape != (self.n_utts,):
+                raise ValueError("lead must hold one flag per utterance")
+            _check(load().mfcc_batch_create_lead(plan._h, self.offsets.ctypes.data, self.lead.ctypes.data, self.n_utts,
+                                                 C.byref(h)), "mfcc_batch_create_lead")
         self._h = h
         self.total_frames = int(load().mfcc_batch_total_frames(h))
         self.total_samples = int(load().mfcc_batch_total_samples(h))
@@ -204,8 +220,8 @@ class Plan:
         return a.reshape(self.params.n_cep, self.params.n_mel)
 
     # ---- the hot entry: device tensors in, device tensor out ----
-    def batch(self, offsets: Sequence[int]) -> Batch:
-        return Batch(self, offsets)
+    def batch(self, offsets: Sequence[int], lead: Optional[Sequence[int]] = None) -> Batch:
+        return Batch(self, offsets, lead)
 
     def compute_batch(self, batch: Batch, pcm, out=None, stream=None, alaw: bool = False):
         """``pcm``: torch CUDA tensor, int16 (or float32 scaled to int16 range, or uint8 G.711 codes — mu-law unless

@@ -219,7 +219,10 @@ int64_t mfcc_plan_dct(const mfcc_plan *plan, float *dst)
 }
 
 // Host half of a batch: offsets -> frame rows -> tile table.  No CUDA calls.
-static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out)
+// h_lead (may be null): h_lead[u] != 0 marks utterance u as a PIECE of a longer recording whose first sample is history — it
+// only serves as the pre-emphasis predecessor of the piece's first frame; the frames start one sample later.
+static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out,
+                            const uint8_t *h_lead = nullptr)
 {
     if (out == nullptr) return MFCC_EINVAL;
     *out = nullptr;
@@ -241,14 +244,15 @@ static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int
         for (int64_t u = 0; u < n_utts; ++u) {
             const int64_t begin = b->offsets[u], end = b->offsets[u + 1];
             if (begin < 0 || end < begin) { delete b; return MFCC_EINVAL; }
-            const int64_t nf = mfcc_num_frames(&p, end - begin);
+            const int64_t lead = (h_lead != nullptr && h_lead[u] != 0 && end > begin) ? 1 : 0;
+            const int64_t nf = mfcc_num_frames(&p, end - begin - lead);
             b->frame_offsets[u + 1] = b->frame_offsets[u] + nf;
             b->utt_first_tile[u] = static_cast<int64_t>(b->tiles.size());
             for (int64_t f = 0; f < nf; f += mfcc::kTileFrames) {
                 Tile t;
                 t.utt_begin = begin;
                 t.utt_end = end;
-                t.first_sample = begin + f * p.hop_len;
+                t.first_sample = begin + lead + f * p.hop_len;
                 t.out_row = b->frame_offsets[u] + f;
                 t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, nf - f));
                 t.flags = 0;
@@ -270,8 +274,14 @@ static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int
 
 int mfcc_batch_create(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out)
 {
+    return mfcc_batch_create_lead(plan, h_offsets, nullptr, n_utts, out);
+}
+
+int mfcc_batch_create_lead(const mfcc_plan *plan, const int64_t *h_offsets, const uint8_t *h_lead, int64_t n_utts,
+                           mfcc_batch **out)
+{
     mfcc_batch *b = nullptr;
-    const int rc = batch_build_host(plan, h_offsets, n_utts, &b);
+    const int rc = batch_build_host(plan, h_offsets, n_utts, &b, h_lead);
     if (out) *out = nullptr;
     if (rc != MFCC_OK) return rc;
     DeviceGuard guard(plan->device);

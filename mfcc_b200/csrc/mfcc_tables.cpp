@@ -153,6 +153,24 @@ int64_t mfcc_num_frames(const mfcc_params *p, int64_t n)
     return n <= L ? 1 : 1 + (n - L + H - 1) / H;
 }
 
+int mfcc_piece_span(const mfcc_params *p, int64_t n, int64_t f0, int64_t f1, int64_t *begin, int64_t *end, int32_t *lead)
+{
+    const int64_t total = mfcc_num_frames(p, n);
+    if (total < 0 || f0 < 0 || f1 < f0 || f1 > total || begin == nullptr || end == nullptr || lead == nullptr) return MFCC_EINVAL;
+    const int64_t L = p->frame_len, H = p->hop_len;
+    *lead = f0 > 0 ? 1 : 0;
+    if (f1 == f0) {                 // no frames: an empty span
+        *begin = *end = 0;
+        *lead = 0;
+        return MFCC_OK;
+    }
+    *begin = f0 * H - *lead;
+    // every piece but the last ends with its last frame; the last one keeps the rest of the recording (what a zero-padded
+    // last frame needs under MFCC_PAD_ZERO_TAIL; under MFCC_PAD_NONE the samples past the last frame are never read)
+    *end = f1 == total ? n : (f1 - 1) * H + L;
+    return MFCC_OK;
+}
+
 int32_t mfcc_out_dim(const mfcc_params *p)
 {
     if (mfcc::validate_params(p) != MFCC_OK) return MFCC_EINVAL;

@@ -57,6 +57,28 @@ def partition(p: MfccParams, offsets: Sequence[int], world_size: int) -> List[Tu
     return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
+def split_stream(p: MfccParams, n_samples: int, pieces: int) -> List[Tuple[int, int, int, int, int]]:
+    """ONE long recording over several GPUs ("long streams may additionally be split at frame boundaries with
+    a (frame_len - hop) + 1-sample read overlap"): `pieces` contiguous frame ranges of near-equal size.  Returns per piece
+    ``(f0, f1, begin, end, lead)``: frames [f0, f1) live in samples [begin, end) of the recording, and ``lead`` = 1 says the
+    first of those samples is history only (the pre-emphasis predecessor of the piece's first frame) — pass it to
+    ``Plan.batch(offsets, lead=...)`` / ``mfcc_batch_create_lead``.  The rows of the pieces, concatenated, are the rows of
+    the whole recording bit for bit.  Pure integer math, the same as ``mfcc_piece_span`` in the C ABI."""
+    if pieces < 1:
+        raise ValueError("pieces must be >= 1")
+    total = int(frame_counts(p, [0, n_samples])[0])
+    L, H = int(p.frame_len), int(p.hop_len)
+    out = []
+    for r in range(pieces):
+        f0, f1 = total * r // pieces, total * (r + 1) // pieces
+        if f1 == f0:
+            out.append((f0, f1, 0, 0, 0))
+            continue
+        lead = 1 if f0 > 0 else 0
+        out.append((f0, f1, f0 * H - lead, n_samples if f1 == total else (f1 - 1) * H + L, lead))
+    return out
+
+
 def local_slice(offsets: Sequence[int], u0: int, u1: int) -> Tuple[int, int, np.ndarray]:
     """Sample range [s0, s1) of utterances [u0, u1) and their offsets rebased to 0."""
     off = np.asarray(offsets, np.int64)

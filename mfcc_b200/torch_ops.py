@@ -4,6 +4,7 @@
     h = ops.Handle(params, offsets, device=0)           # plan + batch (tables and tile table on the device)
     feat = torch.ops.mfcc_b200.compute_batch(pcm, h.id)  # [total_frames, out_dim] f32, on the CURRENT stream
     feat = ops.mfcc_from_dlpack(cupy_or_any_dlpack_array, h)   # zero-copy in, torch tensor (DLPack-exportable) out
+    full = torch.ops.mfcc_b200.post(feat, h.id, 2, 2, 2)  # per-utterance CMVN + delta + delta-delta, [total_frames, 3 out_dim]
 
 The op launches the library's own sm_100a kernels through ``mfcc_compute_batch`` / ``_f32`` / ``_g711`` on
 ``torch.cuda.current_stream()``; it has a fake (meta) implementation so it traces under ``torch.compile`` /
@@ -53,6 +54,20 @@ def compute_batch(pcm: torch.Tensor, handle: int, alaw: bool = False) -> torch.T
 def _(pcm, handle, alaw=False):
     h = _HANDLES[handle]
     return pcm.new_empty(h.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("mfcc_b200::post", mutates_args=(), device_types="cuda")
+def post(feat: torch.Tensor, handle: int, cmvn: int = 2, window: int = 2, order: int = 2) -> torch.Tensor:
+    """Fused per-utterance CMVN + delta + delta-delta (``mfcc_post_batch``) of the handle's batch: the stacked
+    ``[frames, out_dim * (1 + order)]`` matrix, on the current stream."""
+    h = _HANDLES[handle]
+    return h.plan.post(h.batch, feat.contiguous(), cmvn, window, order)
+
+
+@post.register_fake
+def _(feat, handle, cmvn=2, window=2, order=2):
+    h = _HANDLES[handle]
+    return feat.new_empty((h.shape[0], h.shape[1] * (1 + order)), dtype=torch.float32)
 
 
 def mfcc_from_dlpack(x, handle: Handle, alaw: bool = False) -> torch.Tensor:

@@ -31,8 +31,25 @@ int main(void)
     rc = mfcc_compute(plan, pcm, N, out, &got);
     printf("mfcc_compute: %s, %lld frames, c0[0] = %f, kernel %s\n", mfcc_strerror(rc), (long long)got, out[0],
            mfcc_plan_kernel_name(plan));
+    if (rc != MFCC_OK || got != nf) return 8;
+
+    /* the same clip with per-utterance CMVN + delta + delta-delta (39 columns back): the mean-normalised static part
+     * sums to zero over the utterance, column by column */
+    {
+        const int64_t offsets[2] = {0, N};
+        int64_t fo[2] = {0, 0};
+        float *out3 = NULL;
+        double sum0 = 0.0;
+        if (mfcc_host_alloc((void **)&out3, sizeof(float) * (size_t)nf * 39) != MFCC_OK) return 9;
+        rc = mfcc_compute_host_post(plan, pcm, offsets, 1, MFCC_CMVN_MEAN, 2, 2, out3, fo);
+        for (int64_t t = 0; rc == MFCC_OK && t < nf; ++t) sum0 += out3[t * 39];
+        printf("mfcc_compute_host_post: %s, %lld frames x 39, sum of normalised c0 = %.3g\n", mfcc_strerror(rc),
+               (long long)fo[1], sum0);
+        mfcc_host_free(out3);
+        if (rc != MFCC_OK || fo[1] != nf || sum0 > 1e-2 || sum0 < -1e-2) return 10;
+    }
     mfcc_host_free(pcm);
     mfcc_host_free(out);
     mfcc_plan_destroy(plan);
-    return rc == MFCC_OK && got == nf ? 0 : 8;
+    return 0;
 }

@@ -89,6 +89,22 @@ def _gpu_worker(rank, world, port, out_path):
         whole = plan.compute_batch(plan.batch(off), torch.from_numpy(pcm).cuda())
         torch.cuda.synchronize()
         assert full.shape == whole.shape and torch.equal(full, whole)   # sharded + gathered == one GPU, bit for bit
+        # ONE long 48 kHz recording spread over the ranks: pieces cut at frame boundaries with one history sample
+        # (sharding.split_stream + mfcc_batch_create_lead), gathered == the whole recording on one GPU, bit for bit
+        from mfcc_b200 import config_c
+        from mfcc_b200.sharding import split_stream
+        from mfcc_b200.synth import noise_utterance
+        pc = config_c()
+        n = 48000 * 30 + 77
+        x = noise_utterance(n, seed=5)
+        planc = api.Plan(pc, device=rank)
+        f0, f1, sb, se, lead = split_stream(pc, n, world)[rank]
+        bc = planc.batch(np.array([0, se - sb], np.int64), lead=[lead])
+        piece = planc.compute_batch(bc, torch.from_numpy(x[sb:se].copy()).cuda())
+        fullc, countsc = gather_features(piece, bc.total_frames, planc.out_dim)
+        wholec = planc.compute_batch(planc.batch(np.array([0, n], np.int64)), torch.from_numpy(x).cuda())
+        torch.cuda.synchronize()
+        assert bc.total_frames == f1 - f0 and torch.equal(fullc, wholec)
         with open(f"{out_path}.{rank}", "w") as f:
             f.write("ok")
     finally:

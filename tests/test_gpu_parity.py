@@ -617,6 +617,15 @@ def test_torch_custom_op_and_dlpack_entry():
     def front_end(x):
         return torch.ops.mfcc_b200.compute_batch(x, h.id) * 2.0
     assert torch.equal(front_end(d), want * 2.0)
+    # the post-processing op on the same handle: stacked rows, same bits as the plan's own call, traceable
+    full = torch.ops.mfcc_b200.post(want, h.id, 2, 2, 2)
+    assert full.shape == (h.shape[0], 3 * h.shape[1]) and torch.equal(full, h.plan.post(h.batch, want, 2, 2, 2))
+    torch.library.opcheck(torch.ops.mfcc_b200.post.default, (want, h.id, 2, 2, 2), test_utils=("test_schema", "test_faketensor"))
+
+    @torch.compile(fullgraph=True)
+    def front_end39(x):
+        return torch.ops.mfcc_b200.post(torch.ops.mfcc_b200.compute_batch(x, h.id), h.id, 2, 2, 2)
+    assert torch.equal(front_end39(d), full)
     # DLPack in (a capsule from another owner of the memory), DLPack out
     cap = torch.utils.dlpack.to_dlpack(d.float())
     class Foreign:          # an object that only speaks the protocol
@@ -629,6 +638,38 @@ def test_torch_custom_op_and_dlpack_entry():
     assert back.data_ptr() == out.data_ptr()
     del cap
     h.close()
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_pieces_of_a_long_recording_equal_the_whole(name):
+    """One long recording cut into pieces at frame boundaries (sharding.split_stream / mfcc_piece_span), every piece but the
+    first carrying one history sample (mfcc_batch_create_lead): the rows of the pieces, one after the other, are the rows
+    of the whole recording bit for bit — what lets one stream be spread over several GPUs."""
+    from mfcc_b200.sharding import split_stream
+    for pad in (0, PAD_ZERO_TAIL):
+        p = CFG[name]()
+        p.pad_mode = pad
+        plan = api.Plan(p)
+        n = p.sample_rate * 20 + 137                       # 20 s and a ragged end
+        x = noise_utterance(n, seed=31)
+        whole, _ = run_device(plan, x, np.array([0, n]))
+        for pieces in (2, 5):
+            spans = split_stream(p, n, pieces)
+            parts = [x[b:e] for _, _, b, e, _ in spans]
+            off = np.concatenate([[0], np.cumsum([len(q) for q in parts])]).astype(np.int64)
+            b = plan.batch(off, lead=[s[4] for s in spans])
+            assert list(np.diff(b.frame_offsets)) == [f1 - f0 for f0, f1, _, _, _ in spans]
+            got = plan.compute_batch(b, torch.from_numpy(np.concatenate(parts)).cuda())
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy(), whole), (name, pad, pieces)
+        # without the history sample the first row of every later piece differs (y[0] = x[0] instead of x[0] - a x[-1])
+        spans = split_stream(p, n, 2)
+        parts = [x[b + l:e] for _, _, b, e, l in spans]
+        off = np.concatenate([[0], np.cumsum([len(q) for q in parts])]).astype(np.int64)
+        cut, _ = run_device(plan, np.concatenate(parts), off)
+        f1 = spans[0][1]
+        assert np.array_equal(cut[:f1], whole[:f1]) and not np.array_equal(cut[f1], whole[f1])
+        assert np.array_equal(cut[f1 + 1:], whole[f1 + 1:])
 
 
 def test_c_caller_runs_the_device_path(tmp_path):
@@ -646,6 +687,7 @@ def test_c_caller_runs_the_device_path(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "mfcc_compute: ok, 98 frames" in r.stdout and "fused_sp" in r.stdout
+    assert "mfcc_compute_host_post: ok, 98 frames x 39" in r.stdout
 
 
 POISON_SCRIPT = r"""

@@ -178,3 +178,31 @@ def test_wav_parse_formats_chunks_and_damage():
         with pytest.raises(api.MfccError) as e:
             api.wav_parse(bad)
         assert e.value.code == -1, bad[:24]
+
+
+def test_piece_spans_of_a_long_recording():
+    """mfcc_piece_span / sharding.split_stream: pieces cut at frame boundaries, one history sample in front of every piece but
+    the first; the frame counts of the pieces (their samples minus the history sample) add up to the recording's, under
+    both padding modes, for lengths around every edge."""
+    from mfcc_b200 import PAD_ZERO_TAIL, make_params
+    from mfcc_b200.sharding import split_stream, frame_counts
+    rng = np.random.default_rng(9)
+    for pad in (0, PAD_ZERO_TAIL):
+        for p in (make_params(pad_mode=pad), make_params(sample_rate=8000, frame_len=200, hop_len=80, nfft=256, n_mel=20, pad_mode=pad)):
+            L, H = p.frame_len, p.hop_len
+            for n in [0, 1, L - 1, L, L + 1, L + H - 1, L + H, L + 5 * H + 3, 123457] + rng.integers(0, 300000, 6).tolist():
+                total = int(frame_counts(p, [0, n])[0])
+                for pieces in (1, 2, 3, 7):
+                    spans = split_stream(p, n, pieces)
+                    assert spans[0][0] == 0 and spans[-1][1] == total
+                    for (f0, f1, b, e, lead), nxt in zip(spans, spans[1:] + [None]):
+                        assert (b, e, lead) == api.piece_span(p, n, f0, f1)
+                        if nxt is not None:
+                            assert nxt[0] == f1
+                        if f1 == f0:
+                            continue
+                        assert 0 <= b < e <= n and lead == (1 if f0 > 0 else 0)
+                        assert int(frame_counts(p, [0, e - b - lead])[0]) == f1 - f0     # the piece on its own has its frames
+                        assert b + lead == f0 * H                                       # and they start where the whole's do
+    with pytest.raises(api.MfccError):
+        api.piece_span(make_params(), 160000, 5, 2000)
