@@ -167,7 +167,6 @@ void mfcc_plan_destroy(mfcc_plan *plan)
     if (plan->h_post_chunks) cudaFreeHost(plan->h_post_chunks);
     if (plan->d_post_partial) cudaFree(plan->d_post_partial);
     if (plan->d_post_stats) cudaFree(plan->d_post_stats);
-    if (plan->d_post_count) cudaFree(plan->d_post_count);
     if (plan->h_stage_pcm) cudaFreeHost(plan->h_stage_pcm);
     if (plan->h_stage_out) cudaFreeHost(plan->h_stage_out);
     if (plan->tiles_ready) cudaEventDestroy(plan->tiles_ready);
@@ -307,14 +306,12 @@ int mfcc_batch_create_lead(const mfcc_plan *plan, const int64_t *h_offsets, cons
         const size_t nu = static_cast<size_t>(n_utts);
         if (cudaMalloc(&b->d_post_chunks, nc * sizeof(mfcc::PostChunk)) != cudaSuccess ||
             cudaMalloc(&b->d_post_partial, nc * dim * mfcc::kPostPartialBytes) != cudaSuccess ||
-            cudaMalloc(&b->d_post_stats, nu * dim * sizeof(double2)) != cudaSuccess ||
-            cudaMalloc(&b->d_post_count, nu * sizeof(unsigned)) != cudaSuccess) {
+            cudaMalloc(&b->d_post_stats, nu * dim * sizeof(float4)) != cudaSuccess) {
             cudaGetLastError();
             mfcc_batch_destroy(b);
             return MFCC_ENOMEM;
         }
-        if (cudaMemcpy(b->d_post_chunks, b->post_chunks.data(), nc * sizeof(mfcc::PostChunk), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemset(b->d_post_count, 0, nu * sizeof(unsigned)) != cudaSuccess) {
+        if (cudaMemcpy(b->d_post_chunks, b->post_chunks.data(), nc * sizeof(mfcc::PostChunk), cudaMemcpyHostToDevice) != cudaSuccess) {
             mfcc_batch_destroy(b);
             return MFCC_ECUDA;
         }
@@ -332,7 +329,6 @@ void mfcc_batch_destroy(mfcc_batch *b)
     if (b->d_post_chunks) cudaFree(b->d_post_chunks);
     if (b->d_post_partial) cudaFree(b->d_post_partial);
     if (b->d_post_stats) cudaFree(b->d_post_stats);
-    if (b->d_post_count) cudaFree(b->d_post_count);
     delete b;
 }
 
@@ -435,7 +431,6 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         if (rc == MFCC_OK) rc = grow(&plan->d_post_chunks, &plan->d_post_chunks_bytes, pc_bytes);
         if (rc == MFCC_OK) rc = grow(&plan->d_post_partial, &plan->d_post_partial_bytes, static_cast<size_t>(n_post_chunks) * d * mfcc::kPostPartialBytes);
         if (rc == MFCC_OK) rc = grow(&plan->d_post_stats, &plan->d_post_stats_bytes, nu * d * sizeof(float4));
-        if (rc == MFCC_OK) rc = grow(&plan->d_post_count, &plan->d_post_count_bytes, nu * sizeof(unsigned));
         if (rc == MFCC_OK && plan->h_post_chunks_bytes < pc_bytes) {
             if (plan->h_post_chunks) cudaFreeHost(plan->h_post_chunks);
             plan->h_post_chunks = nullptr;
@@ -512,12 +507,11 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     batch->d_tiles = static_cast<Tile *>(plan->d_tiles);
     batch->tiles_borrowed = true;
     ok = cudaMemcpyAsync(plan->d_tiles, plan->h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
-    if (post != nullptr) {   // chunk table of the post-processing kernels: same route; the counters start from zero
+    if (post != nullptr) {   // chunk table of the post-processing kernels: same route
         mfcc::post_build_chunks(batch->frame_offsets, od, batch->post_chunks, batch->utt_first_post_chunk, &batch->post_rows);
         ok = ok && static_cast<int64_t>(batch->post_chunks.size()) == n_post_chunks;
         if (ok) std::memcpy(plan->h_post_chunks, batch->post_chunks.data(), pc_bytes);
         ok = ok && cudaMemcpyAsync(plan->d_post_chunks, plan->h_post_chunks, pc_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
-        ok = ok && cudaMemsetAsync(plan->d_post_count, 0, sizeof(unsigned) * static_cast<size_t>(n_utts), plan->streams[2]) == cudaSuccess;
     }
     ok = ok && cudaEventRecord(plan->tiles_ready, plan->streams[2]) == cudaSuccess;
     ok = ok && cudaStreamWaitEvent(plan->streams[3], plan->tiles_ready, 0) == cudaSuccess;
@@ -536,7 +530,7 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         if (ok && post != nullptr && f1 > f0) {
             const int64_t c0 = batch->utt_first_post_chunk[u0], c1 = batch->utt_first_post_chunk[u1];
             const mfcc::PostView view{static_cast<const mfcc::PostChunk *>(plan->d_post_chunks), c0, c1 - c0, batch->post_rows,
-                                      plan->d_post_partial, plan->d_post_stats, static_cast<unsigned *>(plan->d_post_count), plan->device, plan->sm_count};
+                                      plan->d_post_partial, plan->d_post_stats, plan->device, plan->sm_count};
             ok = mfcc::launch_post(view, d_out, od, post->cmvn, post->order > 0 ? post->window : 1, post->order, 0,
                                    static_cast<float *>(plan->d_post_out), s) == MFCC_OK;
             d_rows = static_cast<const float *>(plan->d_post_out);
@@ -857,7 +851,7 @@ int mfcc_cmvn_batch(const mfcc_plan *plan, const mfcc_batch *batch, float *d_fea
     if (!guard.ok) return MFCC_ECUDA;
     // the fused kernels with no regression: a CTA reads its rows into shared memory, then writes them back normalised
     const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
-                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
+                              batch->d_post_partial, batch->d_post_stats, batch->device, plan->sm_count};
     return mfcc::launch_post(view, d_feat, batch->out_dim, norm_var != 0 ? MFCC_CMVN_MEAN_VAR : MFCC_CMVN_MEAN, 1, 0, 0, d_feat,
                              static_cast<cudaStream_t>(cuda_stream));
 }
@@ -873,7 +867,7 @@ int mfcc_delta_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float
     if (!guard.ok) return MFCC_ECUDA;
     // the fused kernels without normalisation, writing the regression part only
     const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
-                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
+                              batch->d_post_partial, batch->d_post_stats, batch->device, plan->sm_count};
     return mfcc::launch_post(view, d_feat, batch->out_dim, MFCC_CMVN_NONE, window, 1, 1, d_delta,
                              static_cast<cudaStream_t>(cuda_stream));
 }
@@ -894,7 +888,7 @@ int mfcc_post_batch(const mfcc_plan *plan, const mfcc_batch *batch, const float 
     DeviceGuard guard(plan->device);
     if (!guard.ok) return MFCC_ECUDA;
     const mfcc::PostView view{batch->d_post_chunks, 0, static_cast<int64_t>(batch->post_chunks.size()), batch->post_rows,
-                              batch->d_post_partial, batch->d_post_stats, batch->d_post_count, batch->device, plan->sm_count};
+                              batch->d_post_partial, batch->d_post_stats, batch->device, plan->sm_count};
     return mfcc::launch_post(view, d_feat, batch->out_dim, cmvn, delta_order > 0 ? delta_window : 1, delta_order, 0, d_out,
                              static_cast<cudaStream_t>(cuda_stream));
 }

@@ -109,7 +109,7 @@ struct mfcc_plan {
     void *h_post_chunks = nullptr;   size_t h_post_chunks_bytes = 0;
     void *d_post_partial = nullptr;  size_t d_post_partial_bytes = 0;
     void *d_post_stats = nullptr;    size_t d_post_stats_bytes = 0;
-    void *d_post_count = nullptr;    size_t d_post_count_bytes = 0;
+
     cudaEvent_t tiles_ready = nullptr;
     std::vector<cudaEvent_t> chunk_ready;   // one per H2D chunk of the call in flight (reused across calls)
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};   // compute_host: two H2D queues, two compute + D2H queues
@@ -137,7 +137,6 @@ struct mfcc_batch {
     mfcc::PostChunk *d_post_chunks = nullptr;
     void *d_post_partial = nullptr;      // [chunks][out_dim] x kPostPartialBytes: per-group sums about the group's first row
     void *d_post_stats = nullptr;        // [n_utts][out_dim] float4 {mean hi, lo, 1 / sigma hi, lo}
-    unsigned *d_post_count = nullptr;    // [n_utts] chunks of the utterance done so far (zero between calls)
 };
 
 namespace mfcc {
@@ -189,7 +188,6 @@ struct PostView {
     int rows;            // rows per chunk the table was cut with
     void *partial;       // [chunks][dim] x 32 bytes (kPostPartialBytes)
     void *stats;         // [utterances][dim] float4
-    unsigned *count;     // [utterances], zero between calls
     int device;
     int sms;             // SMs of the device (grid of the persistent statistics kernel)
 };

@@ -8,15 +8,17 @@
 //   * every global access is a sweep over a CONTIGUOUS range (a chunk = up to `post_rows` consecutive rows of one
 //     utterance is one contiguous block of the input and one contiguous block of the output), consecutive threads on
 //     consecutive floats;
-//   * the three output parts of a row are produced by the same sweep (thread = output column, rows strided), so an output
-//     sector is written once, completely, by neighbouring threads — not by three passes with a 3 * dim stride;
+//   * the three output parts of a row are produced by the same sweep (thread = output column walking down the rows), so an
+//     output sector is written once, completely, by neighbouring threads — not by three passes with a 3 * dim stride;
 //   * the chunk (plus the +-2 * window halo rows the two regressions need, edge rows replicated as the spec says) is
-//     staged in shared memory once; the delta of the halo rows is recomputed instead of exchanged;
-//   * the grid is one CTA per chunk with 8 CTAs resident per SM (27 KB of shared memory each for 13 cepstra), enough
-//     loads in flight to cover the HBM latency; nothing is allocated per call.
-// Statistics: chunk sums of (x - pivot) and (x - pivot)^2 in double (pivot = the utterance's first row, which keeps the
-// uncentred variance formula free of cancellation), one partial per chunk, combined in chunk order by the LAST chunk of
-// the utterance to finish (counter + fence) — deterministic, no floating-point atomics, no extra launch.
+//     staged in shared memory once, by ONE bulk async copy (TMA engine); the delta of the halo rows is recomputed instead
+//     of exchanged;
+//   * the apply grid is one CTA per chunk with 6 CTAs resident per SM (27 KB of shared memory each for 13 cepstra), the
+//     statistics kernel is persistent with a ring of three bulk copies per CTA: enough bytes in flight to cover the HBM
+//     latency; nothing is allocated per call.
+// Statistics: per group of four chunks sums of (x - pivot) and (x - pivot)^2 (pivot = the group's first row, which keeps the
+// uncentred variance formula free of cancellation), combined in group order by a second tiny kernel — deterministic, no
+// floating-point atomics, no fences.  Three launches per call with CMVN (statistics, finalise, apply), one without.
 //
 // Spec (oracle/mfcc_oracle.c oracle_cmvn_f32 + oracle_delta_f32 applied twice): x' = (x - mu) [* 1 / sqrt(max(var,
 // 1e-20))], d[t] = sum_n n (x'[t + n] - x'[t - n]) / (2 sum n^2) with frame indices clamped to the utterance,
@@ -121,25 +123,25 @@ __device__ __forceinline__ void stage_wait(const Staged &st, uint32_t bar)
 // ---- per-utterance statistics: persistent CTAs, each walks a contiguous range of chunks through a ring of bulk copies ----
 // Work is cut into GROUPS of up to kStatGroup consecutive chunks of one utterance, aligned to the utterance (chunks first +
 // 4 k .. first + 4 k + 3): a thread keeps its running sums in registers across the chunks of a group and the expensive part
-// — the cross-thread reduction, the partial to global memory, the fence and the counter — happens once per group, while the
-// bulk copies of the next chunks are already in flight (ring of kStatRing slots, one mbarrier each).  Which CTA walks which
+// — the cross-thread reduction and the partial to global memory — happens once per group, while the bulk copies of the next
+// chunks are already in flight (ring of kStatRing slots, one mbarrier each).  There is no fence, no counter and no "last
+// CTA" logic in this kernel: the partials are combined by post_finalize_kernel, a separate (tiny) launch — a fence + atomic
+// per group cost more than that launch (stats pass 77 -> see profiles/r2_post.md).  Which CTA walks which
 // group depends on the launch; what is summed in which order depends on the group alone, so every bit of the result is
 // independent of the grid and of the range of the batch a launch covers.
 // Inside a thread the values it meets are summed in f32 about a pivot (the first row of the group: |x - pivot| is a few sigma,
 // so the sums keep 7 digits of a quantity whose mean needs 5, and the uncentred variance formula is free of cancellation);
 // across threads and groups everything is double, in a fixed order, re-referenced to the utterance's first row — no
-// floating-point atomics.  The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the apply kernel then
-// normalises with FP32 instructions only, within 2 ulp of the double evaluation.
+// floating-point atomics.
 constexpr int kStatGroup = 4, kStatRing = 3;
 struct StatPartial { double s, q, pivot, n; };    // sums of (x - pivot), (x - pivot)^2 over n rows
 
 __global__ void __launch_bounds__(kPostThreads, 4)
 post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks, const float *__restrict__ feat, const PostGeom g,
-                  int norm_var, StatPartial *__restrict__ partial, float4 *__restrict__ stats, unsigned *__restrict__ count)
+                  StatPartial *__restrict__ partial)
 {
     extern __shared__ __align__(16) float sm[];     // [16: mbarriers][kStatRing slots of 4 + 4 + rows * dim (rounded up to 4) floats]
     __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
-    __shared__ int s_last;
     const int tid = threadIdx.x, dim = g.dim, per = g.per;
     const int sub = div20(tid, g.m_dim), col = tid - sub * dim;
     const int slot_floats = 8 + ((g.rows * dim + 3) & ~3);
@@ -233,43 +235,46 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks
             for (int j = 0; j < G; ++j) { ts += s2_s[tid + j * dim]; tq += s2_q[tid + j * dim]; }
             partial[static_cast<int64_t>(gstart) * dim + tid] = StatPartial{ts, tq, static_cast<double>(pivot), static_cast<double>(grows)};
         }
-        __syncthreads();
-        if (tid == 0) {      // the fence is cumulative: the partials the other threads wrote before the barrier are ordered with it
-            __threadfence();
-            const unsigned done = static_cast<unsigned>(k + 1 - gstart);
-            s_last = atomicAdd(&count[ck.utt], done) + done == static_cast<unsigned>(ck.n_chunks);
-            __threadfence();
-        }
-        __syncthreads();
-        if (s_last) {
-            if (tid < dim) {
-                // group order, everything re-referenced to the utterance's first row P: sum (x - P) = s + n (p - P),
-                // sum (x - P)^2 = q + 2 (p - P) s + n (p - P)^2
-                const StatPartial *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + tid;
-                const double P = __ldcg(&p->pivot);
-                double ts = 0.0, tq = 0.0;
-                for (int j = 0; j < ck.n_chunks; j += kStatGroup) {
-                    const StatPartial *e = p + static_cast<int64_t>(j) * dim;
-                    const double s = __ldcg(&e->s), q = __ldcg(&e->q), dp = __ldcg(&e->pivot) - P, n = __ldcg(&e->n);
-                    ts += s + n * dp;
-                    tq += q + 2.0 * dp * s + n * dp * dp;
-                }
-                const double T = static_cast<double>(ck.f1 - ck.f0);
-                const double m = ts / T;
-                double var = tq / T - m * m;
-                if (var < 0.0) var = 0.0;
-                const double mu = P + m;
-                const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
-                const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
-                stats[static_cast<int64_t>(ck.utt) * dim + tid] =
-                    make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
-                                static_cast<float>(inv - static_cast<double>(inv_hi)));
-            }
-            if (tid == 0) count[ck.utt] = 0;   // the counters are zero again for the next (stream-ordered) call
-        }
         s0 = q0 = s1 = q1 = 0.0f;
         gstart = k + 1;
         grows = 0;
+    }
+}
+
+// ---- statistics, second step: one warp per utterance combines the group partials (lane = column) ----
+// Group order, everything re-referenced to the utterance's first row P: sum (x - P) = s + n (p - P),
+// sum (x - P)^2 = q + 2 (p - P) s + n (p - P)^2.  The result is stored as two-float pairs {mu_hi, mu_lo, inv_hi, inv_lo}: the
+// apply kernel then normalises with FP32 instructions only, within 2 ulp of the double evaluation (x - mu_hi is exact or
+// correctly rounded at the magnitude of the RESULT, which is what the tolerance is stated on).
+__global__ void __launch_bounds__(kPostThreads)
+post_finalize_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks, int dim, int norm_var,
+                     const StatPartial *__restrict__ partial, float4 *__restrict__ stats)
+{
+    const int w = static_cast<int>((static_cast<int64_t>(blockIdx.x) * kPostThreads + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_chunks) return;
+    const int c = chunk0 + w;
+    const PostChunk ck = chunks[c];
+    if (c != ck.first_chunk) return;                 // the warp of an utterance's first chunk does the utterance
+    const double T = static_cast<double>(ck.f1 - ck.f0);
+    for (int col = lane; col < dim; col += 32) {
+        const StatPartial *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + col;
+        const double P = p->pivot;
+        double ts = 0.0, tq = 0.0;
+        for (int j = 0; j < ck.n_chunks; j += kStatGroup) {
+            const StatPartial e = p[static_cast<int64_t>(j) * dim];
+            const double dp = e.pivot - P;
+            ts += e.s + e.n * dp;
+            tq += e.q + 2.0 * dp * e.s + e.n * dp * dp;
+        }
+        const double m = ts / T;
+        double var = tq / T - m * m;
+        if (var < 0.0) var = 0.0;
+        const double mu = P + m;
+        const double inv = norm_var ? 1.0 / sqrt(var > 1e-20 ? var : 1e-20) : 1.0;
+        const float mu_hi = static_cast<float>(mu), inv_hi = static_cast<float>(inv);
+        stats[static_cast<int64_t>(ck.utt) * dim + col] =
+            make_float4(mu_hi, static_cast<float>(mu - static_cast<double>(mu_hi)), inv_hi,
+                        static_cast<float>(inv - static_cast<double>(inv_hi)));
     }
 }
 
@@ -500,9 +505,11 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
         // persistent: 4 CTAs per SM, at least two chunks each
         const int64_t want = std::min<int64_t>(4 * static_cast<int64_t>(std::max(v.sms, 1)), (v.n_chunks + 1) / 2);
         post_stats_kernel<<<static_cast<unsigned>(std::max<int64_t>(want, 1)), kPostThreads, smem_stats, s>>>(
-            v.chunks, static_cast<int>(v.chunk0), static_cast<int>(v.n_chunks), d_feat, g, cmvn == MFCC_CMVN_MEAN_VAR,
-            static_cast<StatPartial *>(v.partial), static_cast<float4 *>(v.stats), v.count);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+            v.chunks, static_cast<int>(v.chunk0), static_cast<int>(v.n_chunks), d_feat, g, static_cast<StatPartial *>(v.partial));
+        post_finalize_kernel<<<static_cast<unsigned>((v.n_chunks * 32 + kPostThreads - 1) / kPostThreads), kPostThreads, 0, s>>>(
+            v.chunks, static_cast<int>(v.chunk0), static_cast<int>(v.n_chunks), dim, cmvn == MFCC_CMVN_MEAN_VAR,
+            static_cast<const StatPartial *>(v.partial), static_cast<float4 *>(v.stats));
+        g_launches.fetch_add(2, std::memory_order_relaxed);
     }
     const size_t smem = post_smem_bytes(dim, v.rows, window, order);
     if (smem > kPostSmemMax) return MFCC_EINVAL;

@@ -12,7 +12,7 @@ torch.cuda.set_device(0)
 print(json.dumps(bench.measure_post(ctx, steps=4)))
 PY
 python /tmp/post_leg.py > gpurun_out/plain_post.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:post_ -s 6 -c 2 -f -o gpurun_out/r2_prof_post python /tmp/post_leg.py > gpurun_out/ncu_post.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:post_ -s 9 -c 3 -f -o gpurun_out/r2_prof_post python /tmp/post_leg.py > gpurun_out/ncu_post.log 2>&1
 echo "ncu post rc=$?"; tail -2 gpurun_out/ncu_post.log
 if [ "$1" != "nolist" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1"

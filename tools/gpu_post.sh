@@ -13,6 +13,6 @@ print(json.dumps(bench.measure_post(ctx)))
 PY
 timeout 300 python /tmp/post_leg.py > gpurun_out/post_leg.json 2> gpurun_out/post_leg.err; echo "post leg rc=$?"; cat gpurun_out/post_leg.json; tail -3 gpurun_out/post_leg.err
 if [ "$1" = "ncu" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:post_ -s 6 -c 2 -f -o gpurun_out/prof_post python /tmp/post_leg.py > gpurun_out/ncu_post.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:post_ -s 9 -c 3 -f -o gpurun_out/prof_post python /tmp/post_leg.py > gpurun_out/ncu_post.log 2>&1
   echo "ncu rc=$?"; tail -2 gpurun_out/ncu_post.log
 fi
