@@ -53,6 +53,7 @@ struct PostGeom {
     int part0;            // first output part: 0 = static | delta | ..., 1 = the regressions only (mfcc_delta_batch)
     int per;              // (256 / dim) * dim: thread t < per always meets column t % dim
     int nsub;             // per / dim
+    int s_per, s_nsub;    // the same for the thread count of the statistics kernel
     int od, cw, nblk;     // output columns, columns per pass of the stacking sweep, row blocks in it
     unsigned m_dim, m_cw, m_nblk, m_nsub;   // t / d == (t * m) >> 20 for t < 4096, d <= 256
     float inv_den;
@@ -133,16 +134,27 @@ __device__ __forceinline__ void stage_wait(const Staged &st, uint32_t bar)
 // so the sums keep 7 digits of a quantity whose mean needs 5, and the uncentred variance formula is free of cancellation);
 // across threads and groups everything is double, in a fixed order, re-referenced to the utterance's first row — no
 // floating-point atomics.
-constexpr int kStatGroup = 4, kStatRing = 3;
+// threads per CTA, ring depth and resident CTAs per SM of the statistics kernel (build-time switches for A/B timing; one
+// box, whole call in ms: 256 / 3 / 4: 0.2142, 256 / 2 / 6: 0.2116, 128 / 2 / 6: 0.2115, 128 / 3 / 4: 0.2156 — not sensitive)
+#ifndef MFCC_POST_STAT_THREADS
+#define MFCC_POST_STAT_THREADS 256
+#endif
+#ifndef MFCC_POST_STAT_RING
+#define MFCC_POST_STAT_RING 2
+#endif
+#ifndef MFCC_POST_STAT_CTAS
+#define MFCC_POST_STAT_CTAS 6
+#endif
+constexpr int kStatGroup = 4, kStatRing = MFCC_POST_STAT_RING, kStatThreads = MFCC_POST_STAT_THREADS;
 struct StatPartial { double s, q, pivot, n; };    // sums of (x - pivot), (x - pivot)^2 over n rows
 
-__global__ void __launch_bounds__(kPostThreads, 4)
+__global__ void __launch_bounds__(kStatThreads, MFCC_POST_STAT_CTAS)
 post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks, const float *__restrict__ feat, const PostGeom g,
                   StatPartial *__restrict__ partial)
 {
     extern __shared__ __align__(16) float sm[];     // [16: mbarriers][kStatRing slots of 4 + 4 + rows * dim (rounded up to 4) floats]
-    __shared__ double s_s[kPostThreads], s_q[kPostThreads], s2_s[kPostThreads], s2_q[kPostThreads];
-    const int tid = threadIdx.x, dim = g.dim, per = g.per;
+    __shared__ double s_s[kStatThreads], s_q[kStatThreads], s2_s[kStatThreads], s2_q[kStatThreads];
+    const int tid = threadIdx.x, dim = g.dim, per = g.s_per, nsub = g.s_nsub;
     const int sub = div20(tid, g.m_dim), col = tid - sub * dim;
     const int slot_floats = 8 + ((g.rows * dim + 3) & ~3);
     const bool base_aligned = (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
@@ -184,7 +196,7 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
             }
         }
-        for (int i = (w.body > 0 ? w.body - w.a : 0) + tid; i < w.cnt; i += kPostThreads) block[i] = __ldg(w.src + i);
+        for (int i = (w.body > 0 ? w.body - w.a : 0) + tid; i < w.cnt; i += kStatThreads) block[i] = __ldg(w.src + i);
     };
     if (tid == 0)
         for (int r = 0; r < kStatRing; ++r) mbar_init(smem_u32(sm) + 8 * r, 1);
@@ -222,10 +234,10 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks
         if (k + kStatRing < hi) issue(k + kStatRing);
         if (!group_end) continue;
         // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
-        const int G = g.nsub < 4 ? g.nsub : 4;
+        const int G = nsub < 4 ? nsub : 4;
         if (sub < G) {
             double ts = 0.0, tq = 0.0;
-            for (int j = sub; j < g.nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
+            for (int j = sub; j < nsub; j += G) { ts += s_s[col + j * dim]; tq += s_q[col + j * dim]; }
             s2_s[tid] = ts;
             s2_q[tid] = tq;
         }
@@ -476,7 +488,7 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
                 cudaStream_t s)
 {
     if (v.n_chunks <= 0) return MFCC_OK;
-    if (dim > kPostMaxDim || v.chunks == nullptr || v.chunk0 + v.n_chunks > (1 << 30)) return MFCC_EINVAL;
+    if (dim > kPostMaxDim || dim > kStatThreads || v.chunks == nullptr || v.chunk0 + v.n_chunks > (1 << 30)) return MFCC_EINVAL;
     PostGeom g{};
     g.dim = dim;
     g.rows = v.rows;
@@ -486,6 +498,8 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
     g.part0 = part0;
     g.per = (kPostThreads / dim) * dim;
     g.nsub = g.per / dim;
+    g.s_per = (kStatThreads / dim) * dim;
+    g.s_nsub = g.s_per / dim;
     g.od = dim * (1 + order - part0);
     g.cw = std::min(g.od, kPostThreads);
     g.nblk = kPostThreads / g.cw;
@@ -502,9 +516,9 @@ int launch_post(const PostView &v, const float *d_feat, int dim, int cmvn, int w
         if (smem_stats > kPostSmemMax) return MFCC_EINVAL;
         // (the kernel also holds 8 KB of static shared memory: opt in whenever the sum could pass 48 KB — once per device)
         if (smem_stats > 36 * 1024 && ensure_smem_optin(post_stats_kernel, v.device, kPostSmemMax, g_optin_stats) != MFCC_OK) return MFCC_ECUDA;
-        // persistent: 4 CTAs per SM, at least two chunks each
-        const int64_t want = std::min<int64_t>(4 * static_cast<int64_t>(std::max(v.sms, 1)), (v.n_chunks + 1) / 2);
-        post_stats_kernel<<<static_cast<unsigned>(std::max<int64_t>(want, 1)), kPostThreads, smem_stats, s>>>(
+        // persistent: MFCC_POST_STAT_CTAS CTAs per SM, at least two chunks each
+        const int64_t want = std::min<int64_t>(MFCC_POST_STAT_CTAS * static_cast<int64_t>(std::max(v.sms, 1)), (v.n_chunks + 1) / 2);
+        post_stats_kernel<<<static_cast<unsigned>(std::max<int64_t>(want, 1)), kStatThreads, smem_stats, s>>>(
             v.chunks, static_cast<int>(v.chunk0), static_cast<int>(v.n_chunks), d_feat, g, static_cast<StatPartial *>(v.partial));
         post_finalize_kernel<<<static_cast<unsigned>((v.n_chunks * 32 + kPostThreads - 1) / kPostThreads), kPostThreads, 0, s>>>(
             v.chunks, static_cast<int>(v.chunk0), static_cast<int>(v.n_chunks), dim, cmvn == MFCC_CMVN_MEAN_VAR,
