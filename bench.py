@@ -517,14 +517,14 @@ def measure_post(ctx, steps=20, warmup=3, n_utts=4096, frames_per_utt=998):
     b_full = (2 * dim + 3 * dim) * 4      # statistics pass read + apply pass read + stacked row written
     b_apply = (dim + 3 * dim) * 4
     line = {"value": frames / (ms * 1e-3), "unit": "frames/s", "steps": steps, "warmup": warmup, "ms_per_step": ms,
-            "gpu_launches": (l1 - l0), "kernel": "post_stats_kernel + post_apply_kernel<2>",
+            "gpu_launches": (l1 - l0), "kernel": "post_stats_kernel + post_finalize_kernel + post_apply_kernel<2>",
             "api": "mfcc_post_batch (device feature matrix in, stacked static | delta | delta-delta matrix out)",
             "config": {"workload": f"{n_utts} utterances x {frames_per_utt} frames x {dim} cepstra (4 x configs[1]) -> {3 * dim} columns; "
                                    "CMVN mean + variance, regression window 2, order 2", "params": "A",
                        "l2": "input 212 MB and output 638 MB per step both exceed the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": b_full * frames / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": b_full * frames / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                         "algorithmic": f"{b_full} B/frame (2 reads of {dim * 4} B: statistics pass and apply pass; {3 * dim * 4} B written) x {frames} frames per step (two launches)",
+                         "algorithmic": f"{b_full} B/frame (2 reads of {dim * 4} B: statistics pass and apply pass; {3 * dim * 4} B written) x {frames} frames per step (three launches)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
             "delta2_only": {"ms_per_step": res["delta2_only"], "value": frames / (res["delta2_only"] * 1e-3),
                             "roofline_frac": b_apply * frames / (res["delta2_only"] * 1e-3) / 1e9 / hbm_peak,
