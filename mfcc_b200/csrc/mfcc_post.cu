@@ -172,54 +172,54 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks
     const int hi = group_start(chunk0 + static_cast<int>(static_cast<int64_t>(n_chunks) * (blockIdx.x + 1) / gridDim.x));
     if (lo >= hi) return;
 
-    // where chunk k lands in its slot, and whether a bulk copy brings (most of) it: the same arithmetic for issuer and readers
-    struct Where { const float *block; const float *src; int cnt, a, body; };
-    auto where = [&](int k, const PostChunk &ck) {
-        Where w;
-        w.src = feat + ck.row0 * dim;
-        w.cnt = ck.n * dim;
-        w.a = base_aligned ? static_cast<int>((reinterpret_cast<uintptr_t>(w.src) >> 2) & 3) : 0;
-        w.body = base_aligned ? ((w.a + w.cnt) & ~3) : 0;
-        w.block = sm + 16 + ((k - lo) % kStatRing) * slot_floats + 4 + w.a;      // block - a is 16-byte aligned
-        return w;
-    };
-    auto issue = [&](int k) {
+    // Where chunk k lands in its slot: a = floats between the 16-byte boundary below its first float and that float (the
+    // matrix base is aligned, so this is (row0 * dim) mod 4: 32-bit arithmetic on the low bits), block - a is 16-byte aligned.
+    // Readers need only a and the float count; the issuer (warp 0) also the source address.
+    auto shift_of = [&](const PostChunk &ck) { return base_aligned ? static_cast<int>((static_cast<uint32_t>(ck.row0) * static_cast<uint32_t>(dim)) & 3u) : 0; };
+    auto block_of = [&](int k, int a) { return sm + 16 + ((k - lo) % kStatRing) * slot_floats + 4 + a; };
+    auto issue = [&](int k) {            // by warp 0 (by every thread for a matrix that is not 16-byte aligned: plain loads only)
         const PostChunk ck = chunks[k];
-        const Where w = where(k, ck);
-        float *block = const_cast<float *>(w.block);
+        const float *src = feat + ck.row0 * dim;
+        const int cnt = ck.n * dim, a = shift_of(ck);
+        const int body = base_aligned ? ((a + cnt) & ~3) : 0;
+        float *block = block_of(k, a);
         if (tid == 0 && base_aligned) {     // every use of a slot completes one phase of its mbarrier, with or without a copy
             const uint32_t bar = smem_u32(sm) + 8 * ((k - lo) % kStatRing);
-            if (w.body > 0) {
-                mbar_expect_tx(bar, static_cast<uint32_t>(w.body) * 4u);
-                bulk_g2s(smem_u32(block - w.a), w.src - w.a, static_cast<uint32_t>(w.body) * 4u, bar);
+            if (body > 0) {
+                mbar_expect_tx(bar, static_cast<uint32_t>(body) * 4u);
+                bulk_g2s(smem_u32(block - a), src - a, static_cast<uint32_t>(body) * 4u, bar);
             } else {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
             }
         }
-        for (int i = (w.body > 0 ? w.body - w.a : 0) + tid; i < w.cnt; i += kStatThreads) block[i] = __ldg(w.src + i);
+        // what the bulk copy leaves out: the <= 3 floats behind the last 16-byte boundary (everything without it)
+        const int stride = base_aligned ? 32 : kStatThreads;
+        for (int i = (body > 0 ? body - a : 0) + tid; i < cnt; i += stride) block[i] = __ldg(src + i);
     };
+    const bool issuer = tid < 32 || !base_aligned;
     if (tid == 0)
         for (int r = 0; r < kStatRing; ++r) mbar_init(smem_u32(sm) + 8 * r, 1);
     __syncthreads();
-    for (int k = lo; k < hi && k < lo + kStatRing; ++k) issue(k);
+    if (issuer)
+        for (int k = lo; k < hi && k < lo + kStatRing; ++k) issue(k);
     __syncthreads();
 
     float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f, pivot = 0.0f;
     int gstart = lo, grows = 0;
     for (int k = lo; k < hi; ++k) {
         const PostChunk ck = chunks[k];
-        const Where w = where(k, ck);
+        const int cnt = ck.n * dim;
+        const float *x = block_of(k, shift_of(ck));
         if (base_aligned) mbar_wait(smem_u32(sm) + 8 * ((k - lo) % kStatRing), static_cast<uint32_t>(((k - lo) / kStatRing) & 1));
         if (tid < per) {
-            const float *x = w.block;
             if (k == gstart) pivot = x[col];
             int i = tid;
-            for (; i + per < w.cnt; i += 2 * per) {
+            for (; i + per < cnt; i += 2 * per) {
                 const float a = x[i] - pivot, b = x[i + per] - pivot;
                 s0 += a; q0 = fmaf(a, a, q0);
                 s1 += b; q1 = fmaf(b, b, q1);
             }
-            if (i < w.cnt) {
+            if (i < cnt) {
                 const float a = x[i] - pivot;
                 s0 += a; q0 = fmaf(a, a, q0);
             }
@@ -231,7 +231,7 @@ post_stats_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chunks
             s_q[tid] = static_cast<double>(q0) + static_cast<double>(q1);
         }
         __syncthreads();                       // the slot is free (and the group's sums are in shared memory)
-        if (k + kStatRing < hi) issue(k + kStatRing);
+        if (issuer && k + kStatRing < hi) issue(k + kStatRing);
         if (!group_end) continue;
         // column d is met by threads d, d + dim, ...: G threads each add a share of them, then thread d adds the G sums
         const int G = nsub < 4 ? nsub : 4;
@@ -270,10 +270,10 @@ post_finalize_kernel(const PostChunk *__restrict__ chunks, int chunk0, int n_chu
     const double T = static_cast<double>(ck.f1 - ck.f0);
     for (int col = lane; col < dim; col += 32) {
         const StatPartial *p = partial + static_cast<int64_t>(ck.first_chunk) * dim + col;
-        const double P = p->pivot;
-        double ts = 0.0, tq = 0.0;
+        double P = 0.0, ts = 0.0, tq = 0.0;
         for (int j = 0; j < ck.n_chunks; j += kStatGroup) {
             const StatPartial e = p[static_cast<int64_t>(j) * dim];
+            if (j == 0) P = e.pivot;
             const double dp = e.pivot - P;
             ts += e.s + e.n * dp;
             tq += e.q + 2.0 * dp * e.s + e.n * dp * dp;
