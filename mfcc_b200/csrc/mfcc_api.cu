@@ -8,6 +8,10 @@
 // (src/mfcc/main.c:124-127, src/mfcc/codegen.c:166) — a library reports.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -218,9 +222,19 @@ int64_t mfcc_plan_dct(const mfcc_plan *plan, float *dst)
 }
 
 // Host half of a batch: offsets -> frame rows -> tile table.  No CUDA calls.
+// frames of an utterance of n samples under a plan's (already validated) framing: mfcc_num_frames without the re-validation,
+// for the per-utterance loops of the host path (16,384 utterances per call in the ragged telephony batch)
+static inline int64_t frames_of(const mfcc_params &p, int64_t n)
+{
+    const int64_t L = p.frame_len, H = p.hop_len;
+    if (p.pad_mode == MFCC_PAD_NONE) return n < L ? 0 : 1 + (n - L) / H;
+    return n <= 0 ? 0 : (n <= L ? 1 : 1 + (n - L + H - 1) / H);
+}
+
+// Host half of a batch, first step: offsets -> frame rows -> first tile index per utterance.  No tiles yet, no CUDA calls.
 // h_lead (may be null): h_lead[u] != 0 marks utterance u as a PIECE of a longer recording whose first sample is history — it
 // only serves as the pre-emphasis predecessor of the piece's first frame; the frames start one sample later.
-static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out,
+static int batch_build_meta(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out,
                             const uint8_t *h_lead = nullptr)
 {
     if (out == nullptr) return MFCC_EINVAL;
@@ -239,28 +253,16 @@ static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int
         b->offsets.assign(n_utts + 1, 0);
         b->frame_offsets.assign(n_utts + 1, 0);
         b->utt_first_tile.assign(n_utts + 1, 0);
+        if (h_lead != nullptr) b->lead.assign(h_lead, h_lead + n_utts);
         if (n_utts > 0) std::memcpy(b->offsets.data(), h_offsets, sizeof(int64_t) * (n_utts + 1));
         for (int64_t u = 0; u < n_utts; ++u) {
             const int64_t begin = b->offsets[u], end = b->offsets[u + 1];
             if (begin < 0 || end < begin) { delete b; return MFCC_EINVAL; }
             const int64_t lead = (h_lead != nullptr && h_lead[u] != 0 && end > begin) ? 1 : 0;
-            const int64_t nf = mfcc_num_frames(&p, end - begin - lead);
+            const int64_t nf = frames_of(p, end - begin - lead);
             b->frame_offsets[u + 1] = b->frame_offsets[u] + nf;
-            b->utt_first_tile[u] = static_cast<int64_t>(b->tiles.size());
-            for (int64_t f = 0; f < nf; f += mfcc::kTileFrames) {
-                Tile t;
-                t.utt_begin = begin;
-                t.utt_end = end;
-                t.first_sample = begin + lead + f * p.hop_len;
-                t.out_row = b->frame_offsets[u] + f;
-                t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, nf - f));
-                t.flags = 0;
-                b->tiles.push_back(t);
-            }
+            b->utt_first_tile[u + 1] = b->utt_first_tile[u] + (nf + mfcc::kTileFrames - 1) / mfcc::kTileFrames;
         }
-        b->utt_first_tile[n_utts] = static_cast<int64_t>(b->tiles.size());
-        const int64_t total = n_utts > 0 ? b->offsets[n_utts] : 0;
-        for (Tile &t : b->tiles) t.flags = mfcc::tile_flags(p, t, total);
     } catch (const std::bad_alloc &) {
         delete b;
         return MFCC_ENOMEM;
@@ -268,6 +270,45 @@ static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int
     b->total_frames = b->frame_offsets[n_utts];
     b->total_samples = n_utts > 0 ? b->offsets[n_utts] : 0;
     *out = b;
+    return MFCC_OK;
+}
+
+// Second step: the tiles of utterances [u0, u1), written to dst[0 .. utt_first_tile[u1] - utt_first_tile[u0]).  The host path
+// calls this per chunk of utterances, straight into its pinned staging buffer, while the earlier chunks are on the wire.
+static void batch_build_tiles(const mfcc_params &p, const mfcc_batch &b, int64_t u0, int64_t u1, Tile *dst)
+{
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t begin = b.offsets[u], end = b.offsets[u + 1];
+        const int64_t lead = (!b.lead.empty() && b.lead[u] != 0 && end > begin) ? 1 : 0;
+        const int64_t nf = b.frame_offsets[u + 1] - b.frame_offsets[u];
+        for (int64_t f = 0; f < nf; f += mfcc::kTileFrames) {
+            Tile t;
+            t.utt_begin = begin;
+            t.utt_end = end;
+            t.first_sample = begin + lead + f * p.hop_len;
+            t.out_row = b.frame_offsets[u] + f;
+            t.n_frames = static_cast<int32_t>(std::min<int64_t>(mfcc::kTileFrames, nf - f));
+            t.flags = mfcc::tile_flags(p, t, b.total_samples);
+            *dst++ = t;
+        }
+    }
+}
+
+// Both steps at once (mfcc_batch_create): the tiles land in b->tiles.
+static int batch_build_host(const mfcc_plan *plan, const int64_t *h_offsets, int64_t n_utts, mfcc_batch **out,
+                            const uint8_t *h_lead = nullptr)
+{
+    const int rc = batch_build_meta(plan, h_offsets, n_utts, out, h_lead);
+    if (rc != MFCC_OK) return rc;
+    mfcc_batch *b = *out;
+    try {
+        b->tiles.resize(static_cast<size_t>(b->utt_first_tile[n_utts]));
+    } catch (const std::bad_alloc &) {
+        delete b;
+        *out = nullptr;
+        return MFCC_ENOMEM;
+    }
+    batch_build_tiles(plan->p, *b, 0, n_utts, b->tiles.data());
     return MFCC_OK;
 }
 
@@ -397,23 +438,28 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     if (plan == nullptr || n_utts < 0 || (n_utts > 0 && h_offsets == nullptr)) return MFCC_EINVAL;
     const mfcc_params &p = plan->p;
     const int od = plan->host.out_dim;
-    // 1. sizes
-    int64_t total_frames = 0, n_tiles = 0, n_post_chunks = 0;
+    // MFCC_TRACE_HOST=1: host-clock milestones of this call on stderr (where the time of the host path goes)
+    static const bool trace = std::getenv("MFCC_TRACE_HOST") != nullptr;
+    const auto t_entry = std::chrono::steady_clock::now();
+    double t_mark[6] = {0, 0, 0, 0, 0, 0};
+    auto mark = [&](int i) { if (trace) t_mark[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
+    // 1. sizes: the host half of the batch without its tiles (offsets checked, frame rows, tile index per utterance)
+    mfcc_batch *batch = nullptr;
+    {
+        const int rc0 = batch_build_meta(plan, h_offsets, n_utts, &batch);
+        if (rc0 != MFCC_OK) return rc0;
+    }
+    struct BatchOwner { mfcc_batch *b; ~BatchOwner() { if (b) mfcc_batch_destroy(b); } } owner{batch};
+    const int64_t total_frames = batch->total_frames, n_tiles = batch->utt_first_tile[n_utts];
     const int post_rows = post ? mfcc::post_rows_for(od) : 1;
     const int od_out = post ? od * (1 + post->order) : od;     // floats per row that travels back
-    for (int64_t u = 0; u < n_utts; ++u) {
-        if (h_offsets[u] < 0 || h_offsets[u + 1] < h_offsets[u]) return MFCC_EINVAL;
-        const int64_t nf = mfcc_num_frames(&p, h_offsets[u + 1] - h_offsets[u]);
-        total_frames += nf;
-        n_tiles += (nf + mfcc::kTileFrames - 1) / mfcc::kTileFrames;
-        n_post_chunks += (nf + post_rows - 1) / post_rows;
-    }
-    const int64_t total_samples = n_utts > 0 ? h_offsets[n_utts] : 0;
-    if (total_frames == 0) {
-        if (h_frame_offsets)
-            for (int64_t u = 0; u <= n_utts; ++u) h_frame_offsets[u] = 0;
-        return MFCC_OK;
-    }
+    int64_t n_post_chunks = 0;
+    if (post != nullptr)
+        for (int64_t u = 0; u < n_utts; ++u)
+            n_post_chunks += (batch->frame_offsets[u + 1] - batch->frame_offsets[u] + post_rows - 1) / post_rows;
+    const int64_t total_samples = batch->total_samples;
+    if (h_frame_offsets) mfcc_batch_frame_offsets(batch, h_frame_offsets);
+    if (total_frames == 0) return MFCC_OK;
     if (h_pcm == nullptr || h_out == nullptr) return MFCC_EINVAL;
 
     std::lock_guard<std::mutex> lock(plan->host_mutex);
@@ -479,43 +525,52 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     PcmT *d_pcm = static_cast<PcmT *>(plan->h2d_pcm);
     float *d_out = static_cast<float *>(plan->d2h_out);
     bool ok = true;
+    // chunk c on the wire: first the tiles of its utterances (built here, straight into the pinned staging table, while the
+    // earlier chunks fly), then its PCM, on the same copy stream — so the chunk's event covers both.  Building the whole
+    // table up front left the link idle: 1.0 ms for the 96 k tiles of the ragged telephony batch against 0.6 ms that the
+    // first 32 MiB chunk is on the wire.
+    Tile *h_tiles = static_cast<Tile *>(plan->h_tiles), *d_tiles = static_cast<Tile *>(plan->d_tiles);
+    batch->d_tiles = d_tiles;
+    batch->tiles_borrowed = true;
+    // (With the post-processing kernels in the pipeline the table goes up in ONE piece behind the first chunk, as it did
+    // before: measured on configs[1], per-chunk pieces there cost the read-back its overlap with the input stream —
+    // 9.3 ms per call instead of 7.0 — while the plain path gains 10 % (int16) and 25 % (G.711) on the ragged batch.)
+    const bool piecewise = post == nullptr;
     auto queue_h2d = [&](size_t c) {
         cudaStream_t copy = plan->streams[c & 1];
-        const int64_t s0 = h_offsets[cut[c]], s1 = h_offsets[cut[c + 1]];
+        const int64_t u0 = cut[c], u1 = cut[c + 1];
+        const int64_t t0 = batch->utt_first_tile[u0], t1 = batch->utt_first_tile[u1];
+        if (piecewise && t1 > t0) {
+            batch_build_tiles(p, *batch, u0, u1, h_tiles + t0);
+            ok = ok && cudaMemcpyAsync(d_tiles + t0, h_tiles + t0, sizeof(Tile) * static_cast<size_t>(t1 - t0), cudaMemcpyHostToDevice,
+                                       copy) == cudaSuccess;
+        }
+        const int64_t s0 = h_offsets[u0], s1 = h_offsets[u1];
         if (s1 > s0)
             ok = ok && cudaMemcpyAsync(d_pcm + s0, h_pcm + s0, sizeof(PcmT) * (s1 - s0), cudaMemcpyHostToDevice,
                                        copy) == cudaSuccess;
         ok = ok && cudaEventRecord(plan->chunk_ready[c], copy) == cudaSuccess;
     };
-    // Only the FIRST chunk goes out before the tile table: copies of one direction are served in issue order,
-    // so a table queued behind every PCM chunk would hold all kernels back until the last sample has arrived
-    // (measured: 7.2 ms per configs[1] batch instead of 6.4).
+    mark(0);
     queue_h2d(0);
+    mark(1);
 
-    // 3. tile table, built while the DMA runs; it goes up on compute stream 1 (the copy stream is busy)
-    mfcc_batch *batch = nullptr;
-    rc = ok ? batch_build_host(plan, h_offsets, n_utts, &batch) : MFCC_ECUDA;
-    if (rc != MFCC_OK || static_cast<int64_t>(batch->tiles.size()) != n_tiles || batch->total_frames != total_frames) {
-        cudaStreamSynchronize(plan->streams[0]);   // h_pcm is the caller's: nothing may still read it when we return
-        cudaStreamSynchronize(plan->streams[1]);
-        if (batch) mfcc_batch_destroy(batch);
-        cudaGetLastError();
-        return rc != MFCC_OK ? rc : MFCC_ECUDA;
-    }
-    if (h_frame_offsets) mfcc_batch_frame_offsets(batch, h_frame_offsets);
-    std::memcpy(plan->h_tiles, batch->tiles.data(), tile_bytes);
-    batch->d_tiles = static_cast<Tile *>(plan->d_tiles);
-    batch->tiles_borrowed = true;
-    ok = cudaMemcpyAsync(plan->d_tiles, plan->h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
-    if (post != nullptr) {   // chunk table of the post-processing kernels: same route
+    // 3. post-processing only: the whole tile table and the chunk table of the post kernels, behind the first chunk (copies of
+    // one direction are served in issue order: whatever is queued behind every PCM chunk holds the kernels back until the last
+    // sample has arrived)
+    if (post != nullptr) {
+        batch_build_tiles(p, *batch, 0, n_utts, h_tiles);
+        ok = ok && cudaMemcpyAsync(d_tiles, h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
         mfcc::post_build_chunks(batch->frame_offsets, od, batch->post_chunks, batch->utt_first_post_chunk, &batch->post_rows);
         ok = ok && static_cast<int64_t>(batch->post_chunks.size()) == n_post_chunks;
         if (ok) std::memcpy(plan->h_post_chunks, batch->post_chunks.data(), pc_bytes);
         ok = ok && cudaMemcpyAsync(plan->d_post_chunks, plan->h_post_chunks, pc_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
+        ok = ok && cudaEventRecord(plan->tiles_ready, plan->streams[2]) == cudaSuccess;
+        ok = ok && cudaStreamWaitEvent(plan->streams[3], plan->tiles_ready, 0) == cudaSuccess;
     }
-    ok = ok && cudaEventRecord(plan->tiles_ready, plan->streams[2]) == cudaSuccess;
-    ok = ok && cudaStreamWaitEvent(plan->streams[3], plan->tiles_ready, 0) == cudaSuccess;
+    mark(2);
     for (size_t c = 1; c < n_chunks; ++c) queue_h2d(c);
+    mark(3);
 
     // 4. kernels and result copies, gated on the chunk events
     for (size_t c = 0; c < n_chunks && ok; ++c) {
@@ -539,9 +594,13 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
             ok = cudaMemcpyAsync(h_out + f0 * od_out, d_rows + f0 * od_out, sizeof(float) * (f1 - f0) * od_out,
                                  cudaMemcpyDeviceToHost, s) == cudaSuccess;
     }
+    mark(4);
     for (auto &s : plan->streams)
         if (s && cudaStreamSynchronize(s) != cudaSuccess) ok = false;
-    mfcc_batch_destroy(batch);
+    mark(5);
+    if (trace)
+        std::fprintf(stderr, "mfcc host path: %lld utts %lld tiles %zu chunks | sized %.3f first-h2d-queued %.3f post-table %.3f all-h2d-queued %.3f all-launched %.3f done %.3f ms\n",
+                     static_cast<long long>(n_utts), static_cast<long long>(n_tiles), n_chunks, t_mark[0], t_mark[1], t_mark[2], t_mark[3], t_mark[4], t_mark[5]);
     if (!ok) { cudaGetLastError(); return MFCC_ECUDA; }
     return MFCC_OK;
 }

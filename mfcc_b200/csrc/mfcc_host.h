@@ -126,6 +126,7 @@ struct mfcc_batch {
     std::vector<int64_t> frame_offsets;  // [n_utts + 1]
     std::vector<mfcc::Tile> tiles;       // host copy
     std::vector<int64_t> utt_first_tile; // [n_utts + 1] tile index range per utterance
+    std::vector<uint8_t> lead;           // [n_utts] or empty: the utterance starts with one history sample (mfcc_batch_create_lead)
     mfcc::Tile *d_tiles = nullptr;
     bool tiles_borrowed = false;         // d_tiles belongs to the plan (mfcc_compute_host)
     int64_t *d_frame_offsets = nullptr;
