@@ -532,9 +532,8 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     Tile *h_tiles = static_cast<Tile *>(plan->h_tiles), *d_tiles = static_cast<Tile *>(plan->d_tiles);
     batch->d_tiles = d_tiles;
     batch->tiles_borrowed = true;
-    // (With the post-processing kernels in the pipeline the table goes up in ONE piece behind the first chunk, as it did
-    // before: measured on configs[1], per-chunk pieces there cost the read-back its overlap with the input stream —
-    // 9.3 ms per call instead of 7.0 — while the plain path gains 10 % (int16) and 25 % (G.711) on the ragged batch.)
+    // (With the post-processing kernels in the pipeline the table goes up in ONE piece behind the first chunk, together
+    // with the chunk table of those kernels: 153 M frames/s on configs[1] against 151 M with per-chunk pieces.)
     const bool piecewise = post == nullptr;
     auto queue_h2d = [&](size_t c) {
         cudaStream_t copy = plan->streams[c & 1];
@@ -559,8 +558,10 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
     // one direction are served in issue order: whatever is queued behind every PCM chunk holds the kernels back until the last
     // sample has arrived)
     if (post != nullptr) {
-        batch_build_tiles(p, *batch, 0, n_utts, h_tiles);
-        ok = ok && cudaMemcpyAsync(d_tiles, h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
+        if (!piecewise) {
+            batch_build_tiles(p, *batch, 0, n_utts, h_tiles);
+            ok = ok && cudaMemcpyAsync(d_tiles, h_tiles, tile_bytes, cudaMemcpyHostToDevice, plan->streams[2]) == cudaSuccess;
+        }
         mfcc::post_build_chunks(batch->frame_offsets, od, batch->post_chunks, batch->utt_first_post_chunk, &batch->post_rows);
         ok = ok && static_cast<int64_t>(batch->post_chunks.size()) == n_post_chunks;
         if (ok) std::memcpy(plan->h_post_chunks, batch->post_chunks.data(), pc_bytes);
@@ -569,11 +570,9 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         ok = ok && cudaStreamWaitEvent(plan->streams[3], plan->tiles_ready, 0) == cudaSuccess;
     }
     mark(2);
-    for (size_t c = 1; c < n_chunks; ++c) queue_h2d(c);
-    mark(3);
-
-    // 4. kernels and result copies, gated on the chunk events
-    for (size_t c = 0; c < n_chunks && ok; ++c) {
+    // 4. kernels and result copies of a chunk, gated on the chunk's event
+    auto queue_compute = [&](size_t c) {
+        if (!ok) return;
         cudaStream_t s = plan->streams[2 + (c & 1)];
         const int64_t u0 = cut[c], u1 = cut[c + 1];
         const int64_t f0 = batch->frame_offsets[u0], f1 = batch->frame_offsets[u1];
@@ -593,7 +592,25 @@ int compute_host_impl(mfcc_plan *plan, const PcmT *h_pcm, int alaw, const int64_
         if (ok && f1 > f0)
             ok = cudaMemcpyAsync(h_out + f0 * od_out, d_rows + f0 * od_out, sizeof(float) * (f1 - f0) * od_out,
                                  cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    };
+    // The queue is PACED: chunk c goes on the wire only when chunk c - 2 has landed, and the kernels + read-back of chunk
+    // c - 1 are queued right behind it, so two input copies are in flight at any time and nothing else sits in the queues.
+    // Queueing everything up front (round 1) makes the outcome depend on WHEN the host gets there: with the faster table build
+    // of this round the read-back of the post-processing path lost its overlap with the input stream (9.3 ms per configs[1]
+    // call instead of 7.0; a 0.4 ms busy-wait before the queueing restored it).  Measured on one box, M frames/s for
+    // configs[1] plain / with post, ragged 8 kHz int16 / G.711 — unpaced: 162 / 110 / 304 / 472; depth 1: 156 / 151 / 291 /
+    // 467; depth 2: 162 / 152 / 309 / 508; depth 3: 162 / 147 / 304 / 489; depth 4: 162 / 126 / 302 / 486.
+    // (MFCC_HOST_DEPTH overrides the depth for such experiments; 0 = unpaced.)
+    static const int depth = std::getenv("MFCC_HOST_DEPTH") ? std::atoi(std::getenv("MFCC_HOST_DEPTH")) : 2;
+    for (size_t c = 1; c < n_chunks; ++c) {
+        if (depth > 0 && c >= static_cast<size_t>(depth)) ok = ok && cudaEventSynchronize(plan->chunk_ready[c - depth]) == cudaSuccess;
+        queue_h2d(c);
+        if (depth > 0) queue_compute(c - 1);
     }
+    mark(3);
+    if (depth > 0) queue_compute(n_chunks - 1);
+    else
+        for (size_t c = 0; c < n_chunks; ++c) queue_compute(c);
     mark(4);
     for (auto &s : plan->streams)
         if (s && cudaStreamSynchronize(s) != cudaSuccess) ok = false;
