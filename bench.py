@@ -419,6 +419,10 @@ def measure(ctx, name, steps, warmup, e2e_steps, with_cpu, peak=None):
         "batch": {"frames_per_step_per_gpu": frames, "utterances": n_utts, "input_mb_per_step": round(in_bytes / 1e6, 1)},
         "kernel": kernel_name,
         "audio_seconds_per_s": value * p.hop_len / p.sample_rate,
+        # BASELINE.json configs[4] (10,000 hours of 16 kHz PCM over the N GPUs, iterated over the resident batch): what this rate
+        # means for that corpus — device-timed, and end to end from host buffers
+        "configs4_10k_hours": {"device_timed_s": 3.6e7 / (value * p.hop_len / p.sample_rate),
+                               "from_host_buffers_s": 3.6e7 / (e2e_value * p.hop_len / p.sample_rate)} if name == "A" else None,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "steps": e2e_steps, "step_ms": e2e_step_ms,
