@@ -93,6 +93,15 @@
 #ifndef MFCC_SP_I2F
 #define MFCC_SP_I2F 0
 #endif
+// Pass-1 constants (window pairs, and for 32 x 16 the inter-pass twiddles) from the kernel PARAMETER bank under a warp-uniform
+// index (LDCU.128 into uniform registers) instead of shared memory: takes 232 broadcast LDS.128 per 32-frame tile off the
+// shared-memory port (6 % of its wavefronts) and the constants out of the vector registers.  Measured on one box, bit-identical
+// results (tools/time_variants.py): 512-point +5.1 % (1.818 -> 1.910 G frames/s on configs[1]); 256-point, window only (its
+// twiddles are applied in pass 2) -4.6 % — the switch is per geometry: bit 0 = 512-point pass 1, bit 1 = 256-point window,
+// bit 2 = 256-point pass-2 twiddles.
+#ifndef MFCC_SP_CONST_TABLES
+#define MFCC_SP_CONST_TABLES 1
+#endif
 // Which PCM entries this translation unit instantiates (the file is compiled once per input type so that the three sets
 // of kernel variants build in parallel): bit 0 int16 (+ the host half), bit 1 f32, bit 2 G.711 codes.
 #ifndef MFCC_SP_PCM_TYPES
@@ -150,6 +159,8 @@ struct Geo {
     // Where the inter-pass twiddle is applied.  16 x 16: pass 2 has one item per warp, seven plain rows and the longer
     // special row, so the plain rows take the twiddle on load (measured +1.4 %); 32 x 16: pass 1 keeps it (-0.7 % moved).
     static constexpr bool TW_IN_PASS2 = RB == 16 ? MFCC_SP_TW2_16 : MFCC_SP_TW2_32;
+    static constexpr bool CONST_TAB = ((MFCC_SP_CONST_TABLES) >> (RB == 16 ? 1 : 0)) & 1;   // pass-1 constants from the parameter bank
+    static constexpr bool CONST_TW2 = RB == 16 && (((MFCC_SP_CONST_TABLES) >> 2) & 1);       // 16 x 16: the pass-2 twiddles from it
     static constexpr int T_TW = T_WIN + RA / 2 * NZP * 2;  // TW_IN_PASS2 ? [H][RA] (row k1 - 1, column a) : [RA][H] float2
     static constexpr int T_TWH = T_TW + RA * H * 2;        // [RA] float2
     static constexpr int TABF = T_TWH + RA * 2;
@@ -197,6 +208,9 @@ struct SpArgs {
     // s = 1 / (w NFFT), segment index * 128 (byte offset into the rise / fall scratch; -1 ends the list)}: read with a
     // warp-uniform index they arrive in uniform registers, so every branch of the walk is a uniform branch.
     float4 useg[kWarps][kSegParam];
+    // MFCC_SP_CONST_TABLES: the pass-1 constants as parameters too (filled for the geometries that use them)
+    float4 winc[kWarps][14];    // [column pair][b / 2]: window values of rows b, b + 1 of the pair's two columns
+    float4 twc[16][8];          // 32 x 16 only: [column][(k1 - 1) / 2] inter-pass twiddles of k1, k1 + 1
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -766,11 +780,12 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
         if constexpr ((MFCC_SP_ABLATE & 2) == 0) {
             const int pr = warp;
             const float *base = staged + e + lane * STRIDE + 2 * pr;
-            const float *wrow = t_win + pr * (2 * G::NZP);
+            [[maybe_unused]] const float *wrow = t_win + pr * (2 * G::NZP);
+            [[maybe_unused]] const int upr = __shfl_sync(0xffffffffu, pr, 0);
             float2 in[NZ];
 #pragma unroll
             for (int b = 0; b < NZ; b += 2) {
-                const float4 w = lds_f4(wrow + 2 * b);
+                const float4 w = G::CONST_TAB ? a.winc[upr][b / 2] : lds_f4(wrow + 2 * b);
                 const float2 y0 = lds_f2(base + G::padded(RA * b));
                 in[b] = make_float2(y0.x * w.x, y0.y * w.y);
                 if (b + 1 < NZ) {
@@ -793,10 +808,11 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
 #pragma unroll
                     for (int k1 = 1; k1 < H; ++k1) wsa[(k1 - 1) * RA * 32] = make_float2(X[k1].re, X[k1].im);
                 } else {
-                    const float *trow = t_tw + col * (2 * H);
+                    [[maybe_unused]] const float *trow = t_tw + col * (2 * H);
 #pragma unroll
                     for (int k1 = 1; k1 < H; k1 += 2) {
-                        const float4 tw = lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
+                        const float4 tw = G::CONST_TAB ? a.twc[(2 * upr + hh) & 15][(k1 - 1) / 2]
+                                                        : lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
                         const rf::cplx v = rf::cmulc(X[k1], tw.x, tw.y);
                         wsa[(k1 - 1) * RA * 32] = make_float2(v.re, v.im);
                         if (k1 + 1 < H) {
@@ -826,10 +842,11 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     const float2 *row = ws + (k1 - 1) * RA * 32 + lane;
                     rf::cplx z[RA];
                     if constexpr (G::TW_IN_PASS2) {
-                        const float *trow = t_tw + (k1 - 1) * (2 * RA);      // W_N^(a k1), a = 0 .. RA - 1
+                        [[maybe_unused]] const float *trow = t_tw + (k1 - 1) * (2 * RA);      // W_N^(a k1), a = 0 .. RA - 1
+                        [[maybe_unused]] const int uk = __shfl_sync(0xffffffffu, k1 - 1, 0) & 15;
 #pragma unroll
                         for (int c = 0; c < RA; c += 2) {
-                            const float4 tw = lds_f4(trow + 2 * c);
+                            const float4 tw = G::CONST_TW2 ? a.twc[uk][c / 2] : lds_f4(trow + 2 * c);
                             const float2 p = row[c * 32], q = row[(c + 1) * 32];
                             z[c] = c == 0 ? rf::cplx{p.x, p.y} : rf::cmulc(rf::cplx{p.x, p.y}, tw.x, tw.y);
                             z[c + 1] = rf::cmulc(rf::cplx{q.x, q.y}, tw.z, tw.w);
@@ -1291,6 +1308,20 @@ int sp_prepare(mfcc_plan *plan)
     st->smem = sizeof(float) * (static_cast<size_t>(lay.total) + groups_for(RB) * static_cast<size_t>(half_floats));
     if (st->smem > kSmemMax) { delete st; return MFCC_ENOTSUP; }
     st->args.lay = lay;
+    {
+        const float *win = tab.data(), *tw = tab.data() + RA / 2 * NZP * 2;
+        for (int pr = 0; pr < RA / 2 && pr < kWarps; ++pr)
+            for (int q = 0; q < NZP / 2 && q < 14; ++q)
+                st->args.winc[pr][q] = make_float4(win[pr * 2 * NZP + 4 * q], win[pr * 2 * NZP + 4 * q + 1], win[pr * 2 * NZP + 4 * q + 2], win[pr * 2 * NZP + 4 * q + 3]);
+        if (tw_in_pass2)      // rows k1 - 1 of the [H][RA] table, two columns per float4
+            for (int r = 0; r < H && r < 16; ++r)
+                for (int q = 0; q < RA / 2 && q < 8; ++q)
+                    st->args.twc[r][q] = make_float4(tw[r * 2 * RA + 4 * q], tw[r * 2 * RA + 4 * q + 1], tw[r * 2 * RA + 4 * q + 2], tw[r * 2 * RA + 4 * q + 3]);
+        else
+            for (int col = 0; col < RA && col < 16; ++col)
+                for (int q = 0; q < H / 2 && q < 8; ++q)
+                    st->args.twc[col][q] = make_float4(tw[col * 2 * H + 4 * q], tw[col * 2 * H + 4 * q + 1], tw[col * 2 * H + 4 * q + 2], tw[col * 2 * H + 4 * q + 3]);
+    }
     st->args.n_mel = M;
     st->args.n_cep = p.n_cep;
     st->args.logmel = p.output == MFCC_OUT_LOGMEL;
