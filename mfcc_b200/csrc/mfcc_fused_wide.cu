@@ -91,8 +91,15 @@ struct Geo {
     static constexpr int RAW = (TCEIL + 16) / 2;            // floats holding 8 lead + TCEIL + 1 look-ahead int16 samples
     static constexpr int HALF = UNION + WS + R0 + 4;        // + mbarrier (8 B in a 16-B slot)
     static constexpr int T_WIN = 0;                         // [RA][NZP] float: the window values of column a, row b
-    static constexpr int T_TW = T_WIN + RA * NZP;           // [RA][H] float2: W_N^(a k1), k1 = 1 .. H at slot k1 - 1
-    static constexpr int TABF = T_TW + RA * H * 2;
+    // The four quarter-warps of a pass-1 load read four DIFFERENT columns' rows: a row stride of 2 H = 64 floats would put all
+    // four on the same banks (4 wavefronts per LDS.128: 1,536 of the 18,600 wavefronts per 32 frames); 4 floats of padding per
+    // row (stride = 4 mod 32) separates them.  MFCC_WIDE_TWPAD 0 restores the unpadded table for A/B timing.
+#ifndef MFCC_WIDE_TWPAD
+#define MFCC_WIDE_TWPAD 4
+#endif
+    static constexpr int TWS = 2 * H + MFCC_WIDE_TWPAD;     // floats per twiddle row
+    static constexpr int T_TW = T_WIN + RA * NZP;           // [RA][TWS]: float2 W_N^(a k1), k1 = 1 .. H at slot k1 - 1
+    static constexpr int TABF = T_TW + RA * TWS;
     static constexpr int pcol(int c) { return c ^ ((c >> 1) & 1); }
     static_assert(STRIDE % 32 == 4, "quarter-warp bank separation of the staged tile");
     static_assert(HOP % 8 == 0 && HOP % RA == 0, "chunks and column pairs must not straddle a hop block");
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 rf::rdft64<NZ>(x, X);
                 r0row[col * F + f] = X[0].re;
                 float *wsa = ws + ((col ^ ((col >> 1) & 1)) * F + f) * 2;   // column slot pcol(col)
-                const float *trow = t_tw + col * (2 * H);
+                const float *trow = t_tw + col * G::TWS;
 #pragma unroll
                 for (int k1 = 1; k1 <= H; k1 += 2) {
                     const float4 tw = lds_f4(trow + 2 * (k1 - 1));       // twiddles of k1, k1 + 1
@@ -696,12 +703,14 @@ int wide_prepare(mfcc_plan *plan)
             const int i = col + RA * b;
             tab.push_back(b < NZ && i < p.frame_len ? h.window[i] : 0.0f);
         }
-    for (int col = 0; col < RA; ++col)
+    for (int col = 0; col < RA; ++col) {
         for (int sl = 0; sl < H; ++sl) {
             const double ang = -2.0 * M_PI * static_cast<double>(col) * (sl + 1) / N;
             tab.push_back(static_cast<float>(std::cos(ang)));
             tab.push_back(static_cast<float>(std::sin(ang)));
         }
+        for (int pad = 2 * H; pad < G0::TWS; ++pad) tab.push_back(0.0f);   // row padding (bank separation of the quarter-warps)
+    }
     if (static_cast<int>(tab.size()) != G0::TABF) return MFCC_ECUDA;
 
     WideLayout lay{};
