@@ -94,7 +94,7 @@
 #define MFCC_SP_I2F 0
 #endif
 // Pass-1 constants (window pairs, and for 32 x 16 the inter-pass twiddles) from the kernel PARAMETER bank under a warp-uniform
-// index (LDCU.128 into uniform registers) instead of shared memory: takes 232 broadcast LDS.128 per 32-frame tile off the
+// index (uniform constant loads into uniform registers: LDCU.64 pairs in the shipped binary, profiles/r2_sass_sp_A.md) instead of shared memory: takes 232 broadcast LDS.128 per 32-frame tile off the
 // shared-memory port (6 % of its wavefronts) and the constants out of the vector registers.  Measured on one box, bit-identical
 // results (tools/time_variants.py): 512-point +5.1 % (1.818 -> 1.910 G frames/s on configs[1]); 256-point, window only (its
 // twiddles are applied in pass 2) -4.6 % — the switch is per geometry: bit 0 = 512-point pass 1, bit 1 = 256-point window,
@@ -202,7 +202,7 @@ struct SpArgs {
     float preemph, log_floor;
     // tail-warp variants (MEL > 0): ln 2 * d[k][q] for q < MEL / 2 (the mirrored half follows from d[k][M - 1 - q] =
     // (-1)^k d[k][q]).  Kernel parameters live in the constant bank, so with compile-time indices every entry is
-    // a uniform-register FFMA operand fetched four at a time (LDCU.128): no shared-memory loads in the DCT.
+    // a constant-bank FFMA operand (LDC.64 in the shipped binary: the index depends on the warp parity): no shared-memory loads in the DCT.
     float4 dctc[KC / 2][2][kFoldMax / 4];   // [k / 2][k & 1][q / 4]; odd n_mel: the middle band pairs with itself, its entry is halved
     // tail-warp variants: the segment walks of S3 as parameters too, {first bin * 128 (byte offset into P), width w,
     // s = 1 / (w NFFT), segment index * 128 (byte offset into the rise / fall scratch; -1 ends the list)}: read with a
