@@ -95,7 +95,7 @@
 #endif
 // Pass-1 constants (window pairs, and for 32 x 16 the inter-pass twiddles) from the kernel PARAMETER bank under a warp-uniform
 // index (uniform constant loads into uniform registers: LDCU.64 pairs in the shipped binary, profiles/r2_sass_sp_A.md) instead of shared memory: takes 232 broadcast LDS.128 per 32-frame tile off the
-// shared-memory port (6 % of its wavefronts) and the constants out of the vector registers.  Measured on one box, bit-identical
+// shared-memory port (ncu: 117.1 M -> 100.9 M wavefronts per configs[1] launch) and the constants out of the vector registers.  Measured on one box, bit-identical
 // results (tools/time_variants.py): 512-point +5.1 % (1.818 -> 1.910 G frames/s on configs[1]); 256-point, window only (its
 // twiddles are applied in pass 2) -4.6 % — the switch is per geometry: bit 0 = 512-point pass 1, bit 1 = 256-point window,
 // bit 2 = 256-point pass-2 twiddles.
