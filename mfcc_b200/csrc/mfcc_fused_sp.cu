@@ -102,6 +102,11 @@
 #ifndef MFCC_SP_CONST_TABLES
 #define MFCC_SP_CONST_TABLES 1
 #endif
+// The 16 twiddles of the special pass-2 item (rows 0 and H) as constant-bank operands instead of 8 LDS.128: bit 0 = 512-point,
+// bit 1 = 256-point.  Measured (one box, bit-identical): 512-point -0.5 %, 256-point +0.7 % -> on for 256-point only.
+#ifndef MFCC_SP_CONST_TWH
+#define MFCC_SP_CONST_TWH 2
+#endif
 // Which PCM entries this translation unit instantiates (the file is compiled once per input type so that the three sets
 // of kernel variants build in parallel): bit 0 int16 (+ the host half), bit 1 f32, bit 2 G.711 codes.
 #ifndef MFCC_SP_PCM_TYPES
@@ -211,6 +216,8 @@ struct SpArgs {
     // MFCC_SP_CONST_TABLES: the pass-1 constants as parameters too (filled for the geometries that use them)
     float4 winc[kWarps][14];    // [column pair][b / 2]: window values of rows b, b + 1 of the pair's two columns
     float4 twc[16][8];          // 32 x 16 only: [column][(k1 - 1) / 2] inter-pass twiddles of k1, k1 + 1
+    float4 twhc[8];             // row-H twiddles W_(2 RA)^a of columns 2 q, 2 q + 1: compile-time indices, so they are plain
+                                // constant-bank operands of the multiplications (MFCC_SP_CONST_TWH)
 };
 
 __device__ __forceinline__ float2 lds_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
@@ -875,7 +882,8 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     rf::cplx zh[RA];
 #pragma unroll
                     for (int c = 0; c < RA; c += 2) {
-                        const float4 tw = lds_f4(t_twh + 2 * c);
+                        constexpr bool kConstTwh = ((MFCC_SP_CONST_TWH) >> (RB == 16 ? 1 : 0)) & 1;
+                        const float4 tw = kConstTwh ? a.twhc[c / 2] : lds_f4(t_twh + 2 * c);
                         const float2 p = row[c * 32], q = row[(c + 1) * 32];
                         r0[c] = p.x;
                         r0[c + 1] = q.x;
@@ -1308,6 +1316,10 @@ int sp_prepare(mfcc_plan *plan)
     st->smem = sizeof(float) * (static_cast<size_t>(lay.total) + groups_for(RB) * static_cast<size_t>(half_floats));
     if (st->smem > kSmemMax) { delete st; return MFCC_ENOTSUP; }
     st->args.lay = lay;
+    {
+        const float *twh = tab.data() + RA / 2 * NZP * 2 + RA * H * 2;
+        for (int q = 0; q < RA / 2 && q < 8; ++q) st->args.twhc[q] = make_float4(twh[4 * q], twh[4 * q + 1], twh[4 * q + 2], twh[4 * q + 3]);
+    }
     {
         const float *win = tab.data(), *tw = tab.data() + RA / 2 * NZP * 2;
         for (int pr = 0; pr < RA / 2 && pr < kWarps; ++pr)
