@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
         {
             {
                 // 38 scalar loads (lane stride 4 words + the slot: 32 distinct banks), window from the
-                // column's own row of the table (four rows per 16-byte load)
+                // column's own row of the table (four rows per 16-byte load).  (The window rows as kernel parameters — what gave
+                // the 512-point kernel 5 % — were measured here too: a warp reads four different columns, so the loads are
+                // indexed, divergent constant loads, and the kernel runs at 0.62 x: 0.334 -> 0.207 G frames/s.)
                 const int col = slot;
                 const float *base = staged + e + f * STRIDE + col;
                 const float *wrow = t_win + col * G::NZP;
