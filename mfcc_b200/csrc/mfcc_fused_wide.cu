@@ -46,6 +46,20 @@
 #ifndef MFCC_WIDE_LOCK
 #define MFCC_WIDE_LOCK 12
 #endif
+// Two bank-conflict fixes found with the per-line "excessive wavefronts" of an ncu capture (profiles/r2_wide_C.md), each a
+// build switch for A/B timing:
+//   MFCC_WIDE_VMPAD   words between the two folded log-energy arrays of S3b / S4.  The even and the odd cepstra read v+ and
+//                     v- at the same index; with the arrays a multiple of 32 words apart (hmp * F = 320 for 80 bands) the two
+//                     halves of a warp met on the same banks: 9.6 M of the 27.8 M excessive wavefronts of a launch.
+//   MFCC_WIDE_S0SWAP  lanes 4 .. 7 of every eight write the two 16-byte halves of their staged chunk in the opposite order.
+//                     Chunks are 32 bytes apart, so a quarter-warp's eight 16-byte stores covered only half of the banks
+//                     (2-way conflict on both stores: 7.9 M excessive wavefronts); swapped, they cover all 32.
+#ifndef MFCC_WIDE_VMPAD
+#define MFCC_WIDE_VMPAD 8
+#endif
+#ifndef MFCC_WIDE_S0SWAP
+#define MFCC_WIDE_S0SWAP 1
+#endif
 // Poison build (see mfcc_fused_sp.cu): NaN-fill every aliased buffer at the point where the comments say it is dead.
 #ifndef MFCC_POISON
 #define MFCC_POISON 0
@@ -343,6 +357,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                         *reinterpret_cast<float2 *>((2 < e ? dl : dst) + 2) = make_float2(lo4.z, lo4.w);
                         *reinterpret_cast<float2 *>((4 < e ? dl : dst) + 4) = make_float2(hi4.x, hi4.y);
                         *reinterpret_cast<float2 *>(dst + 6) = make_float2(hi4.z, hi4.w);
+                    } else if (MFCC_WIDE_S0SWAP) {
+                        const bool sw = (lane & 4) != 0;
+                        const float4 q0 = sw ? hi4 : lo4, q1 = sw ? lo4 : hi4;
+                        *reinterpret_cast<float4 *>(dst + (sw ? 4 : 0)) = q0;
+                        *reinterpret_cast<float4 *>(dst + (sw ? 0 : 4)) = q1;
                     } else {
                         *reinterpret_cast<float4 *>(dst) = lo4;
                         *reinterpret_cast<float4 *>(dst + 4) = hi4;
@@ -575,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                 }
             } else {
                 const int hm = (a.n_mel + 1) >> 1, total = a.hmp * F;     // hmp = hm rounded up to even: the pad row is zeroed
-                float *vp = scr, *vm = scr + a.hmp * F;
+                float *vp = scr, *vm = scr + a.hmp * F + MFCC_WIDE_VMPAD;
                 for (int i = tid; i < total; i += kHalfThreads) {
                     const int q = i / F;
                     float sum = 0.0f, dif = 0.0f;
@@ -621,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
             const bool second = slot < a.n2;               // this thread also forms c[slot + 32] (uniform per warp: n2 is a multiple of 4)
             float c0 = 0.0f, c1 = 0.0f, e0 = 0.0f, e1 = 0.0f;
             auto dct_terms = [&](int hq) {
-                const float *v = scr + ((slot & 1) ? a.hmp * F : 0) + f;
+                const float *v = scr + ((slot & 1) ? a.hmp * F + MFCC_WIDE_VMPAD : 0) + f;
                 const float2 *da = reinterpret_cast<const float2 *>(t_dct) + slot * hq;                    // {d[s][q], d[s][q+1]}
                 const float2 *db = reinterpret_cast<const float2 *>(t_dct + kSlots * hq * 2) + slot * hq;  // {d[s+32][q], d[s+32][q+1]}, s < n2
 #pragma unroll 4
@@ -686,7 +705,7 @@ const char *wide_match(const mfcc_params &p, const HostTables &h)
     if (p.n_mel < 2 || p.log_floor < 1.17549435e-38f) return nullptr;   // band pairs; lg2.approx.ftz needs a normal floor
     // tail scratch (log band energies [n_mel][F] or log-mel rows [F][n_mel | 1], then the per-segment rise / fall
     // sums [n_mel + 1][F] x 2) must stay below the raw PCM buffer
-    if (3 * F * static_cast<size_t>(p.n_mel + 4) + F > static_cast<size_t>(G0::RAWOFF)) return nullptr;
+    if (3 * F * static_cast<size_t>(p.n_mel + 4) + F + MFCC_WIDE_VMPAD > static_cast<size_t>(G0::RAWOFF)) return nullptr;
     return "fused_wide_tile8_L1200_H480_real64x32";
 }
 
@@ -768,7 +787,7 @@ int wide_prepare(mfcc_plan *plan)
     st->args.mel_magic = (1 << 20) / h.out_dim + 1;
     st->args.hmp = hmp;
     st->args.n2 = n2;
-    st->args.rf = (F * std::max(std::max(h.out_dim | 1, M), 2 * hmp) + 3) / 4 * 4;
+    st->args.rf = (std::max(F * std::max(h.out_dim | 1, M), 2 * F * hmp + MFCC_WIDE_VMPAD) + 3) / 4 * 4;
     st->args.ef = st->args.rf + 2 * F * (M + 3);
     st->args.preemph = p.preemph;
     st->args.log_floor = p.log_floor;
