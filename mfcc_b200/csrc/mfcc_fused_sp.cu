@@ -93,6 +93,10 @@
 #ifndef MFCC_SP_I2F
 #define MFCC_SP_I2F 0
 #endif
+// S0 of bulk-copied int16 tiles: lanes rotate the order of their four 8-byte stores (see the comment at the stores)
+#ifndef MFCC_SP_S0ROT
+#define MFCC_SP_S0ROT 0
+#endif
 // Pass-1 constants (window pairs, and for 32 x 16 the inter-pass twiddles) from the kernel PARAMETER bank under a warp-uniform
 // index (uniform constant loads into uniform registers: LDCU.64 pairs in the shipped binary, profiles/r2_sass_sp_A.md) instead of shared memory: takes 232 broadcast LDS.128 per 32-frame tile off the
 // shared-memory port (ncu: 117.1 M -> 100.9 M wavefronts per configs[1] launch) and the constants out of the vector registers.  Measured on one box, bit-identical
@@ -685,11 +689,33 @@ __global__ void __launch_bounds__(groups_for(RB_) * kHalfThreads, 1) fused_sp_ke
                     float *d2 = dst + 2 + (2 < e ? pad_first : pad);
                     float *d4 = dst + 4 + (4 < e ? pad_first : pad);
                     float *d6 = dst + 6 + pad;
-                    *reinterpret_cast<float2 *>(d2) = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
-                    *reinterpret_cast<float2 *>(d4) = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
-                    *reinterpret_cast<float2 *>(d6) = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
                     const float xe = s16x2_to_f32(pv).x;
-                    *reinterpret_cast<float2 *>(d0) = make_float2(fmaf(na, xe, x01.x), fmaf(na, x01.x, x01.y));
+                    float2 y0 = make_float2(fmaf(na, xe, x01.x), fmaf(na, x01.x, x01.y));
+                    float2 y2 = make_float2(fmaf(na, x01.y, x23.x), fmaf(na, x23.x, x23.y));
+                    float2 y4 = make_float2(fmaf(na, x23.y, x45.x), fmaf(na, x45.x, x45.y));
+                    float2 y6 = make_float2(fmaf(na, x45.y, x67.x), fmaf(na, x67.x, x67.y));
+                    // Chunks are 32 bytes apart, so in one 8-byte store the lanes j, j + 4, j + 8, ... of a half-warp all hit
+                    // the same bank pair (4-way conflict: 11.9 M of the 13.9 M excessive wavefronts of a configs[1] launch).
+                    // MFCC_SP_S0ROT: lanes rotate the ORDER in which they write their four pieces by (lane / 4) mod 4 (2: full
+                    // rotation, conflict-free; 1: halves swapped for lanes with bit 2 set, 2-way) — selects, no extra stores.
+                    if constexpr (MFCC_SP_S0ROT >= 1) {
+                        const bool r2 = MFCC_SP_S0ROT >= 2 ? (lane & 8) != 0 : (lane & 4) != 0;
+                        const float2 t0 = r2 ? y4 : y0, t2 = r2 ? y6 : y2, t4 = r2 ? y0 : y4, t6 = r2 ? y2 : y6;
+                        float *e0 = r2 ? d4 : d0, *e2 = r2 ? d6 : d2, *e4 = r2 ? d0 : d4, *e6 = r2 ? d2 : d6;
+                        y0 = t0; y2 = t2; y4 = t4; y6 = t6;
+                        d0 = e0; d2 = e2; d4 = e4; d6 = e6;
+                        if constexpr (MFCC_SP_S0ROT >= 2) {
+                            const bool r1 = (lane & 4) != 0;
+                            const float2 u0 = r1 ? y2 : y0, u2 = r1 ? y4 : y2, u4 = r1 ? y6 : y4, u6 = r1 ? y0 : y6;
+                            float *g0 = r1 ? d2 : d0, *g2 = r1 ? d4 : d2, *g4 = r1 ? d6 : d4, *g6 = r1 ? d0 : d6;
+                            y0 = u0; y2 = u2; y4 = u4; y6 = u6;
+                            d0 = g0; d2 = g2; d4 = g4; d6 = g6;
+                        }
+                    }
+                    *reinterpret_cast<float2 *>(d0) = y0;
+                    *reinterpret_cast<float2 *>(d2) = y2;
+                    *reinterpret_cast<float2 *>(d4) = y4;
+                    *reinterpret_cast<float2 *>(d6) = y6;
                 }
             }
             // the utterance's first sample has no predecessor: y = x.  It is word e of chunk 0 (thread 0 wrote it
