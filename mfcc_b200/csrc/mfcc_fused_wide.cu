@@ -60,6 +60,11 @@
 #ifndef MFCC_WIDE_S0SWAP
 #define MFCC_WIDE_S0SWAP 1
 #endif
+//   MFCC_WIDE_SEGPERM the walk order of S3 is permuted on the host so that the four segments a warp walks at once start on bins
+//                     that differ modulo 4 (see wide_prepare)
+#ifndef MFCC_WIDE_SEGPERM
+#define MFCC_WIDE_SEGPERM 1
+#endif
 // Poison build (see mfcc_fused_sp.cu): NaN-fill every aliased buffer at the point where the comments say it is dead.
 #ifndef MFCC_POISON
 #define MFCC_POISON 0
@@ -127,7 +132,7 @@ struct Geo {
 };
 
 struct WideLayout {
-    int seg;      // float4 per segment j: {first bin * F (int), width w (int), s = 1 / (w NFFT), unused}
+    int seg;      // float4 per walk position: {first bin * F (int), width w (int), s = 1 / (w NFFT), segment index (int)}
     int dct;      // [32 slots][hmp] d[s][m], then [n2 slots][hmp] d[s + 32][m]; m < hmp = ceil(n_mel / 2) rounded up to
                   // even (the mirrored half follows from the symmetry); zero past n_cep
     int total;
@@ -568,8 +573,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_wide_kernel(const PcmT *__r
                     S += sa;
                 }
                 const float rs = sg.z * T;                  // s = 1 / (w NFFT); pseudo-segments (energy term): s = 0
-                rise[j * F] = rs;
-                fall[j * F] = fmaf(a.inv_n, S, -rs);
+                const int row = __float_as_int(sg.w);      // the segment this walk position holds (the walk order is permuted)
+                rise[row * F] = rs;
+                fall[row * F] = fmaf(a.inv_n, S, -rs);
             }
         }
         lock_at(4);
@@ -737,21 +743,54 @@ int wide_prepare(mfcc_plan *plan)
     WideLayout lay{};
     align4();
     lay.seg = static_cast<int>(tab.size());
-    for (int j = 0; j <= M; ++j) {
-        const int k0 = h.mel_bins[j], w = h.mel_bins[j + 1] - k0;
-        push_int(k0 * F);
-        push_int(w);
-        const double sc = w > 0 ? 1.0 / (static_cast<double>(w) * N) : 0.0;
-        tab.push_back(static_cast<float>(sc));
-        tab.push_back(static_cast<float>(sc * w));
-    }
-    // pseudo-segments below and above the filterbank (energy term only): plain sums, s = 0 and s w = 1 / N
-    const int below[2] = {0, h.mel_bins[0]}, above[2] = {h.mel_bins[M + 1], h.nbins - h.mel_bins[M + 1]};
-    for (const int *g : {below, above}) {
-        push_int(g[0] * F);
-        push_int(g[1]);
-        tab.push_back(0.0f);
-        tab.push_back(static_cast<float>(1.0 / N));
+    {
+        // segments 0 .. M of the filterbank, then (energy term only) the two pseudo-segments below and above it: plain sums
+        struct SegD { int k0, w; float sc; };
+        std::vector<SegD> segs;
+        for (int j = 0; j <= M; ++j) {
+            const int k0 = h.mel_bins[j], w = h.mel_bins[j + 1] - k0;
+            segs.push_back({k0, w, static_cast<float>(w > 0 ? 1.0 / (static_cast<double>(w) * N) : 0.0)});
+        }
+        segs.push_back({0, h.mel_bins[0], 0.0f});
+        segs.push_back({h.mel_bins[M + 1], h.nbins - h.mel_bins[M + 1], 0.0f});
+        // Walk order.  Position j is walked by slot j mod 32 in round j / 32, and the four slots of a warp run in lockstep over
+        // FOUR segments at once: P rows are F = 8 words, so two of them meet on the same banks whenever their first bins agree
+        // modulo 4 (with neighbouring segments in natural order: 7.4 M excessive wavefronts per launch, every load of the walk
+        // twice).  So each group of four positions takes, from the next few segments not yet placed, four whose first bins
+        // differ modulo 4 where that is possible — still neighbours, so their widths (loop counts) stay close.
+        // (Only the filterbank's own segments move: the two pseudo-segments stay at the end, where a plan without the energy
+        // term — nseg = M + 1 — does not walk them.)
+        const int total = M + 1;
+        std::vector<int> order;
+        std::vector<char> used(total, 0);
+        int next = 0;
+        while (static_cast<int>(order.size()) < total) {
+            while (next < total && used[next]) ++next;
+            bool taken[4] = {false, false, false, false};
+            int got = 0;
+            std::vector<int> group;
+            for (int c = next; c < total && c < next + (MFCC_WIDE_SEGPERM ? 10 : 4) && got < 4; ++c) {
+                if (used[c]) continue;
+                const int r = segs[c].k0 & 3;
+                if (MFCC_WIDE_SEGPERM && taken[r]) continue;
+                taken[r] = true;
+                used[c] = 1;
+                group.push_back(c);
+                ++got;
+            }
+            for (int c = next; c < total && got < 4; ++c)      // no distinct residue left nearby: fill up in natural order
+                if (!used[c]) { used[c] = 1; group.push_back(c); ++got; }
+            for (int c : group) order.push_back(c);
+        }
+        order.push_back(M + 1);
+        order.push_back(M + 2);
+        for (int pos = 0; pos < M + 3; ++pos) {
+            const SegD &g = segs[order[pos]];
+            push_int(g.k0 * F);
+            push_int(g.w);
+            tab.push_back(g.sc);
+            push_int(order[pos]);                              // where its two sums go: rise / fall row of the segment
+        }
     }
     align4();
     // DCT entries by slot (see S4).  Band m pairs with M - 1 - m; for odd M the middle band pairs with itself,
